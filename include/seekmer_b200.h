@@ -1,0 +1,196 @@
+/*
+ * seekmer_b200.h — C ABI of the B200-native Seekmer bulk-infer hot path.
+ *
+ * The reference (GuanLab/seekmer) has no FFI layer: its native code is Cython
+ * compiled into the Python package, and the boundary of the hot path is the
+ * Python-level API of `seekmer._mapper.ReadMapper`, `seekmer.mapper` and
+ * `seekmer.infer`.  This header is what a ctypes (or Cython
+ * `cdef extern`) binding on the reference side would bind instead; the stub is
+ * shown in INTEGRATION.md.  Every entry point names the reference interface it
+ * replaces (paths relative to /root/reference/seekmer/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy / Python types.
+ *   - every function returns 0 on success, a negative skm_status on failure;
+ *     skm_last_error() returns a per-thread message for the last failure.
+ *   - handles own their device memory; callers own every buffer they pass.
+ *   - a handle is bound to one device and is not thread-safe; use one mapper
+ *     per host thread / stream (the reference's one ReadMapper per thread,
+ *     mapper.py:174-182).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls with host buffers synchronise the stream before returning; calls
+ *     with device buffers only enqueue work.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with SKM_ERR_CUDA.
+ */
+#ifndef SEEKMER_B200_H
+#define SEEKMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKM_KMER_SIZE 25             /* _kmer.pxd:9-17 */
+#define SKM_MAX_FRAGMENT_LENGTH 2000 /* _mapper.pyx:18 */
+
+typedef enum skm_status {
+    SKM_OK = 0,
+    SKM_ERR_INVALID = -1,   /* bad argument */
+    SKM_ERR_CUDA = -2,      /* CUDA runtime / no device */
+    SKM_ERR_CAPACITY = -3,  /* class table, id pool or list arena exhausted */
+    SKM_ERR_OOM = -4        /* device allocation failed */
+} skm_status;
+
+typedef struct skm_index skm_index;
+typedef struct skm_mapper skm_mapper;
+
+/* ---- index input contract: the arrays held by `KMerIndex` ------------------
+ * (_common.pxd:15-35,57-66; dtypes as produced by `seekmer index`,
+ *  _index_builder.pyx:129-141,551-571) */
+typedef struct skm_kmer_slot {   /* `kmers`: open addressing, linear probing */
+    uint64_t kmer;               /* contig-forward 2-bit 25-mer; all-ones = empty */
+    int32_t entry;               /* contig id */
+    int32_t offset;              /* k-mer position inside the contig */
+} skm_kmer_slot;
+
+typedef struct skm_contig_entry { /* `contigs` */
+    int64_t offset;              /* into `sequences` */
+    int64_t length;
+    uint64_t first_kmer;
+    uint64_t last_kmer;
+    int64_t target_offset;       /* into `targets` */
+    int64_t target_count;
+} skm_contig_entry;
+
+typedef struct skm_target {      /* `targets`: sorted by signed (entry, offset) per contig */
+    int32_t entry;               /* transcript t, or ~t when the contig is reverse in t */
+    int32_t offset;
+} skm_target;
+
+const char *skm_last_error(void);
+int skm_device_count(void);
+const char *skm_version(void);
+
+/* Replaces: KMerIndex.__init__ / KMerIndex.load (_common.pyx:21-48,287-313).
+ * Re-lays the index out for the GPU once: canonical-key open-addressing table
+ * (load <= 0.5, 16-byte slots), 32-byte contig records, 2-bit packed contig
+ * sequences, entry-only int32 target lists.  `inputs_on_device` != 0 means the
+ * four arrays are device pointers on `device` (reference layout); they are
+ * only read. */
+int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
+                     const skm_contig_entry *contigs, int64_t n_contigs,
+                     const char *sequences, int64_t n_bases,
+                     const skm_target *targets, int64_t n_targets,
+                     int64_t n_transcripts, int device, int inputs_on_device,
+                     void *stream, skm_index **out);
+void skm_index_destroy(skm_index *index);
+
+/* info[0]=distinct k-mers, [1]=device table slots, [2]=max target_count,
+ * [3]=device bytes held, [4]=n_contigs, [5]=n_targets, [6]=n_transcripts, [7]=device */
+int skm_index_info(const skm_index *index, int64_t info[8]);
+
+/* Replaces: KMerIndex.map_kmer (_common.pyx:54-97) for a vector of k-mers
+ * (parity test (i) of SURVEY.md §8(c)).  Miss = {entry 0, offset -1}. */
+int skm_map_kmers(const skm_index *index, const uint64_t *kmers, int64_t n,
+                  int32_t *out_entry, int32_t *out_offset, int buffers_on_device,
+                  void *stream);
+
+/* Replaces: ReadMapper.__init__ + MapResult.__init__ state
+ * (_mapper.pyx:39-53, mapper.py:43-58): a device-resident class dictionary
+ * (ordered transcript-id tuple -> count, first-seen unit index), the FLD
+ * histogram and the unaligned counter.  class_capacity = max distinct classes
+ * (0 = default 1<<22), id_capacity = total ids over all classes (0 = 8x). */
+int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t id_capacity,
+                      skm_mapper **out);
+void skm_mapper_destroy(skm_mapper *mapper);
+/* Replaces: MapResult.clear + fresh FLD (mapper.py:143-145). */
+int skm_mapper_reset(skm_mapper *mapper, void *stream);
+
+/* Replaces: one iteration of ReadMapper.__call__ (_mapper.pyx:73-101):
+ * map_read / map_read_pair on every unit of the batch, FLD update (:90-94),
+ * MapResult.update (mapper.py:60-75) into the device dictionary.
+ *
+ *   bases         all reads concatenated, one ASCII byte per base (any byte
+ *                 other than ACGTacgt encodes as 'A' for k-mers and is a
+ *                 wildcard for the 8-base edge checks, _kmer.pxd:253-273,
+ *                 _mapper.pyx:500-501)
+ *   read_offsets  n_reads+1 int64 offsets into `bases`, or NULL when every read
+ *                 has `fixed_read_len` bases
+ *   n_units       reads (single-ended) or pairs; mates are interleaved
+ *                 (2i, 2i+1) as the feeders produce them (common.py:189-190)
+ *   first_unit    global index of unit 0 (keeps first-seen class order across
+ *                 batches and shards)
+ *   out_class     optional int32[n_units]: dictionary slot of the unit's class,
+ *                 -1 = unaligned  (for -m readmap and per-read parity tests)
+ *   out_length    optional int32[n_units]: span.end - span.begin + k (:90)
+ * Reads shorter than k are undefined in the reference; here the call fails
+ * with SKM_ERR_INVALID when read_offsets are on the host, and such reads are
+ * reported unaligned when they are on the device.
+ */
+int skm_map_batch(skm_mapper *mapper, const uint8_t *bases, const int64_t *read_offsets,
+                  int32_t fixed_read_len, int32_t max_read_len, int64_t n_units, int paired,
+                  int64_t first_unit, int buffers_on_device, int32_t *out_class,
+                  int32_t *out_length, void *stream);
+
+/* sizes[0]=n_classes, [1]=total ids, [2]=unaligned units, [3]=aligned units,
+ * [4]=class slots capacity, [5]=status flags raised on device (0 = none) */
+int skm_classes_size(skm_mapper *mapper, int64_t sizes[6], void *stream);
+
+/* Replaces: reading MapResult.counter / fragment_length_counts
+ * (mapper.py:54-58) — the dictionary compacted to CSR.  Classes come out in
+ * table order; sort by first_unit for the reference's insertion order at
+ * job_count=1.  Any pointer may be NULL.  fld has SKM_MAX_FRAGMENT_LENGTH entries. */
+int skm_classes_export(skm_mapper *mapper, int64_t *key_offsets, int32_t *key_ids,
+                       int64_t *counts, int64_t *first_unit, int32_t *slots, int64_t *fld,
+                       int buffers_on_device, void *stream);
+
+/* Replaces: the cross-thread merge under MapResult.lock (_mapper.pyx:100-105)
+ * for the multi-GPU case: add externally produced classes (CSR, counts,
+ * first_unit), FLD and unaligned count into this mapper's dictionary. */
+int skm_classes_merge(skm_mapper *mapper, const int64_t *key_offsets, const int32_t *key_ids,
+                      const int64_t *counts, const int64_t *first_unit, int64_t n_classes,
+                      const int64_t *fld, int64_t unaligned, int buffers_on_device,
+                      void *stream);
+
+/* Replaces: MapResult.effective_lengths (mapper.py:134-141), fp64, same
+ * accumulation order. */
+int skm_effective_lengths(const int64_t *fld, const double *lengths, int64_t n_transcripts,
+                          double *out, int buffers_on_device, int device, void *stream);
+
+/* Replaces: infer.em (infer.py:133-168) for n_replicates independent count
+ * vectors sharing one class structure (E2/E4 of SURVEY.md §8(a)).
+ *   class_ptr[n_classes+1], class_tx[nnz]  CSR by class, ids in tuple order
+ *   counts[n_replicates * n_classes]       fp64 class counts per replicate
+ *   eff_len[n_transcripts]
+ *   x0[n_replicates * n_transcripts]       initial guess (already normalised)
+ *   out_x same shape; out_iters[n_replicates] = EM iterations executed
+ * Convergence: max over {x_t > 1e-8} |x_t - old_t| / x_t <= 0.01 (infer.py:160);
+ * a replicate with no x_t > 1e-8 stops (the reference raises ValueError). */
+int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
+           const double *counts, const double *eff_len, int64_t n_transcripts,
+           const double *x0, int64_t n_replicates, int64_t max_iters, double *out_x,
+           int32_t *out_iters, int buffers_on_device, int device, void *stream);
+
+/* Replaces: scipy.stats.multinomial(n, p).rvs() at infer.py:108-111 — resample
+ * n = sum(counts) reads with replacement, n_replicates times.  Integer-exact,
+ * counter-based (Philox4x32-10 keyed by seed, replicate, draw). out is
+ * int64[n_replicates * n_classes]; replicate ids start at first_replicate. */
+int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicates,
+                    int64_t first_replicate, uint64_t seed, int64_t *out,
+                    int buffers_on_device, int device, void *stream);
+
+/* Workload generation twin of seekmer_b200/synth.py (bench/test support, not
+ * part of the reference surface): fills `bases` (device) with ASCII reads for
+ * global units [first_unit, first_unit+n_units). */
+int skm_synth_reads(const uint8_t *tx_codes, const int64_t *tx_offsets, int64_t n_transcripts,
+                    const uint64_t *cum_weights, uint64_t total_weight, int32_t read_len,
+                    int32_t frag_mean, int32_t frag_sd, int32_t sub_thresh, int32_t n_thresh,
+                    int32_t random_pct, uint64_t seed, int paired, int64_t first_unit,
+                    int64_t n_units, uint8_t *bases, int device, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEKMER_B200_H */

@@ -1,0 +1,295 @@
+"""ctypes binding of ``libseekmer_b200.so`` (the C ABI in ``include/seekmer_b200.h``).
+
+There is no CPU fallback: if the CUDA library is missing or no device is visible, the
+compute entry points raise.  Nothing here imports ``oracle/``.
+"""
+import ctypes
+import pathlib
+
+import numpy
+
+HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = HERE / 'libseekmer_b200.so'
+
+K = 25
+MAX_FRAGMENT_LENGTH = 2000
+
+SLOT_DTYPE = numpy.dtype([('kmer', '<u8'), ('entry', '<i4'), ('offset', '<i4')])
+CONTIG_DTYPE = numpy.dtype([('offset', '<i8'), ('length', '<i8'), ('first_kmer', '<u8'),
+                            ('last_kmer', '<u8'), ('target_offset', '<i8'),
+                            ('target_count', '<i8')])
+TARGET_DTYPE = numpy.dtype([('entry', '<i4'), ('offset', '<i4')])
+
+EXPORTS = (
+    'skm_last_error', 'skm_device_count', 'skm_version', 'skm_index_create', 'skm_index_destroy',
+    'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
+    'skm_mapper_reset', 'skm_map_batch', 'skm_classes_size', 'skm_classes_export',
+    'skm_classes_merge', 'skm_effective_lengths', 'skm_em', 'skm_multinomial', 'skm_synth_reads',
+)
+
+
+class SeekmerCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SeekmerCudaError(
+            'seekmer_b200: %s is missing - build it with `python -m seekmer_b200.build` '
+            '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+    L = ctypes.CDLL(str(LIB_PATH))
+    vp, i64, i32, u64, ci = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64,
+                             ctypes.c_int)
+    L.skm_last_error.restype = ctypes.c_char_p
+    L.skm_last_error.argtypes = []
+    L.skm_version.restype = ctypes.c_char_p
+    L.skm_version.argtypes = []
+    L.skm_device_count.restype = ci
+    L.skm_device_count.argtypes = []
+    L.skm_index_create.restype = ci
+    L.skm_index_create.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i64, ci, ci, vp,
+                                   ctypes.POINTER(vp)]
+    L.skm_index_destroy.restype = None
+    L.skm_index_destroy.argtypes = [vp]
+    L.skm_index_info.restype = ci
+    L.skm_index_info.argtypes = [vp, vp]
+    L.skm_map_kmers.restype = ci
+    L.skm_map_kmers.argtypes = [vp, vp, i64, vp, vp, ci, vp]
+    L.skm_mapper_create.restype = ci
+    L.skm_mapper_create.argtypes = [vp, i64, i64, ctypes.POINTER(vp)]
+    L.skm_mapper_destroy.restype = None
+    L.skm_mapper_destroy.argtypes = [vp]
+    L.skm_mapper_reset.restype = ci
+    L.skm_mapper_reset.argtypes = [vp, vp]
+    L.skm_map_batch.restype = ci
+    L.skm_map_batch.argtypes = [vp, vp, vp, i32, i32, i64, ci, i64, ci, vp, vp, vp]
+    L.skm_classes_size.restype = ci
+    L.skm_classes_size.argtypes = [vp, vp, vp]
+    L.skm_classes_export.restype = ci
+    L.skm_classes_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, vp]
+    L.skm_classes_merge.restype = ci
+    L.skm_classes_merge.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, ci, vp]
+    L.skm_effective_lengths.restype = ci
+    L.skm_effective_lengths.argtypes = [vp, vp, i64, vp, ci, ci, vp]
+    L.skm_em.restype = ci
+    L.skm_em.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, vp, vp, ci, ci, vp]
+    L.skm_multinomial.restype = ci
+    L.skm_multinomial.argtypes = [vp, i64, i64, i64, u64, vp, ci, ci, vp]
+    L.skm_synth_reads.restype = ci
+    L.skm_synth_reads.argtypes = [vp, vp, i64, vp, u64, i32, i32, i32, i32, i32, i32, u64, ci,
+                                  i64, i64, vp, ci, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().skm_last_error()
+        raise SeekmerCudaError('%s (status %d)' % (msg.decode() if msg else 'unknown error', rc))
+
+
+def device_count():
+    return load().skm_device_count()
+
+
+def require_device():
+    if device_count() < 1:
+        raise SeekmerCudaError('seekmer_b200: no CUDA device visible; there is no CPU fallback')
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith('torch')
+
+
+def _ptr(x):
+    """void* of a numpy array, a torch tensor (host or device) or None."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        return ctypes.c_void_p(x.data_ptr())
+    return _np_ptr(x)
+
+
+def current_stream_ptr(device=None):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DeviceIndex:
+    """Handle to the HBM-resident, re-laid-out index (``skm_index``)."""
+
+    def __init__(self, kmers, contigs, sequences, targets, n_transcripts, device=0, stream=None):
+        L = load()
+        require_device()
+        on_device = _is_torch(kmers)
+        if on_device:
+            if not (kmers.is_cuda and contigs.is_cuda and sequences.is_cuda and targets.is_cuda):
+                raise ValueError('torch index arrays must all live on the CUDA device')
+            device = kmers.device.index
+            n_slots = kmers.numel() * kmers.element_size() // 16
+            n_contigs = contigs.numel() * contigs.element_size() // 48
+            n_bases = sequences.numel() * sequences.element_size()
+            n_targets = targets.numel() * targets.element_size() // 8
+            if stream is None:
+                stream = current_stream_ptr(kmers.device)
+        else:
+            kmers = _as_struct(kmers, SLOT_DTYPE)
+            contigs = _as_struct(contigs, CONTIG_DTYPE)
+            sequences = numpy.ascontiguousarray(numpy.asarray(sequences).view('u1'))
+            targets = _as_struct(targets, TARGET_DTYPE)
+            n_slots, n_contigs = kmers.shape[0], contigs.shape[0]
+            n_bases, n_targets = sequences.shape[0], targets.shape[0]
+        self._keep = (kmers, contigs, sequences, targets)
+        handle = ctypes.c_void_p()
+        check(L.skm_index_create(_ptr(kmers), n_slots, _ptr(contigs), n_contigs, _ptr(sequences),
+                                 n_bases, _ptr(targets), n_targets, int(n_transcripts),
+                                 int(device), int(on_device), stream, ctypes.byref(handle)))
+        self._h = handle
+        self._keep = None
+        self.device = int(device)
+
+    def info(self):
+        a = numpy.zeros(8, dtype='i8')
+        check(load().skm_index_info(self._h, _np_ptr(a)))
+        keys = ('n_kmers', 'table_slots', 'max_target_count', 'device_bytes', 'n_contigs',
+                'n_targets', 'n_transcripts', 'device')
+        return dict(zip(keys, a.tolist()))
+
+    def map_kmers(self, kmers):
+        """`KMerIndex.map_kmer` for a vector of encoded k-mers -> (entry, offset) int32 arrays."""
+        kmers = numpy.ascontiguousarray(kmers, dtype='u8')
+        e = numpy.zeros(kmers.shape[0], dtype='i4')
+        o = numpy.zeros(kmers.shape[0], dtype='i4')
+        check(load().skm_map_kmers(self._h, _np_ptr(kmers), kmers.shape[0], _np_ptr(e), _np_ptr(o),
+                                   0, None))
+        return e, o
+
+    def close(self):
+        if getattr(self, '_h', None):
+            load().skm_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_struct(a, dtype):
+    a = numpy.asarray(a)
+    if a.dtype != dtype:
+        if a.dtype.itemsize != dtype.itemsize:
+            raise ValueError('index array has item size %d, expected %d'
+                             % (a.dtype.itemsize, dtype.itemsize))
+        a = numpy.ascontiguousarray(a).view(dtype)
+    return numpy.ascontiguousarray(a)
+
+
+class DeviceMapper:
+    """Handle to a device class dictionary + FLD (``skm_mapper``)."""
+
+    def __init__(self, index, class_capacity=0, id_capacity=0):
+        self.index = index
+        handle = ctypes.c_void_p()
+        check(load().skm_mapper_create(index._h, int(class_capacity), int(id_capacity),
+                                       ctypes.byref(handle)))
+        self._h = handle
+
+    def reset(self, stream=None):
+        check(load().skm_mapper_reset(self._h, stream))
+
+    def map_batch(self, bases, offsets, n_units, paired, first_unit=0, fixed_len=0, max_len=0,
+                  per_read=False, stream=None):
+        """Map one batch.  `bases`/`offsets` are numpy (host) or torch CUDA tensors."""
+        on_device = _is_torch(bases) and bases.is_cuda
+        out_class = out_length = None
+        if per_read:
+            if on_device:
+                import torch
+                out_class = torch.empty(n_units, dtype=torch.int32, device=bases.device)
+                out_length = torch.empty(n_units, dtype=torch.int32, device=bases.device)
+            else:
+                out_class = numpy.empty(n_units, dtype='i4')
+                out_length = numpy.empty(n_units, dtype='i4')
+        if on_device and stream is None:
+            stream = current_stream_ptr(bases.device)
+        if not on_device:
+            if _is_torch(bases):  # pinned host tensor
+                pass
+            else:
+                bases = numpy.ascontiguousarray(bases, dtype='u1')
+                if offsets is not None:
+                    offsets = numpy.ascontiguousarray(offsets, dtype='i8')
+        check(load().skm_map_batch(self._h, _ptr(bases), _ptr(offsets), int(fixed_len),
+                                   int(max_len), int(n_units), int(bool(paired)), int(first_unit),
+                                   int(on_device), _ptr(out_class), _ptr(out_length), stream))
+        return out_class, out_length
+
+    def sizes(self, stream=None):
+        a = numpy.zeros(6, dtype='i8')
+        check(load().skm_classes_size(self._h, _np_ptr(a), stream))
+        keys = ('n_classes', 'n_ids', 'unaligned', 'aligned', 'capacity', 'status')
+        return dict(zip(keys, a.tolist()))
+
+    def export(self, with_slots=False, stream=None):
+        """Host copy of the dictionary, sorted by first-seen unit (the reference's Counter order
+        at job_count=1).  Returns dict(key_offsets, key_ids, counts, first_unit, fld, unaligned,
+        aligned[, slots])."""
+        sz = self.sizes(stream)
+        n, n_ids = sz['n_classes'], sz['n_ids']
+        off = numpy.zeros(n + 1, dtype='i8')
+        ids = numpy.zeros(max(n_ids, 1), dtype='i4')
+        counts = numpy.zeros(max(n, 1), dtype='i8')
+        first = numpy.zeros(max(n, 1), dtype='i8')
+        slots = numpy.zeros(max(n, 1), dtype='i4')
+        fld = numpy.zeros(MAX_FRAGMENT_LENGTH, dtype='i8')
+        check(load().skm_classes_export(self._h, _np_ptr(off), _np_ptr(ids), _np_ptr(counts),
+                                        _np_ptr(first), _np_ptr(slots), _np_ptr(fld), 0, stream))
+        counts, first, slots, ids = counts[:n], first[:n], slots[:n], ids[:n_ids]
+        order = numpy.argsort(first, kind='stable')
+        lens = off[1:] - off[:-1]
+        new_off = numpy.zeros(n + 1, dtype='i8')
+        numpy.cumsum(lens[order], out=new_off[1:])
+        if n:
+            gather = (numpy.repeat(off[:-1][order] - new_off[:-1], lens[order])
+                      + numpy.arange(n_ids, dtype='i8'))
+            ids = ids[gather]
+        out = dict(key_offsets=new_off, key_ids=ids, counts=counts[order], first_unit=first[order],
+                   fld=fld, unaligned=sz['unaligned'], aligned=sz['aligned'])
+        if with_slots:
+            out['slots'] = slots[order]
+        return out
+
+    def merge(self, key_offsets, key_ids, counts, first_unit, fld=None, unaligned=0, stream=None):
+        key_offsets = numpy.ascontiguousarray(key_offsets, dtype='i8')
+        key_ids = numpy.ascontiguousarray(key_ids, dtype='i4')
+        counts = numpy.ascontiguousarray(counts, dtype='i8')
+        first_unit = numpy.ascontiguousarray(first_unit, dtype='i8')
+        if fld is not None:
+            fld = numpy.ascontiguousarray(fld, dtype='i8')
+        check(load().skm_classes_merge(self._h, _np_ptr(key_offsets), _np_ptr(key_ids),
+                                       _np_ptr(counts), _np_ptr(first_unit), counts.shape[0],
+                                       _ptr(fld), int(unaligned), 0, stream))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            load().skm_mapper_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,209 @@
+"""Host-side index object and FASTQ feeders — the `seekmer.common` surface on the infer path.
+
+Mirrors (same names, arguments and error behaviour):
+  KMerIndex                 `_common.pyx:19-48,268-313` + `_common.pxd:57-66`
+  feed_single_ended_reads   `common.py:126-158`
+  feed_pair_ended_reads     `common.py:161-197`
+  decompress_and_open       `common.py:23-75`
+  read_fasta                `common.py:78-105`
+
+`KMerIndex` keeps the six public ndarray attributes of the reference object (the input
+contract produced by `seekmer index`) and lazily uploads / re-lays them out into HBM the first
+time a mapper needs them (`device_index`).  The lookups of `_common.pyx:54-266` themselves live
+in `csrc/kmer.cuh` + `csrc/mapper.cu`.
+"""
+import bz2
+import contextlib
+import gzip
+import io
+import lzma
+import pathlib
+import subprocess
+
+import numpy
+
+from . import _lib
+from ._log import Logger
+
+__all__ = ('BUFFER_SIZE', 'KMerIndex', 'decompress_and_open', 'read_fasta', 'iterate_by_group',
+           'feed_single_ended_reads', 'feed_pair_ended_reads')
+
+BUFFER_SIZE = 65536
+
+_LOG = Logger(__name__)
+
+_INDEX_VERSION = '2019.0.0'
+_EXTERNAL = {'.gz': ('zcat', gzip), '.bz2': ('bzcat', bz2), '.xz': ('xzcat', lzma),
+             '.lzma': ('xzcat', lzma)}
+
+
+class KMerIndex:
+    """The Seekmer index: six numpy arrays plus a lazily created device image."""
+
+    def __init__(self, kmers, contigs, sequences, targets, transcripts, exons):
+        self.kmers = kmers
+        self.contigs = contigs
+        self.sequences = sequences
+        self.targets = targets
+        self.transcripts = transcripts
+        self.exons = exons
+        self._device = {}
+
+    # -- device image ---------------------------------------------------------------
+    def device_index(self, device=0):
+        """HBM-resident re-laid-out index for `device` (created once, then cached)."""
+        dev = self._device.get(device)
+        if dev is None:
+            n_tx = len(self.transcripts) if self.transcripts is not None else 0
+            dev = _lib.DeviceIndex(self.kmers, self.contigs, self.sequences, self.targets, n_tx,
+                                   device=device)
+            self._device[device] = dev
+        return dev
+
+    def release_device(self):
+        for dev in self._device.values():
+            dev.close()
+        self._device = {}
+
+    # -- persistence ----------------------------------------------------------------
+    def save(self, path):
+        """HDF5 when PyTables is importable (`_common.pyx:268-285` layout); `.npz` otherwise or
+        when the suffix is `.npz`."""
+        path = pathlib.Path(path)
+        if path.suffix != '.npz':
+            try:
+                import tables
+            except ImportError:
+                tables = None
+            if tables is not None:
+                filters = tables.Filters(complib='blosc', complevel=9, fletcher32=True)
+                with tables.open_file(str(path), 'w', filters=filters) as f:
+                    f.root._v_attrs['seekmer_version'] = _INDEX_VERSION
+                    f.create_table('/', 'kmers', obj=self.kmers)
+                    f.create_table('/', 'contigs', obj=self.contigs)
+                    f.create_array('/', 'sequences', obj=self.sequences)
+                    f.create_table('/', 'targets', obj=self.targets)
+                    f.create_table('/', 'transcripts', obj=self.transcripts)
+                    f.create_table('/', 'exons', obj=self.exons)
+                _LOG.info('Saved index to "{}"', path)
+                return
+            raise RuntimeError('PyTables (HDF5) is not available; save to a ".npz" path instead')
+        exons = self.exons if self.exons is not None else numpy.zeros(0, dtype='i4')
+        with open(str(path), 'wb') as f:
+            numpy.savez(f, seekmer_version=numpy.asarray(_INDEX_VERSION),
+                        kmers=numpy.asarray(self.kmers), contigs=numpy.asarray(self.contigs),
+                        sequences=numpy.asarray(self.sequences), targets=numpy.asarray(self.targets),
+                        transcripts=numpy.asarray(self.transcripts), exons=numpy.asarray(exons))
+        _LOG.info('Saved index to "{}"', path)
+
+    @classmethod
+    def load(cls, path):
+        path = pathlib.Path(path)
+        if path.suffix == '.npz':
+            with numpy.load(str(path), allow_pickle=False) as z:
+                if str(z['seekmer_version']) != _INDEX_VERSION:
+                    raise RuntimeError('invalid index version.')
+                parts = [z[k] for k in ('kmers', 'contigs', 'sequences', 'targets', 'transcripts',
+                                        'exons')]
+            _LOG.info('Loaded index from "{}"', path)
+            return cls(*parts)
+        try:
+            import tables
+        except ImportError as exc:
+            raise RuntimeError('reading an HDF5 index needs PyTables, which is not installed; '
+                               'convert the index to ".npz" where it is') from exc
+        with tables.open_file(str(path), 'r') as f:
+            if f.root._v_attrs['seekmer_version'] != _INDEX_VERSION:
+                raise RuntimeError('invalid index version.')
+            parts = [f.get_node('/' + k).read() for k in ('kmers', 'contigs', 'sequences',
+                                                          'targets', 'transcripts', 'exons')]
+        _LOG.info('Loaded index from "{}"', path)
+        return cls(*parts)
+
+
+@contextlib.contextmanager
+def decompress_and_open(path):
+    """Binary read handle; `.gz/.bz2/.xz/.lzma` go through the external decompressor when it
+    can be started, else through the stdlib module."""
+    path = pathlib.Path(path)
+    tool = _EXTERNAL.get(path.suffix)
+    if tool is None:
+        with path.open('rb') as f:
+            yield f
+        return
+    command, module = tool
+    try:
+        process = subprocess.Popen([command, str(path)], stdout=subprocess.PIPE)
+    except OSError:
+        _LOG.warn('Unable to call {}, falling back to the {} module.', command, module.__name__)
+        with module.open(str(path), 'rb') as raw, io.BufferedReader(raw) as f:
+            yield f
+        return
+    with process:
+        yield process.stdout
+
+
+def read_fasta(path):
+    name, chunks = None, []
+    with decompress_and_open(path) as f:
+        for line in f:
+            if line[:1] == b'>':
+                if name is not None:
+                    yield name, b''.join(chunks)
+                name, chunks = line[1:].strip(), []
+            else:
+                chunks.append(line.strip())
+    if name is not None:
+        yield name, b''.join(chunks)
+
+
+def iterate_by_group(iterator, group_size):
+    return zip(*([iter(iterator)] * group_size))
+
+
+def _fastq_records(handle):
+    """(name, sequence) per 4-line FASTQ record; a trailing partial record yields what it has,
+    like the reference's line-index logic."""
+    name = None
+    for i, line in enumerate(handle):
+        phase = i & 3
+        if phase == 0:
+            name = line.strip()[1:]
+        elif phase == 1:
+            yield name, line.strip()
+
+
+def feed_single_ended_reads(*paths):
+    """Yield `(count, names, reads)` batches of up to BUFFER_SIZE reads; all files form one
+    sample."""
+    names, reads = [], []
+    for path in paths:
+        with decompress_and_open(path) as f:
+            for name, seq in _fastq_records(f):
+                names.append(name)
+                reads.append(seq)
+                if len(names) >= BUFFER_SIZE:
+                    yield len(names), names, reads
+                    names, reads = [], []
+    if reads:
+        yield len(names), names, reads
+    _LOG.debug('Finished reading sequence file(s)')
+
+
+def feed_pair_ended_reads(*paths):
+    """Yield `(pair_count, names, reads)` with mates interleaved (2i, 2i+1)."""
+    if len(paths) % 2 != 0:
+        raise ValueError('cannot process odd numbers of pair-ended files')
+    names, reads = [], []
+    for path1, path2 in iterate_by_group(paths, 2):
+        with decompress_and_open(path1) as f1, decompress_and_open(path2) as f2:
+            for (name, seq1), (_, seq2) in zip(_fastq_records(f1), _fastq_records(f2)):
+                names.append(name)
+                reads.append(seq1)
+                reads.append(seq2)
+                if len(names) >= BUFFER_SIZE:
+                    yield len(names), names, reads
+                    names, reads = [], []
+    if reads:
+        yield len(names), names, reads
+    _LOG.debug('Finished reading sequence file(s)')

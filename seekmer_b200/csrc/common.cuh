@@ -1,0 +1,82 @@
+// Shared host/device definitions for the seekmer_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/seekmer_b200.h"
+
+#define SKM_API extern "C" __attribute__((visibility("default")))
+
+namespace skm {
+
+constexpr int K = SKM_KMER_SIZE;
+constexpr uint64_t KMER_MASK = (1ULL << (2 * K)) - 1;
+constexpr uint64_t EMPTY_KEY = 0xFFFFFFFFFFFFFFFFULL;
+
+// ---- error plumbing -------------------------------------------------------------
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define SKM_CUDA(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            return ::skm::fail(_e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA, \
+                               std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+        }                                                                               \
+    } while (0)
+
+// ---- device-side index layout (the re-laid-out form of KMerIndex) ------------------
+// 16-byte slot; key = canonical (min of k-mer and its reverse complement) 25-mer,
+// value = contig coordinate expressed for the canonical orientation.
+struct __align__(16) Slot {
+    uint64_t key;
+    int32_t entry;
+    int32_t offset;
+};
+
+// 32-byte contig record = one DRAM sector.
+//   w0 = first_kmer | (target_count low 14 bits  << 50)
+//   w1 = last_kmer  | (target_count high 14 bits << 50)
+struct __align__(32) ContigRec {
+    uint64_t w0;
+    uint64_t w1;
+    int64_t seq_offset;      // base offset into the packed sequence pool
+    uint32_t target_offset;  // into targets[]
+    uint32_t length;         // contig length in bases
+};
+
+struct DevIndex {
+    const Slot *table;
+    uint64_t slot_mask;       // n_slots - 1
+    const ContigRec *contigs;
+    const uint32_t *seq2;     // 16 bases per word, first base in the top bits
+    const int32_t *targets;   // signed entries only
+    int64_t n_contigs;
+    int64_t n_bases;
+    int64_t n_targets;
+};
+
+// status bits raised by kernels (checked by the host after each batch)
+enum : uint32_t {
+    ST_ARENA_FULL = 1u,
+    ST_DICT_FULL = 2u,
+    ST_POOL_FULL = 4u,
+    ST_SHORT_READ = 8u,
+};
+
+}  // namespace skm
+
+struct skm_index {
+    int device = 0;
+    skm::DevIndex d{};
+    skm::Slot *table = nullptr;
+    skm::ContigRec *contigs = nullptr;
+    uint32_t *seq2 = nullptr;
+    int32_t *targets = nullptr;
+    int64_t n_slots = 0, n_kmers = 0, n_contigs = 0, n_bases = 0, n_targets = 0;
+    int64_t n_transcripts = 0, max_target_count = 0, bytes = 0;
+};

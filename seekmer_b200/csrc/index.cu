@@ -1,0 +1,374 @@
+// Index upload and re-layout: KMerIndex arrays (reference layout) -> HBM-resident
+// canonical-key hash table + 32-byte contig records + 2-bit sequence pool + entry-only
+// target lists.  Replaces KMerIndex.__init__/load on the device side
+// (_common.pyx:21-48,287-313) and KMerIndex.map_kmer for vectors of k-mers.
+#include <mutex>
+
+#include "kmer.cuh"
+
+namespace skm {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+int fail(int code, const std::string &msg)
+{
+    g_error = msg;
+    return code;
+}
+const char *last_error() { return g_error.c_str(); }
+
+// ---------------------------------------------------------------------------------
+__global__ void count_occupied_kernel(const skm_kmer_slot *__restrict__ src, int64_t n,
+                                      unsigned long long *__restrict__ count)
+{
+    unsigned long long local = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        local += __ldg(&src[i].kmer) != EMPTY_KEY;
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+// Re-insert every occupied reference slot under its canonical key.  The stored
+// coordinate is expressed for the canonical orientation: if the contig-forward k-mer
+// (what the reference stores) is not the canonical one, the entry is
+// bit-negated, so that map_kmer() in kmer.cuh returns exactly what
+// _common.pyx:82-87 returns for either query strand.
+__global__ void relayout_table_kernel(const skm_kmer_slot *__restrict__ src, int64_t n,
+                                      Slot *__restrict__ table, uint64_t mask)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(src + i));
+        const uint64_t kmer = v.x;
+        if (kmer == EMPTY_KEY) continue;
+        const uint64_t rc = revcomp(kmer);
+        const bool fwd = kmer < rc;
+        const uint64_t canon = fwd ? kmer : rc;
+        int32_t entry = (int32_t)(uint32_t)v.y;
+        const int32_t offset = (int32_t)(uint32_t)(v.y >> 32);
+        if (!fwd) entry = ~entry;
+        uint64_t s = table_hash(canon) & mask;
+        for (;;) {
+            const unsigned long long old = atomicCAS(
+                reinterpret_cast<unsigned long long *>(&table[s].key), EMPTY_KEY, canon);
+            if (old == EMPTY_KEY) {
+                table[s].entry = entry;
+                table[s].offset = offset;
+                break;
+            }
+            s = (s + 1) & mask;
+        }
+    }
+}
+
+__global__ void relayout_contigs_kernel(const skm_contig_entry *__restrict__ src, int64_t n,
+                                        ContigRec *__restrict__ dst, int64_t n_bases,
+                                        int64_t n_targets, unsigned long long *max_tc,
+                                        unsigned int *bad)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const skm_contig_entry c = src[i];
+    if (c.length < K || c.length > 0x7FFFFFFFLL || c.offset < 0 || c.offset + c.length > n_bases
+        || c.target_offset < 0 || c.target_count < 0 || c.target_count >= (1LL << 28)
+        || c.target_offset + c.target_count > n_targets)
+        atomicOr(bad, 1u);
+    ContigRec r;
+    const uint64_t tc = (uint64_t)c.target_count;
+    r.w0 = (c.first_kmer & KMER_MASK) | ((tc & 0x3FFF) << 50);
+    r.w1 = (c.last_kmer & KMER_MASK) | (((tc >> 14) & 0x3FFF) << 50);
+    r.seq_offset = c.offset;
+    r.target_offset = (uint32_t)c.target_offset;
+    r.length = (uint32_t)c.length;
+    dst[i] = r;
+    atomicMax(max_tc, (unsigned long long)tc);
+}
+
+__device__ __forceinline__ uint32_t code_of(uint8_t b)  // _kmer.pxd:253-273
+{
+    const uint8_t u = b & 0xDF;
+    return u == 'T' ? 3u : u == 'G' ? 2u : u == 'C' ? 1u : 0u;
+}
+
+__global__ void pack_sequences_kernel(const uint8_t *__restrict__ src, int64_t n_bases,
+                                      uint32_t *__restrict__ dst, int64_t n_words)
+{
+    const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    uint32_t acc = 0;
+    const int64_t base = w * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int64_t p = base + j;
+        const uint32_t c = p < n_bases ? code_of(__ldg(src + p)) : 0u;
+        acc = (acc << 2) | c;
+    }
+    dst[w] = acc;
+}
+
+__global__ void extract_targets_kernel(const skm_target *__restrict__ src, int64_t n,
+                                       int32_t *__restrict__ dst)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i].entry;
+}
+
+__global__ void map_kmers_kernel(DevIndex ix, const uint64_t *__restrict__ kmers, int64_t n,
+                                 int32_t *__restrict__ out_entry, int32_t *__restrict__ out_offset)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const Coord c = map_kmer(ix, kmers[i] & KMER_MASK);
+        out_entry[i] = c.entry;
+        out_offset[i] = c.offset;
+    }
+}
+
+template <typename T>
+static int to_device(const T *src, int64_t n, bool on_device, cudaStream_t st, const T **out,
+                     T **owned)
+{
+    *owned = nullptr;
+    if (on_device || n == 0) {
+        *out = src;
+        return 0;
+    }
+    T *buf = nullptr;
+    SKM_CUDA(cudaMalloc(&buf, sizeof(T) * (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(buf, src, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+        cudaFree(buf);
+        return fail(SKM_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+    }
+    *out = buf;
+    *owned = buf;
+    return 0;
+}
+
+}  // namespace skm
+
+using namespace skm;
+
+SKM_API const char *skm_last_error(void) { return skm::last_error(); }
+
+SKM_API const char *skm_version(void) { return "seekmer_b200 0.1 (sm_100a)"; }
+
+SKM_API int skm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+SKM_API void skm_index_destroy(skm_index *ix)
+{
+    if (!ix) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ix->device);
+    cudaFree(ix->table);
+    cudaFree(ix->contigs);
+    cudaFree(ix->seq2);
+    cudaFree(ix->targets);
+    cudaSetDevice(prev);
+    delete ix;
+}
+
+SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
+                                const skm_contig_entry *contigs, int64_t n_contigs,
+                                const char *sequences, int64_t n_bases, const skm_target *targets,
+                                int64_t n_targets, int64_t n_transcripts, int device,
+                                int inputs_on_device, void *stream, skm_index **out)
+{
+    if (!out) return fail(SKM_ERR_INVALID, "skm_index_create: out is NULL");
+    *out = nullptr;
+    if (!kmers || !contigs || !sequences || !targets)
+        return fail(SKM_ERR_INVALID, "skm_index_create: NULL index array");
+    if (n_slots <= 0 || (n_slots & (n_slots - 1)) != 0)
+        return fail(SKM_ERR_INVALID, "skm_index_create: k-mer table size must be a power of two");
+    if (n_contigs <= 0 || n_bases <= 0 || n_targets <= 0)
+        return fail(SKM_ERR_INVALID, "skm_index_create: empty index");
+    if (n_targets >= (1LL << 32))
+        return fail(SKM_ERR_INVALID, "skm_index_create: more than 2^32 targets");
+    if (n_contigs >= (1LL << 31))
+        return fail(SKM_ERR_INVALID, "skm_index_create: more than 2^31 contigs");
+    if (skm_device_count() <= device || device < 0)
+        return fail(SKM_ERR_CUDA, "skm_index_create: no such CUDA device (there is no CPU fallback)");
+    SKM_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dev = inputs_on_device != 0;
+
+    skm_index *ix = new skm_index();
+    ix->device = device;
+    ix->n_contigs = n_contigs;
+    ix->n_bases = n_bases;
+    ix->n_targets = n_targets;
+    ix->n_transcripts = n_transcripts;
+
+    unsigned long long *d_scalars = nullptr;  // [0]=count, [1]=max_tc, [2]=bad
+    const skm_kmer_slot *d_kmers = nullptr;
+    skm_kmer_slot *own_kmers = nullptr;
+    const skm_contig_entry *d_contigs = nullptr;
+    skm_contig_entry *own_contigs = nullptr;
+    const char *d_seq = nullptr;
+    char *own_seq = nullptr;
+    const skm_target *d_targets = nullptr;
+    skm_target *own_targets = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(d_scalars);
+        cudaFree(own_kmers);
+        cudaFree(own_contigs);
+        cudaFree(own_seq);
+        cudaFree(own_targets);
+    };
+#define STEP(expr)                 \
+    do {                           \
+        rc = (expr);               \
+        if (rc != 0) {             \
+            cleanup();             \
+            skm_index_destroy(ix); \
+            return rc;             \
+        }                          \
+    } while (0)
+#define STEP_CUDA(expr)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            cleanup();                                                                    \
+            skm_index_destroy(ix);                                                        \
+            return fail(_e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,     \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+        }                                                                                 \
+    } while (0)
+
+    STEP_CUDA(cudaMalloc(&d_scalars, 4 * sizeof(unsigned long long)));
+    STEP_CUDA(cudaMemsetAsync(d_scalars, 0, 4 * sizeof(unsigned long long), st));
+
+    // -- k-mer table
+    STEP(to_device(kmers, n_slots, dev, st, &d_kmers, &own_kmers));
+    {
+        const int threads = 256;
+        const int blocks = (int)std::min<int64_t>((n_slots + threads - 1) / threads, 148 * 16);
+        count_occupied_kernel<<<blocks, threads, 0, st>>>(d_kmers, n_slots, d_scalars);
+        unsigned long long cnt = 0;
+        STEP_CUDA(cudaMemcpyAsync(&cnt, d_scalars, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        STEP_CUDA(cudaStreamSynchronize(st));
+        ix->n_kmers = (int64_t)cnt;
+        int64_t slots = 1024;
+        while (slots < 2 * ix->n_kmers) slots <<= 1;  // load factor <= 0.5
+        ix->n_slots = slots;
+        STEP_CUDA(cudaMalloc(&ix->table, sizeof(Slot) * (size_t)slots));
+        STEP_CUDA(cudaMemsetAsync(ix->table, 0xFF, sizeof(Slot) * (size_t)slots, st));
+        relayout_table_kernel<<<blocks, threads, 0, st>>>(d_kmers, n_slots, ix->table,
+                                                          (uint64_t)slots - 1);
+        STEP_CUDA(cudaGetLastError());
+        ix->bytes += (int64_t)sizeof(Slot) * slots;
+    }
+    // -- contigs
+    STEP(to_device(contigs, n_contigs, dev, st, &d_contigs, &own_contigs));
+    STEP_CUDA(cudaMalloc(&ix->contigs, sizeof(ContigRec) * (size_t)n_contigs));
+    relayout_contigs_kernel<<<(unsigned)((n_contigs + 255) / 256), 256, 0, st>>>(
+        d_contigs, n_contigs, ix->contigs, n_bases, n_targets, d_scalars + 1,
+        reinterpret_cast<unsigned int *>(d_scalars + 2));
+    STEP_CUDA(cudaGetLastError());
+    ix->bytes += (int64_t)sizeof(ContigRec) * n_contigs;
+    // -- sequences (2-bit, one padding word so window reads may touch word+1)
+    STEP(to_device(sequences, n_bases, dev, st, &d_seq, &own_seq));
+    {
+        const int64_t n_words = (n_bases + 15) / 16 + 2;
+        STEP_CUDA(cudaMalloc(&ix->seq2, sizeof(uint32_t) * (size_t)n_words));
+        pack_sequences_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const uint8_t *>(d_seq), n_bases, ix->seq2, n_words);
+        STEP_CUDA(cudaGetLastError());
+        ix->bytes += (int64_t)sizeof(uint32_t) * n_words;
+    }
+    // -- targets
+    STEP(to_device(targets, n_targets, dev, st, &d_targets, &own_targets));
+    STEP_CUDA(cudaMalloc(&ix->targets, sizeof(int32_t) * (size_t)n_targets));
+    extract_targets_kernel<<<(unsigned)((n_targets + 255) / 256), 256, 0, st>>>(
+        d_targets, n_targets, ix->targets);
+    STEP_CUDA(cudaGetLastError());
+    ix->bytes += (int64_t)sizeof(int32_t) * n_targets;
+
+    unsigned long long scal[4] = {0, 0, 0, 0};
+    STEP_CUDA(cudaMemcpyAsync(scal, d_scalars, sizeof(scal), cudaMemcpyDeviceToHost, st));
+    STEP_CUDA(cudaStreamSynchronize(st));
+    ix->max_target_count = (int64_t)scal[1];
+    if (scal[2] != 0) {
+        cleanup();
+        skm_index_destroy(ix);
+        return fail(SKM_ERR_INVALID, "skm_index_create: contig table is inconsistent with "
+                                     "sequences/targets (offset, length or target range out of bounds)");
+    }
+    cleanup();
+#undef STEP
+#undef STEP_CUDA
+    ix->d.table = ix->table;
+    ix->d.slot_mask = (uint64_t)ix->n_slots - 1;
+    ix->d.contigs = ix->contigs;
+    ix->d.seq2 = ix->seq2;
+    ix->d.targets = ix->targets;
+    ix->d.n_contigs = n_contigs;
+    ix->d.n_bases = n_bases;
+    ix->d.n_targets = n_targets;
+    *out = ix;
+    return SKM_OK;
+}
+
+SKM_API int skm_index_info(const skm_index *ix, int64_t info[8])
+{
+    if (!ix || !info) return fail(SKM_ERR_INVALID, "skm_index_info: NULL argument");
+    info[0] = ix->n_kmers;
+    info[1] = ix->n_slots;
+    info[2] = ix->max_target_count;
+    info[3] = ix->bytes;
+    info[4] = ix->n_contigs;
+    info[5] = ix->n_targets;
+    info[6] = ix->n_transcripts;
+    info[7] = ix->device;
+    return SKM_OK;
+}
+
+SKM_API int skm_map_kmers(const skm_index *ix, const uint64_t *kmers, int64_t n,
+                             int32_t *out_entry, int32_t *out_offset, int buffers_on_device,
+                             void *stream)
+{
+    if (!ix || !kmers || !out_entry || !out_offset)
+        return fail(SKM_ERR_INVALID, "skm_map_kmers: NULL argument");
+    if (n <= 0) return SKM_OK;
+    SKM_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t *d_k = kmers;
+    int32_t *d_e = out_entry, *d_o = out_offset;
+    uint64_t *own_k = nullptr;
+    int32_t *own_e = nullptr;
+    if (!buffers_on_device) {
+        SKM_CUDA(cudaMalloc(&own_k, sizeof(uint64_t) * (size_t)n));
+        if (cudaMalloc(&own_e, sizeof(int32_t) * 2 * (size_t)n) != cudaSuccess) {
+            cudaFree(own_k);
+            return fail(SKM_ERR_OOM, "skm_map_kmers: cudaMalloc failed");
+        }
+        cudaMemcpyAsync(own_k, kmers, sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, st);
+        d_k = own_k;
+        d_e = own_e;
+        d_o = own_e + n;
+    }
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>((n + threads - 1) / threads, 148 * 8);
+    map_kmers_kernel<<<blocks, threads, 0, st>>>(ix->d, d_k, n, d_e, d_o);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !buffers_on_device) {
+        cudaMemcpyAsync(out_entry, d_e, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out_offset, d_o, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+    }
+    cudaFree(own_k);
+    cudaFree(own_e);
+    if (e != cudaSuccess) return fail(SKM_ERR_CUDA, std::string("skm_map_kmers: ") + cudaGetErrorString(e));
+    return SKM_OK;
+}

@@ -1,0 +1,166 @@
+// Device primitives: 2-bit k-mers, reverse complement, table hash, probes.
+// Semantics follow the reference's _kmer.pxd / _coordinate.pxd / _common.pyx
+// (cited per function); the implementation is specific to the GPU layout in
+// common.cuh.
+#pragma once
+
+#include "common.cuh"
+
+namespace skm {
+
+struct Coord {
+    int32_t entry;
+    int32_t offset;
+};
+
+__device__ __forceinline__ Coord coord_invalid() { return Coord{0, -1}; }  // _coordinate.pxd:13-24
+
+// Reverse complement of a 25-mer held in the low 50 bits (_kmer.pxd:146-171).
+// brev reverses all 64 bits; swapping the two bits of every pair restores base
+// codes; the k-mer then sits in the top 50 bits.
+__host__ __device__ __forceinline__ uint64_t revcomp(uint64_t kmer)
+{
+#ifdef __CUDA_ARCH__
+    uint64_t r = __brevll(kmer);
+#else
+    uint64_t r = kmer;
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    r = ((r >> 2) & 0x3333333333333333ULL) | ((r & 0x3333333333333333ULL) << 2);
+    r = ((r >> 4) & 0x0f0f0f0f0f0f0f0fULL) | ((r & 0x0f0f0f0f0f0f0f0fULL) << 4);
+    r = ((r >> 8) & 0x00ff00ff00ff00ffULL) | ((r & 0x00ff00ff00ff00ffULL) << 8);
+    r = ((r >> 16) & 0x0000ffff0000ffffULL) | ((r & 0x0000ffff0000ffffULL) << 16);
+    r = (r >> 32) | (r << 32);
+#endif
+    r = ((r >> 1) & 0x5555555555555555ULL) | ((r & 0x5555555555555555ULL) << 1);
+    return ~(r >> (64 - 2 * K)) & KMER_MASK;
+}
+
+// Reverse complement of 8 bases held in the low 16 bits (_sequence.pxd:53-75 on a
+// 2-bit window).
+__device__ __forceinline__ uint32_t revcomp8(uint32_t w)
+{
+    uint32_t r = __brev(w) >> 16;
+    r = ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);
+    return ~r & 0xFFFFu;
+}
+
+// Home-slot hash of the device table.  The reference's SipHash variant
+// (_kmer.pxd:174-219) only has to place keys; exact-membership lookup gives the same
+// answer under any hash (k odd => a k-mer never equals its reverse complement, so at
+// most one slot matches), so the re-laid-out table uses a 2-multiply finaliser.
+__host__ __device__ __forceinline__ uint64_t table_hash(uint64_t canon)
+{
+    uint64_t x = canon;
+    x ^= x >> 31;
+    x *= 0x9E3779B97F4A7C15ULL;
+    x ^= x >> 29;
+    x *= 0xBF58476D1CE4E5B9ULL;
+    x ^= x >> 32;
+    return x;
+}
+
+// The reference's own hash, needed only to build reference-layout tables on the
+// device (index construction support) — _kmer.pxd:174-231.
+__host__ __device__ __forceinline__ void sip_half(uint64_t &a, uint64_t &b, uint64_t &c,
+                                                   uint64_t &d, int s, int t)
+{
+    a += b;
+    c += d;
+    b = ((b << s) | (b >> (64 - s))) ^ a;
+    d = ((d << t) | (d >> (64 - t))) ^ c;
+    a = (a << 32) | (a >> 32);
+}
+
+__host__ __device__ __forceinline__ uint64_t reference_hash(uint64_t m)
+{
+    uint64_t v0 = 5381ULL ^ 0x736f6d6570736575ULL;
+    uint64_t v1 = 42ULL ^ 0x646f72616e646f6dULL;
+    uint64_t v2 = 5381ULL ^ 0x6c7967656e657261ULL;
+    uint64_t v3 = 42ULL ^ 0x7465646279746573ULL;
+    v3 ^= m;
+    for (int r = 0; r < 2; ++r) {
+        sip_half(v0, v1, v2, v3, 13, 16);
+        sip_half(v2, v1, v0, v3, 17, 21);
+    }
+    v0 ^= m;
+    v3 ^= 8ULL << 56;
+    for (int r = 0; r < 2; ++r) {
+        sip_half(v0, v1, v2, v3, 13, 16);
+        sip_half(v2, v1, v0, v3, 17, 21);
+    }
+    v2 ^= 0xff;  // and no `v0 ^= b` — the reference's deviation (_kmer.pxd:209)
+    for (int r = 0; r < 4; ++r) {
+        sip_half(v0, v1, v2, v3, 13, 16);
+        sip_half(v2, v1, v0, v3, 17, 21);
+    }
+    return (v0 ^ v1) ^ (v2 ^ v3);
+}
+
+__device__ __forceinline__ Slot load_slot(const Slot *p)
+{
+    // one 16-byte, read-only, L1-bypassing load: slots are touched once per probe
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(v.x), "=l"(v.y)
+                 : "l"(p));
+    Slot s;
+    s.key = v.x;
+    s.entry = (int32_t)(uint32_t)v.y;
+    s.offset = (int32_t)(uint32_t)(v.y >> 32);
+    return s;
+}
+
+// KMerIndex.map_kmer (_common.pyx:54-97) on the canonical-key table: hit on the
+// canonical key; strand of the query relative to the canonical form decides whether
+// the stored coordinate is returned as is or reverse-complemented (~entry).
+__device__ __forceinline__ Coord map_kmer(const DevIndex &ix, uint64_t kmer)
+{
+    const uint64_t rc = revcomp(kmer);
+    const bool fwd = kmer < rc;
+    const uint64_t canon = fwd ? kmer : rc;
+    uint64_t i = table_hash(canon) & ix.slot_mask;
+    for (;;) {
+        const Slot s = load_slot(ix.table + i);
+        if (s.key == canon) return Coord{fwd ? s.entry : ~s.entry, s.offset};
+        if (s.key == EMPTY_KEY) return coord_invalid();
+        i = (i + 1) & ix.slot_mask;
+    }
+}
+
+struct Contig {
+    uint64_t first_kmer, last_kmer;
+    int64_t seq_offset;
+    uint32_t target_offset;
+    int32_t target_count;
+    int32_t length;
+};
+
+__device__ __forceinline__ Contig load_contig(const DevIndex &ix, int32_t index)
+{
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ix.contigs + index);
+    const ulonglong2 a = __ldg(p);
+    const ulonglong2 b = __ldg(p + 1);
+    Contig c;
+    c.first_kmer = a.x & KMER_MASK;
+    c.last_kmer = a.y & KMER_MASK;
+    c.target_count = (int32_t)((a.x >> 50) | ((a.y >> 50) << 14));
+    c.seq_offset = (int64_t)b.x;
+    c.target_offset = (uint32_t)b.y;
+    c.length = (int32_t)(uint32_t)(b.y >> 32);
+    return c;
+}
+
+// 8 bases starting at absolute base position p of the packed contig pool, as 16 bits
+// (first base in the top two bits).
+__device__ __forceinline__ uint32_t seq_window8(const DevIndex &ix, int64_t p)
+{
+    const int64_t w = p >> 4;
+    const int s = (int)(p & 15);
+    const uint32_t hi = __ldg(ix.seq2 + w);
+    uint32_t lo = 0;
+    if (s > 8) lo = __ldg(ix.seq2 + w + 1);
+    const uint64_t both = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)(both >> (48 - 2 * s)) & 0xFFFFu;
+}
+
+}  // namespace skm

@@ -1,0 +1,1127 @@
+// Read -> equivalence-class mapping on the GPU.
+//
+// One thread maps one read (both mates of a pair sit in adjacent lanes), a warp pulls
+// chunks of 32 reads from a global work counter, packs their ASCII bases to 2 bits
+// (+1 wildcard bit) into shared memory, runs the reference's per-read state machine
+// against the HBM-resident index, intersects the mates, and tallies the ordered
+// transcript-id tuple into a device-resident class dictionary.  The fragment-length
+// histogram is accumulated in shared memory and flushed once per block.
+//
+// Reference semantics restated here (paths under /root/reference/seekmer/):
+//   map_read            _mapper.pyx:151-193      find_first_kmer   :199-216
+//   filter_to_left      _mapper.pyx:222-275      filter_to_right   :281-343
+//   intersect (mates)   _mapper.pyx:350-397      map_read_pair     :111-145
+//   sift4_align_left    _mapper.pyx:404-445      sift4_align_right :452-493
+//   map_contig          _common.pyx:143-179      filter_on_contig  :185-235
+//   get_contig_sequence _common.pyx:103-137      get_tail_kmer     :241-266
+//   batch driver + FLD  _mapper.pyx:73-101       tuple ids         :528-537
+#include <algorithm>
+
+#include "kmer.cuh"
+
+namespace skm {
+
+constexpr int BLOCK_THREADS = 256;
+constexpr int WARPS = BLOCK_THREADS / 32;
+constexpr int LIST_CAP = 16;       // per-read target list entries kept in shared memory
+constexpr int ALIGN_LENGTH = 8;    // _mapper.pyx:22
+constexpr int MAX_OFFSET = 2;      // _mapper.pyx:24
+constexpr int MAX_DISTANCE = 4;    // _mapper.pyx:26
+constexpr int INVALID_SHIFT = 0x7FFF;  // _mapper.pyx:28
+constexpr int FLD_BINS = SKM_MAX_FRAGMENT_LENGTH;
+
+struct DictDev {
+    ulonglong2 *keys;             // 128-bit tuple hash; all-ones = empty
+    unsigned long long *counts;
+    unsigned long long *first;    // smallest global unit index that produced the class
+    uint32_t *pool_off;
+    uint32_t *len;
+    int32_t *pool;                // transcript ids of every class, tuple order
+    uint64_t mask;                // slots - 1
+    uint64_t pool_cap;
+    unsigned long long *scalars;  // [0]=pool cursor [1]=n_classes [2]=unaligned [3]=aligned
+    unsigned long long *fld;      // FLD_BINS
+    uint32_t *status;
+};
+
+struct MapArgs {
+    const uint8_t *bases;
+    const int64_t *offsets;   // n_reads + 1, or NULL with fixed_len
+    int32_t fixed_len;
+    int32_t code_words;       // u64 words of 2-bit codes per read (from max read length)
+    int32_t words;            // code_words + wildcard words
+    int32_t paired;
+    int64_t n_units;
+    int64_t first_unit;
+    int32_t *out_class;
+    int32_t *out_length;
+    int32_t *arena;           // spill space for target lists longer than LIST_CAP
+    uint64_t arena_cap;
+    unsigned long long *cursors;  // [0]=work counter [1]=arena cursor
+};
+
+// ---- a read packed in shared memory, interleaved [word][lane] ---------------------
+struct ReadView {
+    const uint64_t *w;  // &reads[warp][0][lane]; word k at w[k * 32]
+    int len;
+    int code_words;
+
+    __device__ __forceinline__ uint64_t word(int k) const { return w[k * 32]; }
+    __device__ __forceinline__ uint32_t code(int p) const
+    {
+        return (uint32_t)(word(p >> 5) >> (62 - 2 * (p & 31))) & 3u;
+    }
+    __device__ __forceinline__ bool wild(int p) const
+    {
+        return (word(code_words + (p >> 6)) >> (p & 63)) & 1ULL;
+    }
+    // 25-mer starting at base p (_kmer.pxd:46-68)
+    __device__ __forceinline__ uint64_t kmer(int p) const
+    {
+        const int k = p >> 5, s = p & 31;
+        uint64_t x = word(k) << (2 * s);
+        if (s > 7) x |= word(k + 1) >> (64 - 2 * s);
+        return x >> 14;
+    }
+    // _match_base (_mapper.pyx:500-501): equal, or the read byte is not one of "ACGT"
+    __device__ __forceinline__ bool match(uint32_t ref_code, int p) const
+    {
+        return wild(p) || code(p) == ref_code;
+    }
+};
+
+// ---- a target list: shared memory (stride 32) or arena (stride 1) ------------------
+struct List {
+    int32_t *p;
+    int stride;
+    int n;
+    __device__ __forceinline__ int32_t get(int i) const { return p[i * stride]; }
+    __device__ __forceinline__ void set(int i, int32_t v) { p[i * stride] = v; }
+};
+
+struct Span {
+    int begin, end;
+    Coord anchor;
+};
+
+struct Ctx {
+    const DevIndex &ix;
+    const MapArgs &a;
+    int32_t *smem_list;  // &lists[warp][0][lane]
+    uint32_t *status;
+};
+
+__device__ __forceinline__ uint32_t ref_base(uint32_t ref8, int r) { return (ref8 >> (14 - 2 * r)) & 3u; }
+
+__device__ int sift4_align_left(uint32_t ref8, const ReadView &q, int offset)
+{
+    int reference_cursor = ALIGN_LENGTH - 1;
+    int query_cursor = offset + ALIGN_LENGTH - 1;
+    query_cursor -= 1;
+    int distance = 0;
+    while (reference_cursor >= 0 && query_cursor >= offset) {
+        if (q.match(ref_base(ref8, reference_cursor), query_cursor)) {
+            reference_cursor -= 1;
+            query_cursor -= 1;
+            continue;
+        }
+        if (reference_cursor != query_cursor - offset) {
+            reference_cursor = min(query_cursor - offset, reference_cursor);
+            query_cursor = reference_cursor + offset;
+        }
+#pragma unroll
+        for (int i = 0; i < MAX_OFFSET; ++i) {
+            if (query_cursor - i >= offset - 1 && query_cursor - i >= 0
+                && q.match(ref_base(ref8, reference_cursor), query_cursor - i)) {
+                distance += i - 1;
+                query_cursor -= i - 1;
+                reference_cursor += 1;
+                break;
+            }
+            if (reference_cursor - i >= 0
+                && q.match(ref_base(ref8, reference_cursor - i), query_cursor)) {
+                distance += i - 1;
+                query_cursor += 1;
+                reference_cursor -= i - 1;
+                break;
+            }
+        }
+        distance += 1;
+        query_cursor -= 1;
+        reference_cursor -= 1;
+        if (distance > MAX_DISTANCE) return INVALID_SHIFT;
+    }
+    if (reference_cursor >= 0) return reference_cursor + 1;
+    if (query_cursor >= offset) return -1 - query_cursor + offset;
+    return 0;
+}
+
+__device__ int sift4_align_right(uint32_t ref8, const ReadView &q, int offset)
+{
+    int reference_cursor = 0;
+    int query_cursor = offset;
+    int distance = 0;
+    while (reference_cursor < ALIGN_LENGTH && query_cursor < offset + ALIGN_LENGTH) {
+        if (q.match(ref_base(ref8, reference_cursor), query_cursor)) {
+            reference_cursor += 1;
+            query_cursor += 1;
+            continue;
+        }
+        if (reference_cursor != query_cursor - offset) {
+            reference_cursor = max(query_cursor - offset, reference_cursor);
+            query_cursor = reference_cursor + offset;
+        }
+#pragma unroll
+        for (int i = 0; i < MAX_OFFSET; ++i) {
+            if (query_cursor + i < offset + ALIGN_LENGTH + 1 && query_cursor + i < q.len
+                && q.match(ref_base(ref8, reference_cursor), query_cursor + i)) {
+                distance += i - 1;
+                query_cursor += i - 1;
+                reference_cursor -= 1;
+                break;
+            }
+            if (reference_cursor + i < ALIGN_LENGTH
+                && q.match(ref_base(ref8, reference_cursor + i), query_cursor)) {
+                distance += i - 1;
+                query_cursor -= 1;
+                reference_cursor += i - 1;
+                break;
+            }
+        }
+        distance += 1;
+        query_cursor += 1;
+        reference_cursor += 1;
+        if (distance > MAX_DISTANCE) return INVALID_SHIFT;
+    }
+    if (reference_cursor < ALIGN_LENGTH) return ALIGN_LENGTH - reference_cursor;
+    if (query_cursor < offset + ALIGN_LENGTH) return query_cursor - offset - ALIGN_LENGTH;
+    return 0;
+}
+
+// get_contig_sequence(coordinate, +-8) as a 16-bit window
+__device__ __forceinline__ uint32_t contig_window(const DevIndex &ix, const Contig &c, Coord a,
+                                                  bool left_edge)
+{
+    const int64_t p = c.seq_offset + a.offset;
+    if (a.entry >= 0) return seq_window8(ix, left_edge ? p : p + K - ALIGN_LENGTH);
+    return revcomp8(seq_window8(ix, left_edge ? p + K - ALIGN_LENGTH : p));
+}
+
+__device__ __forceinline__ uint64_t tail_kmer(const Contig &c, Coord a)
+{
+    const uint64_t kmer = a.offset == 0 ? c.first_kmer : c.last_kmer;
+    return a.entry < 0 ? revcomp(kmer) : kmer;
+}
+
+__device__ void map_contig(const Ctx &cx, Coord a, List &l)
+{
+    const bool forward = a.entry >= 0;
+    const int32_t index = forward ? a.entry : ~a.entry;
+    const Contig c = load_contig(cx.ix, index);
+    const int n = c.target_count;
+    l.p = cx.smem_list;
+    l.stride = 32;
+    if (n > LIST_CAP) {
+        const unsigned long long off = atomicAdd(&cx.a.cursors[1], (unsigned long long)n);
+        if (off + (unsigned long long)n > cx.a.arena_cap) {
+            atomicOr(cx.status, ST_ARENA_FULL);
+            l.n = 0;
+            return;
+        }
+        l.p = cx.a.arena + off;
+        l.stride = 1;
+    }
+    const int32_t *t = cx.ix.targets + c.target_offset;
+    if (forward) {
+        for (int i = 0; i < n; ++i) l.set(i, __ldg(t + i));
+    } else {
+        for (int i = 0; i < n; ++i) l.set(i, ~__ldg(t + (n - 1 - i)));
+    }
+    l.n = n;
+}
+
+__device__ bool filter_on_contig(const Ctx &cx, const Contig &c, Coord a, List &l)
+{
+    if (l.n == 0) return true;
+    const bool forward = a.entry >= 0;
+    const int32_t *t = cx.ix.targets + c.target_offset;
+    const int length = c.target_count;
+    int read_index = 0, write_index = 0, track = 0;
+    if (length == 0) return false;
+    int32_t index_entry = forward ? __ldg(t) : ~__ldg(t + length - 1);
+    int32_t target_entry = l.get(0);
+    while (true) {
+        if (target_entry == index_entry) {
+            l.set(write_index, target_entry);
+            read_index += 1;
+            write_index += 1;
+            track += 1;
+            if (read_index == l.n || track == length) break;
+            target_entry = l.get(read_index);
+            index_entry = forward ? __ldg(t + track) : ~__ldg(t + length - 1 - track);
+        } else if (target_entry < index_entry) {
+            read_index += 1;
+            if (read_index == l.n) break;
+            target_entry = l.get(read_index);
+        } else {
+            track += 1;
+            if (track == length) break;
+            index_entry = forward ? __ldg(t + track) : ~__ldg(t + length - 1 - track);
+        }
+    }
+    if (write_index == 0) return false;
+    l.n = write_index;
+    return true;
+}
+
+__device__ void find_first_kmer(const Ctx &cx, const ReadView &r, Span &s, List &l)
+{
+    uint64_t kmer = r.kmer(s.begin);
+    s.anchor = map_kmer(cx.ix, kmer);
+    if (s.anchor.offset >= 0) {
+        s.end = s.begin;
+        map_contig(cx, s.anchor, l);
+        return;
+    }
+    for (int i = s.begin + K; i < r.len; ++i) {
+        kmer = ((kmer << 2) | r.code(i)) & KMER_MASK;
+        s.anchor = map_kmer(cx.ix, kmer);
+        if (s.anchor.offset < 0) continue;
+        s.begin = i + 1 - K;
+        s.end = s.begin;
+        map_contig(cx, s.anchor, l);
+        return;
+    }
+}
+
+__device__ void filter_targets_to_left(const Ctx &cx, const ReadView &r, Span &s, List &l)
+{
+    bool forward = s.anchor.entry >= 0;
+    Contig c = load_contig(cx.ix, forward ? s.anchor.entry : ~s.anchor.entry);
+    int move = forward ? s.anchor.offset : c.length - s.anchor.offset - K;
+    int shift;
+    while (s.begin > move) {
+        s.begin -= move;
+        s.anchor.offset -= forward ? move : -move;
+        shift = sift4_align_left(contig_window(cx.ix, c, s.anchor, true), r, s.begin);
+        if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
+            l.n = 0;
+            return;
+        }
+        s.begin -= shift + 1;
+        if (s.begin < 0) {
+            s.begin = 0;
+            return;
+        }
+        uint64_t kmer = (tail_kmer(c, s.anchor) >> 2) | ((uint64_t)r.code(s.begin) << (2 * K - 2));
+        s.anchor = map_kmer(cx.ix, kmer);
+        bool ok = s.anchor.offset >= 0;
+        if (ok) {
+            c = load_contig(cx.ix, s.anchor.entry >= 0 ? s.anchor.entry : ~s.anchor.entry);
+            ok = filter_on_contig(cx, c, s.anchor, l);
+        }
+        if (!ok) {
+            if (s.begin < K) {
+                s.begin = 0;
+                return;
+            }
+            s.begin -= K;
+            kmer = r.kmer(s.begin);
+            s.anchor = map_kmer(cx.ix, kmer);
+            ok = s.anchor.offset >= 0;
+            if (ok) {
+                c = load_contig(cx.ix, s.anchor.entry >= 0 ? s.anchor.entry : ~s.anchor.entry);
+                ok = filter_on_contig(cx, c, s.anchor, l);
+            }
+            if (!ok) {
+                l.n = 0;
+                return;
+            }
+        }
+        forward = s.anchor.entry >= 0;
+        move = forward ? s.anchor.offset : c.length - s.anchor.offset - K;
+    }
+    s.anchor.offset -= forward ? s.begin : -s.begin;
+    shift = sift4_align_left(contig_window(cx.ix, c, s.anchor, true), r, 0);
+    if (shift == INVALID_SHIFT) l.n = 0;
+}
+
+__device__ void filter_targets_to_right(const Ctx &cx, const ReadView &r, Span &s, List &l)
+{
+    uint64_t kmer = r.kmer(s.end);
+    s.anchor = map_kmer(cx.ix, kmer);
+    bool forward = s.anchor.entry >= 0;
+    Contig c = load_contig(cx.ix, forward ? s.anchor.entry : ~s.anchor.entry);
+    int move = forward ? c.length - s.anchor.offset - K : s.anchor.offset;
+    int shift;
+    while (r.len - s.end - K > move) {
+        s.end += move;
+        s.anchor.offset += forward ? move : -move;
+        shift = sift4_align_right(contig_window(cx.ix, c, s.anchor, false), r,
+                                  s.end + K - ALIGN_LENGTH);
+        if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
+            l.n = 0;
+            return;
+        }
+        s.end += shift + 1;
+        if (s.end + K > r.len) {
+            s.end = r.len - K;
+            return;
+        }
+        kmer = ((tail_kmer(c, s.anchor) << 2) | r.code(s.end + K - 1)) & KMER_MASK;
+        s.anchor = map_kmer(cx.ix, kmer);
+        bool ok = s.anchor.offset >= 0;
+        if (ok) {
+            c = load_contig(cx.ix, s.anchor.entry >= 0 ? s.anchor.entry : ~s.anchor.entry);
+            ok = filter_on_contig(cx, c, s.anchor, l);
+        }
+        if (!ok) {  // :312-315; the block at :316-329 is unreachable (idempotent re-test)
+            l.n = 0;
+            return;
+        }
+        forward = s.anchor.entry >= 0;
+        move = forward ? c.length - s.anchor.offset - K : s.anchor.offset;
+    }
+    if (forward) s.anchor.offset += r.len - s.end - K;
+    else s.anchor.offset -= r.len - s.end - K;
+    shift = sift4_align_right(contig_window(cx.ix, c, s.anchor, false), r, r.len - ALIGN_LENGTH);
+    if (shift == INVALID_SHIFT) l.n = 0;
+}
+
+__device__ void map_read(const Ctx &cx, const ReadView &r, Span &s, List &l)
+{
+    s.anchor = coord_invalid();
+    s.begin = 0;
+    s.end = 0;
+    l.n = 0;
+    find_first_kmer(cx, r, s, l);
+    if (l.n == 0) return;
+    if (s.begin > 0) filter_targets_to_left(cx, r, s, l);
+    if (l.n != 0 && s.end < r.len - K) filter_targets_to_right(cx, r, s, l);
+    if (l.n != 0) return;
+    s.anchor = coord_invalid();
+    s.begin += K;
+    if (s.begin + K > r.len) s.begin = r.len - K;
+    s.end = s.begin;
+    find_first_kmer(cx, r, s, l);
+    if (l.n == 0) return;
+    if (s.begin > 0) filter_targets_to_left(cx, r, s, l);
+    if (l.n != 0 && s.end < r.len - K) filter_targets_to_right(cx, r, s, l);
+}
+
+// mate intersection (_mapper.pyx:350-397): list 1 ascending vs list 2 descending, negated
+__device__ bool intersect(List &l1, const List &l2)
+{
+    if (l1.n == 0) return true;
+    if (l2.n == 0) return false;
+    int cursor1_read = 0, cursor1_write = 0, cursor2 = l2.n - 1;
+    while (cursor1_read != l1.n && cursor2 != -1) {
+        const int32_t entry1 = l1.get(cursor1_read);
+        const int32_t entry2 = ~l2.get(cursor2);
+        if (entry1 == entry2) {
+            l1.set(cursor1_write, entry1);
+            cursor1_read += 1;
+            cursor1_write += 1;
+            cursor2 -= 1;
+        } else if (entry1 < entry2) {
+            cursor1_read += 1;
+        } else {
+            cursor2 -= 1;
+        }
+    }
+    if (cursor1_write == 0) return false;
+    l1.n = cursor1_write;
+    return true;
+}
+
+// ---- class dictionary ---------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 cmp, ulonglong2 val)
+{
+    ulonglong2 old;
+    asm volatile(
+        "{\n\t"
+        ".reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t"
+        "}\n"
+        : "=l"(old.x), "=l"(old.y)
+        : "l"(cmp.x), "l"(cmp.y), "l"(val.x), "l"(val.y), "l"(addr)
+        : "memory");
+    return old;
+}
+
+// 128-bit identity of an ordered id tuple (length included).  Never all-ones.
+__device__ __forceinline__ ulonglong2 tuple_key(const int32_t *ids, int stride, int n, bool strip_sign)
+{
+    uint64_t h1 = 0x9E3779B97F4A7C15ULL ^ (uint64_t)n;
+    uint64_t h2 = 0xD6E8FEB86659FD93ULL + (uint64_t)n;
+    for (int i = 0; i < n; ++i) {
+        int32_t e = ids[i * stride];
+        if (strip_sign && e < 0) e = ~e;  // _get_ids, _mapper.pyx:533-536
+        const uint64_t v = (uint64_t)(uint32_t)e;
+        h1 = mix64(h1 ^ v) + 0x632BE59BD9B4E019ULL;
+        h2 = (h2 ^ (v + 0x9E3779B97F4A7C15ULL + (h2 << 6) + (h2 >> 2))) * 0xBF58476D1CE4E5B9ULL;
+        h2 ^= h2 >> 29;
+    }
+    h2 = mix64(h2);
+    if (h1 == EMPTY_KEY) h1 = 0;
+    return make_ulonglong2(h1, h2);
+}
+
+// Find-or-insert; returns the slot, or -1 when the table is full.  The winner of the
+// 128-bit CAS copies the tuple into the id pool; nobody reads it before the kernel ends.
+__device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const int32_t *ids,
+                                       int stride, int n, bool strip_sign)
+{
+    uint64_t s = (key.x ^ (key.y >> 17)) & d.mask;
+    const ulonglong2 empty = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
+    for (uint64_t probes = 0; probes <= d.mask; ++probes) {
+        // 64-bit halves are individually atomic; only a definite foreign h1 skips the CAS
+        const uint64_t seen = *reinterpret_cast<volatile const uint64_t *>(&d.keys[s].x);
+        if (seen == EMPTY_KEY || seen == key.x) {
+            const ulonglong2 old = cas128(d.keys + s, empty, key);
+            if (old.x == EMPTY_KEY && old.y == EMPTY_KEY) {
+                const unsigned long long off = atomicAdd(&d.scalars[0], (unsigned long long)n);
+                if (off + (unsigned long long)n > d.pool_cap) {
+                    atomicOr(d.status, ST_POOL_FULL);
+                    d.pool_off[s] = 0;
+                    d.len[s] = 0;
+                } else {
+                    for (int i = 0; i < n; ++i) {
+                        int32_t e = ids[i * stride];
+                        if (strip_sign && e < 0) e = ~e;
+                        d.pool[off + i] = e;
+                    }
+                    d.pool_off[s] = (uint32_t)off;
+                    d.len[s] = (uint32_t)n;
+                }
+                atomicAdd(&d.scalars[1], 1ULL);
+                return (int64_t)s;
+            }
+            if (old.x == key.x && old.y == key.y) return (int64_t)s;
+        }
+        s = (s + 1) & d.mask;
+    }
+    atomicOr(d.status, ST_DICT_FULL);
+    return -1;
+}
+
+// ---- the kernel ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lut_entry(uint32_t b)
+{
+    // bits 1:0 = 2-bit code (_kmer.pxd:253-273), bit 2 = "not one of ACGT" (_mapper.pyx:501)
+    const uint32_t u = b & 0xDFu;
+    const uint32_t code = u == 'T' ? 3u : u == 'G' ? 2u : u == 'C' ? 1u : 0u;
+    const bool upper = b == 'A' || b == 'C' || b == 'G' || b == 'T';
+    return code | (upper ? 0u : 4u);
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 3)
+map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *sm_reads = reinterpret_cast<uint64_t *>(smem_raw);             // [WARPS][words][32]
+    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_reads + WARPS * a.words * 32);  // [WARPS][CAP][32]
+    uint32_t *sm_fld = reinterpret_cast<uint32_t *>(sm_lists + WARPS * LIST_CAP * 32);
+    uint8_t *sm_lut = reinterpret_cast<uint8_t *>(sm_fld + FLD_BINS);
+
+    for (int i = threadIdx.x; i < FLD_BINS; i += BLOCK_THREADS) sm_fld[i] = 0;
+    for (int i = threadIdx.x; i < 256; i += BLOCK_THREADS) sm_lut[i] = (uint8_t)lut_entry(i);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *my_words = sm_reads + (size_t)warp * a.words * 32 + lane;
+    Ctx cx{ix, a, sm_lists + warp * LIST_CAP * 32 + lane, dict.status};
+
+    const int64_t n_reads = a.paired ? 2 * a.n_units : a.n_units;
+    const int64_t n_chunks = (n_reads + 31) >> 5;
+
+    for (;;) {
+        long long chunk = 0;
+        if (lane == 0) chunk = (long long)atomicAdd(&a.cursors[0], 1ULL);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n_chunks) break;
+        const int64_t read_idx = chunk * 32 + lane;
+        const bool valid = read_idx < n_reads;
+
+        // ---- stage this lane's read: ASCII -> 2-bit codes + wildcard bits ----------
+        int len = 0;
+        if (valid) {
+            int64_t off;
+            if (a.offsets) {
+                off = a.offsets[read_idx];
+                len = (int)(a.offsets[read_idx + 1] - off);
+            } else {
+                off = read_idx * (int64_t)a.fixed_len;
+                len = a.fixed_len;
+            }
+            const int max_len = a.code_words * 32;
+            if (len > max_len) len = max_len;  // host guarantees max_read_len; defensive
+            const uint8_t *src = a.bases + off;
+            uint64_t acc = 0, wacc = 0;
+            int cw = 0, ww = a.code_words;
+            int j = 0;
+            auto push = [&](uint32_t byte) {
+                const uint32_t v = sm_lut[byte];
+                acc = (acc << 2) | (v & 3u);
+                wacc |= (uint64_t)(v >> 2) << (j & 63);
+                if ((j & 31) == 31) {
+                    my_words[cw * 32] = acc;
+                    cw += 1;
+                    acc = 0;
+                    if ((j & 63) == 63) {
+                        my_words[ww * 32] = wacc;
+                        ww += 1;
+                        wacc = 0;
+                    }
+                }
+                j += 1;
+            };
+            while (j < len && (reinterpret_cast<uintptr_t>(src + j) & 7)) push(__ldg(src + j));
+            while (j + 8 <= len) {
+                const uint64_t w8 = __ldg(reinterpret_cast<const unsigned long long *>(src + j));
+#pragma unroll
+                for (int b = 0; b < 8; ++b) push((uint32_t)(w8 >> (8 * b)) & 0xFFu);
+            }
+            while (j < len) push(__ldg(src + j));
+            if (len & 31) my_words[cw * 32] = acc << (2 * (32 - (len & 31)));
+            if (len & 63) my_words[ww * 32] = wacc;
+        }
+        __syncwarp();
+
+        // ---- per-read state machine ----------------------------------------------
+        ReadView rv{my_words, len, a.code_words};
+        Span sp;
+        sp.begin = 0;
+        sp.end = 0;
+        sp.anchor = coord_invalid();
+        List l{cx.smem_list, 32, 0};
+        if (valid) {
+            if (len >= K) map_read(cx, rv, sp, l);
+            else atomicOr(dict.status, ST_SHORT_READ);
+        }
+        __syncwarp();
+
+        // ---- mates -> unit (map_read_pair, _mapper.pyx:111-145) --------------------
+        bool is_unit = valid;
+        int64_t unit = read_idx;
+        if (a.paired) {
+            const int b2 = __shfl_down_sync(0xffffffffu, sp.begin, 1);
+            const int e2 = __shfl_down_sync(0xffffffffu, sp.anchor.entry, 1);
+            const int o2 = __shfl_down_sync(0xffffffffu, sp.anchor.offset, 1);
+            const int n2 = __shfl_down_sync(0xffffffffu, l.n, 1);
+            const int len2 = __shfl_down_sync(0xffffffffu, len, 1);
+            const int st2 = __shfl_down_sync(0xffffffffu, l.stride, 1);
+            const unsigned long long p2 =
+                __shfl_down_sync(0xffffffffu, (unsigned long long)(uintptr_t)l.p, 1);
+            is_unit = valid && !(lane & 1);
+            unit = read_idx >> 1;
+            if (is_unit) {
+                List l2{reinterpret_cast<int32_t *>((uintptr_t)p2), st2, n2};
+                if (!intersect(l, l2)) {
+                    l.n = 0;
+                    sp.begin = 0;
+                    sp.end = -K;
+                } else if (sp.anchor.entry != ~e2) {
+                    sp.begin = 0;
+                    sp.end = -K;
+                } else {
+                    sp.end = len - K;
+                    int interval = o2 - sp.anchor.offset;
+                    if (sp.anchor.entry < 0) interval = -interval;
+                    sp.end += interval + (len2 - K) - b2;
+                }
+            }
+        }
+
+        // ---- FLD (_mapper.pyx:90-94), class tally (mapper.py:60-75) -----------------
+        int64_t slot = -1;
+        if (is_unit) {
+            int length = sp.end - sp.begin + K;
+            if (a.out_length) a.out_length[unit] = length;
+            if (length > 0) {
+                if (length >= FLD_BINS) length = FLD_BINS - 1;
+                atomicAdd(&sm_fld[length], 1u);
+            }
+            if (l.n > 0) {
+                const ulonglong2 key = tuple_key(l.p, l.stride, l.n, true);
+                slot = dict_find_or_insert(dict, key, l.p, l.stride, l.n, true);
+            }
+            if (a.out_class) a.out_class[unit] = (int32_t)slot;
+        }
+        __syncwarp();
+        // warp-aggregated count / first-seen update: one atomic per distinct class per warp
+        {
+            const unsigned same = __match_any_sync(0xffffffffu, slot);
+            const int leader = __ffs(same) - 1;
+            if (slot >= 0 && lane == leader) {
+                atomicAdd(&dict.counts[slot], (unsigned long long)__popc(same));
+                const unsigned long long g = (unsigned long long)(a.first_unit + unit);
+                if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
+                    atomicMin(&dict.first[slot], g);
+            }
+            const unsigned units = __ballot_sync(0xffffffffu, is_unit);
+            const unsigned mapped = __ballot_sync(0xffffffffu, is_unit && slot >= 0);
+            if (lane == 0) {
+                const int n_al = __popc(mapped);
+                const int n_un = __popc(units) - n_al;
+                if (n_un) atomicAdd(&dict.scalars[2], (unsigned long long)n_un);
+                if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
+            }
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    for (int i = threadIdx.x; i < FLD_BINS; i += BLOCK_THREADS) {
+        const uint32_t v = sm_fld[i];
+        if (v) atomicAdd(&dict.fld[i], (unsigned long long)v);
+    }
+}
+
+// ---- export / merge -------------------------------------------------------------------
+// Compaction of the dictionary to CSR.  One 64-bit atomic hands out the class index
+// (high 24 bits) and the id start (low 40 bits) together, so starts are monotone in the
+// class index and key_offsets is a proper CSR row pointer.  Class order is arbitrary;
+// callers sort by first_unit for the reference's insertion order.
+__global__ void dict_export_kernel(const DictDev d, int64_t slots, unsigned long long *cursor,
+                                   int64_t *key_offsets, int32_t *key_ids, int64_t *counts,
+                                   int64_t *first_unit, int32_t *slot_ids)
+{
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= slots) return;
+    if (d.keys[s].x == EMPTY_KEY && d.keys[s].y == EMPTY_KEY) return;
+    const uint32_t n = d.len[s];
+    const unsigned long long old = atomicAdd(cursor, (1ULL << 40) | (unsigned long long)n);
+    const unsigned long long c = old >> 40;
+    const unsigned long long p = old & ((1ULL << 40) - 1);
+    if (key_offsets) key_offsets[c] = (int64_t)p;
+    if (key_ids) {
+        const int32_t *src = d.pool + d.pool_off[s];
+        for (uint32_t i = 0; i < n; ++i) key_ids[p + i] = src[i];
+    }
+    if (counts) counts[c] = (int64_t)d.counts[s];
+    if (first_unit) first_unit[c] = (int64_t)d.first[s];
+    if (slot_ids) slot_ids[c] = (int32_t)s;
+}
+
+__global__ void set_i64_kernel(int64_t *dst, int64_t v) { *dst = v; }
+
+__global__ void dict_merge_kernel(const DictDev d, const int64_t *key_offsets, const int32_t *key_ids,
+                                  const int64_t *counts, const int64_t *first_unit, int64_t n_classes)
+{
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_classes) return;
+    const int64_t start = key_offsets[c];
+    const int n = (int)(key_offsets[c + 1] - start);
+    if (n <= 0) return;
+    const ulonglong2 key = tuple_key(key_ids + start, 1, n, false);
+    const int64_t slot = dict_find_or_insert(d, key, key_ids + start, 1, n, false);
+    if (slot < 0) return;
+    atomicAdd(&d.counts[slot], (unsigned long long)counts[c]);
+    atomicMin(&d.first[slot], (unsigned long long)first_unit[c]);
+    atomicAdd(&d.scalars[3], (unsigned long long)counts[c]);
+}
+
+__global__ void add_i64_kernel(unsigned long long *dst, const int64_t *src, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += (unsigned long long)src[i];
+}
+
+}  // namespace skm
+
+using namespace skm;
+
+struct skm_mapper {
+    skm_index *index = nullptr;
+    int device = 0;
+    DictDev d{};
+    int64_t slots = 0, pool_cap = 0;
+    unsigned long long *cursors = nullptr;  // [0]=work [1]=arena [2..3]=export cursors
+    int32_t *arena = nullptr;
+    uint64_t arena_cap = 0;
+    int sm_count = 148;
+    // staging for host-buffer calls
+    uint8_t *d_bases = nullptr;
+    size_t d_bases_cap = 0;
+    int64_t *d_offsets = nullptr;
+    size_t d_offsets_cap = 0;
+    int32_t *d_out = nullptr;
+    size_t d_out_cap = 0;
+};
+
+static int ensure(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4;
+    SKM_CUDA(cudaMalloc(p, want));
+    *cap = want;
+    return 0;
+}
+
+SKM_API void skm_mapper_destroy(skm_mapper *m)
+{
+    if (!m) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(m->device);
+    cudaFree(m->d.keys);
+    cudaFree(m->d.counts);
+    cudaFree(m->d.first);
+    cudaFree(m->d.pool_off);
+    cudaFree(m->d.len);
+    cudaFree(m->d.pool);
+    cudaFree(m->d.scalars);
+    cudaFree(m->d.fld);
+    cudaFree(m->d.status);
+    cudaFree(m->cursors);
+    cudaFree(m->arena);
+    cudaFree(m->d_bases);
+    cudaFree(m->d_offsets);
+    cudaFree(m->d_out);
+    cudaSetDevice(prev);
+    delete m;
+}
+
+SKM_API int skm_mapper_reset(skm_mapper *m, void *stream)
+{
+    if (!m) return fail(SKM_ERR_INVALID, "skm_mapper_reset: NULL mapper");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA(cudaMemsetAsync(m->d.keys, 0xFF, sizeof(ulonglong2) * (size_t)m->slots, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.counts, 0, sizeof(unsigned long long) * (size_t)m->slots, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.first, 0xFF, sizeof(unsigned long long) * (size_t)m->slots, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.len, 0, sizeof(uint32_t) * (size_t)m->slots, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.pool_off, 0, sizeof(uint32_t) * (size_t)m->slots, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.scalars, 0, sizeof(unsigned long long) * 4, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.fld, 0, sizeof(unsigned long long) * FLD_BINS, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.status, 0, sizeof(uint32_t), st));
+    return SKM_OK;
+}
+
+SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t id_capacity,
+                                 skm_mapper **out)
+{
+    if (!out) return fail(SKM_ERR_INVALID, "skm_mapper_create: out is NULL");
+    *out = nullptr;
+    if (!index) return fail(SKM_ERR_INVALID, "skm_mapper_create: NULL index");
+    SKM_CUDA(cudaSetDevice(index->device));
+    if (class_capacity <= 0) class_capacity = 1LL << 22;
+    int64_t slots = 1024;
+    while (slots < 2 * class_capacity) slots <<= 1;
+    if (id_capacity <= 0) id_capacity = 8 * class_capacity;
+    if (id_capacity >= (1LL << 32)) id_capacity = (1LL << 32) - 1;
+    skm_mapper *m = new skm_mapper();
+    m->index = index;
+    m->device = index->device;
+    m->slots = slots;
+    m->pool_cap = id_capacity;
+    cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
+    // list arena: room for every resident thread to spill its largest possible list a few
+    // times over, bounded to 2 GiB
+    uint64_t arena = (uint64_t)std::max<int64_t>(index->max_target_count, 64) * 2048ULL * (uint64_t)m->sm_count;
+    arena = std::min<uint64_t>(std::max<uint64_t>(arena, 1ULL << 22), 1ULL << 29);
+    m->arena_cap = arena;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    };
+    A((void **)&m->d.keys, sizeof(ulonglong2) * (size_t)slots);
+    A((void **)&m->d.counts, sizeof(unsigned long long) * (size_t)slots);
+    A((void **)&m->d.first, sizeof(unsigned long long) * (size_t)slots);
+    A((void **)&m->d.pool_off, sizeof(uint32_t) * (size_t)slots);
+    A((void **)&m->d.len, sizeof(uint32_t) * (size_t)slots);
+    A((void **)&m->d.pool, sizeof(int32_t) * (size_t)id_capacity);
+    A((void **)&m->d.scalars, sizeof(unsigned long long) * 4);
+    A((void **)&m->d.fld, sizeof(unsigned long long) * FLD_BINS);
+    A((void **)&m->d.status, sizeof(uint32_t));
+    A((void **)&m->cursors, sizeof(unsigned long long) * 4);
+    A((void **)&m->arena, sizeof(int32_t) * (size_t)arena);
+    if (e != cudaSuccess) {
+        skm_mapper_destroy(m);
+        return fail(SKM_ERR_OOM, std::string("skm_mapper_create: ") + cudaGetErrorString(e));
+    }
+    m->d.mask = (uint64_t)slots - 1;
+    m->d.pool_cap = (uint64_t)id_capacity;
+    int rc = skm_mapper_reset(m, nullptr);
+    if (rc == 0 && cudaStreamSynchronize(nullptr) != cudaSuccess) rc = fail(SKM_ERR_CUDA, "reset failed");
+    if (rc != 0) {
+        skm_mapper_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return SKM_OK;
+}
+
+static size_t map_smem_bytes(int words)
+{
+    return sizeof(uint64_t) * WARPS * (size_t)words * 32 + sizeof(int32_t) * WARPS * LIST_CAP * 32
+           + sizeof(uint32_t) * FLD_BINS + 256;
+}
+
+static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
+{
+    uint32_t status = 0;
+    SKM_CUDA(cudaMemcpyAsync(&status, m->d.status, sizeof(status), cudaMemcpyDeviceToHost, st));
+    SKM_CUDA(cudaStreamSynchronize(st));
+    if (status & (ST_ARENA_FULL | ST_DICT_FULL | ST_POOL_FULL)) {
+        std::string msg = std::string(who) + ": device capacity exhausted:";
+        if (status & ST_ARENA_FULL) msg += " target-list arena";
+        if (status & ST_DICT_FULL) msg += " class table (raise class_capacity)";
+        if (status & ST_POOL_FULL) msg += " class id pool (raise id_capacity)";
+        return fail(SKM_ERR_CAPACITY, msg);
+    }
+    return SKM_OK;
+}
+
+SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *read_offsets,
+                             int32_t fixed_read_len, int32_t max_read_len, int64_t n_units,
+                             int paired, int64_t first_unit, int buffers_on_device,
+                             int32_t *out_class, int32_t *out_length, void *stream)
+{
+    if (!m || !bases) return fail(SKM_ERR_INVALID, "skm_map_batch: NULL argument");
+    if (n_units < 0) return fail(SKM_ERR_INVALID, "skm_map_batch: negative unit count");
+    if (n_units == 0) return SKM_OK;
+    if (!read_offsets && fixed_read_len < K)
+        return fail(SKM_ERR_INVALID, "skm_map_batch: need read_offsets or fixed_read_len >= 25");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_reads = paired ? 2 * n_units : n_units;
+
+    if (!read_offsets) max_read_len = fixed_read_len;
+    if (!buffers_on_device && read_offsets) {
+        int64_t mx = 0, mn = INT64_MAX;
+        for (int64_t i = 0; i < n_reads; ++i) {
+            const int64_t L = read_offsets[i + 1] - read_offsets[i];
+            mx = std::max(mx, L);
+            mn = std::min(mn, L);
+        }
+        if (mn < K) return fail(SKM_ERR_INVALID, "skm_map_batch: read shorter than k=25 (undefined in the reference)");
+        max_read_len = (int32_t)mx;
+    }
+    if (max_read_len < K) return fail(SKM_ERR_INVALID, "skm_map_batch: max_read_len must be >= 25");
+    if (max_read_len > 4096) return fail(SKM_ERR_INVALID, "skm_map_batch: reads longer than 4096 bases are not supported");
+
+    MapArgs a{};
+    a.fixed_len = read_offsets ? 0 : fixed_read_len;
+    a.code_words = (max_read_len + 31) / 32;
+    a.words = a.code_words + (max_read_len + 63) / 64;
+    a.paired = paired ? 1 : 0;
+    a.n_units = n_units;
+    a.first_unit = first_unit;
+    a.arena = m->arena;
+    a.arena_cap = m->arena_cap;
+    a.cursors = m->cursors;
+
+    if (buffers_on_device) {
+        a.bases = bases;
+        a.offsets = read_offsets;
+        a.out_class = out_class;
+        a.out_length = out_length;
+    } else {
+        const int64_t n_bases = read_offsets ? read_offsets[n_reads] - read_offsets[0]
+                                             : n_reads * (int64_t)fixed_read_len;
+        int rc = ensure((void **)&m->d_bases, &m->d_bases_cap, (size_t)n_bases + 16);
+        if (rc) return rc;
+        const uint8_t *src = bases + (read_offsets ? read_offsets[0] : 0);
+        SKM_CUDA(cudaMemcpyAsync(m->d_bases, src, (size_t)n_bases, cudaMemcpyHostToDevice, st));
+        a.bases = m->d_bases - (read_offsets ? read_offsets[0] : 0);
+        if (read_offsets) {
+            rc = ensure((void **)&m->d_offsets, &m->d_offsets_cap, sizeof(int64_t) * (size_t)(n_reads + 1));
+            if (rc) return rc;
+            SKM_CUDA(cudaMemcpyAsync(m->d_offsets, read_offsets, sizeof(int64_t) * (size_t)(n_reads + 1),
+                                     cudaMemcpyHostToDevice, st));
+            a.offsets = m->d_offsets;
+        }
+        if (out_class || out_length) {
+            rc = ensure((void **)&m->d_out, &m->d_out_cap, sizeof(int32_t) * 2 * (size_t)n_units);
+            if (rc) return rc;
+            a.out_class = out_class ? m->d_out : nullptr;
+            a.out_length = out_length ? m->d_out + n_units : nullptr;
+        }
+    }
+
+    SKM_CUDA(cudaMemsetAsync(m->cursors, 0, sizeof(unsigned long long) * 2, st));
+    const size_t smem = map_smem_bytes(a.words);
+    SKM_CUDA(cudaFuncSetAttribute(map_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_reads_kernel, BLOCK_THREADS, smem));
+    if (per_sm < 1) return fail(SKM_ERR_INVALID, "skm_map_batch: reads too long for shared-memory staging");
+    const int64_t chunks = (n_reads + 31) / 32;
+    const int64_t want = (chunks + WARPS - 1) / WARPS;
+    const int grid = (int)std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>(want, 1));
+    map_reads_kernel<<<grid, BLOCK_THREADS, smem, st>>>(m->index->d, m->d, a);
+    SKM_CUDA(cudaGetLastError());
+
+    if (!buffers_on_device) {
+        if (out_class)
+            SKM_CUDA(cudaMemcpyAsync(out_class, a.out_class, sizeof(int32_t) * (size_t)n_units,
+                                     cudaMemcpyDeviceToHost, st));
+        if (out_length)
+            SKM_CUDA(cudaMemcpyAsync(out_length, a.out_length, sizeof(int32_t) * (size_t)n_units,
+                                     cudaMemcpyDeviceToHost, st));
+        return check_status(m, st, "skm_map_batch");
+    }
+    return SKM_OK;
+}
+
+SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[6], void *stream)
+{
+    if (!m || !sizes) return fail(SKM_ERR_INVALID, "skm_classes_size: NULL argument");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long sc[4];
+    uint32_t status = 0;
+    SKM_CUDA(cudaMemcpyAsync(sc, m->d.scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
+    SKM_CUDA(cudaMemcpyAsync(&status, m->d.status, sizeof(status), cudaMemcpyDeviceToHost, st));
+    SKM_CUDA(cudaStreamSynchronize(st));
+    sizes[0] = (int64_t)sc[1];
+    sizes[1] = (int64_t)sc[0];
+    sizes[2] = (int64_t)sc[2];
+    sizes[3] = (int64_t)sc[3];
+    sizes[4] = m->slots / 2;
+    sizes[5] = (int64_t)status;
+    return SKM_OK;
+}
+
+SKM_API int skm_classes_export(skm_mapper *m, int64_t *key_offsets, int32_t *key_ids,
+                                  int64_t *counts, int64_t *first_unit, int32_t *slots,
+                                  int64_t *fld, int buffers_on_device, void *stream)
+{
+    if (!m) return fail(SKM_ERR_INVALID, "skm_classes_export: NULL mapper");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_status(m, st, "skm_classes_export");
+    if (rc) return rc;
+    int64_t sizes[6];
+    rc = skm_classes_size(m, sizes, stream);
+    if (rc) return rc;
+    const int64_t n_cls = sizes[0], n_ids = sizes[1];
+    const bool host = !buffers_on_device;
+
+    int64_t *d_off = key_offsets, *d_counts = counts, *d_first = first_unit;
+    int32_t *d_ids = key_ids, *d_slots = slots;
+    void *owned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    if (host) {
+        auto A = [&](int k, void **p, bool wanted, size_t bytes) {
+            *p = nullptr;
+            if (!wanted || e != cudaSuccess) return;
+            e = cudaMalloc(&owned[k], std::max<size_t>(bytes, 16));
+            *p = owned[k];
+        };
+        A(0, (void **)&d_off, key_offsets != nullptr, sizeof(int64_t) * (size_t)(n_cls + 1));
+        A(1, (void **)&d_ids, key_ids != nullptr, sizeof(int32_t) * (size_t)n_ids);
+        A(2, (void **)&d_counts, counts != nullptr, sizeof(int64_t) * (size_t)n_cls);
+        A(3, (void **)&d_first, first_unit != nullptr, sizeof(int64_t) * (size_t)n_cls);
+        A(4, (void **)&d_slots, slots != nullptr, sizeof(int32_t) * (size_t)n_cls);
+    }
+    auto cleanup = [&]() {
+        for (void *p : owned) cudaFree(p);
+    };
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(SKM_ERR_OOM, std::string("skm_classes_export: ") + cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(m->cursors + 2, 0, sizeof(unsigned long long), st);
+    if (n_cls > 0)
+        dict_export_kernel<<<(unsigned)((m->slots + 255) / 256), 256, 0, st>>>(
+            m->d, m->slots, m->cursors + 2, d_off, d_ids, d_counts, d_first, d_slots);
+    if (d_off) set_i64_kernel<<<1, 1, 0, st>>>(d_off + n_cls, n_ids);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && host) {
+        if (key_offsets) cudaMemcpyAsync(key_offsets, d_off, sizeof(int64_t) * (size_t)(n_cls + 1), cudaMemcpyDeviceToHost, st);
+        if (key_ids && n_ids > 0) cudaMemcpyAsync(key_ids, d_ids, sizeof(int32_t) * (size_t)n_ids, cudaMemcpyDeviceToHost, st);
+        if (counts && n_cls > 0) cudaMemcpyAsync(counts, d_counts, sizeof(int64_t) * (size_t)n_cls, cudaMemcpyDeviceToHost, st);
+        if (first_unit && n_cls > 0) cudaMemcpyAsync(first_unit, d_first, sizeof(int64_t) * (size_t)n_cls, cudaMemcpyDeviceToHost, st);
+        if (slots && n_cls > 0) cudaMemcpyAsync(slots, d_slots, sizeof(int32_t) * (size_t)n_cls, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess && fld)
+        cudaMemcpyAsync(fld, m->d.fld, sizeof(int64_t) * FLD_BINS,
+                        host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(SKM_ERR_CUDA, std::string("skm_classes_export: ") + cudaGetErrorString(e));
+    return SKM_OK;
+}
+
+SKM_API int skm_classes_merge(skm_mapper *m, const int64_t *key_offsets, const int32_t *key_ids,
+                                 const int64_t *counts, const int64_t *first_unit, int64_t n_classes,
+                                 const int64_t *fld, int64_t unaligned, int buffers_on_device,
+                                 void *stream)
+{
+    if (!m) return fail(SKM_ERR_INVALID, "skm_classes_merge: NULL mapper");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_classes > 0 && (!key_offsets || !key_ids || !counts || !first_unit))
+        return fail(SKM_ERR_INVALID, "skm_classes_merge: NULL class arrays");
+    int64_t *d_off = nullptr, *d_cnt = nullptr, *d_first = nullptr, *d_fld = nullptr;
+    int32_t *d_ids = nullptr;
+    const int64_t *p_off = key_offsets, *p_cnt = counts, *p_first = first_unit, *p_fld = fld;
+    const int32_t *p_ids = key_ids;
+    cudaError_t e = cudaSuccess;
+    if (!buffers_on_device) {
+        const int64_t n_ids = n_classes > 0 ? key_offsets[n_classes] : 0;
+        auto up = [&](void **d, const void *h, size_t bytes) {
+            if (e != cudaSuccess || bytes == 0) return;
+            e = cudaMalloc(d, bytes);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st);
+        };
+        if (n_classes > 0) {
+            up((void **)&d_off, key_offsets, sizeof(int64_t) * (size_t)(n_classes + 1));
+            up((void **)&d_ids, key_ids, sizeof(int32_t) * (size_t)n_ids);
+            up((void **)&d_cnt, counts, sizeof(int64_t) * (size_t)n_classes);
+            up((void **)&d_first, first_unit, sizeof(int64_t) * (size_t)n_classes);
+        }
+        if (fld) up((void **)&d_fld, fld, sizeof(int64_t) * FLD_BINS);
+        p_off = d_off;
+        p_ids = d_ids;
+        p_cnt = d_cnt;
+        p_first = d_first;
+        p_fld = d_fld;
+    }
+    if (e == cudaSuccess && n_classes > 0) {
+        dict_merge_kernel<<<(unsigned)((n_classes + 127) / 128), 128, 0, st>>>(m->d, p_off, p_ids, p_cnt,
+                                                                             p_first, n_classes);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && fld) {
+        add_i64_kernel<<<(FLD_BINS + 255) / 256, 256, 0, st>>>(m->d.fld, p_fld, FLD_BINS);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && unaligned > 0) {
+        int64_t *d_un = nullptr;
+        e = cudaMalloc((void **)&d_un, sizeof(int64_t));
+        if (e == cudaSuccess) {
+            cudaMemcpyAsync(d_un, &unaligned, sizeof(int64_t), cudaMemcpyHostToDevice, st);
+            add_i64_kernel<<<1, 32, 0, st>>>(m->d.scalars + 2, d_un, 1);
+            cudaStreamSynchronize(st);
+            cudaFree(d_un);
+        }
+    }
+    int rc = SKM_OK;
+    if (e == cudaSuccess) rc = check_status(m, st, "skm_classes_merge");
+    cudaFree(d_off);
+    cudaFree(d_ids);
+    cudaFree(d_cnt);
+    cudaFree(d_first);
+    cudaFree(d_fld);
+    if (e != cudaSuccess) return fail(SKM_ERR_CUDA, std::string("skm_classes_merge: ") + cudaGetErrorString(e));
+    return rc;
+}

@@ -1,0 +1,276 @@
+"""Inference workflow — the `seekmer.infer` surface (`infer.py:27-353`).
+
+Mirrors: run, quantify, em, output_results, add_subcommand_parser — same signatures, same
+output folder (run_info.json, abundance.tsv, abundance.h5, optional readmap.txt).
+
+What changes underneath: `em` runs as fp64 segmented-reduction kernels (`skm_em`); the
+bootstrap resampling of `quantify(..., bootstrap=True)` is an on-device multinomial
+(`skm_multinomial`); and `run` batches all bootstrap replicates through one EM call
+(`quantify_bootstraps`) instead of the reference's serial loop (`infer.py:79-82`).
+There is no CPU EM fallback.
+"""
+import datetime
+import json
+import pathlib
+import shlex
+import sys
+
+import numpy
+
+from . import _lib
+from . import common
+from . import mapper
+from ._log import Logger
+
+__all__ = ['run', 'quantify', 'quantify_bootstraps', 'em', 'output_results',
+           'add_subcommand_parser']
+
+_LOG = Logger(__name__)
+
+
+def run(index_path, output_path, fastq_paths, job_count, save_readmap, single_ended, bootstrap,
+        debug, **__):
+    """The entrypoint of the inference module (`infer.py:27-85`)."""
+    start_time = datetime.datetime.utcnow()
+    try:
+        output_path.mkdir(parents=True)
+    except FileExistsError:
+        _LOG.warn('The output folder exists. Overriding...')
+    readmap = (output_path / 'readmap.txt').open('wt') if save_readmap else None
+    _LOG.info('Inferring transcript abundance')
+    index = common.KMerIndex.load(index_path)
+    _LOG.info('Mapping all reads')
+    if single_ended:
+        read_feeder = common.feed_single_ended_reads(*fastq_paths)
+    else:
+        read_feeder = common.feed_pair_ended_reads(*fastq_paths)
+    map_result = mapper.map_reads(index, read_feeder, job_count=job_count, readmap=readmap,
+                                  debug=debug)
+    _LOG.info('Mapped all reads')
+    mean_fragment_length = map_result.harmonic_mean_fragment_length
+    _LOG.info('Estimated fragment length: {:.2f}', mean_fragment_length)
+    summarized_results = map_result.summarize()
+    _LOG.info('Quantifying transcripts')
+    _LOG.info('Aligned {} reads ({:.2%})', summarized_results.aligned,
+              summarized_results.aligned / max(summarized_results.total, 1))
+    main_result = quantify(summarized_results)
+    _LOG.info('Quantified transcripts')
+    bootstrapped_results = quantify_bootstraps(summarized_results, main_result, bootstrap)
+    output_results(output_path, index, start_time, summarized_results, main_result,
+                   bootstrapped_results)
+    _LOG.info('Wrote results to {}'.format(output_path))
+
+
+def _csr_from_class_map(class_map, n_classes):
+    """(2, nnz) class_map -> (ptr int64[C+1], tx int32[nnz]) keeping nnz order within a class."""
+    rows = numpy.asarray(class_map[0], dtype='i8')
+    cols = numpy.asarray(class_map[1], dtype='i8')
+    if rows.size > 1 and (rows[1:] < rows[:-1]).any():
+        order = numpy.argsort(rows, kind='stable')
+        rows, cols = rows[order], cols[order]
+    ptr = numpy.zeros(n_classes + 1, dtype='i8')
+    numpy.cumsum(numpy.bincount(rows, minlength=n_classes), out=ptr[1:])
+    return ptr, numpy.ascontiguousarray(cols, dtype='i4')
+
+
+def _em_device(x0, l, class_map, class_counts, device=0):
+    """x0: (R, T) normalised guesses; class_counts: (R, C). Returns (x (R, T), iters (R,))."""
+    x0 = numpy.ascontiguousarray(numpy.atleast_2d(x0), dtype='f8')
+    counts = numpy.ascontiguousarray(numpy.atleast_2d(class_counts), dtype='f8')
+    l = numpy.ascontiguousarray(l, dtype='f8')
+    n_rep, n_tx = x0.shape
+    n_classes = counts.shape[1]
+    ptr, tx = _csr_from_class_map(class_map, n_classes)
+    out = numpy.zeros_like(x0)
+    iters = numpy.zeros(n_rep, dtype='i4')
+    _lib.require_device()
+    _lib.check(_lib.load().skm_em(
+        _lib._np_ptr(ptr), _lib._np_ptr(tx), n_classes, tx.shape[0], _lib._np_ptr(counts),
+        _lib._np_ptr(l), n_tx, _lib._np_ptr(x0), n_rep, 0, _lib._np_ptr(out), _lib._np_ptr(iters),
+        0, device, None))
+    return out, iters
+
+
+def em(x, l, class_map, class_count, return_iters=False):
+    """Expectation-maximization (`infer.py:133-168`) on the GPU; fp64, same stop rule."""
+    out, iters = _em_device(x, l, class_map, numpy.asarray(class_count, dtype='f8'))
+    return (out[0], int(iters[0])) if return_iters else out[0]
+
+
+def _finish(x):
+    """TPM post-processing of `infer.py:127-129`."""
+    with numpy.errstate(all='ignore'):
+        x /= x.sum() / 1000000
+        x[x < 0.001] = 0
+        x /= x.sum() / 1000000
+    return x
+
+
+def _resample(class_count, n_replicates, seed, first_replicate=0, device=0):
+    counts = numpy.ascontiguousarray(class_count, dtype='i8')
+    if not (counts == class_count).all():
+        raise ValueError('bootstrap needs integral class counts')
+    out = numpy.zeros((n_replicates, counts.shape[0]), dtype='i8')
+    _lib.require_device()
+    _lib.check(_lib.load().skm_multinomial(_lib._np_ptr(counts), counts.shape[0], n_replicates,
+                                           first_replicate, int(seed) & (2 ** 64 - 1),
+                                           _lib._np_ptr(out), 0, device, None))
+    return out
+
+
+def _draw_seed():
+    # the reference resamples from numpy's global RNG (`infer.py:111`); take the seed from the
+    # same stream so `numpy.random.seed(...)` makes runs repeatable
+    return int(numpy.random.randint(0, 2 ** 31 - 1)) | (int(numpy.random.randint(0, 2 ** 31 - 1)) << 31)
+
+
+def quantify(results, x0=None, bootstrap=False, seed=None):
+    """Estimate the transcript abundance (`infer.py:88-130`)."""
+    transcript_length = results.effective_lengths.astype('f8')
+    if results.class_map.size == 0:
+        return numpy.zeros(results.effective_lengths.size).astype('f8')
+    if bootstrap:
+        class_count = _resample(results.class_count, 1,
+                                _draw_seed() if seed is None else seed)[0].astype('f8')
+    else:
+        class_count = results.class_count
+    if x0 is None:
+        x = numpy.ones(transcript_length.size, dtype='f8') / transcript_length
+    else:
+        x = x0.copy()
+    x /= x.sum()
+    x = em(x, transcript_length, results.class_map, class_count)
+    return _finish(x)
+
+
+def quantify_bootstraps(results, x0, n_replicates, seed=None, return_iters=False,
+                        first_replicate=0):
+    """`[quantify(results, x0=x0, bootstrap=True) for _ in range(n)]` (`infer.py:79-82`) as one
+    batched resample + one batched EM.  Returns a list of n arrays."""
+    if n_replicates <= 0:
+        return ([], numpy.zeros(0, dtype='i4')) if return_iters else []
+    transcript_length = results.effective_lengths.astype('f8')
+    if results.class_map.size == 0:
+        z = [numpy.zeros(transcript_length.size, dtype='f8') for _ in range(n_replicates)]
+        return (z, numpy.zeros(n_replicates, dtype='i4')) if return_iters else z
+    if seed is None:
+        seed = _draw_seed()
+    counts = _resample(results.class_count, n_replicates, seed, first_replicate).astype('f8')
+    x = x0.copy()
+    x /= x.sum()
+    xs, iters = _em_device(numpy.tile(x, (n_replicates, 1)), transcript_length, results.class_map,
+                           counts)
+    out = [_finish(xs[i].copy()) for i in range(n_replicates)]
+    return (out, iters) if return_iters else out
+
+
+# ---- writers (`infer.py:171-325`) -------------------------------------------------------------
+def output_results(output_path, index, start_time, results, main_abundance,
+                   bootstrapped_abundance):
+    run_info = _generate_run_info(bootstrapped_abundance, index, results, start_time)
+    with (output_path / 'run_info.json').open('w') as f:
+        json.dump(run_info, f)
+    est_counts = _infer_est_counts(index, results, main_abundance)
+    _output_abundance_table(output_path, index, results, est_counts, main_abundance)
+    _output_hdf5(output_path, index, results, run_info, est_counts, bootstrapped_abundance)
+
+
+def _generate_run_info(bootstrapped_abundance, index, results, start_time):
+    if results.class_map.size:
+        class_target_count = numpy.bincount(results.class_map[0],
+                                            minlength=results.class_count.size)
+        unique_count = results.class_count[class_target_count == 1].sum()
+    else:
+        unique_count = 0.0
+    total = max(results.total, 1)
+    return {
+        'n_targets': len(index.transcripts),
+        'n_bootstraps': len(bootstrapped_abundance),
+        'n_processed': results.total,
+        'n_pseudoaligned': results.aligned,
+        'n_unique': int(unique_count),
+        'p_pseudoaligned': results.aligned / total,
+        'p_unique': float(unique_count) / total,
+        'kallisto_version': '0.44.0',
+        'index_version': 9000,
+        'start_time': start_time.isoformat(sep=' '),
+        'call': ' '.join([shlex.quote(arg) for arg in sys.argv]),
+    }
+
+
+def _infer_est_counts(index, results, main_abundance):
+    est_counts = main_abundance * index.transcripts['length']
+    with numpy.errstate(all='ignore'):
+        est_counts *= results.aligned / est_counts.sum()
+    return est_counts
+
+
+def _output_abundance_table(output_path, index, results, est_counts, main_abundance):
+    """Kallisto-style TSV; `%g` floats like pandas' `float_format='%g'` (`infer.py:219-230`)."""
+    ids = index.transcripts['transcript_id']
+    lengths = index.transcripts['length']
+    eff = results.effective_lengths.astype('f4')
+    with (output_path / 'abundance.tsv').open('w') as f:
+        f.write('target_id\tlength\teff_length\test_count\ttpm\n')
+        for i in range(len(ids)):
+            f.write('%s\t%g\t%g\t%g\t%g\n' % (ids[i].decode(), lengths[i], eff[i], est_counts[i],
+                                             main_abundance[i]))
+
+
+def _output_hdf5(output_path, index, results, run_info, est_counts, bootstrapped_abundance):
+    """`abundance.h5` (`infer.py:255-325`); needs PyTables.  Where HDF5 is unavailable the same
+    arrays are written to `abundance.npz` and a warning is logged."""
+    arrays = {
+        'aux/call': numpy.frombuffer(run_info['call'].encode(), dtype='S1'),
+        'aux/index_version': numpy.asarray([run_info['index_version']]),
+        'aux/start_time': numpy.frombuffer(run_info['start_time'].encode(), dtype='S1'),
+        'aux/num_bootstrap': numpy.asarray([run_info['n_bootstraps']]),
+        'aux/num_processed': numpy.asarray([run_info['n_processed']]),
+        'aux/kallisto_version': numpy.frombuffer(run_info['kallisto_version'].encode(), dtype='S1'),
+        'aux/ids': index.transcripts['transcript_id'],
+        'aux/lengths': index.transcripts['length'],
+        'aux/fld': results.fragment_length_frequencies.astype('i4'),
+        'aux/eff_lengths': results.effective_lengths.astype('f8'),
+        'aux/bias_observed': numpy.ones(4096, dtype='i4'),
+        'aux/bias_normalized': numpy.ones(4096, dtype='f8'),
+        'est_counts': est_counts.astype('f8'),
+    }
+    for i, bootstrap in enumerate(bootstrapped_abundance):
+        arrays['bootstrap/bs{}'.format(i)] = bootstrap
+    try:
+        import tables
+    except ImportError:
+        _LOG.warn('PyTables is not installed: writing abundance.npz instead of abundance.h5')
+        numpy.savez(str(output_path / 'abundance.npz'),
+                    **{k.replace('/', '__'): v for k, v in arrays.items()})
+        return
+    with tables.open_file(str(output_path / 'abundance.h5'), mode='w',
+                          filters=tables.Filters()) as file:
+        groups = {}
+        for key, value in arrays.items():
+            if '/' in key:
+                group_name, name = key.split('/')
+                if group_name not in groups:
+                    groups[group_name] = file.create_group('/', group_name)
+                file.create_carray(groups[group_name], name, obj=value)
+            else:
+                file.create_carray('/', key, obj=value)
+
+
+def add_subcommand_parser(subparsers):
+    """`seekmer infer` arguments (`infer.py:328-353`)."""
+    parser = subparsers.add_parser('infer', help='infer transcript abundance')
+    parser.add_argument('index_path', type=pathlib.Path, metavar='index',
+                        help='specify a Seekmer index file')
+    parser.add_argument('output_path', type=pathlib.Path, metavar='output',
+                        help='specify a output folder')
+    parser.add_argument('fastq_paths', type=pathlib.Path, metavar='fastq', nargs='+',
+                        help='specify a FASTQ read file')
+    parser.add_argument('-j', '--jobs', type=int, dest='job_count', metavar='N', default=1,
+                        help='specify the maximum parallel job number')
+    parser.add_argument('-m', '--save-readmap', action='store_true', dest='save_readmap',
+                        help='output an readmap file')
+    parser.add_argument('-s', '--single-ended', action='store_true', dest='single_ended',
+                        help='specify whether the reads are single-ended')
+    parser.add_argument('-b', '--bootstrap', type=int, dest='bootstrap', default=0,
+                        help='specify the number of bootstrapped estimation')

@@ -134,11 +134,14 @@ def make_transcriptome(n_transcripts, seed=1, mean_exons=10, median_exon=150, mi
     n_exon_total = int(n_exons.sum())
     exon_len = numpy.maximum(
         min_exon, rng.lognormal(numpy.log(median_exon), 0.6, size=n_exon_total).astype('i8'))
+    gene_exon_start = numpy.zeros(n_genes + 1, dtype='i8')
+    numpy.cumsum(n_exons, out=gene_exon_start[1:])
+    # every gene is at least min_length long with all exons kept (first exon absorbs the deficit)
+    gene_len = numpy.bincount(exon_gene, weights=exon_len, minlength=n_genes).astype('i8')
+    exon_len[gene_exon_start[:-1]] += numpy.maximum(min_length - gene_len, 0)
     exon_off = numpy.zeros(n_exon_total + 1, dtype='i8')
     numpy.cumsum(exon_len, out=exon_off[1:])
     pool = rng.integers(0, 4, size=int(exon_off[-1]), dtype='u1')
-    gene_exon_start = numpy.zeros(n_genes + 1, dtype='i8')
-    numpy.cumsum(n_exons, out=gene_exon_start[1:])
     flipped_gene = rng.random(n_genes) < 0.5
     # --- isoforms: keep mask per (transcript, exon of its gene)
     tx_gene = numpy.repeat(numpy.arange(n_genes), n_iso)

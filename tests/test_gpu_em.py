@@ -1,0 +1,120 @@
+"""GPU parity tests for EM / bootstrap / effective lengths vs the numpy oracle and the golden
+vectors of the reference's infer.em / infer.quantify.  Tolerance: rel 1e-6 (north_star), with
+equal iteration counts; integer work (resampling) bit-exact."""
+import numpy
+import pytest
+
+from conftest import SYNTH_CASES
+from seekmer_b200 import _lib, infer, mapper
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+
+
+def rel_close(a, b, rtol=RTOL):
+    a, b = numpy.asarray(a), numpy.asarray(b)
+    scale = numpy.maximum(numpy.abs(b), 1e-300)
+    return bool((numpy.abs(a - b) <= rtol * scale + 1e-300).all())
+
+
+class FakeIndex:
+    def __init__(self, lengths):
+        self.transcripts = numpy.zeros(len(lengths), dtype=[('transcript_id', 'S8'), ('length', 'f8')])
+        self.transcripts['length'] = lengths
+
+
+def summarized(g, prefix, lengths):
+    mr = mapper.MapResult(FakeIndex(lengths))
+    mr.fragment_length_counts = g[prefix + 'fld'].astype('i8')
+    return mapper.SummarizedResult(
+        aligned=int(g[prefix + 'class_count'].sum()), unaligned=0, total=int(g[prefix + 'class_count'].sum()),
+        class_map=g[prefix + 'class_map'], class_count=g[prefix + 'class_count'],
+        fragment_length_frequencies=mr.fragment_length_counts, effective_lengths=mr.effective_lengths)
+
+
+@pytest.mark.parametrize('case', ['chr21'] + sorted(SYNTH_CASES))
+def test_em_and_quantify_golden(golden_chr21, golden_synth, case):
+    g, prefix = (golden_chr21, '') if case == 'chr21' else (golden_synth, case + '_')
+    lengths = g['transcripts']['length']
+    res = summarized(g, prefix, lengths)
+    # effective lengths: same accumulation order => bit-exact
+    assert (res.effective_lengths == g[prefix + 'eff_lengths']).all()
+    eff = res.effective_lengths
+    x0 = numpy.ones(eff.size) / eff
+    x0 /= x0.sum()
+    x, iters = infer.em(x0, eff, res.class_map, res.class_count, return_iters=True)
+    assert iters == int(g[prefix + 'em_iters'])
+    assert rel_close(x, g[prefix + 'em_x'])
+    tpm = infer.quantify(res)
+    assert rel_close(tpm, g[prefix + 'tpm'])
+    assert ((tpm == 0) == (g[prefix + 'tpm'] == 0)).all()
+
+
+def synthetic_structure(T, C, seed):
+    rng = numpy.random.Generator(numpy.random.PCG64(seed))
+    sizes = numpy.minimum(rng.geometric(0.3, size=C), 6)
+    fam = rng.integers(0, T // 8, size=C)
+    rows = numpy.repeat(numpy.arange(C), sizes)
+    cols = (numpy.repeat(fam * 8, sizes) + rng.integers(0, 8, size=rows.size)) % T
+    # a few very promiscuous transcripts and one huge class
+    cols[rng.integers(0, rows.size, size=rows.size // 50)] = 3
+    class_map = numpy.stack([rows, cols]).astype('i8')
+    counts = rng.multinomial(3000000, rng.dirichlet(numpy.ones(C) * 0.3)).astype('f8')
+    eff = rng.uniform(200, 4000, size=T)
+    return class_map, counts, eff
+
+
+def test_em_larger_structure_vs_oracle(orc):
+    class_map, counts, eff = synthetic_structure(20000, 100000, 3)
+    x0 = numpy.ones(eff.size) / eff
+    x0 /= x0.sum()
+    want, want_iters = orc.em(x0.copy(), eff, class_map, counts, return_iters=True)
+    got, iters = infer.em(x0, eff, class_map, counts, return_iters=True)
+    assert iters == want_iters
+    assert rel_close(got, want)
+
+
+def test_em_zero_count_classes_and_dead_transcripts(orc):
+    class_map, counts, eff = synthetic_structure(4000, 20000, 4)
+    counts[::3] = 0  # bootstrap-like zero classes: inner = inf / nan semantics
+    x0 = numpy.ones(eff.size) / eff
+    x0[::7] = 0
+    x0 /= x0.sum()
+    want, want_iters = orc.em(x0.copy(), eff, class_map, counts, return_iters=True)
+    got, iters = infer.em(x0, eff, class_map, counts, return_iters=True)
+    assert iters == want_iters
+    assert rel_close(got, want)
+    assert ((got == 0) == (want == 0)).all()
+
+
+def test_multinomial_bit_exact_and_batched_bootstrap(orc):
+    class_map, counts, eff = synthetic_structure(3000, 12000, 5)
+    counts = numpy.floor(counts / 10)
+    R, seed = 37, 0xDEADBEEFCAFE
+    want = orc.bootstrap_counts(counts, R, seed)
+    got = infer._resample(counts, R, seed)
+    assert (got == want).all()
+    assert (got.sum(axis=1) == counts.sum()).all()
+    # replicate ids are global: a shard starting at replicate 20 reproduces rows 20..
+    assert (infer._resample(counts, 5, seed, first_replicate=20) == want[20:25]).all()
+
+    res = mapper.SummarizedResult(int(counts.sum()), 0, int(counts.sum()), class_map, counts, None, eff)
+    main = orc.quantify(eff, class_map, counts)
+    outs, iters = infer.quantify_bootstraps(res, main, R, seed=seed, return_iters=True)
+    for r in range(R):
+        w, wi = orc.quantify(eff, class_map, want[r].astype('f8'), x0=main, return_iters=True)
+        assert iters[r] == wi, r
+        assert rel_close(outs[r], w), r
+
+
+def test_effective_lengths_bit_exact(orc):
+    rng = numpy.random.Generator(numpy.random.PCG64(6))
+    fld = numpy.zeros(2000, dtype='i8')
+    fld[25] = 17
+    fld[150:600] = rng.integers(0, 5000, size=450)
+    fld[1999] = 3
+    lengths = numpy.concatenate([rng.integers(25, 20000, size=5000), [1, 24, 25, 1999, 2000, 2001]]).astype('f8')
+    mr = mapper.MapResult(FakeIndex(lengths))
+    mr.fragment_length_counts = fld
+    assert (mr.effective_lengths == orc.effective_lengths(fld, lengths)).all()

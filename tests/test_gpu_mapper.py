@@ -1,0 +1,232 @@
+"""GPU parity tests for the mapping path: CUDA (through the C ABI) vs the CPU oracle and the
+golden vectors.  Bit-exact: per-unit ordered id tuples, raw fragment lengths, FLD, class
+counts, first-seen class order."""
+import numpy
+import pytest
+
+import adversarial
+from conftest import N_GOLDEN_UNITS, SYNTH_CASES
+from seekmer_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_map(arrays, bases, offsets, n_units, paired, n_tx=0, batches=1, **kw):
+    """Map through the C ABI with host buffers; returns per-unit tuples, lengths, export."""
+    ix = _lib.DeviceIndex(*arrays, n_tx)
+    mp = _lib.DeviceMapper(ix, **kw)
+    per = 2 if paired else 1
+    cls, lens = [], []
+    bounds = numpy.linspace(0, n_units, batches + 1).astype('i8')
+    for b in range(batches):
+        u0, u1 = int(bounds[b]), int(bounds[b + 1])
+        if u1 == u0:
+            continue
+        o = offsets[u0 * per:u1 * per + 1]
+        c, l = mp.map_batch(bases[o[0]:o[-1]], o - o[0], u1 - u0, paired, first_unit=u0,
+                            max_len=int((o[1:] - o[:-1]).max()), per_read=True)
+        cls.append(c)
+        lens.append(l)
+    table = mp.export(with_slots=True)
+    off, ids = table['key_offsets'].tolist(), table['key_ids'].tolist()
+    by_slot = {s: tuple(ids[off[i]:off[i + 1]]) for i, s in enumerate(table['slots'].tolist())}
+    cls = numpy.concatenate(cls)
+    tuples = [by_slot[s] if s >= 0 else () for s in cls.tolist()]
+    mp.close()
+    ix.close()
+    return tuples, numpy.concatenate(lens), table
+
+
+def table_dict(table):
+    off, ids, cnt = table['key_offsets'].tolist(), table['key_ids'].tolist(), table['counts'].tolist()
+    d = {tuple(ids[off[i]:off[i + 1]]): cnt[i] for i in range(len(cnt))}
+    if table['unaligned']:
+        d[()] = table['unaligned']
+    return d
+
+
+def check_against_oracle(orc, arrays, bases, offsets, n_units, paired, **kw):
+    oidx = orc.OracleIndex(*arrays)
+    want = orc.map_batch(oidx, bases, offsets, paired)
+    tuples, lens, table = gpu_map(arrays, bases, offsets, n_units, paired, **kw)
+    wt = want.tuples()
+    bad = [i for i in range(n_units) if tuples[i] != wt[i]]
+    assert not bad, 'first mismatch at unit %d: gpu %r oracle %r' % (bad[0], tuples[bad[0]], wt[bad[0]])
+    assert (lens == want.length).all()
+    assert (table['fld'] == want.fld).all()
+    assert table_dict(table) == orc.tally_dict(want.ptr, want.ids)
+    # first-seen order == Counter insertion order at job_count=1
+    cls_ptr, cls_ids, cls_count, una = orc.tally(want.ptr, want.ids)
+    assert (table['key_offsets'] == cls_ptr).all()
+    assert (table['key_ids'] == cls_ids).all()
+    assert (table['counts'] == cls_count).all()
+    assert table['unaligned'] == una
+    assert table['aligned'] == int(cls_count.sum())
+    return table
+
+
+def test_map_kmers_parity(orc, golden_chr21):
+    arrays = golden_chr21.index_arrays()
+    oidx = orc.OracleIndex(*arrays)
+    ix = _lib.DeviceIndex(*arrays, 42)
+    info = ix.info()
+    kmers = arrays[0]
+    occ = kmers['kmer'][kmers['kmer'] != numpy.uint64(0xFFFFFFFFFFFFFFFF)]
+    assert info['n_kmers'] == occ.shape[0]
+    assert info['table_slots'] >= 2 * occ.shape[0]
+    rng = numpy.random.Generator(numpy.random.PCG64(1))
+    rc = numpy.asarray([orc.reverse_complement(int(k)) for k in occ[:4000]], dtype='u8')
+    miss = rng.integers(0, 1 << 50, size=4000, dtype='u8')
+    q = numpy.concatenate([occ, rc, miss])
+    e, o = ix.map_kmers(q)
+    # every stored k-mer maps to its stored position, forward
+    slot_of = {int(k): i for i, k in enumerate(kmers['kmer'])}
+    for j in rng.choice(q.shape[0], size=6000, replace=False):
+        assert (int(e[j]), int(o[j])) == oidx.map_kmer(int(q[j]))
+    pos = numpy.asarray([slot_of[int(k)] for k in occ])
+    assert (e[:occ.shape[0]] == kmers['entry'][pos]).all()
+    assert (o[:occ.shape[0]] == kmers['offset'][pos]).all()
+    ix.close()
+
+
+def test_chr21_fixture(orc, golden_chr21):
+    g = golden_chr21
+    reads = [bytes(r) for r in g['reads']]
+    bases, offs = orc.pack_reads(reads)
+    tuples, lens, table = gpu_map(g.index_arrays(), bases, offs, 21, True)
+    assert tuples == g.tuples('')
+    assert (table['fld'] == g['fld']).all()
+    assert table['unaligned'] == 0  # test/test_mapper.py:76
+    assert (orc.class_map_from_csr(table['key_offsets'], table['key_ids']) == g['class_map']).all()
+    assert (table['counts'] == g['class_count']).all()
+
+
+@pytest.mark.parametrize('case', sorted(SYNTH_CASES))
+def test_synthetic_golden(orc, golden_synth, small_tx, case):
+    g = golden_synth
+    kw = SYNTH_CASES[case]
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **kw)
+    bases, _ = sim.generate(0, N_GOLDEN_UNITS)
+    offs = sim.offsets(N_GOLDEN_UNITS)
+    tuples, lens, table = gpu_map(g.index_arrays(), bases, offs, N_GOLDEN_UNITS, kw['paired'], batches=3)
+    assert tuples == g.tuples(case + '_')
+    assert (table['fld'] == g[case + '_fld']).all()
+    assert (orc.class_map_from_csr(table['key_offsets'], table['key_ids']) == g[case + '_class_map']).all()
+    assert (table['counts'] == g[case + '_class_count']).all()
+
+
+@pytest.mark.parametrize('paired', [True, False])
+def test_adversarial_ragged(orc, golden_synth, small_tx, paired):
+    g = golden_synth
+    reads = adversarial.make_reads(small_tx, paired)
+    bases, offs = orc.pack_reads(reads)
+    n = len(reads) // 2 if paired else len(reads)
+    tuples, lens, table = gpu_map(g.index_arrays(), bases, offs, n, paired)
+    key = 'adv_pe_' if paired else 'adv_se_'
+    assert tuples == g.tuples(key)
+    assert (table['fld'] == g[key + 'fld']).all()
+
+
+@pytest.mark.parametrize('L,mu,sd,paired,sub', [(100, 250, 30, True, 0.01), (150, 350, 50, True, 0.01),
+                                                 (75, 250, 30, False, 0.02), (25, 250, 30, True, 0.0),
+                                                 (251, 400, 60, True, 0.03)])
+def test_medium_vs_oracle(orc, medium, L, mu, sd, paired, sub):
+    tx, arrays = medium
+    sim = synth.ReadSimulator(tx, synth.make_expression(tx.n_transcripts), L, mu, sd, sub_rate=sub,
+                              paired=paired, seed=21)
+    n = 40000
+    bases, _ = sim.generate(0, n)
+    check_against_oracle(orc, arrays, bases, sim.offsets(n), n, paired, batches=2)
+
+
+def test_long_target_lists_spill_to_arena(orc, ref):
+    """Contigs shared by more than LIST_CAP=16 transcripts exercise the arena path."""
+    tx = synth.make_transcriptome(400, seed=5, max_isoforms=40, mean_exons=8)
+    arrays = ref.ref_build_index(tx.sequences())
+    assert int(numpy.asarray(arrays[1])['target_count'].max()) > 16
+    sim = synth.ReadSimulator(tx, synth.make_expression(tx.n_transcripts), 100, 250, 30, seed=3)
+    n = 20000
+    bases, _ = sim.generate(0, n)
+    check_against_oracle(orc, arrays, bases, sim.offsets(n), n, True)
+
+
+def test_device_buffers_match_host_buffers(golden_synth, small_tx):
+    import torch
+    g = golden_synth
+    kw = SYNTH_CASES['pe100']
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **kw)
+    n = 3000
+    bases, _ = sim.generate(0, n)
+    ix = _lib.DeviceIndex(*g.index_arrays(), 60)
+    a = _lib.DeviceMapper(ix)
+    b = _lib.DeviceMapper(ix)
+    ca, la = a.map_batch(bases, None, n, True, fixed_len=100, per_read=True)
+    d_bases = torch.from_numpy(bases).cuda()
+    cb, lb = b.map_batch(d_bases, None, n, True, fixed_len=100, per_read=True)
+    torch.cuda.synchronize()
+    ta, tb = a.export(), b.export()
+    assert (la == lb.cpu().numpy()).all()
+    for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
+        assert (ta[k] == tb[k]).all()
+    assert ta['unaligned'] == tb['unaligned']
+    # reset clears everything
+    a.reset()
+    s = a.sizes()
+    assert s['n_classes'] == 0 and s['aligned'] == 0 and s['unaligned'] == 0
+    assert a.export()['fld'].sum() == 0
+
+
+def test_capacity_errors_are_loud(golden_synth, small_tx):
+    g = golden_synth
+    kw = SYNTH_CASES['pe100']
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **kw)
+    bases, _ = sim.generate(0, 3000)
+    ix = _lib.DeviceIndex(*g.index_arrays(), 60)
+    mp = _lib.DeviceMapper(ix, class_capacity=8, id_capacity=16)
+    with pytest.raises(_lib.SeekmerCudaError, match='capacity'):
+        mp.map_batch(bases, None, 3000, True, fixed_len=100)
+    with pytest.raises(_lib.SeekmerCudaError):
+        mp.map_batch(bases[:48], numpy.asarray([0, 24, 48], dtype='i8'), 1, True)  # shorter than k
+
+
+def test_merge_equals_single_mapper(golden_synth, small_tx):
+    """Two shards mapped separately then merged == one mapper over everything (multi-GPU merge)."""
+    g = golden_synth
+    kw = SYNTH_CASES['pe150']
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **kw)
+    n = 3000
+    bases, _ = sim.generate(0, n)
+    ix = _lib.DeviceIndex(*g.index_arrays(), 60)
+    whole = _lib.DeviceMapper(ix)
+    whole.map_batch(bases, None, n, True, fixed_len=150)
+    a, b = _lib.DeviceMapper(ix), _lib.DeviceMapper(ix)
+    half = n // 2
+    a.map_batch(bases[:half * 300], None, half, True, first_unit=0, fixed_len=150)
+    b.map_batch(bases[half * 300:], None, n - half, True, first_unit=half, fixed_len=150)
+    tb = b.export()
+    a.merge(tb['key_offsets'], tb['key_ids'], tb['counts'], tb['first_unit'], tb['fld'], tb['unaligned'])
+    ta, tw = a.export(), whole.export()
+    for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
+        assert (ta[k] == tw[k]).all(), k
+    assert ta['unaligned'] == tw['unaligned'] and ta['aligned'] == tw['aligned']
+
+
+def test_synth_reads_device_twin(small_tx):
+    import ctypes
+    import torch
+    expr = synth.make_expression(small_tx.n_transcripts, seed=3)
+    for kw in (SYNTH_CASES['pe150'], SYNTH_CASES['se75']):
+        sim = synth.ReadSimulator(small_tx, expr, **kw)
+        n, first = 2500, 123456789012
+        want, _ = sim.generate(first, n)
+        codes = torch.from_numpy(small_tx.codes).cuda()
+        offs = torch.from_numpy(small_tx.offsets).cuda()
+        cum = torch.from_numpy(sim.cum_weights.view('i8')).cuda()
+        out = torch.empty(want.shape[0], dtype=torch.uint8, device='cuda')
+        L = _lib.load()
+        _lib.check(L.skm_synth_reads(_lib._ptr(codes), _lib._ptr(offs), small_tx.n_transcripts, _lib._ptr(cum),
+                                     sim.total_weight, sim.L, sim.mu, sim.sd, sim.sub_thresh, sim.n_thresh,
+                                     sim.random_pct, sim.seed, int(sim.paired), first, n, _lib._ptr(out), 0,
+                                     _lib.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert (out.cpu().numpy() == want).all()

@@ -1,0 +1,140 @@
+"""CPU-side tests: C-ABI surface, host mirrors of the reference API, synthetic generators."""
+import ctypes
+import re
+
+import numpy
+import pytest
+
+from conftest import ROOT
+from seekmer_b200 import _lib, common, mapper, synth
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / 'include' / 'seekmer_b200.h').read_text()
+    declared = set(re.findall(r'\b(skm_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS)
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert b'sm_100a' in _lib.load().skm_version()
+
+
+def test_no_cpu_fallback_without_device(golden_chr21):
+    if _lib.device_count() > 0:
+        pytest.skip('a GPU is present')
+    with pytest.raises(_lib.SeekmerCudaError, match='no CPU fallback'):
+        _lib.DeviceIndex(*golden_chr21.index_arrays(), 42)
+    idx = common.KMerIndex(*golden_chr21.index_arrays(), golden_chr21['transcripts'], None)
+    with pytest.raises(_lib.SeekmerCudaError):
+        mapper.map_reads(idx, iter([(1, [b'a'], [b'A' * 50])]))
+    mr = mapper.MapResult(idx)
+    with pytest.raises(_lib.SeekmerCudaError):
+        mr.effective_lengths
+
+
+def test_product_never_imports_the_oracle():
+    for path in (ROOT / 'seekmer_b200').rglob('*'):
+        if path.suffix in ('.py', '.cu', '.cuh') and path.is_file():
+            text = path.read_text()
+            assert 'import oracle' not in text and 'from oracle' not in text, path
+            assert 'seekmer_oracle' not in text, path
+
+
+def write_fastq(path, names, reads):
+    with open(str(path), 'wb') as f:
+        for n, r in zip(names, reads):
+            f.write(b'@' + n + b'\n' + r + b'\n+\n' + b'#' * len(r) + b'\n')
+
+
+def test_feeders_concatenate_files_into_one_sample(tmp_path):
+    # mirrors test/test_mapper.py:20-68
+    names = [b'r%d desc' % i for i in range(21)]
+    r1 = [b'ACGTN' * 20 for _ in range(21)]
+    r2 = [b'acgtn' * 20 for _ in range(21)]
+    write_fastq(tmp_path / 'a_1.fastq', names, r1)
+    write_fastq(tmp_path / 'a_2.fastq', names, r2)
+    batches = list(common.feed_single_ended_reads(tmp_path / 'a_1.fastq'))
+    assert len(batches) == 1 and batches[0][0] == 21 and len(batches[0][2]) == 21
+    batches = list(common.feed_single_ended_reads(tmp_path / 'a_1.fastq', tmp_path / 'a_1.fastq'))
+    assert len(batches) == 1 and batches[0][0] == 42
+    n, nm, rd = next(common.feed_pair_ended_reads(tmp_path / 'a_1.fastq', tmp_path / 'a_2.fastq'))
+    assert n == 21 and len(rd) == 42 and rd[0] == r1[0] and rd[1] == r2[0] and nm[0] == names[0]
+    n, _, rd = next(common.feed_pair_ended_reads(*[tmp_path / 'a_1.fastq', tmp_path / 'a_2.fastq'] * 2))
+    assert n == 42 and len(rd) == 84
+    with pytest.raises(ValueError):
+        list(common.feed_pair_ended_reads(tmp_path / 'a_1.fastq'))
+
+
+def test_feeder_batches_and_gzip(tmp_path, monkeypatch):
+    import gzip
+    monkeypatch.setattr(common, 'BUFFER_SIZE', 8)
+    names = [b'x%d' % i for i in range(21)]
+    reads = [b'ACGT' * 10] * 21
+    write_fastq(tmp_path / 's.fastq', names, reads)
+    with open(str(tmp_path / 's.fastq'), 'rb') as f, gzip.open(str(tmp_path / 's.fastq.gz'), 'wb') as z:
+        z.write(f.read())
+    for p in (tmp_path / 's.fastq', tmp_path / 's.fastq.gz'):
+        sizes = [b[0] for b in common.feed_single_ended_reads(p)]
+        assert sizes == [8, 8, 5]
+
+
+def test_map_result_model_and_summarize(golden_chr21):
+    g = golden_chr21
+    idx = common.KMerIndex(*g.index_arrays(), g['transcripts'], None)
+    mr = mapper.MapResult(idx)
+    tuples = g.tuples('')
+    mr.update([b'n'] * len(tuples), tuples + [()])
+    assert mr.counter[()] == 1
+    mr.merge_fragment_lengths(g['fld'])
+    assert mr.harmonic_mean_fragment_length == pytest.approx(float(g['harmonic_mean']), rel=1e-14)
+    # summarize without touching the device: patch effective_lengths
+    mapper.MapResult.effective_lengths, saved = property(lambda self: g['eff_lengths']), mapper.MapResult.effective_lengths
+    try:
+        s = mr.summarize()
+    finally:
+        mapper.MapResult.effective_lengths = saved
+    assert (s.class_map == g['class_map']).all() and s.class_map.dtype == numpy.int64
+    assert (s.class_count == g['class_count']).all()
+    assert (s.aligned, s.unaligned, s.total) == (21, 1, 22)
+    assert mr.counter[()] == 1
+    mr.clear()
+    assert not mr.counter
+    assert mapper.MAX_FRAGMENT_LENGTH == 2000
+
+
+def test_index_npz_roundtrip_and_version_check(tmp_path, golden_chr21):
+    g = golden_chr21
+    idx = common.KMerIndex(*g.index_arrays(), g['transcripts'], None)
+    idx.save(tmp_path / 'i.npz')
+    back = common.KMerIndex.load(tmp_path / 'i.npz')
+    for name in ('kmers', 'contigs', 'sequences', 'targets', 'transcripts'):
+        assert (numpy.asarray(getattr(back, name)) == numpy.asarray(getattr(idx, name))).all()
+    z = dict(numpy.load(str(tmp_path / 'i.npz')))
+    z['seekmer_version'] = numpy.asarray('1999.0.0')
+    numpy.savez(str(tmp_path / 'bad.npz'), **z)
+    with pytest.raises(RuntimeError, match='invalid index version'):
+        common.KMerIndex.load(tmp_path / 'bad.npz')
+
+
+def test_synthetic_generators_are_deterministic_and_sliceable():
+    tx = synth.make_transcriptome(120, seed=4)
+    tx2 = synth.make_transcriptome(120, seed=4)
+    assert (tx.codes == tx2.codes).all() and (tx.offsets == tx2.offsets).all()
+    assert tx.lengths.min() >= 400 and tx.strand_flipped.any() and not tx.strand_flipped.all()
+    expr = synth.make_expression(120)
+    sim = synth.ReadSimulator(tx, expr, 100, 250, 30)
+    a, truth = sim.generate(0, 500)
+    b, _ = sim.generate(200, 100)
+    assert (a.reshape(500, 200)[200:300] == b.reshape(100, 200)).all()
+    assert set(numpy.unique(a)) <= set(b'ACGTN')
+    # error-free, non-random pairs reproduce the transcript
+    clean = synth.ReadSimulator(tx, expr, 100, 250, 30, sub_rate=0, n_rate=0, random_rate_pct=0)
+    r, t = clean.generate(0, 50)
+    r = r.reshape(50, 200)
+    for i in range(50):
+        s = tx.sequence(int(t['transcript'][i]))
+        st, fr = int(t['start'][i]), int(t['fragment'][i])
+        m1, m2 = s[st:st + 100], synth.reverse_complement_ascii(s[st + fr - 100:st + fr])
+        got = (r[i, :100].tobytes(), r[i, 100:].tobytes())
+        assert got == ((m2, m1) if t['swap'][i] else (m1, m2))
+    assert 200 < numpy.mean(t['fragment']) < 300
