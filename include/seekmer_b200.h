@@ -190,6 +190,14 @@ int skm_synth_reads(const uint8_t *tx_codes, const int64_t *tx_offsets, int64_t 
                     int32_t random_pct, uint64_t seed, int paired, int64_t first_unit,
                     int64_t n_units, uint8_t *bases, int device, void *stream);
 
+/* Index-construction support (device buffers only): place n contig-forward k-mers with
+ * their positions into `table` (n_slots, power of two) in the reference layout — home slot
+ * from the reference hash of the canonical k-mer (_kmer.pxd:174-219), linear probing
+ * (_index_builder.pyx:313-342).  Used by seekmer_b200/index_build.py. */
+int skm_build_kmer_table(const uint64_t *kmers, const int32_t *entry, const int32_t *offset,
+                         int64_t n, skm_kmer_slot *table, int64_t n_slots, int device,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

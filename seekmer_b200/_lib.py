@@ -25,6 +25,7 @@ EXPORTS = (
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
     'skm_mapper_reset', 'skm_map_batch', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_effective_lengths', 'skm_em', 'skm_multinomial', 'skm_synth_reads',
+    'skm_build_kmer_table',
 )
 
 
@@ -85,6 +86,8 @@ def load():
     L.skm_synth_reads.restype = ci
     L.skm_synth_reads.argtypes = [vp, vp, i64, vp, u64, i32, i32, i32, i32, i32, i32, u64, ci,
                                   i64, i64, vp, ci, vp]
+    L.skm_build_kmer_table.restype = ci
+    L.skm_build_kmer_table.argtypes = [vp, vp, vp, i64, vp, i64, ci, vp]
     _lib = L
     return L
 

@@ -35,7 +35,8 @@ __global__ void count_occupied_kernel(const skm_kmer_slot *__restrict__ src, int
 // bit-negated, so that map_kmer() in kmer.cuh returns exactly what
 // _common.pyx:82-87 returns for either query strand.
 __global__ void relayout_table_kernel(const skm_kmer_slot *__restrict__ src, int64_t n,
-                                      Slot *__restrict__ table, uint64_t mask)
+                                      Slot *__restrict__ table, uint64_t mask, int64_t n_contigs,
+                                      unsigned int *bad)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -47,6 +48,9 @@ __global__ void relayout_table_kernel(const skm_kmer_slot *__restrict__ src, int
         const uint64_t canon = fwd ? kmer : rc;
         int32_t entry = (int32_t)(uint32_t)v.y;
         const int32_t offset = (int32_t)(uint32_t)(v.y >> 32);
+        // a usable position (offset >= 0) must name an existing contig; slots the reference
+        // assembler left with a negative offset act as misses and are kept verbatim
+        if (offset >= 0 && (entry < 0 || entry >= n_contigs)) atomicOr(bad, 2u);
         if (!fwd) entry = ~entry;
         uint64_t s = table_hash(canon) & mask;
         for (;;) {
@@ -70,7 +74,10 @@ __global__ void relayout_contigs_kernel(const skm_contig_entry *__restrict__ src
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const skm_contig_entry c = src[i];
-    if (c.length < K || c.length > 0x7FFFFFFFLL || c.offset < 0 || c.offset + c.length > n_bases
+    // The reference assembler can emit a degenerate contig (shorter than k, no targets, not
+    // referenced by any k-mer: slot 0 doubles as "no link" there), so only
+    // memory safety is enforced here.
+    if (c.length < 0 || c.length > 0x7FFFFFFFLL || c.offset < 0 || c.offset + c.length > n_bases
         || c.target_offset < 0 || c.target_count < 0 || c.target_count >= (1LL << 28)
         || c.target_offset + c.target_count > n_targets)
         atomicOr(bad, 1u);
@@ -122,6 +129,33 @@ __global__ void map_kmers_kernel(DevIndex ix, const uint64_t *__restrict__ kmers
         const Coord c = map_kmer(ix, kmers[i] & KMER_MASK);
         out_entry[i] = c.entry;
         out_offset[i] = c.offset;
+    }
+}
+
+// Index-construction support: place contig-forward k-mers into a table in the REFERENCE
+// layout (home slot = reference SipHash variant of the canonical k-mer, linear probing,
+// _index_builder.pyx:313-342), so that indexes built on the device are byte-compatible
+// with what `seekmer index` writes.
+__global__ void build_reference_table_kernel(const uint64_t *__restrict__ kmers,
+                                             const int32_t *__restrict__ entry,
+                                             const int32_t *__restrict__ offset, int64_t n,
+                                             skm_kmer_slot *__restrict__ table, uint64_t mask)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t kmer = kmers[i] & KMER_MASK;
+        const uint64_t rc = revcomp(kmer);
+        uint64_t s = reference_hash(kmer < rc ? kmer : rc) & mask;
+        for (;;) {
+            const unsigned long long old = atomicCAS(
+                reinterpret_cast<unsigned long long *>(&table[s].kmer), EMPTY_KEY, kmer);
+            if (old == EMPTY_KEY) {
+                table[s].entry = entry[i];
+                table[s].offset = offset[i];
+                break;
+            }
+            s = (s + 1) & mask;
+        }
     }
 }
 
@@ -265,7 +299,8 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         STEP_CUDA(cudaMalloc(&ix->table, sizeof(Slot) * (size_t)slots));
         STEP_CUDA(cudaMemsetAsync(ix->table, 0xFF, sizeof(Slot) * (size_t)slots, st));
         relayout_table_kernel<<<blocks, threads, 0, st>>>(d_kmers, n_slots, ix->table,
-                                                          (uint64_t)slots - 1);
+                                                          (uint64_t)slots - 1, n_contigs,
+                                                          reinterpret_cast<unsigned int *>(d_scalars + 2));
         STEP_CUDA(cudaGetLastError());
         ix->bytes += (int64_t)sizeof(Slot) * slots;
     }
@@ -302,8 +337,10 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
     if (scal[2] != 0) {
         cleanup();
         skm_index_destroy(ix);
-        return fail(SKM_ERR_INVALID, "skm_index_create: contig table is inconsistent with "
-                                     "sequences/targets (offset, length or target range out of bounds)");
+        return fail(SKM_ERR_INVALID, (scal[2] & 2u)
+                        ? "skm_index_create: a k-mer slot points to a contig that does not exist"
+                        : "skm_index_create: contig table is inconsistent with sequences/targets "
+                          "(offset, length or target range out of bounds)");
     }
     cleanup();
 #undef STEP
@@ -370,5 +407,26 @@ SKM_API int skm_map_kmers(const skm_index *ix, const uint64_t *kmers, int64_t n,
     cudaFree(own_k);
     cudaFree(own_e);
     if (e != cudaSuccess) return fail(SKM_ERR_CUDA, std::string("skm_map_kmers: ") + cudaGetErrorString(e));
+    return SKM_OK;
+}
+
+SKM_API int skm_build_kmer_table(const uint64_t *kmers, const int32_t *entry, const int32_t *offset,
+                                 int64_t n, skm_kmer_slot *table, int64_t n_slots, int device,
+                                 void *stream)
+{
+    if (!kmers || !entry || !offset || !table) return fail(SKM_ERR_INVALID, "skm_build_kmer_table: NULL argument");
+    if (n_slots <= 0 || (n_slots & (n_slots - 1)) != 0 || n >= n_slots)
+        return fail(SKM_ERR_INVALID, "skm_build_kmer_table: table size must be a power of two larger than n");
+    if (skm_device_count() <= device || device < 0)
+        return fail(SKM_ERR_CUDA, "skm_build_kmer_table: no such CUDA device");
+    SKM_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SKM_CUDA(cudaMemsetAsync(table, 0xFF, sizeof(skm_kmer_slot) * (size_t)n_slots, st));
+    if (n > 0) {
+        const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+        build_reference_table_kernel<<<blocks, 256, 0, st>>>(kmers, entry, offset, n, table,
+                                                            (uint64_t)n_slots - 1);
+        SKM_CUDA(cudaGetLastError());
+    }
     return SKM_OK;
 }

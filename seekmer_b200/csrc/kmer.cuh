@@ -154,6 +154,9 @@ __device__ __forceinline__ Contig load_contig(const DevIndex &ix, int32_t index)
 // (first base in the top two bits).
 __device__ __forceinline__ uint32_t seq_window8(const DevIndex &ix, int64_t p)
 {
+    // positions outside the pool can only come from a corrupt index (undefined behaviour in
+    // the reference); clamp so the read stays inside the allocation
+    p = p < 0 ? 0 : (p > ix.n_bases ? ix.n_bases : p);
     const int64_t w = p >> 4;
     const int s = (int)(p & 15);
     const uint32_t hi = __ldg(ix.seq2 + w);
