@@ -275,6 +275,33 @@ class DeviceMapper:
             out['slots'] = slots[order]
         return out
 
+    def export_torch(self, stream=None):
+        """Dictionary as torch tensors on the mapper's GPU, sorted by first-seen unit — the table
+        shape `seekmer_b200.dist.merge_class_tables` exchanges (no host round trip)."""
+        import torch
+        dev = torch.device('cuda', self.index.device)
+        if stream is None:
+            stream = current_stream_ptr(dev)
+        sz = self.sizes(stream)
+        n, n_ids = sz['n_classes'], sz['n_ids']
+        off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        ids = torch.zeros(n_ids, dtype=torch.int32, device=dev)
+        counts = torch.zeros(n, dtype=torch.int64, device=dev)
+        first = torch.zeros(n, dtype=torch.int64, device=dev)
+        fld = torch.zeros(MAX_FRAGMENT_LENGTH, dtype=torch.int64, device=dev)
+        check(load().skm_classes_export(self._h, _ptr(off), _ptr(ids) if n_ids else None,
+                                        _ptr(counts) if n else None, _ptr(first) if n else None,
+                                        None, _ptr(fld), 1, stream))
+        order = torch.argsort(first, stable=True)
+        lens = (off[1:] - off[:-1])[order]
+        new_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        new_off[1:] = torch.cumsum(lens, 0)
+        src = (torch.repeat_interleave(off[:-1][order] - new_off[:-1], lens)
+               + torch.arange(n_ids, device=dev))
+        return dict(key_offsets=new_off, key_ids=ids[src], counts=counts[order], first_unit=first[order],
+                    fld=fld, scalars=torch.tensor([sz['unaligned'], sz['aligned']], dtype=torch.int64,
+                                                  device=dev))
+
     def merge(self, key_offsets, key_ids, counts, first_unit, fld=None, unaligned=0, stream=None):
         key_offsets = numpy.ascontiguousarray(key_offsets, dtype='i8')
         key_ids = numpy.ascontiguousarray(key_ids, dtype='i4')

@@ -54,9 +54,11 @@ class MapResult:
         self.index = index
         self.readmap = readmap
         self.fragment_length_counts = numpy.zeros(MAX_FRAGMENT_LENGTH, dtype='i8')
+        self._table = None  # exported device dictionary, valid while the counter mirrors it
 
     def update(self, read_names, iterable):
         """Add per-read mapping results (list of ordered id tuples)."""
+        self._table = None
         self.counter.update(iterable)
         if self.readmap is not None:
             for read_name, targets in zip(read_names, iterable):
@@ -67,11 +69,14 @@ class MapResult:
     def update_counts(self, classes):
         """Add already tallied classes: iterable of (ordered id tuple, count) in first-seen
         order — what the device dictionary exports."""
+        self._table = None
         counter = self.counter
         for key, count in classes:
             counter[key] += count
 
     def summarize(self):
+        if self._table is not None:
+            return summarize_table(self._table, self)
         unaligned = self.counter.pop((), 0)
         n = len(self.counter)
         class_count = numpy.fromiter(self.counter.values(), dtype='f8', count=n)
@@ -122,7 +127,28 @@ class MapResult:
         return out
 
     def clear(self):
+        self._table = None
         self.counter.clear()
+
+
+def summarize_table(table, map_result):
+    """`MapResult.summarize` (`mapper.py:77-104`) straight from an exported class table
+    (classes already in first-seen order): no per-class Python objects."""
+    off = numpy.asarray(table['key_offsets'], dtype='i8')
+    sizes = off[1:] - off[:-1]
+    n = sizes.shape[0]
+    class_count = numpy.asarray(table['counts'], dtype='f8')
+    if int(off[-1]):
+        class_map = numpy.stack([numpy.repeat(numpy.arange(n, dtype='i8'), sizes),
+                                 numpy.asarray(table['key_ids'], dtype='i8')])
+    else:
+        class_map = numpy.asarray([]).T
+    aligned = class_count.sum()
+    unaligned = int(table['unaligned'])
+    return SummarizedResult(
+        aligned=int(aligned), unaligned=unaligned, total=int(aligned + unaligned), class_map=class_map,
+        class_count=class_count, fragment_length_frequencies=map_result.fragment_length_counts,
+        effective_lengths=map_result.effective_lengths)
 
 
 def _device_of(index):
@@ -185,9 +211,12 @@ class ReadMapper:
             mapper.close()
         classes = _class_tuples(table)
         with self.map_result.lock:
+            fresh = not self.map_result.counter
             self.map_result.update_counts(classes)
             if table['unaligned']:
                 self.map_result.counter[()] += table['unaligned']
+            if fresh:
+                self.map_result._table = table
         self.fragment_length_counts += table['fld']
         with self.map_result.lock:
             self.map_result.merge_fragment_lengths(self.fragment_length_counts)
