@@ -45,8 +45,8 @@ struct DictDev {
 };
 
 struct MapArgs {
-    const uint8_t *bases;
-    const int64_t *offsets;   // n_reads + 1, or NULL with fixed_len
+    const uint64_t *packed;   // [n_reads][words] from pack_reads_kernel
+    const int32_t *lens;      // per-read length, or NULL with fixed_len
     int32_t fixed_len;
     int32_t code_words;       // u64 words of 2-bit codes per read (from max read length)
     int32_t words;            // code_words + wildcard words
@@ -107,7 +107,7 @@ struct Span {
 struct Ctx {
     const DevIndex &ix;
     const MapArgs &a;
-    int32_t *smem_list;  // &lists[warp][0][lane]
+    int32_t *smem_list;  // &lists[warp][0][0][lane]
     uint32_t *status;
 };
 
@@ -213,13 +213,12 @@ __device__ __forceinline__ uint64_t tail_kmer(const Contig &c, Coord a)
     return a.entry < 0 ? revcomp(kmer) : kmer;
 }
 
-__device__ void map_contig(const Ctx &cx, Coord a, List &l)
+// map_contig (_common.pyx:143-179) for an already loaded contig record
+__device__ void map_contig(const Ctx &cx, const Contig &c, Coord a, List &l, int32_t *smem_list)
 {
     const bool forward = a.entry >= 0;
-    const int32_t index = forward ? a.entry : ~a.entry;
-    const Contig c = load_contig(cx.ix, index);
     const int n = c.target_count;
-    l.p = cx.smem_list;
+    l.p = smem_list;
     l.stride = 32;
     if (n > LIST_CAP) {
         const unsigned long long off = atomicAdd(&cx.a.cursors[1], (unsigned long long)n);
@@ -240,6 +239,7 @@ __device__ void map_contig(const Ctx &cx, Coord a, List &l)
     l.n = n;
 }
 
+// _filter_on_contig (_common.pyx:185-235): sorted-merge intersection, direction aware
 __device__ bool filter_on_contig(const Ctx &cx, const Contig &c, Coord a, List &l)
 {
     if (l.n == 0) return true;
@@ -274,139 +274,16 @@ __device__ bool filter_on_contig(const Ctx &cx, const Contig &c, Coord a, List &
     return true;
 }
 
-__device__ void find_first_kmer(const Ctx &cx, const ReadView &r, Span &s, List &l)
+// 8-base window at a contig EDGE, taken from the record's first/last k-mer instead of the
+// sequence pool: inside the walk loops the anchor always sits on the first or last k-mer of
+// its contig (offset 0 or length-k, _mapper.pyx:229-236,289-295), and first_kmer/last_kmer
+// are the encodings of the contig's first/last 25 bases (_index_builder.pyx:565-567).
+__device__ __forceinline__ uint32_t edge_window(const Contig &c, Coord a, bool left_edge)
 {
-    uint64_t kmer = r.kmer(s.begin);
-    s.anchor = map_kmer(cx.ix, kmer);
-    if (s.anchor.offset >= 0) {
-        s.end = s.begin;
-        map_contig(cx, s.anchor, l);
-        return;
-    }
-    for (int i = s.begin + K; i < r.len; ++i) {
-        kmer = ((kmer << 2) | r.code(i)) & KMER_MASK;
-        s.anchor = map_kmer(cx.ix, kmer);
-        if (s.anchor.offset < 0) continue;
-        s.begin = i + 1 - K;
-        s.end = s.begin;
-        map_contig(cx, s.anchor, l);
-        return;
-    }
-}
-
-__device__ void filter_targets_to_left(const Ctx &cx, const ReadView &r, Span &s, List &l)
-{
-    bool forward = s.anchor.entry >= 0;
-    Contig c = load_contig(cx.ix, forward ? s.anchor.entry : ~s.anchor.entry);
-    int move = forward ? s.anchor.offset : c.length - s.anchor.offset - K;
-    int shift;
-    while (s.begin > move) {
-        s.begin -= move;
-        s.anchor.offset -= forward ? move : -move;
-        shift = sift4_align_left(contig_window(cx.ix, c, s.anchor, true), r, s.begin);
-        if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
-            l.n = 0;
-            return;
-        }
-        s.begin -= shift + 1;
-        if (s.begin < 0) {
-            s.begin = 0;
-            return;
-        }
-        uint64_t kmer = (tail_kmer(c, s.anchor) >> 2) | ((uint64_t)r.code(s.begin) << (2 * K - 2));
-        s.anchor = map_kmer(cx.ix, kmer);
-        bool ok = s.anchor.offset >= 0;
-        if (ok) {
-            c = load_contig(cx.ix, s.anchor.entry >= 0 ? s.anchor.entry : ~s.anchor.entry);
-            ok = filter_on_contig(cx, c, s.anchor, l);
-        }
-        if (!ok) {
-            if (s.begin < K) {
-                s.begin = 0;
-                return;
-            }
-            s.begin -= K;
-            kmer = r.kmer(s.begin);
-            s.anchor = map_kmer(cx.ix, kmer);
-            ok = s.anchor.offset >= 0;
-            if (ok) {
-                c = load_contig(cx.ix, s.anchor.entry >= 0 ? s.anchor.entry : ~s.anchor.entry);
-                ok = filter_on_contig(cx, c, s.anchor, l);
-            }
-            if (!ok) {
-                l.n = 0;
-                return;
-            }
-        }
-        forward = s.anchor.entry >= 0;
-        move = forward ? s.anchor.offset : c.length - s.anchor.offset - K;
-    }
-    s.anchor.offset -= forward ? s.begin : -s.begin;
-    shift = sift4_align_left(contig_window(cx.ix, c, s.anchor, true), r, 0);
-    if (shift == INVALID_SHIFT) l.n = 0;
-}
-
-__device__ void filter_targets_to_right(const Ctx &cx, const ReadView &r, Span &s, List &l)
-{
-    uint64_t kmer = r.kmer(s.end);
-    s.anchor = map_kmer(cx.ix, kmer);
-    bool forward = s.anchor.entry >= 0;
-    Contig c = load_contig(cx.ix, forward ? s.anchor.entry : ~s.anchor.entry);
-    int move = forward ? c.length - s.anchor.offset - K : s.anchor.offset;
-    int shift;
-    while (r.len - s.end - K > move) {
-        s.end += move;
-        s.anchor.offset += forward ? move : -move;
-        shift = sift4_align_right(contig_window(cx.ix, c, s.anchor, false), r,
-                                  s.end + K - ALIGN_LENGTH);
-        if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
-            l.n = 0;
-            return;
-        }
-        s.end += shift + 1;
-        if (s.end + K > r.len) {
-            s.end = r.len - K;
-            return;
-        }
-        kmer = ((tail_kmer(c, s.anchor) << 2) | r.code(s.end + K - 1)) & KMER_MASK;
-        s.anchor = map_kmer(cx.ix, kmer);
-        bool ok = s.anchor.offset >= 0;
-        if (ok) {
-            c = load_contig(cx.ix, s.anchor.entry >= 0 ? s.anchor.entry : ~s.anchor.entry);
-            ok = filter_on_contig(cx, c, s.anchor, l);
-        }
-        if (!ok) {  // :312-315; the block at :316-329 is unreachable (idempotent re-test)
-            l.n = 0;
-            return;
-        }
-        forward = s.anchor.entry >= 0;
-        move = forward ? c.length - s.anchor.offset - K : s.anchor.offset;
-    }
-    if (forward) s.anchor.offset += r.len - s.end - K;
-    else s.anchor.offset -= r.len - s.end - K;
-    shift = sift4_align_right(contig_window(cx.ix, c, s.anchor, false), r, r.len - ALIGN_LENGTH);
-    if (shift == INVALID_SHIFT) l.n = 0;
-}
-
-__device__ void map_read(const Ctx &cx, const ReadView &r, Span &s, List &l)
-{
-    s.anchor = coord_invalid();
-    s.begin = 0;
-    s.end = 0;
-    l.n = 0;
-    find_first_kmer(cx, r, s, l);
-    if (l.n == 0) return;
-    if (s.begin > 0) filter_targets_to_left(cx, r, s, l);
-    if (l.n != 0 && s.end < r.len - K) filter_targets_to_right(cx, r, s, l);
-    if (l.n != 0) return;
-    s.anchor = coord_invalid();
-    s.begin += K;
-    if (s.begin + K > r.len) s.begin = r.len - K;
-    s.end = s.begin;
-    find_first_kmer(cx, r, s, l);
-    if (l.n == 0) return;
-    if (s.begin > 0) filter_targets_to_left(cx, r, s, l);
-    if (l.n != 0 && s.end < r.len - K) filter_targets_to_right(cx, r, s, l);
+    const uint32_t head = (uint32_t)(c.first_kmer >> (2 * K - 16)) & 0xFFFFu;  // first 8 bases
+    const uint32_t tail = (uint32_t)c.last_kmer & 0xFFFFu;                      // last 8 bases
+    if (a.entry >= 0) return left_edge ? head : tail;
+    return revcomp8(left_edge ? tail : head);
 }
 
 // mate intersection (_mapper.pyx:350-397): list 1 ascending vs list 2 descending, negated
@@ -518,7 +395,7 @@ __device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const i
     return -1;
 }
 
-// ---- the kernel ---------------------------------------------------------------------
+// ---- the kernels ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t lut_entry(uint32_t b)
 {
     // bits 1:0 = 2-bit code (_kmer.pxd:253-273), bit 2 = "not one of ACGT" (_mapper.pyx:501)
@@ -528,160 +405,435 @@ __device__ __forceinline__ uint32_t lut_entry(uint32_t b)
     return code | (upper ? 0u : 4u);
 }
 
+// Pass 1: ASCII reads -> packed reads (2-bit codes, first base in the top bits of each u64,
+// followed by one wildcard bit per base).  Fully convergent streaming kernel; the byte ->
+// (code, wildcard) table lives in shared memory.
+__global__ void __launch_bounds__(256)
+pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ offsets,
+                  int32_t fixed_len, int32_t code_words, int32_t words, int64_t n_reads,
+                  uint64_t *__restrict__ packed, int32_t *__restrict__ lens)
+{
+    __shared__ uint8_t sm_lut[256];
+    sm_lut[threadIdx.x] = (uint8_t)lut_entry(threadIdx.x);
+    __syncthreads();
+    const int64_t read = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (read >= n_reads) return;
+    int64_t off;
+    int len;
+    if (offsets) {
+        off = offsets[read];
+        len = (int)(offsets[read + 1] - off);
+    } else {
+        off = read * (int64_t)fixed_len;
+        len = fixed_len;
+    }
+    if (lens) lens[read] = len;
+    const int max_len = code_words * 32;
+    if (len > max_len) len = max_len;  // the host sizes code_words from the longest read
+    const uint8_t *src = bases + off;
+    uint64_t *out = packed + read * (int64_t)words;
+    uint64_t acc = 0, wacc = 0;
+    int cw = 0, ww = code_words;
+    int j = 0;
+    auto push = [&](uint32_t byte) {
+        const uint32_t v = sm_lut[byte];
+        acc = (acc << 2) | (v & 3u);
+        wacc |= (uint64_t)(v >> 2) << (j & 63);
+        if ((j & 31) == 31) {
+            out[cw] = acc;
+            cw += 1;
+            acc = 0;
+            if ((j & 63) == 63) {
+                out[ww] = wacc;
+                ww += 1;
+                wacc = 0;
+            }
+        }
+        j += 1;
+    };
+    while (j < len && (reinterpret_cast<uintptr_t>(src + j) & 7)) push(__ldg(src + j));
+    while (j + 8 <= len) {
+        const uint64_t w8 = __ldg(reinterpret_cast<const unsigned long long *>(src + j));
+#pragma unroll
+        for (int b = 0; b < 8; ++b) push((uint32_t)(w8 >> (8 * b)) & 0xFFu);
+    }
+    while (j < len) push(__ldg(src + j));
+    if (len & 31) out[cw] = acc << (2 * (32 - (len & 31)));
+    if (len & 63) out[ww] = wacc;
+}
+
+// Pass 2: the mapper.  Every lane is a persistent worker that owns one unit (read or pair) at
+// a time and advances it through the reference's state machine in ROUNDS.  A round has uniform
+// phases that all lanes execute together regardless of where their read is:
+//   refill -> k-mer lookup (hash + probe) -> contig record load -> target-list op ->
+//   state transition (walk-loop heads with the SIFT4 edge check) -> class tally.
+// A lane whose read needs no lookup this round simply sits the phase out; a lane that
+// finishes its unit takes the next one from the warp's queue in the next round, so lanes do
+// not wait for the slowest read of a warp.
+enum : int {
+    S_IDLE = 0,     // needs a new unit
+    S_LOAD,         // needs its (next) read staged into shared memory
+    S_FIND,         // _find_first_kmer scan: lookup of the k-mer at `pos` pending
+    S_LEFT_J,       // left walk: junction k-mer lookup pending (_mapper.pyx:247-251)
+    S_LEFT_F,       // left walk: fallback lookup pending (:257-261)
+    S_RIGHT_C,      // right walk start: contig record of the cached anchor pending (:283-290)
+    S_RIGHT_J,      // right walk: junction k-mer lookup pending (:309-313)
+    S_EXIT          // no more work
+};
+
+enum : int { ACT_NONE = 0, ACT_LEFT_HEAD, ACT_AFTER_LEFT, ACT_RIGHT_HEAD, ACT_AFTER_ATTEMPT, ACT_READ_DONE };
+
+constexpr int WARP_QUEUE = 128;  // units a warp takes from the global counter at a time
+
 __global__ void __launch_bounds__(BLOCK_THREADS, 3)
 map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *sm_reads = reinterpret_cast<uint64_t *>(smem_raw);             // [WARPS][words][32]
-    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_reads + WARPS * a.words * 32);  // [WARPS][CAP][32]
-    uint32_t *sm_fld = reinterpret_cast<uint32_t *>(sm_lists + WARPS * LIST_CAP * 32);
-    uint8_t *sm_lut = reinterpret_cast<uint8_t *>(sm_fld + FLD_BINS);
+    uint64_t *sm_reads = reinterpret_cast<uint64_t *>(smem_raw);                       // [WARPS][words][32]
+    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_reads + WARPS * a.words * 32);  // [WARPS][2][CAP][32]
+    uint32_t *sm_fld = reinterpret_cast<uint32_t *>(sm_lists + WARPS * 2 * LIST_CAP * 32);
 
     for (int i = threadIdx.x; i < FLD_BINS; i += BLOCK_THREADS) sm_fld[i] = 0;
-    for (int i = threadIdx.x; i < 256; i += BLOCK_THREADS) sm_lut[i] = (uint8_t)lut_entry(i);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t *my_words = sm_reads + (size_t)warp * a.words * 32 + lane;
-    Ctx cx{ix, a, sm_lists + warp * LIST_CAP * 32 + lane, dict.status};
+    int32_t *my_list0 = sm_lists + (size_t)warp * 2 * LIST_CAP * 32 + lane;
+    int32_t *my_list1 = my_list0 + LIST_CAP * 32;
+    Ctx cx{ix, a, my_list0, dict.status};
 
-    const int64_t n_reads = a.paired ? 2 * a.n_units : a.n_units;
-    const int64_t n_chunks = (n_reads + 31) >> 5;
+    // warp-level unit queue
+    long long q_next = 0, q_end = 0;
+    bool q_dry = false;
+
+    // per-lane state
+    int state = S_IDLE;
+    long long unit = -1;
+    int mate = 0;
+    ReadView rv{my_words, 0, a.code_words};
+    Span sp{0, 0, coord_invalid()};
+    Coord anchor0 = coord_invalid();
+    List l{my_list0, 32, 0};
+    int attempt = 0, pos = 0, move = 0;
+    bool forward = true;
+    uint64_t kmer = 0;
+    // mate 1 results while mate 2 is mapped
+    int m1_begin = 0, m1_len = 0;
+    Coord m1_anchor = coord_invalid();
+    List m1{my_list0, 32, 0};
 
     for (;;) {
-        long long chunk = 0;
-        if (lane == 0) chunk = (long long)atomicAdd(&a.cursors[0], 1ULL);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk >= n_chunks) break;
-        const int64_t read_idx = chunk * 32 + lane;
-        const bool valid = read_idx < n_reads;
-
-        // ---- stage this lane's read: ASCII -> 2-bit codes + wildcard bits ----------
-        int len = 0;
-        if (valid) {
-            int64_t off;
-            if (a.offsets) {
-                off = a.offsets[read_idx];
-                len = (int)(a.offsets[read_idx + 1] - off);
-            } else {
-                off = read_idx * (int64_t)a.fixed_len;
-                len = a.fixed_len;
-            }
-            const int max_len = a.code_words * 32;
-            if (len > max_len) len = max_len;  // host guarantees max_read_len; defensive
-            const uint8_t *src = a.bases + off;
-            uint64_t acc = 0, wacc = 0;
-            int cw = 0, ww = a.code_words;
-            int j = 0;
-            auto push = [&](uint32_t byte) {
-                const uint32_t v = sm_lut[byte];
-                acc = (acc << 2) | (v & 3u);
-                wacc |= (uint64_t)(v >> 2) << (j & 63);
-                if ((j & 31) == 31) {
-                    my_words[cw * 32] = acc;
-                    cw += 1;
-                    acc = 0;
-                    if ((j & 63) == 63) {
-                        my_words[ww * 32] = wacc;
-                        ww += 1;
-                        wacc = 0;
+        // ---- refill: hand units to idle lanes ---------------------------------------
+        {
+            const unsigned idle = __ballot_sync(0xffffffffu, state == S_IDLE);
+            if (idle) {
+                const int n_idle = __popc(idle);
+                if (q_next >= q_end && !q_dry) {
+                    long long base = 0;
+                    if (lane == 0) base = (long long)atomicAdd(&a.cursors[0], (unsigned long long)WARP_QUEUE);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    q_next = base;
+                    q_end = min(base + (long long)WARP_QUEUE, (long long)a.n_units);
+                    if (q_next >= q_end) q_dry = true;
+                }
+                const int rank = __popc(idle & ((1u << lane) - 1u));
+                if (state == S_IDLE) {
+                    if (q_next + rank < q_end) {
+                        unit = q_next + rank;
+                        mate = 0;
+                        state = S_LOAD;
+                    } else if (q_dry) {
+                        state = S_EXIT;
                     }
                 }
-                j += 1;
-            };
-            while (j < len && (reinterpret_cast<uintptr_t>(src + j) & 7)) push(__ldg(src + j));
-            while (j + 8 <= len) {
-                const uint64_t w8 = __ldg(reinterpret_cast<const unsigned long long *>(src + j));
-#pragma unroll
-                for (int b = 0; b < 8; ++b) push((uint32_t)(w8 >> (8 * b)) & 0xFFu);
+                q_next = min(q_next + (long long)n_idle, q_end);
             }
-            while (j < len) push(__ldg(src + j));
-            if (len & 31) my_words[cw * 32] = acc << (2 * (32 - (len & 31)));
-            if (len & 63) my_words[ww * 32] = wacc;
+            if (__all_sync(0xffffffffu, state == S_EXIT)) break;
         }
-        __syncwarp();
 
-        // ---- per-read state machine ----------------------------------------------
-        ReadView rv{my_words, len, a.code_words};
-        Span sp;
-        sp.begin = 0;
-        sp.end = 0;
-        sp.anchor = coord_invalid();
-        List l{cx.smem_list, 32, 0};
-        if (valid) {
-            if (len >= K) map_read(cx, rv, sp, l);
-            else atomicOr(dict.status, ST_SHORT_READ);
+        // ---- stage the packed read of (unit, mate) -------------------------------------
+        if (state == S_LOAD) {
+            const long long read_idx = a.paired ? 2 * unit + mate : unit;
+            const uint64_t *src = a.packed + read_idx * (long long)a.words;
+            for (int k = 0; k < a.words; ++k) my_words[k * 32] = __ldg(src + k);
+            int len = a.lens ? __ldg(a.lens + read_idx) : a.fixed_len;
+            const int max_len = a.code_words * 32;
+            if (len > max_len) len = max_len;
+            rv.len = len;
+            sp.begin = 0;
+            sp.end = 0;
+            sp.anchor = coord_invalid();
+            l.p = mate ? my_list1 : my_list0;
+            l.stride = 32;
+            l.n = 0;
+            attempt = 0;
+            pos = 0;
+            if (len >= K) {
+                kmer = rv.kmer(0);
+                state = S_FIND;
+            } else {
+                atomicOr(dict.status, ST_SHORT_READ);
+                kmer = 0;
+                state = S_FIND;
+                pos = -1;  // handled below: the read is reported unaligned without any lookup
+            }
         }
-        __syncwarp();
 
-        // ---- mates -> unit (map_read_pair, _mapper.pyx:111-145) --------------------
-        bool is_unit = valid;
-        int64_t unit = read_idx;
-        if (a.paired) {
-            const int b2 = __shfl_down_sync(0xffffffffu, sp.begin, 1);
-            const int e2 = __shfl_down_sync(0xffffffffu, sp.anchor.entry, 1);
-            const int o2 = __shfl_down_sync(0xffffffffu, sp.anchor.offset, 1);
-            const int n2 = __shfl_down_sync(0xffffffffu, l.n, 1);
-            const int len2 = __shfl_down_sync(0xffffffffu, len, 1);
-            const int st2 = __shfl_down_sync(0xffffffffu, l.stride, 1);
-            const unsigned long long p2 =
-                __shfl_down_sync(0xffffffffu, (unsigned long long)(uintptr_t)l.p, 1);
-            is_unit = valid && !(lane & 1);
-            unit = read_idx >> 1;
-            if (is_unit) {
-                List l2{reinterpret_cast<int32_t *>((uintptr_t)p2), st2, n2};
-                if (!intersect(l, l2)) {
-                    l.n = 0;
-                    sp.begin = 0;
-                    sp.end = -K;
-                } else if (sp.anchor.entry != ~e2) {
-                    sp.begin = 0;
-                    sp.end = -K;
+        // ---- phase A: k-mer lookup (KMerIndex.map_kmer) ----------------------------------
+        const bool short_read = state == S_FIND && pos < 0;
+        const bool want_lookup = (state == S_FIND || state == S_LEFT_J || state == S_LEFT_F || state == S_RIGHT_J)
+                                 && !short_read;
+        Coord hit = coord_invalid();
+        if (want_lookup) hit = map_kmer(ix, kmer);
+
+        // ---- phase B: contig record ----------------------------------------------------
+        const bool want_contig = (want_lookup && hit.offset >= 0) || state == S_RIGHT_C;
+        Contig c{};
+        if (want_contig) {
+            const int32_t e = state == S_RIGHT_C ? anchor0.entry : hit.entry;
+            c = load_contig(ix, e >= 0 ? e : ~e);
+        }
+
+        // ---- phase C1: target-list operation ---------------------------------------------
+        bool ok = false;
+        if (want_lookup) {
+            sp.anchor = hit;
+            if (hit.offset >= 0) {
+                if (state == S_FIND) {
+                    map_contig(cx, c, hit, l, mate ? my_list1 : my_list0);
+                    ok = l.n != 0;
                 } else {
-                    sp.end = len - K;
-                    int interval = o2 - sp.anchor.offset;
-                    if (sp.anchor.entry < 0) interval = -interval;
-                    sp.end += interval + (len2 - K) - b2;
+                    ok = filter_on_contig(cx, c, hit, l);
                 }
             }
         }
 
-        // ---- FLD (_mapper.pyx:90-94), class tally (mapper.py:60-75) -----------------
-        int64_t slot = -1;
-        if (is_unit) {
-            int length = sp.end - sp.begin + K;
-            if (a.out_length) a.out_length[unit] = length;
-            if (length > 0) {
-                if (length >= FLD_BINS) length = FLD_BINS - 1;
-                atomicAdd(&sm_fld[length], 1u);
+        // ---- phase C2: transitions ---------------------------------------------------------
+        int act = ACT_NONE;
+        switch (state) {
+        case S_FIND:
+            if (short_read) {
+                act = ACT_READ_DONE;
+            } else if (hit.offset < 0) {
+                // _find_first_kmer keeps rolling (:208-212); exhausted => targets stay empty and
+                // map_read returns at :170-171 / :186-187 (no retry after a failed scan)
+                pos += 1;
+                if (pos + K <= rv.len) kmer = ((kmer << 2) | rv.code(pos + K - 1)) & KMER_MASK;
+                else act = ACT_READ_DONE;
+            } else {
+                sp.begin = pos;
+                sp.end = pos;
+                anchor0 = hit;
+                if (!ok) {
+                    act = ACT_READ_DONE;
+                } else if (sp.begin > 0) {
+                    forward = hit.entry >= 0;
+                    move = forward ? hit.offset : c.length - hit.offset - K;
+                    act = ACT_LEFT_HEAD;
+                } else {
+                    act = ACT_AFTER_LEFT;
+                }
             }
-            if (l.n > 0) {
-                const ulonglong2 key = tuple_key(l.p, l.stride, l.n, true);
-                slot = dict_find_or_insert(dict, key, l.p, l.stride, l.n, true);
+            break;
+        case S_LEFT_J:
+            if (ok) {
+                forward = hit.entry >= 0;
+                move = forward ? hit.offset : c.length - hit.offset - K;
+                act = ACT_LEFT_HEAD;
+            } else if (sp.begin < K) {
+                sp.begin = 0;  // :252-256
+                act = ACT_AFTER_LEFT;
+            } else {
+                sp.begin -= K;  // :257-259
+                kmer = rv.kmer(sp.begin);
+                state = S_LEFT_F;
             }
-            if (a.out_class) a.out_class[unit] = (int32_t)slot;
+            break;
+        case S_LEFT_F:
+            if (ok) {
+                forward = hit.entry >= 0;
+                move = forward ? hit.offset : c.length - hit.offset - K;
+                act = ACT_LEFT_HEAD;
+            } else {
+                l.n = 0;  // :260-263
+                act = ACT_AFTER_LEFT;
+            }
+            break;
+        case S_RIGHT_C:
+            // :283-290 — the k-mer at `end` is the one _find_first_kmer hit; its lookup is cached
+            sp.anchor = anchor0;
+            forward = anchor0.entry >= 0;
+            move = forward ? c.length - anchor0.offset - K : anchor0.offset;
+            act = ACT_RIGHT_HEAD;
+            break;
+        case S_RIGHT_J:
+            if (ok) {
+                forward = hit.entry >= 0;
+                move = forward ? c.length - hit.offset - K : hit.offset;
+                act = ACT_RIGHT_HEAD;
+            } else {
+                l.n = 0;  // :312-315 (the block at :316-329 is unreachable)
+                act = ACT_AFTER_ATTEMPT;
+            }
+            break;
+        default:
+            break;
         }
-        __syncwarp();
-        // warp-aggregated count / first-seen update: one atomic per distinct class per warp
-        {
+
+        if (act == ACT_LEFT_HEAD) {  // loop of _filter_targets_to_left (:234-275)
+            if (sp.begin > move) {
+                sp.begin -= move;
+                sp.anchor.offset -= forward ? move : -move;
+                const int shift = sift4_align_left(edge_window(c, sp.anchor, true), rv, sp.begin);
+                if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
+                    l.n = 0;
+                    act = ACT_AFTER_LEFT;
+                } else {
+                    sp.begin -= shift + 1;
+                    if (sp.begin < 0) {
+                        sp.begin = 0;
+                        act = ACT_AFTER_LEFT;
+                    } else {
+                        kmer = (tail_kmer(c, sp.anchor) >> 2) | ((uint64_t)rv.code(sp.begin) << (2 * K - 2));
+                        state = S_LEFT_J;
+                        act = ACT_NONE;
+                    }
+                }
+            } else {
+                sp.anchor.offset -= forward ? sp.begin : -sp.begin;
+                const int shift = sift4_align_left(contig_window(ix, c, sp.anchor, true), rv, 0);
+                if (shift == INVALID_SHIFT) l.n = 0;
+                act = ACT_AFTER_LEFT;
+            }
+        }
+        if (act == ACT_AFTER_LEFT) {  // map_read :174-176 / :190-192
+            if (l.n != 0 && sp.end < rv.len - K) {
+                state = S_RIGHT_C;
+                act = ACT_NONE;
+            } else {
+                act = ACT_AFTER_ATTEMPT;
+            }
+        }
+        if (act == ACT_RIGHT_HEAD) {  // loop of _filter_targets_to_right (:293-343)
+            if (rv.len - sp.end - K > move) {
+                sp.end += move;
+                sp.anchor.offset += forward ? move : -move;
+                const int shift = sift4_align_right(edge_window(c, sp.anchor, false), rv,
+                                                    sp.end + K - ALIGN_LENGTH);
+                if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
+                    l.n = 0;
+                    act = ACT_AFTER_ATTEMPT;
+                } else {
+                    sp.end += shift + 1;
+                    if (sp.end + K > rv.len) {
+                        sp.end = rv.len - K;
+                        act = ACT_AFTER_ATTEMPT;
+                    } else {
+                        kmer = ((tail_kmer(c, sp.anchor) << 2) | rv.code(sp.end + K - 1)) & KMER_MASK;
+                        state = S_RIGHT_J;
+                        act = ACT_NONE;
+                    }
+                }
+            } else {
+                if (forward) sp.anchor.offset += rv.len - sp.end - K;
+                else sp.anchor.offset -= rv.len - sp.end - K;
+                const int shift = sift4_align_right(contig_window(ix, c, sp.anchor, false), rv,
+                                                    rv.len - ALIGN_LENGTH);
+                if (shift == INVALID_SHIFT) l.n = 0;
+                act = ACT_AFTER_ATTEMPT;
+            }
+        }
+        if (act == ACT_AFTER_ATTEMPT) {  // map_read :177-193
+            if (l.n != 0 || attempt == 1) {
+                act = ACT_READ_DONE;
+            } else {
+                attempt = 1;
+                sp.anchor = coord_invalid();
+                sp.begin += K;
+                if (sp.begin + K > rv.len) sp.begin = rv.len - K;
+                sp.end = sp.begin;
+                pos = sp.begin;
+                kmer = rv.kmer(pos);
+                l.p = mate ? my_list1 : my_list0;
+                l.stride = 32;
+                state = S_FIND;
+                act = ACT_NONE;
+            }
+        }
+
+        // ---- read finished: next mate, or unit finished -----------------------------------
+        long long slot = -1;
+        bool unit_done = false;
+        if (act == ACT_READ_DONE) {
+            if (a.paired && mate == 0) {
+                m1_begin = sp.begin;
+                m1_anchor = sp.anchor;
+                m1_len = rv.len;
+                m1 = l;
+                mate = 1;
+                state = S_LOAD;
+            } else {
+                unit_done = true;
+                int length;
+                if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
+                    int begin1 = m1_begin, end1;
+                    if (!intersect(m1, l)) {
+                        m1.n = 0;
+                        begin1 = 0;
+                        end1 = -K;
+                    } else if (m1_anchor.entry != ~sp.anchor.entry) {
+                        begin1 = 0;
+                        end1 = -K;
+                    } else {
+                        end1 = m1_len - K;
+                        int interval = sp.anchor.offset - m1_anchor.offset;
+                        if (m1_anchor.entry < 0) interval = -interval;
+                        end1 += interval + (rv.len - K) - sp.begin;
+                    }
+                    length = end1 - begin1 + K;
+                    l = m1;
+                } else {
+                    length = sp.end - sp.begin + K;
+                }
+                if (a.out_length) a.out_length[unit] = length;
+                if (length > 0) {  // _mapper.pyx:90-94
+                    if (length >= FLD_BINS) length = FLD_BINS - 1;
+                    atomicAdd(&sm_fld[length], 1u);
+                }
+                state = S_IDLE;
+            }
+        }
+
+        // ---- phase D: class tally (mapper.py:60-75), uniform over lanes that finished a unit ---
+        if (__any_sync(0xffffffffu, unit_done)) {
+            if (unit_done) {
+                if (l.n > 0) {
+                    const ulonglong2 key = tuple_key(l.p, l.stride, l.n, true);
+                    slot = dict_find_or_insert(dict, key, l.p, l.stride, l.n, true);
+                }
+                if (a.out_class) a.out_class[unit] = (int32_t)slot;
+            }
+            __syncwarp();
+            // one atomic per distinct class per warp
             const unsigned same = __match_any_sync(0xffffffffu, slot);
             const int leader = __ffs(same) - 1;
             if (slot >= 0 && lane == leader) {
                 atomicAdd(&dict.counts[slot], (unsigned long long)__popc(same));
+            }
+            if (slot >= 0) {
                 const unsigned long long g = (unsigned long long)(a.first_unit + unit);
                 if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
                     atomicMin(&dict.first[slot], g);
             }
-            const unsigned units = __ballot_sync(0xffffffffu, is_unit);
-            const unsigned mapped = __ballot_sync(0xffffffffu, is_unit && slot >= 0);
+            const unsigned done = __ballot_sync(0xffffffffu, unit_done);
+            const unsigned mapped = __ballot_sync(0xffffffffu, unit_done && slot >= 0);
             if (lane == 0) {
                 const int n_al = __popc(mapped);
-                const int n_un = __popc(units) - n_al;
+                const int n_un = __popc(done) - n_al;
                 if (n_un) atomicAdd(&dict.scalars[2], (unsigned long long)n_un);
                 if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
             }
         }
-        __syncwarp();
     }
 
     __syncthreads();
@@ -761,6 +913,10 @@ struct skm_mapper {
     size_t d_offsets_cap = 0;
     int32_t *d_out = nullptr;
     size_t d_out_cap = 0;
+    uint64_t *d_packed = nullptr;  // pack_reads_kernel output
+    size_t d_packed_cap = 0;
+    int32_t *d_lens = nullptr;
+    size_t d_lens_cap = 0;
 };
 
 static int ensure(void **p, size_t *cap, size_t need)
@@ -795,6 +951,8 @@ SKM_API void skm_mapper_destroy(skm_mapper *m)
     cudaFree(m->d_bases);
     cudaFree(m->d_offsets);
     cudaFree(m->d_out);
+    cudaFree(m->d_packed);
+    cudaFree(m->d_lens);
     cudaSetDevice(prev);
     delete m;
 }
@@ -871,8 +1029,8 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
 
 static size_t map_smem_bytes(int words)
 {
-    return sizeof(uint64_t) * WARPS * (size_t)words * 32 + sizeof(int32_t) * WARPS * LIST_CAP * 32
-           + sizeof(uint32_t) * FLD_BINS + 256;
+    return sizeof(uint64_t) * WARPS * (size_t)words * 32 + sizeof(int32_t) * WARPS * 2 * LIST_CAP * 32
+           + sizeof(uint32_t) * FLD_BINS;
 }
 
 static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
@@ -929,9 +1087,9 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     a.arena_cap = m->arena_cap;
     a.cursors = m->cursors;
 
+    const uint8_t *d_bases = bases;
+    const int64_t *d_offsets = read_offsets;
     if (buffers_on_device) {
-        a.bases = bases;
-        a.offsets = read_offsets;
         a.out_class = out_class;
         a.out_length = out_length;
     } else {
@@ -941,13 +1099,13 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
         if (rc) return rc;
         const uint8_t *src = bases + (read_offsets ? read_offsets[0] : 0);
         SKM_CUDA(cudaMemcpyAsync(m->d_bases, src, (size_t)n_bases, cudaMemcpyHostToDevice, st));
-        a.bases = m->d_bases - (read_offsets ? read_offsets[0] : 0);
+        d_bases = m->d_bases - (read_offsets ? read_offsets[0] : 0);
         if (read_offsets) {
             rc = ensure((void **)&m->d_offsets, &m->d_offsets_cap, sizeof(int64_t) * (size_t)(n_reads + 1));
             if (rc) return rc;
             SKM_CUDA(cudaMemcpyAsync(m->d_offsets, read_offsets, sizeof(int64_t) * (size_t)(n_reads + 1),
                                      cudaMemcpyHostToDevice, st));
-            a.offsets = m->d_offsets;
+            d_offsets = m->d_offsets;
         }
         if (out_class || out_length) {
             rc = ensure((void **)&m->d_out, &m->d_out_cap, sizeof(int32_t) * 2 * (size_t)n_units);
@@ -957,14 +1115,32 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
         }
     }
 
+    // pass 1: pack
+    {
+        int rc = ensure((void **)&m->d_packed, &m->d_packed_cap, sizeof(uint64_t) * (size_t)n_reads * a.words);
+        if (rc) return rc;
+        int32_t *lens = nullptr;
+        if (read_offsets) {
+            rc = ensure((void **)&m->d_lens, &m->d_lens_cap, sizeof(int32_t) * (size_t)n_reads);
+            if (rc) return rc;
+            lens = m->d_lens;
+        }
+        const int64_t blocks = (n_reads + 255) / 256;
+        pack_reads_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_bases, d_offsets, a.fixed_len, a.code_words, a.words,
+                                                           n_reads, m->d_packed, lens);
+        SKM_CUDA(cudaGetLastError());
+        a.packed = m->d_packed;
+        a.lens = lens;
+    }
+
+    // pass 2: map
     SKM_CUDA(cudaMemsetAsync(m->cursors, 0, sizeof(unsigned long long) * 2, st));
     const size_t smem = map_smem_bytes(a.words);
     SKM_CUDA(cudaFuncSetAttribute(map_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_reads_kernel, BLOCK_THREADS, smem));
     if (per_sm < 1) return fail(SKM_ERR_INVALID, "skm_map_batch: reads too long for shared-memory staging");
-    const int64_t chunks = (n_reads + 31) / 32;
-    const int64_t want = (chunks + WARPS - 1) / WARPS;
+    const int64_t want = (n_units + BLOCK_THREADS - 1) / BLOCK_THREADS;
     const int grid = (int)std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>(want, 1));
     map_reads_kernel<<<grid, BLOCK_THREADS, smem, st>>>(m->index->d, m->d, a);
     SKM_CUDA(cudaGetLastError());
