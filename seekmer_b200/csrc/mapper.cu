@@ -1,11 +1,11 @@
 // Read -> equivalence-class mapping on the GPU.
 //
-// One thread maps one read (both mates of a pair sit in adjacent lanes), a warp pulls
-// chunks of 32 reads from a global work counter, packs their ASCII bases to 2 bits
-// (+1 wildcard bit) into shared memory, runs the reference's per-read state machine
-// against the HBM-resident index, intersects the mates, and tallies the ordered
-// transcript-id tuple into a device-resident class dictionary.  The fragment-length
-// histogram is accumulated in shared memory and flushed once per block.
+// Two passes per batch: pack_reads_kernel turns the ASCII reads into 2-bit codes plus one
+// wildcard bit per base; map_reads_kernel runs the reference's per-read state machine against
+// the HBM-resident index with persistent lanes and warp-voted phases (see the kernel comment),
+// intersects the mates and tallies the ordered transcript-id tuple into a device-resident
+// class dictionary.  The fragment-length histogram is accumulated in shared memory and
+// flushed once per block.
 //
 // Reference semantics restated here (paths under /root/reference/seekmer/):
 //   map_read            _mapper.pyx:151-193      find_first_kmer   :199-216
@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "kmer.cuh"
+#include "sift4.cuh"
 
 namespace skm {
 
@@ -25,9 +26,7 @@ constexpr int BLOCK_THREADS = 256;
 constexpr int WARPS = BLOCK_THREADS / 32;
 constexpr int LIST_CAP = 16;       // per-read target list entries kept in shared memory
 constexpr int ALIGN_LENGTH = 8;    // _mapper.pyx:22
-constexpr int MAX_OFFSET = 2;      // _mapper.pyx:24
-constexpr int MAX_DISTANCE = 4;    // _mapper.pyx:26
-constexpr int INVALID_SHIFT = 0x7FFF;  // _mapper.pyx:28
+constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
 constexpr int FLD_BINS = SKM_MAX_FRAGMENT_LENGTH;
 
 struct DictDev {
@@ -110,93 +109,6 @@ struct Ctx {
     int32_t *smem_list;  // &lists[warp][0][0][lane]
     uint32_t *status;
 };
-
-__device__ __forceinline__ uint32_t ref_base(uint32_t ref8, int r) { return (ref8 >> (14 - 2 * r)) & 3u; }
-
-__device__ int sift4_align_left(uint32_t ref8, const ReadView &q, int offset)
-{
-    int reference_cursor = ALIGN_LENGTH - 1;
-    int query_cursor = offset + ALIGN_LENGTH - 1;
-    query_cursor -= 1;
-    int distance = 0;
-    while (reference_cursor >= 0 && query_cursor >= offset) {
-        if (q.match(ref_base(ref8, reference_cursor), query_cursor)) {
-            reference_cursor -= 1;
-            query_cursor -= 1;
-            continue;
-        }
-        if (reference_cursor != query_cursor - offset) {
-            reference_cursor = min(query_cursor - offset, reference_cursor);
-            query_cursor = reference_cursor + offset;
-        }
-#pragma unroll
-        for (int i = 0; i < MAX_OFFSET; ++i) {
-            if (query_cursor - i >= offset - 1 && query_cursor - i >= 0
-                && q.match(ref_base(ref8, reference_cursor), query_cursor - i)) {
-                distance += i - 1;
-                query_cursor -= i - 1;
-                reference_cursor += 1;
-                break;
-            }
-            if (reference_cursor - i >= 0
-                && q.match(ref_base(ref8, reference_cursor - i), query_cursor)) {
-                distance += i - 1;
-                query_cursor += 1;
-                reference_cursor -= i - 1;
-                break;
-            }
-        }
-        distance += 1;
-        query_cursor -= 1;
-        reference_cursor -= 1;
-        if (distance > MAX_DISTANCE) return INVALID_SHIFT;
-    }
-    if (reference_cursor >= 0) return reference_cursor + 1;
-    if (query_cursor >= offset) return -1 - query_cursor + offset;
-    return 0;
-}
-
-__device__ int sift4_align_right(uint32_t ref8, const ReadView &q, int offset)
-{
-    int reference_cursor = 0;
-    int query_cursor = offset;
-    int distance = 0;
-    while (reference_cursor < ALIGN_LENGTH && query_cursor < offset + ALIGN_LENGTH) {
-        if (q.match(ref_base(ref8, reference_cursor), query_cursor)) {
-            reference_cursor += 1;
-            query_cursor += 1;
-            continue;
-        }
-        if (reference_cursor != query_cursor - offset) {
-            reference_cursor = max(query_cursor - offset, reference_cursor);
-            query_cursor = reference_cursor + offset;
-        }
-#pragma unroll
-        for (int i = 0; i < MAX_OFFSET; ++i) {
-            if (query_cursor + i < offset + ALIGN_LENGTH + 1 && query_cursor + i < q.len
-                && q.match(ref_base(ref8, reference_cursor), query_cursor + i)) {
-                distance += i - 1;
-                query_cursor += i - 1;
-                reference_cursor -= 1;
-                break;
-            }
-            if (reference_cursor + i < ALIGN_LENGTH
-                && q.match(ref_base(ref8, reference_cursor + i), query_cursor)) {
-                distance += i - 1;
-                query_cursor -= 1;
-                reference_cursor += i - 1;
-                break;
-            }
-        }
-        distance += 1;
-        query_cursor += 1;
-        reference_cursor += 1;
-        if (distance > MAX_DISTANCE) return INVALID_SHIFT;
-    }
-    if (reference_cursor < ALIGN_LENGTH) return ALIGN_LENGTH - reference_cursor;
-    if (query_cursor < offset + ALIGN_LENGTH) return query_cursor - offset - ALIGN_LENGTH;
-    return 0;
-}
 
 // get_contig_sequence(coordinate, +-8) as a 16-bit window
 __device__ __forceinline__ uint32_t contig_window(const DevIndex &ix, const Contig &c, Coord a,
@@ -463,71 +375,201 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__
 }
 
 // Pass 2: the mapper.  Every lane is a persistent worker that owns one unit (read or pair) at
-// a time and advances it through the reference's state machine in ROUNDS.  A round has uniform
-// phases that all lanes execute together regardless of where their read is:
-//   refill -> k-mer lookup (hash + probe) -> contig record load -> target-list op ->
-//   state transition (walk-loop heads with the SIFT4 edge check) -> class tally.
-// A lane whose read needs no lookup this round simply sits the phase out; a lane that
-// finishes its unit takes the next one from the warp's queue in the next round, so lanes do
-// not wait for the slowest read of a warp.
+// a time and advances it through the reference's per-read state machine.  The state machine
+// is cut at its expensive operations into PHASES; each lane records which phase it needs
+// next, and in every iteration the warp VOTES and executes the phase most lanes are waiting
+// for.  Lanes that need another phase sit the iteration out; lanes that finish a unit take
+// the next one from the warp's queue.  Every heavy piece of code therefore exists once and
+// runs with many active lanes, instead of 32 lanes each in a different inlined copy.
+//
+//   P_LOAD    stage the packed read of (unit, mate) into shared memory
+//   P_LOOKUP  KMerIndex.map_kmer (hash + probe) for the pending k-mer; misses are resolved
+//             here (_find_first_kmer keeps rolling, walk fallbacks)
+//   P_LIST    contig record + map_contig / _filter_on_contig for the hit
+//   P_WALK    one head of the left/right contig-walk loops, or the final edge check: jump to
+//             the contig edge, 8-base SIFT4 check (direction-generic), next junction k-mer
+//   P_TALLY   map_read_pair mate intersection, FLD, class dictionary
+enum : int { P_IDLE = 0, P_LOAD, P_LOOKUP, P_LIST, P_WALK, P_TALLY, P_EXIT };
+// who asked for the pending lookup / list operation
 enum : int {
-    S_IDLE = 0,     // needs a new unit
-    S_LOAD,         // needs its (next) read staged into shared memory
-    S_FIND,         // _find_first_kmer scan: lookup of the k-mer at `pos` pending
-    S_LEFT_J,       // left walk: junction k-mer lookup pending (_mapper.pyx:247-251)
-    S_LEFT_F,       // left walk: fallback lookup pending (:257-261)
-    S_RIGHT_C,      // right walk start: contig record of the cached anchor pending (:283-290)
-    S_RIGHT_J,      // right walk: junction k-mer lookup pending (:309-313)
-    S_EXIT          // no more work
+    C_FIND = 0,  // _find_first_kmer scan (_mapper.pyx:199-216)
+    C_LEFT_J,    // left walk junction (:247-251)
+    C_LEFT_F,    // left walk fallback (:257-261)
+    C_RIGHT_C,   // right walk start: contig of the cached first hit (:283-290)
+    C_RIGHT_J    // right walk junction (:309-313)
 };
 
-enum : int { ACT_NONE = 0, ACT_LEFT_HEAD, ACT_AFTER_LEFT, ACT_RIGHT_HEAD, ACT_AFTER_ATTEMPT, ACT_READ_DONE };
-
 constexpr int WARP_QUEUE = 128;  // units a warp takes from the global counter at a time
+
+struct Lane {
+    int st, ctx, dir;
+    long long unit;
+    int mate, attempt, pos, move;
+    bool forward;
+    uint64_t kmer;
+    Coord hit, anchor0;
+    Span sp;
+    List l;
+    // mate 1 results while mate 2 is mapped
+    int m1_begin, m1_len;
+    Coord m1_anchor;
+    List m1;
+};
+
+struct LaneMem {
+    ReadView rv;
+    int32_t *list0, *list1;
+    uint64_t *ctg;  // stash of the current contig: [0]=first_kmer [1]=last_kmer [2]=seq_offset, stride 32
+    int paired;
+};
+
+__device__ __forceinline__ void read_done(Lane &L, const LaneMem &M)
+{
+    if (M.paired && L.mate == 0) {
+        L.m1_begin = L.sp.begin;
+        L.m1_anchor = L.sp.anchor;
+        L.m1_len = M.rv.len;
+        L.m1 = L.l;
+        L.mate = 1;
+        L.st = P_LOAD;
+    } else {
+        L.st = P_TALLY;
+    }
+}
+
+__device__ __forceinline__ void after_attempt(Lane &L, const LaneMem &M)  // map_read :177-193
+{
+    if (L.l.n != 0 || L.attempt == 1) {
+        read_done(L, M);
+        return;
+    }
+    L.attempt = 1;
+    L.sp.anchor = coord_invalid();
+    L.sp.begin += K;
+    if (L.sp.begin + K > M.rv.len) L.sp.begin = M.rv.len - K;
+    L.sp.end = L.sp.begin;
+    L.pos = L.sp.begin;
+    L.kmer = M.rv.kmer(L.pos);
+    L.l.p = L.mate ? M.list1 : M.list0;
+    L.l.stride = 32;
+    L.ctx = C_FIND;
+    L.st = P_LOOKUP;
+}
+
+__device__ __forceinline__ void after_left(Lane &L, const LaneMem &M)  // map_read :174-176
+{
+    if (L.l.n != 0 && L.sp.end < M.rv.len - K) {
+        L.ctx = C_RIGHT_C;
+        L.st = P_LIST;
+    } else {
+        after_attempt(L, M);
+    }
+}
+
+// _filter_targets_to_left :250-263 when the junction lookup or its filter failed
+__device__ __forceinline__ void left_junction_failed(Lane &L, const LaneMem &M)
+{
+    if (L.ctx == C_LEFT_J) {
+        if (L.sp.begin < K) {
+            L.sp.begin = 0;
+            after_left(L, M);
+        } else {
+            L.sp.begin -= K;
+            L.kmer = M.rv.kmer(L.sp.begin);
+            L.ctx = C_LEFT_F;
+            L.st = P_LOOKUP;
+        }
+    } else {  // C_LEFT_F
+        L.l.n = 0;
+        after_left(L, M);
+    }
+}
+
+// 9 read bases starting at base s >= 0, first base in bits 17:16
+__device__ __forceinline__ uint32_t extract_codes9(const ReadView &rv, int s)
+{
+    const int k = s >> 5, sh = s & 31;
+    uint64_t x = rv.word(k) << (2 * sh);
+    if (sh > 23) x |= rv.word(k + 1) >> (64 - 2 * sh);  // k + 1 <= code_words: in bounds
+    return (uint32_t)(x >> 46);
+}
+
+// wildcard bits of 9 read bases starting at base s >= 0: bit i <-> base s + i
+__device__ __forceinline__ uint32_t extract_wild9(const ReadView &rv, int s, int total_words)
+{
+    const int k = rv.code_words + (s >> 6), b = s & 63;
+    uint64_t x = rv.word(k) >> b;
+    if (b > 55 && k + 1 < total_words) x |= rv.word(k + 1) << (64 - b);
+    return (uint32_t)x & 0x1FFu;
+}
+
+// sift4_align_left(window, read, qoff) for dir == 0, sift4_align_right for dir == 1 (sift4.cuh)
+__device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView &rv, int qoff, int dir, int total_words)
+{
+    int s = qoff - (1 - dir);  // the left routine may look one base left of its window (:421)
+    const int pad = s < 0 ? 1 : 0;
+    s += pad;
+    uint32_t codes = extract_codes9(rv, s) >> (2 * pad);
+    uint32_t wild = (extract_wild9(rv, s, total_words) << pad) & 0x1FFu;
+    if (dir) {
+        wild = reverse_bits(wild, 9);
+    } else {
+        codes = reverse_pairs(codes, 9);
+        ref16 = reverse_pairs(ref16, 8);
+    }
+    return sift4_unified(ref16, codes, wild, 1 - dir, dir ? rv.len - qoff : qoff + 8);
+}
 
 __global__ void __launch_bounds__(BLOCK_THREADS, 3)
 map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *sm_reads = reinterpret_cast<uint64_t *>(smem_raw);                       // [WARPS][words][32]
-    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_reads + WARPS * a.words * 32);  // [WARPS][2][CAP][32]
+    uint64_t *sm_reads = reinterpret_cast<uint64_t *>(smem_raw);               // [WARPS][words][32]
+    uint64_t *sm_ctg = sm_reads + WARPS * a.words * 32;                        // [WARPS][3][32]
+    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + WARPS * 3 * 32);  // [WARPS][2][CAP][32]
     uint32_t *sm_fld = reinterpret_cast<uint32_t *>(sm_lists + WARPS * 2 * LIST_CAP * 32);
 
     for (int i = threadIdx.x; i < FLD_BINS; i += BLOCK_THREADS) sm_fld[i] = 0;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    LaneMem M;
+    M.rv = ReadView{sm_reads + (size_t)warp * a.words * 32 + lane, 0, a.code_words};
+    M.ctg = sm_ctg + (size_t)warp * 3 * 32 + lane;
+    M.list0 = sm_lists + (size_t)warp * 2 * LIST_CAP * 32 + lane;
+    M.list1 = M.list0 + LIST_CAP * 32;
+    M.paired = a.paired;
     uint64_t *my_words = sm_reads + (size_t)warp * a.words * 32 + lane;
-    int32_t *my_list0 = sm_lists + (size_t)warp * 2 * LIST_CAP * 32 + lane;
-    int32_t *my_list1 = my_list0 + LIST_CAP * 32;
-    Ctx cx{ix, a, my_list0, dict.status};
+    Ctx cx{ix, a, M.list0, dict.status};
 
-    // warp-level unit queue
-    long long q_next = 0, q_end = 0;
+    long long q_next = 0, q_end = 0;  // warp-level unit queue
     bool q_dry = false;
 
-    // per-lane state
-    int state = S_IDLE;
-    long long unit = -1;
-    int mate = 0;
-    ReadView rv{my_words, 0, a.code_words};
-    Span sp{0, 0, coord_invalid()};
-    Coord anchor0 = coord_invalid();
-    List l{my_list0, 32, 0};
-    int attempt = 0, pos = 0, move = 0;
-    bool forward = true;
-    uint64_t kmer = 0;
-    // mate 1 results while mate 2 is mapped
-    int m1_begin = 0, m1_len = 0;
-    Coord m1_anchor = coord_invalid();
-    List m1{my_list0, 32, 0};
+    Lane L;
+    L.st = P_IDLE;
+    L.ctx = C_FIND;
+    L.dir = 0;
+    L.unit = -1;
+    L.mate = 0;
+    L.attempt = 0;
+    L.pos = 0;
+    L.move = 0;
+    L.forward = true;
+    L.kmer = 0;
+    L.hit = coord_invalid();
+    L.anchor0 = coord_invalid();
+    L.sp = Span{0, 0, coord_invalid()};
+    L.l = List{M.list0, 32, 0};
+    L.m1_begin = 0;
+    L.m1_len = 0;
+    L.m1_anchor = coord_invalid();
+    L.m1 = List{M.list0, 32, 0};
 
     for (;;) {
-        // ---- refill: hand units to idle lanes ---------------------------------------
+        // ---- refill: hand units to idle lanes -----------------------------------------
         {
-            const unsigned idle = __ballot_sync(0xffffffffu, state == S_IDLE);
+            const unsigned idle = __ballot_sync(0xffffffffu, L.st == P_IDLE);
             if (idle) {
-                const int n_idle = __popc(idle);
                 if (q_next >= q_end && !q_dry) {
                     long long base = 0;
                     if (lane == 0) base = (long long)atomicAdd(&a.cursors[0], (unsigned long long)WARP_QUEUE);
@@ -537,296 +579,231 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                     if (q_next >= q_end) q_dry = true;
                 }
                 const int rank = __popc(idle & ((1u << lane) - 1u));
-                if (state == S_IDLE) {
+                if (L.st == P_IDLE) {
                     if (q_next + rank < q_end) {
-                        unit = q_next + rank;
-                        mate = 0;
-                        state = S_LOAD;
+                        L.unit = q_next + rank;
+                        L.mate = 0;
+                        L.st = P_LOAD;
                     } else if (q_dry) {
-                        state = S_EXIT;
+                        L.st = P_EXIT;
                     }
                 }
-                q_next = min(q_next + (long long)n_idle, q_end);
-            }
-            if (__all_sync(0xffffffffu, state == S_EXIT)) break;
-        }
-
-        // ---- stage the packed read of (unit, mate) -------------------------------------
-        if (state == S_LOAD) {
-            const long long read_idx = a.paired ? 2 * unit + mate : unit;
-            const uint64_t *src = a.packed + read_idx * (long long)a.words;
-            for (int k = 0; k < a.words; ++k) my_words[k * 32] = __ldg(src + k);
-            int len = a.lens ? __ldg(a.lens + read_idx) : a.fixed_len;
-            const int max_len = a.code_words * 32;
-            if (len > max_len) len = max_len;
-            rv.len = len;
-            sp.begin = 0;
-            sp.end = 0;
-            sp.anchor = coord_invalid();
-            l.p = mate ? my_list1 : my_list0;
-            l.stride = 32;
-            l.n = 0;
-            attempt = 0;
-            pos = 0;
-            if (len >= K) {
-                kmer = rv.kmer(0);
-                state = S_FIND;
-            } else {
-                atomicOr(dict.status, ST_SHORT_READ);
-                kmer = 0;
-                state = S_FIND;
-                pos = -1;  // handled below: the read is reported unaligned without any lookup
+                q_next = min(q_next + (long long)__popc(idle), q_end);
             }
         }
 
-        // ---- phase A: k-mer lookup (KMerIndex.map_kmer) ----------------------------------
-        const bool short_read = state == S_FIND && pos < 0;
-        const bool want_lookup = (state == S_FIND || state == S_LEFT_J || state == S_LEFT_F || state == S_RIGHT_J)
-                                 && !short_read;
-        Coord hit = coord_invalid();
-        if (want_lookup) hit = map_kmer(ix, kmer);
-
-        // ---- phase B: contig record ----------------------------------------------------
-        const bool want_contig = (want_lookup && hit.offset >= 0) || state == S_RIGHT_C;
-        Contig c{};
-        if (want_contig) {
-            const int32_t e = state == S_RIGHT_C ? anchor0.entry : hit.entry;
-            c = load_contig(ix, e >= 0 ? e : ~e);
+        // ---- vote -----------------------------------------------------------------------
+        const int n_load = __popc(__ballot_sync(0xffffffffu, L.st == P_LOAD));
+        const int n_lookup = __popc(__ballot_sync(0xffffffffu, L.st == P_LOOKUP));
+        const int n_list = __popc(__ballot_sync(0xffffffffu, L.st == P_LIST));
+        const int n_walk = __popc(__ballot_sync(0xffffffffu, L.st == P_WALK));
+        const int n_tally = __popc(__ballot_sync(0xffffffffu, L.st == P_TALLY));
+        int phase = P_LOAD, best = n_load;
+        if (n_lookup > best) { phase = P_LOOKUP; best = n_lookup; }
+        if (n_list > best) { phase = P_LIST; best = n_list; }
+        if (n_walk > best) { phase = P_WALK; best = n_walk; }
+        if (n_tally > best) { phase = P_TALLY; best = n_tally; }
+        if (best == 0) {
+            if (__all_sync(0xffffffffu, L.st == P_EXIT)) break;
+            continue;  // only idle lanes: refill again
         }
+        const bool mine = L.st == phase;
 
-        // ---- phase C1: target-list operation ---------------------------------------------
-        bool ok = false;
-        if (want_lookup) {
-            sp.anchor = hit;
-            if (hit.offset >= 0) {
-                if (state == S_FIND) {
-                    map_contig(cx, c, hit, l, mate ? my_list1 : my_list0);
-                    ok = l.n != 0;
-                } else {
-                    ok = filter_on_contig(cx, c, hit, l);
+        if (phase == P_LOAD) {
+            if (mine) {
+                const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
+                const uint64_t *src = a.packed + read_idx * (long long)a.words;
+                for (int k = 0; k < a.words; ++k) my_words[k * 32] = __ldg(src + k);
+                int len = a.lens ? __ldg(a.lens + read_idx) : a.fixed_len;
+                const int max_len = a.code_words * 32;
+                if (len > max_len) len = max_len;
+                M.rv.len = len;
+                L.sp = Span{0, 0, coord_invalid()};
+                L.l = List{L.mate ? M.list1 : M.list0, 32, 0};
+                L.attempt = 0;
+                L.pos = 0;
+                if (len >= K) {
+                    L.kmer = M.rv.kmer(0);
+                    L.ctx = C_FIND;
+                    L.st = P_LOOKUP;
+                } else {  // undefined in the reference; reported unaligned and flagged
+                    atomicOr(dict.status, ST_SHORT_READ);
+                    read_done(L, M);
                 }
             }
-        }
-
-        // ---- phase C2: transitions ---------------------------------------------------------
-        int act = ACT_NONE;
-        switch (state) {
-        case S_FIND:
-            if (short_read) {
-                act = ACT_READ_DONE;
-            } else if (hit.offset < 0) {
-                // _find_first_kmer keeps rolling (:208-212); exhausted => targets stay empty and
-                // map_read returns at :170-171 / :186-187 (no retry after a failed scan)
-                pos += 1;
-                if (pos + K <= rv.len) kmer = ((kmer << 2) | rv.code(pos + K - 1)) & KMER_MASK;
-                else act = ACT_READ_DONE;
-            } else {
-                sp.begin = pos;
-                sp.end = pos;
-                anchor0 = hit;
-                if (!ok) {
-                    act = ACT_READ_DONE;
-                } else if (sp.begin > 0) {
-                    forward = hit.entry >= 0;
-                    move = forward ? hit.offset : c.length - hit.offset - K;
-                    act = ACT_LEFT_HEAD;
+        } else if (phase == P_LOOKUP) {
+            if (mine) {
+                const Coord hit = map_kmer(ix, L.kmer);
+                L.hit = hit;
+                L.sp.anchor = hit;
+                if (hit.offset >= 0) {
+                    L.st = P_LIST;
+                } else if (L.ctx == C_FIND) {
+                    // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
+                    // targets empty and map_read returns (:170-171, :186-187)
+                    L.pos += 1;
+                    if (L.pos + K <= M.rv.len) L.kmer = ((L.kmer << 2) | M.rv.code(L.pos + K - 1)) & KMER_MASK;
+                    else read_done(L, M);
+                } else if (L.ctx == C_RIGHT_J) {
+                    L.l.n = 0;  // :312-315
+                    after_attempt(L, M);
                 } else {
-                    act = ACT_AFTER_LEFT;
+                    left_junction_failed(L, M);
                 }
             }
-            break;
-        case S_LEFT_J:
-            if (ok) {
-                forward = hit.entry >= 0;
-                move = forward ? hit.offset : c.length - hit.offset - K;
-                act = ACT_LEFT_HEAD;
-            } else if (sp.begin < K) {
-                sp.begin = 0;  // :252-256
-                act = ACT_AFTER_LEFT;
-            } else {
-                sp.begin -= K;  // :257-259
-                kmer = rv.kmer(sp.begin);
-                state = S_LEFT_F;
-            }
-            break;
-        case S_LEFT_F:
-            if (ok) {
-                forward = hit.entry >= 0;
-                move = forward ? hit.offset : c.length - hit.offset - K;
-                act = ACT_LEFT_HEAD;
-            } else {
-                l.n = 0;  // :260-263
-                act = ACT_AFTER_LEFT;
-            }
-            break;
-        case S_RIGHT_C:
-            // :283-290 — the k-mer at `end` is the one _find_first_kmer hit; its lookup is cached
-            sp.anchor = anchor0;
-            forward = anchor0.entry >= 0;
-            move = forward ? c.length - anchor0.offset - K : anchor0.offset;
-            act = ACT_RIGHT_HEAD;
-            break;
-        case S_RIGHT_J:
-            if (ok) {
-                forward = hit.entry >= 0;
-                move = forward ? c.length - hit.offset - K : hit.offset;
-                act = ACT_RIGHT_HEAD;
-            } else {
-                l.n = 0;  // :312-315 (the block at :316-329 is unreachable)
-                act = ACT_AFTER_ATTEMPT;
-            }
-            break;
-        default:
-            break;
-        }
-
-        if (act == ACT_LEFT_HEAD) {  // loop of _filter_targets_to_left (:234-275)
-            if (sp.begin > move) {
-                sp.begin -= move;
-                sp.anchor.offset -= forward ? move : -move;
-                const int shift = sift4_align_left(edge_window(c, sp.anchor, true), rv, sp.begin);
-                if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
-                    l.n = 0;
-                    act = ACT_AFTER_LEFT;
+        } else if (phase == P_LIST) {
+            if (mine) {
+                const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.hit;
+                const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
+                M.ctg[0] = c.first_kmer;
+                M.ctg[32] = c.last_kmer;
+                M.ctg[64] = (uint64_t)c.seq_offset;
+                bool ok = true;
+                if (L.ctx == C_FIND) {
+                    map_contig(cx, c, at, L.l, L.mate ? M.list1 : M.list0);
+                    L.sp.begin = L.pos;
+                    L.sp.end = L.pos;
+                    L.anchor0 = at;
+                    ok = L.l.n != 0;
+                } else if (L.ctx != C_RIGHT_C) {
+                    ok = filter_on_contig(cx, c, at, L.l);
                 } else {
-                    sp.begin -= shift + 1;
-                    if (sp.begin < 0) {
-                        sp.begin = 0;
-                        act = ACT_AFTER_LEFT;
+                    L.sp.anchor = at;  // :283-284 — same k-mer as the scan hit, lookup cached
+                }
+                L.forward = at.entry >= 0;
+                const int to_start = L.forward ? at.offset : c.length - at.offset - K;
+                const int to_end = L.forward ? c.length - at.offset - K : at.offset;
+                if (L.ctx == C_FIND) {
+                    if (!ok) {
+                        read_done(L, M);  // `if is_empty(targets): return span`
+                    } else if (L.sp.begin > 0) {
+                        L.move = to_start;
+                        L.dir = 0;
+                        L.st = P_WALK;
                     } else {
-                        kmer = (tail_kmer(c, sp.anchor) >> 2) | ((uint64_t)rv.code(sp.begin) << (2 * K - 2));
-                        state = S_LEFT_J;
-                        act = ACT_NONE;
+                        after_left(L, M);
                     }
-                }
-            } else {
-                sp.anchor.offset -= forward ? sp.begin : -sp.begin;
-                const int shift = sift4_align_left(contig_window(ix, c, sp.anchor, true), rv, 0);
-                if (shift == INVALID_SHIFT) l.n = 0;
-                act = ACT_AFTER_LEFT;
-            }
-        }
-        if (act == ACT_AFTER_LEFT) {  // map_read :174-176 / :190-192
-            if (l.n != 0 && sp.end < rv.len - K) {
-                state = S_RIGHT_C;
-                act = ACT_NONE;
-            } else {
-                act = ACT_AFTER_ATTEMPT;
-            }
-        }
-        if (act == ACT_RIGHT_HEAD) {  // loop of _filter_targets_to_right (:293-343)
-            if (rv.len - sp.end - K > move) {
-                sp.end += move;
-                sp.anchor.offset += forward ? move : -move;
-                const int shift = sift4_align_right(edge_window(c, sp.anchor, false), rv,
-                                                    sp.end + K - ALIGN_LENGTH);
-                if (shift == INVALID_SHIFT || shift + 1 + move <= 0) {
-                    l.n = 0;
-                    act = ACT_AFTER_ATTEMPT;
-                } else {
-                    sp.end += shift + 1;
-                    if (sp.end + K > rv.len) {
-                        sp.end = rv.len - K;
-                        act = ACT_AFTER_ATTEMPT;
+                } else if (L.ctx == C_RIGHT_C || L.ctx == C_RIGHT_J) {
+                    if (ok) {
+                        L.move = to_end;
+                        L.dir = 1;
+                        L.st = P_WALK;
                     } else {
-                        kmer = ((tail_kmer(c, sp.anchor) << 2) | rv.code(sp.end + K - 1)) & KMER_MASK;
-                        state = S_RIGHT_J;
-                        act = ACT_NONE;
+                        L.l.n = 0;  // :312-315
+                        after_attempt(L, M);
                     }
+                } else if (ok) {
+                    L.move = to_start;
+                    L.dir = 0;
+                    L.st = P_WALK;
+                } else {
+                    left_junction_failed(L, M);
                 }
-            } else {
-                if (forward) sp.anchor.offset += rv.len - sp.end - K;
-                else sp.anchor.offset -= rv.len - sp.end - K;
-                const int shift = sift4_align_right(contig_window(ix, c, sp.anchor, false), rv,
-                                                    rv.len - ALIGN_LENGTH);
-                if (shift == INVALID_SHIFT) l.n = 0;
-                act = ACT_AFTER_ATTEMPT;
             }
-        }
-        if (act == ACT_AFTER_ATTEMPT) {  // map_read :177-193
-            if (l.n != 0 || attempt == 1) {
-                act = ACT_READ_DONE;
-            } else {
-                attempt = 1;
-                sp.anchor = coord_invalid();
-                sp.begin += K;
-                if (sp.begin + K > rv.len) sp.begin = rv.len - K;
-                sp.end = sp.begin;
-                pos = sp.begin;
-                kmer = rv.kmer(pos);
-                l.p = mate ? my_list1 : my_list0;
-                l.stride = 32;
-                state = S_FIND;
-                act = ACT_NONE;
+        } else if (phase == P_WALK) {
+            if (mine) {
+                // heads of the loops of _filter_targets_to_left (:234-275) and _to_right (:293-343)
+                Contig c;
+                c.first_kmer = M.ctg[0];
+                c.last_kmer = M.ctg[32];
+                c.seq_offset = (int64_t)M.ctg[64];
+                const int dir = L.dir;
+                int rem = dir ? M.rv.len - L.sp.end - K : L.sp.begin;  // bases left towards the read end
+                const bool in_loop = rem > L.move;
+                const int step = in_loop ? L.move : rem;
+                const int delta = L.forward ? step : -step;
+                L.sp.anchor.offset += dir ? delta : -delta;
+                uint32_t ref16;
+                int qoff;
+                if (in_loop) {
+                    rem -= L.move;
+                    ref16 = edge_window(c, L.sp.anchor, dir == 0);
+                    qoff = dir ? M.rv.len - rem - ALIGN_LENGTH : rem;
+                } else {
+                    ref16 = contig_window(ix, c, L.sp.anchor, dir == 0);
+                    qoff = dir ? M.rv.len - ALIGN_LENGTH : 0;
+                }
+                const int shift = sift4_edge(ref16, M.rv, qoff, dir, a.words);
+                bool finished = true;  // this direction is over (success or failure)
+                if (in_loop) {
+                    if (shift == INVALID_SHIFT || shift + 1 + L.move <= 0) {
+                        L.l.n = 0;
+                    } else {
+                        rem -= shift + 1;
+                        if (rem < 0) rem = 0;  // :244-246 / :306-308, list intact
+                        else finished = false;
+                    }
+                    if (L.l.n != 0) {
+                        if (dir) L.sp.end = M.rv.len - rem - K;
+                        else L.sp.begin = rem;
+                    } else if (!dir) {
+                        L.sp.begin = rem;  // the failed left walk leaves begin where it stopped (:235,241-242)
+                    } else {
+                        L.sp.end = M.rv.len - rem - K;
+                    }
+                    if (!finished) {
+                        const uint64_t tail = tail_kmer(c, L.sp.anchor);
+                        if (dir) L.kmer = ((tail << 2) | M.rv.code(L.sp.end + K - 1)) & KMER_MASK;
+                        else L.kmer = (tail >> 2) | ((uint64_t)M.rv.code(L.sp.begin) << (2 * K - 2));
+                        L.ctx = dir ? C_RIGHT_J : C_LEFT_J;
+                        L.st = P_LOOKUP;
+                    }
+                } else if (shift == INVALID_SHIFT) {
+                    L.l.n = 0;
+                }
+                if (finished) {
+                    if (dir) after_attempt(L, M);
+                    else after_left(L, M);
+                }
             }
-        }
-
-        // ---- read finished: next mate, or unit finished -----------------------------------
-        long long slot = -1;
-        bool unit_done = false;
-        if (act == ACT_READ_DONE) {
-            if (a.paired && mate == 0) {
-                m1_begin = sp.begin;
-                m1_anchor = sp.anchor;
-                m1_len = rv.len;
-                m1 = l;
-                mate = 1;
-                state = S_LOAD;
-            } else {
-                unit_done = true;
+        } else {  // P_TALLY
+            long long slot = -1;
+            if (mine) {
                 int length;
                 if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
-                    int begin1 = m1_begin, end1;
-                    if (!intersect(m1, l)) {
-                        m1.n = 0;
+                    int begin1 = L.m1_begin, end1;
+                    if (!intersect(L.m1, L.l)) {
+                        L.m1.n = 0;
                         begin1 = 0;
                         end1 = -K;
-                    } else if (m1_anchor.entry != ~sp.anchor.entry) {
+                    } else if (L.m1_anchor.entry != ~L.sp.anchor.entry) {
                         begin1 = 0;
                         end1 = -K;
                     } else {
-                        end1 = m1_len - K;
-                        int interval = sp.anchor.offset - m1_anchor.offset;
-                        if (m1_anchor.entry < 0) interval = -interval;
-                        end1 += interval + (rv.len - K) - sp.begin;
+                        end1 = L.m1_len - K;
+                        int interval = L.sp.anchor.offset - L.m1_anchor.offset;
+                        if (L.m1_anchor.entry < 0) interval = -interval;
+                        end1 += interval + (M.rv.len - K) - L.sp.begin;
                     }
                     length = end1 - begin1 + K;
-                    l = m1;
+                    L.l = L.m1;
                 } else {
-                    length = sp.end - sp.begin + K;
+                    length = L.sp.end - L.sp.begin + K;
                 }
-                if (a.out_length) a.out_length[unit] = length;
+                if (a.out_length) a.out_length[L.unit] = length;
                 if (length > 0) {  // _mapper.pyx:90-94
                     if (length >= FLD_BINS) length = FLD_BINS - 1;
                     atomicAdd(&sm_fld[length], 1u);
                 }
-                state = S_IDLE;
-            }
-        }
-
-        // ---- phase D: class tally (mapper.py:60-75), uniform over lanes that finished a unit ---
-        if (__any_sync(0xffffffffu, unit_done)) {
-            if (unit_done) {
-                if (l.n > 0) {
-                    const ulonglong2 key = tuple_key(l.p, l.stride, l.n, true);
-                    slot = dict_find_or_insert(dict, key, l.p, l.stride, l.n, true);
+                if (L.l.n > 0) {
+                    const ulonglong2 key = tuple_key(L.l.p, L.l.stride, L.l.n, true);
+                    slot = dict_find_or_insert(dict, key, L.l.p, L.l.stride, L.l.n, true);
                 }
-                if (a.out_class) a.out_class[unit] = (int32_t)slot;
+                if (a.out_class) a.out_class[L.unit] = (int32_t)slot;
+                if (slot >= 0) {
+                    const unsigned long long g = (unsigned long long)(a.first_unit + L.unit);
+                    if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
+                        atomicMin(&dict.first[slot], g);
+                }
+                L.st = P_IDLE;
             }
             __syncwarp();
-            // one atomic per distinct class per warp
+            // one count atomic per distinct class per warp (mapper.py:60-75)
             const unsigned same = __match_any_sync(0xffffffffu, slot);
-            const int leader = __ffs(same) - 1;
-            if (slot >= 0 && lane == leader) {
+            if (slot >= 0 && lane == __ffs(same) - 1)
                 atomicAdd(&dict.counts[slot], (unsigned long long)__popc(same));
-            }
-            if (slot >= 0) {
-                const unsigned long long g = (unsigned long long)(a.first_unit + unit);
-                if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
-                    atomicMin(&dict.first[slot], g);
-            }
-            const unsigned done = __ballot_sync(0xffffffffu, unit_done);
-            const unsigned mapped = __ballot_sync(0xffffffffu, unit_done && slot >= 0);
+            const unsigned done = __ballot_sync(0xffffffffu, mine);
+            const unsigned mapped = __ballot_sync(0xffffffffu, mine && slot >= 0);
             if (lane == 0) {
                 const int n_al = __popc(mapped);
                 const int n_un = __popc(done) - n_al;
@@ -834,6 +811,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
             }
         }
+        __syncwarp();
     }
 
     __syncthreads();
@@ -1029,7 +1007,7 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
 
 static size_t map_smem_bytes(int words)
 {
-    return sizeof(uint64_t) * WARPS * (size_t)words * 32 + sizeof(int32_t) * WARPS * 2 * LIST_CAP * 32
+    return sizeof(uint64_t) * WARPS * ((size_t)words + 3) * 32 + sizeof(int32_t) * WARPS * 2 * LIST_CAP * 32
            + sizeof(uint32_t) * FLD_BINS;
 }
 
