@@ -4,12 +4,13 @@ There is no CPU fallback: if the CUDA library is missing or no device is visible
 compute entry points raise.  Nothing here imports ``oracle/``.
 """
 import ctypes
+import os
 import pathlib
 
 import numpy
 
 HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = HERE / 'libseekmer_b200.so'
+LIB_PATH = pathlib.Path(os.environ.get('SEEKMER_B200_LIB', HERE / 'libseekmer_b200.so'))
 
 K = 25
 MAX_FRAGMENT_LENGTH = 2000

@@ -23,16 +23,16 @@ def stale():
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, extra_flags=(), output=None):
+    if output is None and not force and not stale():
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
     objs = []
     procs = []
     (HERE / '_obj').mkdir(exist_ok=True)
     for src in sources():
-        obj = HERE / '_obj' / (src.stem + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-Xptxas', '-v', '-c', str(src), '-o', str(obj)]
+        obj = HERE / '_obj' / (src.stem + ('' if output is None else '.' + pathlib.Path(output).stem) + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-Xptxas', '-v', '-c', str(src), '-o', str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     for src, p in procs:
@@ -42,11 +42,12 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed for %s' % src.name)
         if verbose:
             sys.stderr.write(out)
-    tmp = LIB.with_suffix('.tmp%d.so' % os.getpid())
+    target = LIB if output is None else pathlib.Path(output)
+    tmp = target.with_suffix('.tmp%d.so' % os.getpid())
     subprocess.run([nvcc, '-shared', '-o', str(tmp)] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'],
                    check=True)
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, target)
+    return target
 
 
 if __name__ == '__main__':

@@ -293,8 +293,10 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         STEP_CUDA(cudaMemcpyAsync(&cnt, d_scalars, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         STEP_CUDA(cudaStreamSynchronize(st));
         ix->n_kmers = (int64_t)cnt;
+        // load factor <= 0.25: an unsuccessful linear-probing search then inspects ~1.4 slots
+        // on average (2.4 at 0.5); a warp waits for its slowest probe, and HBM is plentiful
         int64_t slots = 1024;
-        while (slots < 2 * ix->n_kmers) slots <<= 1;  // load factor <= 0.5
+        while (slots < 4 * ix->n_kmers) slots <<= 1;
         ix->n_slots = slots;
         STEP_CUDA(cudaMalloc(&ix->table, sizeof(Slot) * (size_t)slots));
         STEP_CUDA(cudaMemsetAsync(ix->table, 0xFF, sizeof(Slot) * (size_t)slots, st));

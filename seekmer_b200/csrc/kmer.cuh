@@ -98,11 +98,9 @@ __host__ __device__ __forceinline__ uint64_t reference_hash(uint64_t m)
 
 __device__ __forceinline__ Slot load_slot(const Slot *p)
 {
-    // one 16-byte, read-only, L1-bypassing load: slots are touched once per probe
-    ulonglong2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
-                 : "=l"(v.x), "=l"(v.y)
-                 : "l"(p));
+    // one 16-byte read-only load, allocating in L1: when a probe has to continue, the next
+    // slot is in the same 128-byte line 7 times out of 8
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
     Slot s;
     s.key = v.x;
     s.entry = (int32_t)(uint32_t)v.y;
@@ -110,21 +108,39 @@ __device__ __forceinline__ Slot load_slot(const Slot *p)
     return s;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Home slot of a k-mer in the device table.
+__device__ __forceinline__ uint32_t home_slot(const DevIndex &ix, uint64_t kmer)
+{
+    const uint64_t rc = revcomp(kmer);
+    return (uint32_t)(table_hash(kmer < rc ? kmer : rc) & ix.slot_mask);
+}
+
 // KMerIndex.map_kmer (_common.pyx:54-97) on the canonical-key table: hit on the
 // canonical key; strand of the query relative to the canonical form decides whether
 // the stored coordinate is returned as is or reverse-complemented (~entry).
-__device__ __forceinline__ Coord map_kmer(const DevIndex &ix, uint64_t kmer)
+// `slot` = home_slot(ix, kmer), computed (and prefetched) when the k-mer was produced.
+__device__ __forceinline__ Coord map_kmer_at(const DevIndex &ix, uint64_t kmer, uint32_t slot)
 {
     const uint64_t rc = revcomp(kmer);
     const bool fwd = kmer < rc;
     const uint64_t canon = fwd ? kmer : rc;
-    uint64_t i = table_hash(canon) & ix.slot_mask;
+    uint64_t i = slot;
     for (;;) {
         const Slot s = load_slot(ix.table + i);
         if (s.key == canon) return Coord{fwd ? s.entry : ~s.entry, s.offset};
         if (s.key == EMPTY_KEY) return coord_invalid();
         i = (i + 1) & ix.slot_mask;
     }
+}
+
+__device__ __forceinline__ Coord map_kmer(const DevIndex &ix, uint64_t kmer)
+{
+    return map_kmer_at(ix, kmer, home_slot(ix, kmer));
 }
 
 struct Contig {

@@ -24,7 +24,13 @@ namespace skm {
 
 constexpr int BLOCK_THREADS = 256;
 constexpr int WARPS = BLOCK_THREADS / 32;
-constexpr int LIST_CAP = 16;       // per-read target list entries kept in shared memory
+#ifndef SKM_LIST_CAP
+#define SKM_LIST_CAP 16
+#endif
+#ifndef SKM_MIN_BLOCKS
+#define SKM_MIN_BLOCKS 3
+#endif
+constexpr int LIST_CAP = SKM_LIST_CAP;  // per-read target list entries kept in shared memory
 constexpr int ALIGN_LENGTH = 8;    // _mapper.pyx:22
 constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
 constexpr int FLD_BINS = SKM_MAX_FRAGMENT_LENGTH;
@@ -407,6 +413,7 @@ struct Lane {
     int mate, attempt, pos, move;
     bool forward;
     uint64_t kmer;
+    uint32_t slot;  // home slot of `kmer`, prefetched into L2 when the k-mer was produced
     Coord hit, anchor0;
     Span sp;
     List l;
@@ -417,11 +424,21 @@ struct Lane {
 };
 
 struct LaneMem {
+    const DevIndex *ix;
     ReadView rv;
     int32_t *list0, *list1;
     uint64_t *ctg;  // stash of the current contig: [0]=first_kmer [1]=last_kmer [2]=seq_offset, stride 32
     int paired;
 };
+
+// Record the next k-mer to look up and start pulling its home slot towards L2: the probe
+// phase that consumes it runs one or more warp iterations later.
+__device__ __forceinline__ void want_kmer(Lane &L, const LaneMem &M, uint64_t kmer)
+{
+    L.kmer = kmer;
+    L.slot = home_slot(*M.ix, kmer);
+    prefetch_l2(M.ix->table + L.slot);
+}
 
 __device__ __forceinline__ void read_done(Lane &L, const LaneMem &M)
 {
@@ -449,7 +466,7 @@ __device__ __forceinline__ void after_attempt(Lane &L, const LaneMem &M)  // map
     if (L.sp.begin + K > M.rv.len) L.sp.begin = M.rv.len - K;
     L.sp.end = L.sp.begin;
     L.pos = L.sp.begin;
-    L.kmer = M.rv.kmer(L.pos);
+    want_kmer(L, M, M.rv.kmer(L.pos));
     L.l.p = L.mate ? M.list1 : M.list0;
     L.l.stride = 32;
     L.ctx = C_FIND;
@@ -459,6 +476,7 @@ __device__ __forceinline__ void after_attempt(Lane &L, const LaneMem &M)  // map
 __device__ __forceinline__ void after_left(Lane &L, const LaneMem &M)  // map_read :174-176
 {
     if (L.l.n != 0 && L.sp.end < M.rv.len - K) {
+        prefetch_l2(M.ix->contigs + (L.anchor0.entry >= 0 ? L.anchor0.entry : ~L.anchor0.entry));
         L.ctx = C_RIGHT_C;
         L.st = P_LIST;
     } else {
@@ -475,7 +493,7 @@ __device__ __forceinline__ void left_junction_failed(Lane &L, const LaneMem &M)
             after_left(L, M);
         } else {
             L.sp.begin -= K;
-            L.kmer = M.rv.kmer(L.sp.begin);
+            want_kmer(L, M, M.rv.kmer(L.sp.begin));
             L.ctx = C_LEFT_F;
             L.st = P_LOOKUP;
         }
@@ -520,7 +538,7 @@ __device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView &rv, in
     return sift4_unified(ref16, codes, wild, 1 - dir, dir ? rv.len - qoff : qoff + 8);
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS, 3)
+__global__ void __launch_bounds__(BLOCK_THREADS, SKM_MIN_BLOCKS)
 map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -534,6 +552,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     LaneMem M;
+    M.ix = &ix;
     M.rv = ReadView{sm_reads + (size_t)warp * a.words * 32 + lane, 0, a.code_words};
     M.ctg = sm_ctg + (size_t)warp * 3 * 32 + lane;
     M.list0 = sm_lists + (size_t)warp * 2 * LIST_CAP * 32 + lane;
@@ -556,6 +575,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
     L.move = 0;
     L.forward = true;
     L.kmer = 0;
+    L.slot = 0;
     L.hit = coord_invalid();
     L.anchor0 = coord_invalid();
     L.sp = Span{0, 0, coord_invalid()};
@@ -592,20 +612,18 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
             }
         }
 
-        // ---- vote -----------------------------------------------------------------------
-        const int n_load = __popc(__ballot_sync(0xffffffffu, L.st == P_LOAD));
-        const int n_lookup = __popc(__ballot_sync(0xffffffffu, L.st == P_LOOKUP));
-        const int n_list = __popc(__ballot_sync(0xffffffffu, L.st == P_LIST));
-        const int n_walk = __popc(__ballot_sync(0xffffffffu, L.st == P_WALK));
-        const int n_tally = __popc(__ballot_sync(0xffffffffu, L.st == P_TALLY));
-        int phase = P_LOAD, best = n_load;
-        if (n_lookup > best) { phase = P_LOOKUP; best = n_lookup; }
-        if (n_list > best) { phase = P_LIST; best = n_list; }
-        if (n_walk > best) { phase = P_WALK; best = n_walk; }
-        if (n_tally > best) { phase = P_TALLY; best = n_tally; }
-        if (best == 0) {
-            if (__all_sync(0xffffffffu, L.st == P_EXIT)) break;
-            continue;  // only idle lanes: refill again
+        // ---- vote: the phase with the most waiting lanes runs --------------------------------
+        int phase;
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, L.st);
+            const bool runnable = L.st >= P_LOAD && L.st <= P_TALLY;
+            const unsigned ballot = runnable ? ((unsigned)__popc(peers) << 3) | (unsigned)L.st : 0u;
+            const unsigned best = __reduce_max_sync(0xffffffffu, ballot);
+            if (best == 0) {
+                if (__all_sync(0xffffffffu, L.st == P_EXIT)) break;
+                continue;  // only idle lanes: refill again
+            }
+            phase = (int)(best & 7u);
         }
         const bool mine = L.st == phase;
 
@@ -623,7 +641,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 L.attempt = 0;
                 L.pos = 0;
                 if (len >= K) {
-                    L.kmer = M.rv.kmer(0);
+                    want_kmer(L, M, M.rv.kmer(0));
                     L.ctx = C_FIND;
                     L.st = P_LOOKUP;
                 } else {  // undefined in the reference; reported unaligned and flagged
@@ -633,17 +651,20 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
             }
         } else if (phase == P_LOOKUP) {
             if (mine) {
-                const Coord hit = map_kmer(ix, L.kmer);
+                const Coord hit = map_kmer_at(ix, L.kmer, L.slot);
                 L.hit = hit;
                 L.sp.anchor = hit;
                 if (hit.offset >= 0) {
+                    prefetch_l2(ix.contigs + (hit.entry >= 0 ? hit.entry : ~hit.entry));
                     L.st = P_LIST;
                 } else if (L.ctx == C_FIND) {
                     // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
                     // targets empty and map_read returns (:170-171, :186-187)
                     L.pos += 1;
-                    if (L.pos + K <= M.rv.len) L.kmer = ((L.kmer << 2) | M.rv.code(L.pos + K - 1)) & KMER_MASK;
-                    else read_done(L, M);
+                    if (L.pos + K <= M.rv.len)
+                        want_kmer(L, M, ((L.kmer << 2) | M.rv.code(L.pos + K - 1)) & KMER_MASK);
+                    else
+                        read_done(L, M);
                 } else if (L.ctx == C_RIGHT_J) {
                     L.l.n = 0;  // :312-315
                     after_attempt(L, M);
@@ -743,8 +764,8 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                     }
                     if (!finished) {
                         const uint64_t tail = tail_kmer(c, L.sp.anchor);
-                        if (dir) L.kmer = ((tail << 2) | M.rv.code(L.sp.end + K - 1)) & KMER_MASK;
-                        else L.kmer = (tail >> 2) | ((uint64_t)M.rv.code(L.sp.begin) << (2 * K - 2));
+                        if (dir) want_kmer(L, M, ((tail << 2) | M.rv.code(L.sp.end + K - 1)) & KMER_MASK);
+                        else want_kmer(L, M, (tail >> 2) | ((uint64_t)M.rv.code(L.sp.begin) << (2 * K - 2)));
                         L.ctx = dir ? C_RIGHT_J : C_LEFT_J;
                         L.st = P_LOOKUP;
                     }

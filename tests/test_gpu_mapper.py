@@ -73,7 +73,7 @@ def test_map_kmers_parity(orc, golden_chr21):
     kmers = arrays[0]
     occ = kmers['kmer'][kmers['kmer'] != numpy.uint64(0xFFFFFFFFFFFFFFFF)]
     assert info['n_kmers'] == occ.shape[0]
-    assert info['table_slots'] >= 2 * occ.shape[0]
+    assert info['table_slots'] >= 4 * occ.shape[0]
     rng = numpy.random.Generator(numpy.random.PCG64(1))
     rc = numpy.asarray([orc.reverse_complement(int(k)) for k in occ[:4000]], dtype='u8')
     miss = rng.integers(0, 1 << 50, size=4000, dtype='u8')
