@@ -95,14 +95,33 @@ struct ReadView {
     }
 };
 
-// ---- a target list: shared memory (stride 32) or arena (stride 1) ------------------
+// ---- a target list: shared memory ([entry][lane], 128-byte stride) or arena (dense) ----
+// Shared-memory lists are addressed with explicit ld/st.shared (a generic pointer with a
+// run-time stride would force generic loads); `sa` == 0 selects the global arena.
 struct List {
-    int32_t *p;
-    int stride;
+    uint32_t sa;   // shared-window address of element 0, or 0
+    int32_t *gp;   // arena pointer when sa == 0
     int n;
-    __device__ __forceinline__ int32_t get(int i) const { return p[i * stride]; }
-    __device__ __forceinline__ void set(int i, int32_t v) { p[i * stride] = v; }
+    __device__ __forceinline__ int32_t get(int i) const
+    {
+        if (sa) {
+            int32_t v;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa + 128u * (uint32_t)i));
+            return v;
+        }
+        return gp[i];
+    }
+    __device__ __forceinline__ void set(int i, int32_t v)
+    {
+        if (sa) asm volatile("st.shared.s32 [%0], %1;" ::"r"(sa + 128u * (uint32_t)i), "r"(v) : "memory");
+        else gp[i] = v;
+    }
 };
+
+__device__ __forceinline__ List shared_list(const int32_t *smem_ptr)
+{
+    return List{(uint32_t)__cvta_generic_to_shared(smem_ptr), nullptr, 0};
+}
 
 struct Span {
     int begin, end;
@@ -132,12 +151,11 @@ __device__ __forceinline__ uint64_t tail_kmer(const Contig &c, Coord a)
 }
 
 // map_contig (_common.pyx:143-179) for an already loaded contig record
-__device__ void map_contig(const Ctx &cx, const Contig &c, Coord a, List &l, int32_t *smem_list)
+__device__ void map_contig(const Ctx &cx, const Contig &c, Coord a, List &l, const int32_t *smem_list)
 {
     const bool forward = a.entry >= 0;
     const int n = c.target_count;
-    l.p = smem_list;
-    l.stride = 32;
+    l = shared_list(smem_list);
     if (n > LIST_CAP) {
         const unsigned long long off = atomicAdd(&cx.a.cursors[1], (unsigned long long)n);
         if (off + (unsigned long long)n > cx.a.arena_cap) {
@@ -145,8 +163,8 @@ __device__ void map_contig(const Ctx &cx, const Contig &c, Coord a, List &l, int
             l.n = 0;
             return;
         }
-        l.p = cx.a.arena + off;
-        l.stride = 1;
+        l.sa = 0;
+        l.gp = cx.a.arena + off;
     }
     const int32_t *t = cx.ix.targets + c.target_offset;
     if (forward) {
@@ -230,6 +248,11 @@ __device__ bool intersect(List &l1, const List &l2)
 }
 
 // ---- class dictionary ---------------------------------------------------------------
+struct DenseIds {
+    const int32_t *p;
+    __device__ __forceinline__ int32_t get(int i) const { return p[i]; }
+};
+
 __device__ __forceinline__ uint64_t mix64(uint64_t x)
 {
     x ^= x >> 33;
@@ -258,12 +281,13 @@ __device__ __forceinline__ ulonglong2 cas128(ulonglong2 *addr, ulonglong2 cmp, u
 }
 
 // 128-bit identity of an ordered id tuple (length included).  Never all-ones.
-__device__ __forceinline__ ulonglong2 tuple_key(const int32_t *ids, int stride, int n, bool strip_sign)
+template <typename Ids>
+__device__ __forceinline__ ulonglong2 tuple_key(const Ids &ids, int n, bool strip_sign)
 {
     uint64_t h1 = 0x9E3779B97F4A7C15ULL ^ (uint64_t)n;
     uint64_t h2 = 0xD6E8FEB86659FD93ULL + (uint64_t)n;
     for (int i = 0; i < n; ++i) {
-        int32_t e = ids[i * stride];
+        int32_t e = ids.get(i);
         if (strip_sign && e < 0) e = ~e;  // _get_ids, _mapper.pyx:533-536
         const uint64_t v = (uint64_t)(uint32_t)e;
         h1 = mix64(h1 ^ v) + 0x632BE59BD9B4E019ULL;
@@ -277,8 +301,9 @@ __device__ __forceinline__ ulonglong2 tuple_key(const int32_t *ids, int stride, 
 
 // Find-or-insert; returns the slot, or -1 when the table is full.  The winner of the
 // 128-bit CAS copies the tuple into the id pool; nobody reads it before the kernel ends.
-__device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const int32_t *ids,
-                                       int stride, int n, bool strip_sign)
+template <typename Ids>
+__device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const Ids &ids, int n,
+                                       bool strip_sign)
 {
     uint64_t s = (key.x ^ (key.y >> 17)) & d.mask;
     const ulonglong2 empty = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
@@ -295,7 +320,7 @@ __device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const i
                     d.len[s] = 0;
                 } else {
                     for (int i = 0; i < n; ++i) {
-                        int32_t e = ids[i * stride];
+                        int32_t e = ids.get(i);
                         if (strip_sign && e < 0) e = ~e;
                         d.pool[off + i] = e;
                     }
@@ -414,7 +439,7 @@ struct Lane {
     bool forward;
     uint64_t kmer;
     uint32_t slot;  // home slot of `kmer`, prefetched into L2 when the k-mer was produced
-    Coord hit, anchor0;
+    Coord anchor0;
     Span sp;
     List l;
     // mate 1 results while mate 2 is mapped
@@ -467,8 +492,7 @@ __device__ __forceinline__ void after_attempt(Lane &L, const LaneMem &M)  // map
     L.sp.end = L.sp.begin;
     L.pos = L.sp.begin;
     want_kmer(L, M, M.rv.kmer(L.pos));
-    L.l.p = L.mate ? M.list1 : M.list0;
-    L.l.stride = 32;
+    L.l = shared_list(L.mate ? M.list1 : M.list0);
     L.ctx = C_FIND;
     L.st = P_LOOKUP;
 }
@@ -576,14 +600,13 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
     L.forward = true;
     L.kmer = 0;
     L.slot = 0;
-    L.hit = coord_invalid();
     L.anchor0 = coord_invalid();
     L.sp = Span{0, 0, coord_invalid()};
-    L.l = List{M.list0, 32, 0};
+    L.l = shared_list(M.list0);
     L.m1_begin = 0;
     L.m1_len = 0;
     L.m1_anchor = coord_invalid();
-    L.m1 = List{M.list0, 32, 0};
+    L.m1 = shared_list(M.list0);
 
     for (;;) {
         // ---- refill: hand units to idle lanes -----------------------------------------
@@ -637,7 +660,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 if (len > max_len) len = max_len;
                 M.rv.len = len;
                 L.sp = Span{0, 0, coord_invalid()};
-                L.l = List{L.mate ? M.list1 : M.list0, 32, 0};
+                L.l = shared_list(L.mate ? M.list1 : M.list0);
                 L.attempt = 0;
                 L.pos = 0;
                 if (len >= K) {
@@ -652,7 +675,6 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
         } else if (phase == P_LOOKUP) {
             if (mine) {
                 const Coord hit = map_kmer_at(ix, L.kmer, L.slot);
-                L.hit = hit;
                 L.sp.anchor = hit;
                 if (hit.offset >= 0) {
                     prefetch_l2(ix.contigs + (hit.entry >= 0 ? hit.entry : ~hit.entry));
@@ -674,7 +696,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
             }
         } else if (phase == P_LIST) {
             if (mine) {
-                const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.hit;
+                const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
                 const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
                 M.ctg[0] = c.first_kmer;
                 M.ctg[32] = c.last_kmer;
@@ -807,8 +829,8 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                     atomicAdd(&sm_fld[length], 1u);
                 }
                 if (L.l.n > 0) {
-                    const ulonglong2 key = tuple_key(L.l.p, L.l.stride, L.l.n, true);
-                    slot = dict_find_or_insert(dict, key, L.l.p, L.l.stride, L.l.n, true);
+                    const ulonglong2 key = tuple_key(L.l, L.l.n, true);
+                    slot = dict_find_or_insert(dict, key, L.l, L.l.n, true);
                 }
                 if (a.out_class) a.out_class[L.unit] = (int32_t)slot;
                 if (slot >= 0) {
@@ -878,8 +900,9 @@ __global__ void dict_merge_kernel(const DictDev d, const int64_t *key_offsets, c
     const int64_t start = key_offsets[c];
     const int n = (int)(key_offsets[c + 1] - start);
     if (n <= 0) return;
-    const ulonglong2 key = tuple_key(key_ids + start, 1, n, false);
-    const int64_t slot = dict_find_or_insert(d, key, key_ids + start, 1, n, false);
+    const DenseIds ids{key_ids + start};
+    const ulonglong2 key = tuple_key(ids, n, false);
+    const int64_t slot = dict_find_or_insert(d, key, ids, n, false);
     if (slot < 0) return;
     atomicAdd(&d.counts[slot], (unsigned long long)counts[c]);
     atomicMin(&d.first[slot], (unsigned long long)first_unit[c]);
