@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument('--transcripts', type=int, default=200_000)
     ap.add_argument('--bootstraps', type=int, default=100)
     ap.add_argument('--cpu-sample', type=int, default=2_000_000, help='pairs timed on the CPU baseline')
-    ap.add_argument('--e2e-batch', type=int, default=4_000_000, help='pairs per host-buffer call')
+    ap.add_argument('--e2e-batch', type=int, default=0, help='pairs per host-buffer call (0 = one call; the library '
+                    'double-buffers H2D copies against the kernels internally)')
     ap.add_argument('--no-em', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
@@ -246,8 +247,9 @@ def run_ours(args):
 
     def step_e2e():
         mp.reset()
-        for s in range(0, n_pairs, args.e2e_batch):
-            n = min(args.e2e_batch, n_pairs - s)
+        batch = args.e2e_batch or n_pairs
+        for s in range(0, n_pairs, batch):
+            n = min(batch, n_pairs - s)
             mp.map_batch(h_np[s * 2 * READ_LEN:(s + n) * 2 * READ_LEN], None, n, True, first_unit=first_unit + s,
                          fixed_len=READ_LEN)
         tab = mp.export_torch()

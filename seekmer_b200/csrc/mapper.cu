@@ -929,10 +929,14 @@ struct skm_mapper {
     uint64_t arena_cap = 0;
     int sm_count = 148;
     // staging for host-buffer calls
-    uint8_t *d_bases = nullptr;
-    size_t d_bases_cap = 0;
-    int64_t *d_offsets = nullptr;
-    size_t d_offsets_cap = 0;
+    uint8_t *d_bases[2] = {nullptr, nullptr};  // double-buffered H2D staging
+    size_t d_bases_cap[2] = {0, 0};
+    int64_t *d_offsets[2] = {nullptr, nullptr};
+    size_t d_offsets_cap[2] = {0, 0};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr};
+    size_t smem_configured = 0;
+    int blocks_per_sm = 0;
     int32_t *d_out = nullptr;
     size_t d_out_cap = 0;
     uint64_t *d_packed = nullptr;  // pack_reads_kernel output
@@ -970,8 +974,13 @@ SKM_API void skm_mapper_destroy(skm_mapper *m)
     cudaFree(m->d.status);
     cudaFree(m->cursors);
     cudaFree(m->arena);
-    cudaFree(m->d_bases);
-    cudaFree(m->d_offsets);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(m->d_bases[i]);
+        cudaFree(m->d_offsets[i]);
+        if (m->ev_copy[i]) cudaEventDestroy(m->ev_copy[i]);
+        if (m->ev_compute[i]) cudaEventDestroy(m->ev_compute[i]);
+    }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     cudaFree(m->d_out);
     cudaFree(m->d_packed);
     cudaFree(m->d_lens);
@@ -1033,6 +1042,11 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
     A((void **)&m->d.status, sizeof(uint32_t));
     A((void **)&m->cursors, sizeof(unsigned long long) * 4);
     A((void **)&m->arena, sizeof(int32_t) * (size_t)arena);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&m->ev_copy[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_compute[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         skm_mapper_destroy(m);
         return fail(SKM_ERR_OOM, std::string("skm_mapper_create: ") + cudaGetErrorString(e));
@@ -1070,10 +1084,50 @@ static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
     return SKM_OK;
 }
 
+// pack + map of one device-resident chunk on stream `st`
+static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_offsets, MapArgs a,
+                        int64_t n_units, int64_t first_unit, int32_t *d_out_class, int32_t *d_out_length,
+                        cudaStream_t st)
+{
+    const int64_t n_reads = a.paired ? 2 * n_units : n_units;
+    int rc = ensure((void **)&m->d_packed, &m->d_packed_cap, sizeof(uint64_t) * (size_t)n_reads * a.words);
+    if (rc) return rc;
+    int32_t *lens = nullptr;
+    if (d_offsets) {
+        rc = ensure((void **)&m->d_lens, &m->d_lens_cap, sizeof(int32_t) * (size_t)n_reads);
+        if (rc) return rc;
+        lens = m->d_lens;
+    }
+    pack_reads_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_bases, d_offsets, a.fixed_len, a.code_words,
+                                                                        a.words, n_reads, m->d_packed, lens);
+    SKM_CUDA(cudaGetLastError());
+    a.packed = m->d_packed;
+    a.lens = lens;
+    a.n_units = n_units;
+    a.first_unit = first_unit;
+    a.out_class = d_out_class;
+    a.out_length = d_out_length;
+    SKM_CUDA(cudaMemsetAsync(m->cursors, 0, sizeof(unsigned long long) * 2, st));
+    const size_t smem = map_smem_bytes(a.words);
+    if (smem != m->smem_configured) {
+        SKM_CUDA(cudaFuncSetAttribute(map_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_reads_kernel, BLOCK_THREADS, smem));
+        if (per_sm < 1) return fail(SKM_ERR_INVALID, "skm_map_batch: reads too long for shared-memory staging");
+        m->smem_configured = smem;
+        m->blocks_per_sm = per_sm;
+    }
+    const int64_t want = (n_units + BLOCK_THREADS - 1) / BLOCK_THREADS;
+    const int grid = (int)std::min<int64_t>((int64_t)m->blocks_per_sm * m->sm_count, std::max<int64_t>(want, 1));
+    map_reads_kernel<<<grid, BLOCK_THREADS, smem, st>>>(m->index->d, m->d, a);
+    SKM_CUDA(cudaGetLastError());
+    return SKM_OK;
+}
+
 SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *read_offsets,
-                             int32_t fixed_read_len, int32_t max_read_len, int64_t n_units,
-                             int paired, int64_t first_unit, int buffers_on_device,
-                             int32_t *out_class, int32_t *out_length, void *stream)
+                          int32_t fixed_read_len, int32_t max_read_len, int64_t n_units, int paired,
+                          int64_t first_unit, int buffers_on_device, int32_t *out_class, int32_t *out_length,
+                          void *stream)
 {
     if (!m || !bases) return fail(SKM_ERR_INVALID, "skm_map_batch: NULL argument");
     if (n_units < 0) return fail(SKM_ERR_INVALID, "skm_map_batch: negative unit count");
@@ -1082,7 +1136,8 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
         return fail(SKM_ERR_INVALID, "skm_map_batch: need read_offsets or fixed_read_len >= 25");
     SKM_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n_reads = paired ? 2 * n_units : n_units;
+    const int per_unit = paired ? 2 : 1;
+    const int64_t n_reads = per_unit * n_units;
 
     if (!read_offsets) max_read_len = fixed_read_len;
     if (!buffers_on_device && read_offsets) {
@@ -1103,80 +1158,58 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     a.code_words = (max_read_len + 31) / 32;
     a.words = a.code_words + (max_read_len + 63) / 64;
     a.paired = paired ? 1 : 0;
-    a.n_units = n_units;
-    a.first_unit = first_unit;
     a.arena = m->arena;
     a.arena_cap = m->arena_cap;
     a.cursors = m->cursors;
 
-    const uint8_t *d_bases = bases;
-    const int64_t *d_offsets = read_offsets;
-    if (buffers_on_device) {
-        a.out_class = out_class;
-        a.out_length = out_length;
-    } else {
-        const int64_t n_bases = read_offsets ? read_offsets[n_reads] - read_offsets[0]
-                                             : n_reads * (int64_t)fixed_read_len;
-        int rc = ensure((void **)&m->d_bases, &m->d_bases_cap, (size_t)n_bases + 16);
+    if (buffers_on_device)
+        return launch_chunk(m, bases, read_offsets, a, n_units, first_unit, out_class, out_length, st);
+
+    // ---- host buffers: double-buffered H2D copies overlapped with pack + map --------------
+    int32_t *d_class = nullptr, *d_length = nullptr;
+    if (out_class || out_length) {
+        int rc = ensure((void **)&m->d_out, &m->d_out_cap, sizeof(int32_t) * 2 * (size_t)n_units);
         if (rc) return rc;
-        const uint8_t *src = bases + (read_offsets ? read_offsets[0] : 0);
-        SKM_CUDA(cudaMemcpyAsync(m->d_bases, src, (size_t)n_bases, cudaMemcpyHostToDevice, st));
-        d_bases = m->d_bases - (read_offsets ? read_offsets[0] : 0);
-        if (read_offsets) {
-            rc = ensure((void **)&m->d_offsets, &m->d_offsets_cap, sizeof(int64_t) * (size_t)(n_reads + 1));
-            if (rc) return rc;
-            SKM_CUDA(cudaMemcpyAsync(m->d_offsets, read_offsets, sizeof(int64_t) * (size_t)(n_reads + 1),
-                                     cudaMemcpyHostToDevice, st));
-            d_offsets = m->d_offsets;
-        }
-        if (out_class || out_length) {
-            rc = ensure((void **)&m->d_out, &m->d_out_cap, sizeof(int32_t) * 2 * (size_t)n_units);
-            if (rc) return rc;
-            a.out_class = out_class ? m->d_out : nullptr;
-            a.out_length = out_length ? m->d_out + n_units : nullptr;
-        }
+        d_class = out_class ? m->d_out : nullptr;
+        d_length = out_length ? m->d_out + n_units : nullptr;
     }
-
-    // pass 1: pack
-    {
-        int rc = ensure((void **)&m->d_packed, &m->d_packed_cap, sizeof(uint64_t) * (size_t)n_reads * a.words);
+    const int64_t avg_unit_bytes = std::max<int64_t>(
+        1, (read_offsets ? read_offsets[n_reads] - read_offsets[0] : n_reads * (int64_t)fixed_read_len) / n_units);
+    const int64_t chunk_units = std::max<int64_t>(65536, std::min<int64_t>(n_units, (384LL << 20) / avg_unit_bytes));
+    // the caller's stream must have finished with previous work on the staging buffers
+    SKM_CUDA(cudaEventRecord(m->ev_compute[0], st));
+    SKM_CUDA(cudaEventRecord(m->ev_compute[1], st));
+    int slot = 0;
+    for (int64_t u0 = 0; u0 < n_units; u0 += chunk_units, slot ^= 1) {
+        const int64_t nu = std::min(chunk_units, n_units - u0);
+        const int64_t r0 = u0 * per_unit, nr = nu * per_unit;
+        const int64_t b0 = read_offsets ? read_offsets[r0] : r0 * (int64_t)fixed_read_len;
+        const int64_t b1 = read_offsets ? read_offsets[r0 + nr] : (r0 + nr) * (int64_t)fixed_read_len;
+        int rc = ensure((void **)&m->d_bases[slot], &m->d_bases_cap[slot], (size_t)(b1 - b0) + 16);
         if (rc) return rc;
-        int32_t *lens = nullptr;
         if (read_offsets) {
-            rc = ensure((void **)&m->d_lens, &m->d_lens_cap, sizeof(int32_t) * (size_t)n_reads);
+            rc = ensure((void **)&m->d_offsets[slot], &m->d_offsets_cap[slot], sizeof(int64_t) * (size_t)(nr + 1));
             if (rc) return rc;
-            lens = m->d_lens;
         }
-        const int64_t blocks = (n_reads + 255) / 256;
-        pack_reads_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_bases, d_offsets, a.fixed_len, a.code_words, a.words,
-                                                           n_reads, m->d_packed, lens);
-        SKM_CUDA(cudaGetLastError());
-        a.packed = m->d_packed;
-        a.lens = lens;
+        // copy stream: wait until the kernels that last read this slot are done, then copy
+        SKM_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_compute[slot], 0));
+        SKM_CUDA(cudaMemcpyAsync(m->d_bases[slot], bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, m->copy_stream));
+        if (read_offsets)
+            SKM_CUDA(cudaMemcpyAsync(m->d_offsets[slot], read_offsets + r0, sizeof(int64_t) * (size_t)(nr + 1),
+                                     cudaMemcpyHostToDevice, m->copy_stream));
+        SKM_CUDA(cudaEventRecord(m->ev_copy[slot], m->copy_stream));
+        // compute stream: wait for the copy, pack + map
+        SKM_CUDA(cudaStreamWaitEvent(st, m->ev_copy[slot], 0));
+        rc = launch_chunk(m, m->d_bases[slot] - b0, read_offsets ? m->d_offsets[slot] - r0 : nullptr, a, nu,
+                          first_unit + u0, d_class ? d_class + u0 : nullptr, d_length ? d_length + u0 : nullptr, st);
+        if (rc) return rc;
+        SKM_CUDA(cudaEventRecord(m->ev_compute[slot], st));
     }
-
-    // pass 2: map
-    SKM_CUDA(cudaMemsetAsync(m->cursors, 0, sizeof(unsigned long long) * 2, st));
-    const size_t smem = map_smem_bytes(a.words);
-    SKM_CUDA(cudaFuncSetAttribute(map_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_reads_kernel, BLOCK_THREADS, smem));
-    if (per_sm < 1) return fail(SKM_ERR_INVALID, "skm_map_batch: reads too long for shared-memory staging");
-    const int64_t want = (n_units + BLOCK_THREADS - 1) / BLOCK_THREADS;
-    const int grid = (int)std::min<int64_t>((int64_t)per_sm * m->sm_count, std::max<int64_t>(want, 1));
-    map_reads_kernel<<<grid, BLOCK_THREADS, smem, st>>>(m->index->d, m->d, a);
-    SKM_CUDA(cudaGetLastError());
-
-    if (!buffers_on_device) {
-        if (out_class)
-            SKM_CUDA(cudaMemcpyAsync(out_class, a.out_class, sizeof(int32_t) * (size_t)n_units,
-                                     cudaMemcpyDeviceToHost, st));
-        if (out_length)
-            SKM_CUDA(cudaMemcpyAsync(out_length, a.out_length, sizeof(int32_t) * (size_t)n_units,
-                                     cudaMemcpyDeviceToHost, st));
-        return check_status(m, st, "skm_map_batch");
-    }
-    return SKM_OK;
+    if (out_class)
+        SKM_CUDA(cudaMemcpyAsync(out_class, d_class, sizeof(int32_t) * (size_t)n_units, cudaMemcpyDeviceToHost, st));
+    if (out_length)
+        SKM_CUDA(cudaMemcpyAsync(out_length, d_length, sizeof(int32_t) * (size_t)n_units, cudaMemcpyDeviceToHost, st));
+    return check_status(m, st, "skm_map_batch");
 }
 
 SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[6], void *stream)
