@@ -1200,7 +1200,10 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
         SKM_CUDA(cudaEventRecord(m->ev_copy[slot], m->copy_stream));
         // compute stream: wait for the copy, pack + map
         SKM_CUDA(cudaStreamWaitEvent(st, m->ev_copy[slot], 0));
-        rc = launch_chunk(m, m->d_bases[slot] - b0, read_offsets ? m->d_offsets[slot] - r0 : nullptr, a, nu,
+        // the kernels index reads from 0 within the chunk; explicit offsets keep their global
+        // byte values, so only then is the base pointer shifted back by b0
+        rc = launch_chunk(m, read_offsets ? m->d_bases[slot] - b0 : m->d_bases[slot],
+                          read_offsets ? m->d_offsets[slot] : nullptr, a, nu,
                           first_unit + u0, d_class ? d_class + u0 : nullptr, d_length ? d_length + u0 : nullptr, st);
         if (rc) return rc;
         SKM_CUDA(cudaEventRecord(m->ev_compute[slot], st));

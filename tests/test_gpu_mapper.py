@@ -230,3 +230,34 @@ def test_synth_reads_device_twin(small_tx):
                                      _lib.current_stream_ptr()))
         torch.cuda.synchronize()
         assert (out.cpu().numpy() == want).all()
+
+
+@pytest.mark.parametrize('ragged', [False, True])
+def test_pipelined_host_chunks_match_single_pass(orc, medium, ragged):
+    """Host-buffer calls are split into chunks whose H2D copies overlap the kernels; many small
+    chunks must give exactly what one device-resident pass gives (fixed and ragged reads)."""
+    import torch
+    tx, arrays = medium
+    sim = synth.ReadSimulator(tx, synth.make_expression(tx.n_transcripts), 100, 250, 30, seed=8)
+    n = 300000
+    bases, _ = sim.generate(0, n)
+    offsets = None
+    if ragged:  # drop the last 0..9 bases of every read
+        rng = numpy.random.Generator(numpy.random.PCG64(5))
+        keep = 100 - rng.integers(0, 10, size=2 * n)
+        mask = (numpy.arange(100)[None, :] < keep[:, None]).reshape(-1)
+        bases = numpy.ascontiguousarray(bases[mask])
+        offsets = numpy.zeros(2 * n + 1, dtype='i8')
+        numpy.cumsum(keep, out=offsets[1:])
+    ix = _lib.DeviceIndex(*arrays, tx.n_transcripts)
+    host, dev = _lib.DeviceMapper(ix), _lib.DeviceMapper(ix)
+    hc, hl = host.map_batch(bases, offsets, n, True, fixed_len=0 if ragged else 100, max_len=100, per_read=True)
+    d_off = None if offsets is None else torch.from_numpy(offsets).cuda()
+    dc, dl = dev.map_batch(torch.from_numpy(bases).cuda(), d_off, n, True, fixed_len=0 if ragged else 100,
+                           max_len=100, per_read=True)
+    torch.cuda.synchronize()
+    th, td = host.export(), dev.export()
+    assert (hl == dl.cpu().numpy()).all()
+    for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
+        assert (th[k] == td[k]).all(), k
+    assert th['unaligned'] == td['unaligned'] and th['aligned'] == td['aligned']
