@@ -16,20 +16,20 @@
 //   get_contig_sequence _common.pyx:103-137      get_tail_kmer     :241-266
 //   batch driver + FLD  _mapper.pyx:73-101       tuple ids         :528-537
 #include <algorithm>
+#include <cstdlib>
 
 #include "kmer.cuh"
 #include "sift4.cuh"
 
 namespace skm {
 
-constexpr int BLOCK_THREADS = 256;
-constexpr int WARPS = BLOCK_THREADS / 32;
 #ifndef SKM_LIST_CAP
 #define SKM_LIST_CAP 16
 #endif
-#ifndef SKM_MIN_BLOCKS
-#define SKM_MIN_BLOCKS 3
+#ifndef SKM_Q_THREADS
+#define SKM_Q_THREADS 512
 #endif
+constexpr int Q_THREADS = SKM_Q_THREADS;  // worker threads per block (one block per SM)
 constexpr int LIST_CAP = SKM_LIST_CAP;  // per-read target list entries kept in shared memory
 constexpr int ALIGN_LENGTH = 8;    // _mapper.pyx:22
 constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
@@ -65,13 +65,14 @@ struct MapArgs {
     unsigned long long *cursors;  // [0]=work counter [1]=arena cursor
 };
 
-// ---- a read packed in shared memory, interleaved [word][lane] ---------------------
+// ---- a read packed in shared memory, item-interleaved [word][row][lane] ---------------
 struct ReadView {
-    const uint64_t *w;  // &reads[warp][0][lane]; word k at w[k * 32]
+    const uint64_t *w;  // &reads[0][row][lane]; word k at w[k * stride]
     int len;
     int code_words;
+    int stride;         // items in the block's pool (rows * 32)
 
-    __device__ __forceinline__ uint64_t word(int k) const { return w[k * 32]; }
+    __device__ __forceinline__ uint64_t word(int k) const { return w[k * stride]; }
     __device__ __forceinline__ uint32_t code(int p) const
     {
         return (uint32_t)(word(p >> 5) >> (62 - 2 * (p & 31))) & 3u;
@@ -95,32 +96,33 @@ struct ReadView {
     }
 };
 
-// ---- a target list: shared memory ([entry][lane], 128-byte stride) or arena (dense) ----
+// ---- a target list: shared memory ([entry][row][lane]) or arena (dense) ----------------
 // Shared-memory lists are addressed with explicit ld/st.shared (a generic pointer with a
 // run-time stride would force generic loads); `sa` == 0 selects the global arena.
 struct List {
     uint32_t sa;   // shared-window address of element 0, or 0
+    uint32_t sb;   // byte stride between elements in shared memory (pool items * 4)
     int32_t *gp;   // arena pointer when sa == 0
     int n;
     __device__ __forceinline__ int32_t get(int i) const
     {
         if (sa) {
             int32_t v;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa + 128u * (uint32_t)i));
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa + sb * (uint32_t)i));
             return v;
         }
         return gp[i];
     }
     __device__ __forceinline__ void set(int i, int32_t v)
     {
-        if (sa) asm volatile("st.shared.s32 [%0], %1;" ::"r"(sa + 128u * (uint32_t)i), "r"(v) : "memory");
+        if (sa) asm volatile("st.shared.s32 [%0], %1;" ::"r"(sa + sb * (uint32_t)i), "r"(v) : "memory");
         else gp[i] = v;
     }
 };
 
-__device__ __forceinline__ List shared_list(const int32_t *smem_ptr)
+__device__ __forceinline__ List shared_list(const int32_t *smem_ptr, int pool_items)
 {
-    return List{(uint32_t)__cvta_generic_to_shared(smem_ptr), nullptr, 0};
+    return List{(uint32_t)__cvta_generic_to_shared(smem_ptr), 4u * (uint32_t)pool_items, nullptr, 0};
 }
 
 struct Span {
@@ -131,8 +133,8 @@ struct Span {
 struct Ctx {
     const DevIndex &ix;
     const MapArgs &a;
-    int32_t *smem_list;  // &lists[warp][0][0][lane]
     uint32_t *status;
+    int pool_items;
 };
 
 // get_contig_sequence(coordinate, +-8) as a 16-bit window
@@ -155,7 +157,7 @@ __device__ void map_contig(const Ctx &cx, const Contig &c, Coord a, List &l, con
 {
     const bool forward = a.entry >= 0;
     const int n = c.target_count;
-    l = shared_list(smem_list);
+    l = shared_list(smem_list, cx.pool_items);
     if (n > LIST_CAP) {
         const unsigned long long off = atomicAdd(&cx.a.cursors[1], (unsigned long long)n);
         if (off + (unsigned long long)n > cx.a.arena_cap) {
@@ -405,22 +407,30 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__
     if (len & 63) out[ww] = wacc;
 }
 
-// Pass 2: the mapper.  Every lane is a persistent worker that owns one unit (read or pair) at
-// a time and advances it through the reference's per-read state machine.  The state machine
-// is cut at its expensive operations into PHASES; each lane records which phase it needs
-// next, and in every iteration the warp VOTES and executes the phase most lanes are waiting
-// for.  Lanes that need another phase sit the iteration out; lanes that finish a unit take
-// the next one from the warp's queue.  Every heavy piece of code therefore exists once and
-// runs with many active lanes, instead of 32 lanes each in a different inlined copy.
+// Pass 2: the mapper.  A block is a pool of ITEMS (a unit = read or pair, with its packed
+// read, its two target lists and ~100 bytes of state) resident in shared memory, and a set
+// of worker warps.  The reference's per-read state machine is cut at its memory accesses into
+// PHASES:
 //
-//   P_LOAD    stage the packed read of (unit, mate) into shared memory
+//   P_LOAD    take the next unit (mate 0) and stage the packed read into shared memory
 //   P_LOOKUP  KMerIndex.map_kmer (hash + probe) for the pending k-mer; misses are resolved
 //             here (_find_first_kmer keeps rolling, walk fallbacks)
 //   P_LIST    contig record + map_contig / _filter_on_contig for the hit
 //   P_WALK    one head of the left/right contig-walk loops, or the final edge check: jump to
 //             the contig edge, 8-base SIFT4 check (direction-generic), next junction k-mer
 //   P_TALLY   map_read_pair mate intersection, FLD, class dictionary
-enum : int { P_IDLE = 0, P_LOAD, P_LOOKUP, P_LIST, P_WALK, P_TALLY, P_EXIT };
+//
+// Item (row, lane) is only ever worked on by lane `lane` of some warp, so all of its shared
+// memory ([field][row][lane]) is bank-conflict free.  For each phase and lane a 32-bit mask
+// says which rows are waiting for that phase.  A warp iteration: every lane reads its five
+// masks, the warp votes for the phase most of its lanes can serve, each lane claims one
+// waiting row of that phase (atomicAnd), loads the item state, runs the phase, stores the
+// state and sets the row's bit in the mask of the phase the item needs next (atomicOr).
+// With rows >> phases nearly every lane finds work in the voted phase, so each heavy piece
+// of code runs once, fully populated, instead of diverging 32 ways; the address an item will
+// need next is prefetched into L2 when it is queued, so by the time some warp claims it the
+// line is usually on its way.
+enum : int { P_LOAD = 0, P_LOOKUP, P_LIST, P_WALK, P_TALLY, N_PHASES, P_DEAD };
 // who asked for the pending lookup / list operation
 enum : int {
     C_FIND = 0,  // _find_first_kmer scan (_mapper.pyx:199-216)
@@ -430,7 +440,40 @@ enum : int {
     C_RIGHT_J    // right walk junction (:309-313)
 };
 
-constexpr int WARP_QUEUE = 128;  // units a warp takes from the global counter at a time
+// item state words in shared memory
+enum : int {
+    S_UNIT = 0,   // unit index within the launch
+    S_FLAGS,      // ctx[2:0] dir[3] mate[4] attempt[5] forward[6] l-in-arena[7] m1-in-arena[8]
+    S_POSLEN,     // pos[15:0] read length[31:16]
+    S_MOVE,
+    S_KMER_LO,
+    S_KMER_HI,
+    S_SLOT,
+    S_A0_ENTRY,
+    S_A0_OFFSET,
+    S_SPAN,       // begin[15:0] end[31:16] (signed)
+    S_AN_ENTRY,
+    S_AN_OFFSET,
+    S_NS,         // l.n[15:0] m1.n[31:16]
+    S_LARENA,     // arena offsets of spilled lists
+    S_M1ARENA,
+    S_M1SPAN,     // m1_begin[15:0] m1_len[31:16]
+    S_M1_ENTRY,
+    S_M1_OFFSET,
+    S_WORDS
+};
+constexpr int CTG_WORDS = 3;  // contig stash: first_kmer, last_kmer, seq_offset
+
+struct Pool {
+    uint64_t *reads;   // [words][rows][32]
+    uint64_t *ctg;     // [CTG_WORDS][rows][32]
+    int32_t *lists;    // [2 * LIST_CAP][rows][32]
+    uint32_t *state;   // [S_WORDS][rows][32]
+    uint32_t *masks;   // [N_PHASES][32]
+    uint32_t *fld;     // [FLD_BINS]
+    int *live;         // items that may still produce work
+    int items;         // rows * 32
+};
 
 struct Lane {
     int st, ctx, dir;
@@ -452,12 +495,83 @@ struct LaneMem {
     const DevIndex *ix;
     ReadView rv;
     int32_t *list0, *list1;
-    uint64_t *ctg;  // stash of the current contig: [0]=first_kmer [1]=last_kmer [2]=seq_offset, stride 32
+    uint64_t *ctg;  // stash of the current contig: word k at ctg[k * items]
+    int items;
     int paired;
+    int32_t *arena;
 };
 
+__device__ __forceinline__ int sx16(uint32_t v) { return (int)(int16_t)(uint16_t)v; }
+
+__device__ __forceinline__ void lane_load(Lane &L, LaneMem &M, const Pool &P, int item)
+{
+    const uint32_t *s = P.state + item;
+    const int n = P.items;
+    L.unit = (long long)s[S_UNIT * n];
+    const uint32_t f = s[S_FLAGS * n];
+    L.ctx = (int)(f & 7u);
+    L.dir = (int)((f >> 3) & 1u);
+    L.mate = (int)((f >> 4) & 1u);
+    L.attempt = (int)((f >> 5) & 1u);
+    L.forward = (f >> 6) & 1u;
+    const uint32_t pl = s[S_POSLEN * n];
+    L.pos = (int)(pl & 0xFFFFu);
+    M.rv.len = (int)(pl >> 16);
+    L.move = (int)s[S_MOVE * n];
+    L.kmer = (uint64_t)s[S_KMER_LO * n] | ((uint64_t)s[S_KMER_HI * n] << 32);
+    L.slot = s[S_SLOT * n];
+    L.anchor0 = Coord{(int32_t)s[S_A0_ENTRY * n], (int32_t)s[S_A0_OFFSET * n]};
+    const uint32_t sp = s[S_SPAN * n];
+    L.sp.begin = sx16(sp);
+    L.sp.end = sx16(sp >> 16);
+    L.sp.anchor = Coord{(int32_t)s[S_AN_ENTRY * n], (int32_t)s[S_AN_OFFSET * n]};
+    const uint32_t ns = s[S_NS * n];
+    L.l = shared_list(L.mate ? M.list1 : M.list0, n);
+    L.l.n = (int)(ns & 0xFFFFu);
+    if (f & 128u) {
+        L.l.sa = 0;
+        L.l.gp = M.arena + s[S_LARENA * n];
+    }
+    L.m1 = shared_list(M.list0, n);
+    L.m1.n = (int)(ns >> 16);
+    if (f & 256u) {
+        L.m1.sa = 0;
+        L.m1.gp = M.arena + s[S_M1ARENA * n];
+    }
+    const uint32_t ms = s[S_M1SPAN * n];
+    L.m1_begin = sx16(ms);
+    L.m1_len = (int)(ms >> 16);
+    L.m1_anchor = Coord{(int32_t)s[S_M1_ENTRY * n], (int32_t)s[S_M1_OFFSET * n]};
+}
+
+__device__ __forceinline__ void lane_store(const Lane &L, const LaneMem &M, const Pool &P, int item)
+{
+    uint32_t *s = P.state + item;
+    const int n = P.items;
+    s[S_UNIT * n] = (uint32_t)L.unit;
+    s[S_FLAGS * n] = (uint32_t)L.ctx | ((uint32_t)L.dir << 3) | ((uint32_t)L.mate << 4)
+                     | ((uint32_t)L.attempt << 5) | (L.forward ? 64u : 0u) | (L.l.sa ? 0u : 128u)
+                     | (L.m1.sa ? 0u : 256u);
+    s[S_POSLEN * n] = ((uint32_t)L.pos & 0xFFFFu) | ((uint32_t)M.rv.len << 16);
+    s[S_MOVE * n] = (uint32_t)L.move;
+    s[S_KMER_LO * n] = (uint32_t)L.kmer;
+    s[S_KMER_HI * n] = (uint32_t)(L.kmer >> 32);
+    s[S_SLOT * n] = L.slot;
+    s[S_A0_ENTRY * n] = (uint32_t)L.anchor0.entry;
+    s[S_A0_OFFSET * n] = (uint32_t)L.anchor0.offset;
+    s[S_SPAN * n] = ((uint32_t)L.sp.begin & 0xFFFFu) | ((uint32_t)L.sp.end << 16);
+    s[S_AN_ENTRY * n] = (uint32_t)L.sp.anchor.entry;
+    s[S_AN_OFFSET * n] = (uint32_t)L.sp.anchor.offset;
+    s[S_NS * n] = ((uint32_t)L.l.n & 0xFFFFu) | ((uint32_t)L.m1.n << 16);
+    if (!L.l.sa) s[S_LARENA * n] = (uint32_t)(L.l.gp - M.arena);
+    if (!L.m1.sa) s[S_M1ARENA * n] = (uint32_t)(L.m1.gp - M.arena);
+    s[S_M1SPAN * n] = ((uint32_t)L.m1_begin & 0xFFFFu) | ((uint32_t)L.m1_len << 16);
+    s[S_M1_ENTRY * n] = (uint32_t)L.m1_anchor.entry;
+    s[S_M1_OFFSET * n] = (uint32_t)L.m1_anchor.offset;
+}
+
 // Record the next k-mer to look up and start pulling its home slot towards L2: the probe
-// phase that consumes it runs one or more warp iterations later.
+// phase that consumes it runs when some warp claims the item again.
 __device__ __forceinline__ void want_kmer(Lane &L, const LaneMem &M, uint64_t kmer)
 {
     L.kmer = kmer;
@@ -492,7 +606,7 @@ __device__ __forceinline__ void after_attempt(Lane &L, const LaneMem &M)  // map
     L.sp.end = L.sp.begin;
     L.pos = L.sp.begin;
     want_kmer(L, M, M.rv.kmer(L.pos));
-    L.l = shared_list(L.mate ? M.list1 : M.list0);
+    L.l = shared_list(L.mate ? M.list1 : M.list0, M.items);
     L.ctx = C_FIND;
     L.st = P_LOOKUP;
 }
@@ -562,105 +676,116 @@ __device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView &rv, in
     return sift4_unified(ref16, codes, wild, 1 - dir, dir ? rv.len - qoff : qoff + 8);
 }
 
-__global__ void __launch_bounds__(BLOCK_THREADS, SKM_MIN_BLOCKS)
-map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
+__global__ void __launch_bounds__(Q_THREADS, 1)
+map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a, const int rows)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *sm_reads = reinterpret_cast<uint64_t *>(smem_raw);               // [WARPS][words][32]
-    uint64_t *sm_ctg = sm_reads + WARPS * a.words * 32;                        // [WARPS][3][32]
-    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + WARPS * 3 * 32);  // [WARPS][2][CAP][32]
-    uint32_t *sm_fld = reinterpret_cast<uint32_t *>(sm_lists + WARPS * 2 * LIST_CAP * 32);
+    Pool P;
+    P.items = rows * 32;
+    P.reads = reinterpret_cast<uint64_t *>(smem_raw);
+    P.ctg = P.reads + (size_t)a.words * P.items;
+    P.lists = reinterpret_cast<int32_t *>(P.ctg + (size_t)CTG_WORDS * P.items);
+    P.state = reinterpret_cast<uint32_t *>(P.lists + (size_t)2 * LIST_CAP * P.items);
+    P.masks = P.state + (size_t)S_WORDS * P.items;
+    P.fld = P.masks + N_PHASES * 32;
+    P.live = reinterpret_cast<int *>(P.fld + FLD_BINS);
 
-    for (int i = threadIdx.x; i < FLD_BINS; i += BLOCK_THREADS) sm_fld[i] = 0;
+    for (int i = threadIdx.x; i < FLD_BINS; i += blockDim.x) P.fld[i] = 0;
+    for (int i = threadIdx.x; i < N_PHASES * 32; i += blockDim.x)
+        P.masks[i] = i < 32 ? (rows == 32 ? 0xFFFFFFFFu : (1u << rows) - 1u) : 0u;  // all in P_LOAD
+    for (int i = threadIdx.x; i < P.items; i += blockDim.x) P.state[S_FLAGS * P.items + i] = 0;  // mate 0
+    if (threadIdx.x == 0) *P.live = P.items;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     LaneMem M;
     M.ix = &ix;
-    M.rv = ReadView{sm_reads + (size_t)warp * a.words * 32 + lane, 0, a.code_words};
-    M.ctg = sm_ctg + (size_t)warp * 3 * 32 + lane;
-    M.list0 = sm_lists + (size_t)warp * 2 * LIST_CAP * 32 + lane;
-    M.list1 = M.list0 + LIST_CAP * 32;
+    M.items = P.items;
     M.paired = a.paired;
-    uint64_t *my_words = sm_reads + (size_t)warp * a.words * 32 + lane;
-    Ctx cx{ix, a, M.list0, dict.status};
+    M.arena = a.arena;
+    M.rv.code_words = a.code_words;
+    M.rv.stride = P.items;
+    M.rv.len = 0;
+    Ctx cx{ix, a, dict.status, P.items};
+    volatile uint32_t *vmasks = P.masks;
 
-    long long q_next = 0, q_end = 0;  // warp-level unit queue
-    bool q_dry = false;
-
-    Lane L;
-    L.st = P_IDLE;
-    L.ctx = C_FIND;
-    L.dir = 0;
-    L.unit = -1;
-    L.mate = 0;
-    L.attempt = 0;
-    L.pos = 0;
-    L.move = 0;
-    L.forward = true;
-    L.kmer = 0;
-    L.slot = 0;
-    L.anchor0 = coord_invalid();
-    L.sp = Span{0, 0, coord_invalid()};
-    L.l = shared_list(M.list0);
-    L.m1_begin = 0;
-    L.m1_len = 0;
-    L.m1_anchor = coord_invalid();
-    L.m1 = shared_list(M.list0);
+    unsigned iter = (unsigned)warp * 5u;
 
     for (;;) {
-        // ---- refill: hand units to idle lanes -----------------------------------------
-        {
-            const unsigned idle = __ballot_sync(0xffffffffu, L.st == P_IDLE);
-            if (idle) {
-                if (q_next >= q_end && !q_dry) {
-                    long long base = 0;
-                    if (lane == 0) base = (long long)atomicAdd(&a.cursors[0], (unsigned long long)WARP_QUEUE);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    q_next = base;
-                    q_end = min(base + (long long)WARP_QUEUE, (long long)a.n_units);
-                    if (q_next >= q_end) q_dry = true;
-                }
-                const int rank = __popc(idle & ((1u << lane) - 1u));
-                if (L.st == P_IDLE) {
-                    if (q_next + rank < q_end) {
-                        L.unit = q_next + rank;
-                        L.mate = 0;
-                        L.st = P_LOAD;
-                    } else if (q_dry) {
-                        L.st = P_EXIT;
-                    }
-                }
-                q_next = min(q_next + (long long)__popc(idle), q_end);
-            }
-        }
-
-        // ---- vote: the phase with the most waiting lanes runs --------------------------------
+        // ---- vote: the phase most lanes have a waiting row for ---------------------------
+        uint32_t mm = 0;
         int phase;
         {
-            const unsigned peers = __match_any_sync(0xffffffffu, L.st);
-            const bool runnable = L.st >= P_LOAD && L.st <= P_TALLY;
-            const unsigned ballot = runnable ? ((unsigned)__popc(peers) << 3) | (unsigned)L.st : 0u;
-            const unsigned best = __reduce_max_sync(0xffffffffu, ballot);
+            uint32_t m[N_PHASES];
+            unsigned best = 0;
+#pragma unroll
+            for (int p = 0; p < N_PHASES; ++p) {
+                m[p] = vmasks[p * 32 + lane];
+                const unsigned c = (unsigned)__popc(__ballot_sync(0xffffffffu, m[p] != 0));
+                const unsigned cand = c ? (c << 3) | (unsigned)p : 0u;
+                best = cand > best ? cand : best;
+            }
             if (best == 0) {
-                if (__all_sync(0xffffffffu, L.st == P_EXIT)) break;
-                continue;  // only idle lanes: refill again
+                int live = 0;
+                if (lane == 0) live = *reinterpret_cast<volatile int *>(P.live);
+                live = __shfl_sync(0xffffffffu, live, 0);
+                if (live == 0) break;
+                __nanosleep(100);
+                continue;
             }
             phase = (int)(best & 7u);
+#pragma unroll
+            for (int p = 0; p < N_PHASES; ++p)
+                if (p == phase) mm = m[p];
         }
-        const bool mine = L.st == phase;
+        // ---- claim one waiting row of that phase ---------------------------------------------
+        bool mine = false;
+        int row = 0;
+        if (mm) {
+            const unsigned rot = iter & 31u;
+            const uint32_t mr = __funnelshift_r(mm, mm, rot);
+            row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
+            const uint32_t old = atomicAnd(&P.masks[phase * 32 + lane], ~(1u << row));
+            mine = (old >> row) & 1u;
+        }
+        iter += 1;
+        __threadfence_block();
+        const int item = row * 32 + lane;
+        Lane L;
+        L.st = phase;
+        if (mine) {
+            M.rv.w = P.reads + item;
+            M.ctg = P.ctg + item;
+            M.list0 = P.lists + item;
+            M.list1 = M.list0 + (size_t)LIST_CAP * P.items;
+            lane_load(L, M, P, item);
+        }
 
         if (phase == P_LOAD) {
-            if (mine) {
+            // ---- new units for finished items (mate 0) ---------------------------------------
+            const bool need = mine && L.mate == 0;
+            const unsigned nb = __ballot_sync(0xffffffffu, need);
+            if (nb) {
+                // one global atomic per warp: a unit is only taken when an item is ready for it
+                long long base = 0;
+                if (lane == 0) base = (long long)atomicAdd(&a.cursors[0], (unsigned long long)__popc(nb));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (need) {
+                    L.unit = base + __popc(nb & ((1u << lane) - 1u));
+                    if (L.unit >= a.n_units) L.st = P_DEAD;
+                }
+            }
+            if (mine && L.st == P_LOAD) {
                 const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
                 const uint64_t *src = a.packed + read_idx * (long long)a.words;
-                for (int k = 0; k < a.words; ++k) my_words[k * 32] = __ldg(src + k);
+                uint64_t *dst = P.reads + item;
+                for (int k = 0; k < a.words; ++k) dst[k * P.items] = __ldg(src + k);
                 int len = a.lens ? __ldg(a.lens + read_idx) : a.fixed_len;
                 const int max_len = a.code_words * 32;
                 if (len > max_len) len = max_len;
                 M.rv.len = len;
                 L.sp = Span{0, 0, coord_invalid()};
-                L.l = shared_list(L.mate ? M.list1 : M.list0);
+                L.l = shared_list(L.mate ? M.list1 : M.list0, P.items);
                 L.attempt = 0;
                 L.pos = 0;
                 if (len >= K) {
@@ -699,8 +824,8 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
                 const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
                 M.ctg[0] = c.first_kmer;
-                M.ctg[32] = c.last_kmer;
-                M.ctg[64] = (uint64_t)c.seq_offset;
+                M.ctg[P.items] = c.last_kmer;
+                M.ctg[2 * P.items] = (uint64_t)c.seq_offset;
                 bool ok = true;
                 if (L.ctx == C_FIND) {
                     map_contig(cx, c, at, L.l, L.mate ? M.list1 : M.list0);
@@ -748,8 +873,8 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 // heads of the loops of _filter_targets_to_left (:234-275) and _to_right (:293-343)
                 Contig c;
                 c.first_kmer = M.ctg[0];
-                c.last_kmer = M.ctg[32];
-                c.seq_offset = (int64_t)M.ctg[64];
+                c.last_kmer = M.ctg[P.items];
+                c.seq_offset = (int64_t)M.ctg[2 * P.items];
                 const int dir = L.dir;
                 int rem = dir ? M.rv.len - L.sp.end - K : L.sp.begin;  // bases left towards the read end
                 const bool in_loop = rem > L.move;
@@ -826,7 +951,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 if (a.out_length) a.out_length[L.unit] = length;
                 if (length > 0) {  // _mapper.pyx:90-94
                     if (length >= FLD_BINS) length = FLD_BINS - 1;
-                    atomicAdd(&sm_fld[length], 1u);
+                    atomicAdd(&P.fld[length], 1u);
                 }
                 if (L.l.n > 0) {
                     const ulonglong2 key = tuple_key(L.l, L.l.n, true);
@@ -838,7 +963,11 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                     if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
                         atomicMin(&dict.first[slot], g);
                 }
-                L.st = P_IDLE;
+                // the item is free again: mate 0 of a new unit
+                L.mate = 0;
+                L.l = shared_list(M.list0, P.items);
+                L.m1 = shared_list(M.list0, P.items);
+                L.st = P_LOAD;
             }
             __syncwarp();
             // one count atomic per distinct class per warp (mapper.py:60-75)
@@ -854,12 +983,22 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
             }
         }
+        // ---- publish: state first, then the row's bit in the next phase's mask --------------
+        if (mine) {
+            if (L.st == P_DEAD) {
+                atomicSub(P.live, 1);
+            } else {
+                lane_store(L, M, P, item);
+                __threadfence_block();
+                atomicOr(&P.masks[L.st * 32 + lane], 1u << row);
+            }
+        }
         __syncwarp();
     }
 
     __syncthreads();
-    for (int i = threadIdx.x; i < FLD_BINS; i += BLOCK_THREADS) {
-        const uint32_t v = sm_fld[i];
+    for (int i = threadIdx.x; i < FLD_BINS; i += blockDim.x) {
+        const uint32_t v = P.fld[i];
         if (v) atomicAdd(&dict.fld[i], (unsigned long long)v);
     }
 }
@@ -935,8 +1074,8 @@ struct skm_mapper {
     size_t d_offsets_cap[2] = {0, 0};
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr};
-    size_t smem_configured = 0;
-    int blocks_per_sm = 0;
+    size_t smem_configured = 0, smem_max = 0;
+    int threads = Q_THREADS, rows_limit = 0;  // SKM_THREADS / SKM_ROWS override for experiments
     int32_t *d_out = nullptr;
     size_t d_out_cap = 0;
     uint64_t *d_packed = nullptr;  // pack_reads_kernel output
@@ -1011,6 +1150,14 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
     *out = nullptr;
     if (!index) return fail(SKM_ERR_INVALID, "skm_mapper_create: NULL index");
     SKM_CUDA(cudaSetDevice(index->device));
+    // Random 16/32-byte probes dominate the traffic: ask L2 to fetch single 32-byte sectors from
+    // DRAM instead of the default 64 bytes (a hint; SKM_L2_FETCH overrides for experiments).
+    {
+        const char *g = getenv("SKM_L2_FETCH");
+        const size_t gran = g ? (size_t)atoi(g) : 32;
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     if (class_capacity <= 0) class_capacity = 1LL << 22;
     int64_t slots = 1024;
     while (slots < 2 * class_capacity) slots <<= 1;
@@ -1022,6 +1169,13 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
     m->slots = slots;
     m->pool_cap = id_capacity;
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
+    {
+        int optin = 0;
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
+        m->smem_max = (size_t)optin;
+        if (const char *t = getenv("SKM_THREADS")) m->threads = std::max(32, std::min(Q_THREADS, atoi(t) & ~31));
+        if (const char *r = getenv("SKM_ROWS")) m->rows_limit = atoi(r);
+    }
     // list arena: room for every resident thread to spill its largest possible list a few
     // times over, bounded to 2 GiB
     uint64_t arena = (uint64_t)std::max<int64_t>(index->max_target_count, 64) * 2048ULL * (uint64_t)m->sm_count;
@@ -1063,10 +1217,14 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
     return SKM_OK;
 }
 
-static size_t map_smem_bytes(int words)
+static size_t map_item_bytes(int words)
 {
-    return sizeof(uint64_t) * WARPS * ((size_t)words + 3) * 32 + sizeof(int32_t) * WARPS * 2 * LIST_CAP * 32
-           + sizeof(uint32_t) * FLD_BINS;
+    return sizeof(uint64_t) * ((size_t)words + CTG_WORDS) + sizeof(int32_t) * 2 * LIST_CAP + sizeof(uint32_t) * S_WORDS;
+}
+
+static size_t map_smem_bytes(int words, int rows)
+{
+    return map_item_bytes(words) * 32 * (size_t)rows + sizeof(uint32_t) * (N_PHASES * 32 + FLD_BINS) + 16;
 }
 
 static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
@@ -1108,18 +1266,18 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     a.out_class = d_out_class;
     a.out_length = d_out_length;
     SKM_CUDA(cudaMemsetAsync(m->cursors, 0, sizeof(unsigned long long) * 2, st));
-    const size_t smem = map_smem_bytes(a.words);
-    if (smem != m->smem_configured) {
+    // one block per SM; as many item rows as shared memory holds (at most 32: one mask bit each)
+    int rows = (int)std::min<size_t>(32, (m->smem_max - map_smem_bytes(a.words, 0)) / (map_item_bytes(a.words) * 32));
+    if (m->rows_limit > 0) rows = std::min(rows, m->rows_limit);
+    if (rows < 1) return fail(SKM_ERR_INVALID, "skm_map_batch: reads too long for shared-memory staging");
+    const size_t smem = map_smem_bytes(a.words, rows);
+    if (smem > m->smem_configured) {
         SKM_CUDA(cudaFuncSetAttribute(map_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        SKM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, map_reads_kernel, BLOCK_THREADS, smem));
-        if (per_sm < 1) return fail(SKM_ERR_INVALID, "skm_map_batch: reads too long for shared-memory staging");
         m->smem_configured = smem;
-        m->blocks_per_sm = per_sm;
     }
-    const int64_t want = (n_units + BLOCK_THREADS - 1) / BLOCK_THREADS;
-    const int grid = (int)std::min<int64_t>((int64_t)m->blocks_per_sm * m->sm_count, std::max<int64_t>(want, 1));
-    map_reads_kernel<<<grid, BLOCK_THREADS, smem, st>>>(m->index->d, m->d, a);
+    const int64_t want = (n_units + rows * 32 - 1) / (rows * 32);
+    const int grid = (int)std::min<int64_t>(m->sm_count, std::max<int64_t>(want, 1));
+    map_reads_kernel<<<grid, m->threads, smem, st>>>(m->index->d, m->d, a, rows);
     SKM_CUDA(cudaGetLastError());
     return SKM_OK;
 }
