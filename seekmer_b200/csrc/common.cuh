@@ -38,20 +38,28 @@ struct __align__(16) Slot {
     int32_t offset;
 };
 
-// 32-byte contig record = one DRAM sector.
+// 64-byte contig record = one DRAM burst: header plus the first 8 entries of the contig's
+// target list (most lists fit; longer ones continue in targets[]).
 //   w0 = first_kmer | (target_count low 14 bits  << 50)
 //   w1 = last_kmer  | (target_count high 14 bits << 50)
-struct __align__(32) ContigRec {
+constexpr int INLINE_TARGETS = 8;
+struct __align__(64) ContigRec {
     uint64_t w0;
     uint64_t w1;
     int64_t seq_offset;      // base offset into the packed sequence pool
     uint32_t target_offset;  // into targets[]
     uint32_t length;         // contig length in bases
+    int32_t inline_targets[INLINE_TARGETS];  // targets[target_offset .. +8), zero padded
 };
+
+// The k-mer table is probed by BUCKET: 4 consecutive 16-byte slots = 64 bytes = one DRAM burst.
+// A key lives in the first bucket from its home bucket onwards that had a free slot when it was
+// inserted; buckets fill front to back, so "last slot empty" <=> "bucket not full".
+constexpr int BUCKET_SLOTS = 4;
 
 struct DevIndex {
     const Slot *table;
-    uint64_t slot_mask;       // n_slots - 1
+    uint64_t bucket_mask;     // n_slots / BUCKET_SLOTS - 1
     const ContigRec *contigs;
     const uint32_t *seq2;     // 16 bases per word, first base in the top bits
     const int32_t *targets;   // signed entries only

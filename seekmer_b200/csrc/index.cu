@@ -52,7 +52,8 @@ __global__ void relayout_table_kernel(const skm_kmer_slot *__restrict__ src, int
         // assembler left with a negative offset act as misses and are kept verbatim
         if (offset >= 0 && (entry < 0 || entry >= n_contigs)) atomicOr(bad, 2u);
         if (!fwd) entry = ~entry;
-        uint64_t s = table_hash(canon) & mask;
+        // first free slot from the home bucket onwards (slots fill front to back per bucket)
+        uint64_t s = (uint64_t)home_bucket_of(canon, mask / BUCKET_SLOTS) * BUCKET_SLOTS;
         for (;;) {
             const unsigned long long old = atomicCAS(
                 reinterpret_cast<unsigned long long *>(&table[s].key), EMPTY_KEY, canon);
@@ -67,6 +68,7 @@ __global__ void relayout_table_kernel(const skm_kmer_slot *__restrict__ src, int
 }
 
 __global__ void relayout_contigs_kernel(const skm_contig_entry *__restrict__ src, int64_t n,
+                                        const skm_target *__restrict__ targets,
                                         ContigRec *__restrict__ dst, int64_t n_bases,
                                         int64_t n_targets, unsigned long long *max_tc,
                                         unsigned int *bad)
@@ -77,11 +79,13 @@ __global__ void relayout_contigs_kernel(const skm_contig_entry *__restrict__ src
     // The reference assembler can emit a degenerate contig (shorter than k, no targets, not
     // referenced by any k-mer: slot 0 doubles as "no link" there), so only
     // memory safety is enforced here.
-    if (c.length < 0 || c.length > 0x7FFFFFFFLL || c.offset < 0 || c.offset + c.length > n_bases
-        || c.target_offset < 0 || c.target_count < 0 || c.target_count >= (1LL << 28)
-        || c.target_offset + c.target_count > n_targets)
-        atomicOr(bad, 1u);
+    const bool broken = c.length < 0 || c.length > 0x7FFFFFFFLL || c.offset < 0 || c.offset + c.length > n_bases
+                        || c.target_offset < 0 || c.target_count < 0 || c.target_count >= (1LL << 28)
+                        || c.target_offset + c.target_count > n_targets;
+    if (broken) atomicOr(bad, 1u);
     ContigRec r;
+    for (int j = 0; j < INLINE_TARGETS; ++j)
+        r.inline_targets[j] = (!broken && j < c.target_count) ? targets[c.target_offset + j].entry : 0;
     const uint64_t tc = (uint64_t)c.target_count;
     r.w0 = (c.first_kmer & KMER_MASK) | ((tc & 0x3FFF) << 50);
     r.w1 = (c.last_kmer & KMER_MASK) | (((tc >> 14) & 0x3FFF) << 50);
@@ -293,8 +297,8 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         STEP_CUDA(cudaMemcpyAsync(&cnt, d_scalars, sizeof(cnt), cudaMemcpyDeviceToHost, st));
         STEP_CUDA(cudaStreamSynchronize(st));
         ix->n_kmers = (int64_t)cnt;
-        // load factor <= 0.25: an unsuccessful linear-probing search then inspects ~1.4 slots
-        // on average (2.4 at 0.5); a warp waits for its slowest probe, and HBM is plentiful
+        // load factor <= 0.25 with 4-slot buckets: a lookup, hit or miss, is answered by its home
+        // bucket (one 64-byte burst) except when 4+ keys share it (~0.4 %); HBM is plentiful
         int64_t slots = 1024;
         while (slots < 4 * ix->n_kmers) slots <<= 1;
         ix->n_slots = slots;
@@ -306,11 +310,19 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         STEP_CUDA(cudaGetLastError());
         ix->bytes += (int64_t)sizeof(Slot) * slots;
     }
+    // -- targets
+    STEP(to_device(targets, n_targets, dev, st, &d_targets, &own_targets));
+    STEP_CUDA(cudaMalloc(&ix->targets, sizeof(int32_t) * (size_t)n_targets));
+    extract_targets_kernel<<<(unsigned)((n_targets + 255) / 256), 256, 0, st>>>(
+        d_targets, n_targets, ix->targets);
+    STEP_CUDA(cudaGetLastError());
+    ix->bytes += (int64_t)sizeof(int32_t) * n_targets;
+
     // -- contigs
     STEP(to_device(contigs, n_contigs, dev, st, &d_contigs, &own_contigs));
     STEP_CUDA(cudaMalloc(&ix->contigs, sizeof(ContigRec) * (size_t)n_contigs));
     relayout_contigs_kernel<<<(unsigned)((n_contigs + 255) / 256), 256, 0, st>>>(
-        d_contigs, n_contigs, ix->contigs, n_bases, n_targets, d_scalars + 1,
+        d_contigs, n_contigs, d_targets, ix->contigs, n_bases, n_targets, d_scalars + 1,
         reinterpret_cast<unsigned int *>(d_scalars + 2));
     STEP_CUDA(cudaGetLastError());
     ix->bytes += (int64_t)sizeof(ContigRec) * n_contigs;
@@ -324,14 +336,6 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         STEP_CUDA(cudaGetLastError());
         ix->bytes += (int64_t)sizeof(uint32_t) * n_words;
     }
-    // -- targets
-    STEP(to_device(targets, n_targets, dev, st, &d_targets, &own_targets));
-    STEP_CUDA(cudaMalloc(&ix->targets, sizeof(int32_t) * (size_t)n_targets));
-    extract_targets_kernel<<<(unsigned)((n_targets + 255) / 256), 256, 0, st>>>(
-        d_targets, n_targets, ix->targets);
-    STEP_CUDA(cudaGetLastError());
-    ix->bytes += (int64_t)sizeof(int32_t) * n_targets;
-
     unsigned long long scal[4] = {0, 0, 0, 0};
     STEP_CUDA(cudaMemcpyAsync(scal, d_scalars, sizeof(scal), cudaMemcpyDeviceToHost, st));
     STEP_CUDA(cudaStreamSynchronize(st));
@@ -348,7 +352,7 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
 #undef STEP
 #undef STEP_CUDA
     ix->d.table = ix->table;
-    ix->d.slot_mask = (uint64_t)ix->n_slots - 1;
+    ix->d.bucket_mask = (uint64_t)ix->n_slots / BUCKET_SLOTS - 1;
     ix->d.contigs = ix->contigs;
     ix->d.seq2 = ix->seq2;
     ix->d.targets = ix->targets;

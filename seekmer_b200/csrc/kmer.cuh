@@ -96,51 +96,55 @@ __host__ __device__ __forceinline__ uint64_t reference_hash(uint64_t m)
     return (v0 ^ v1) ^ (v2 ^ v3);
 }
 
-__device__ __forceinline__ Slot load_slot(const Slot *p)
-{
-    // one 16-byte read-only load, allocating in L1: when a probe has to continue, the next
-    // slot is in the same 128-byte line 7 times out of 8
-    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
-    Slot s;
-    s.key = v.x;
-    s.entry = (int32_t)(uint32_t)v.y;
-    s.offset = (int32_t)(uint32_t)(v.y >> 32);
-    return s;
-}
-
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// Home slot of a k-mer in the device table.
-__device__ __forceinline__ uint32_t home_slot(const DevIndex &ix, uint64_t kmer)
+// Home bucket of a k-mer in the device table.
+__host__ __device__ __forceinline__ uint32_t home_bucket_of(uint64_t canon, uint64_t bucket_mask)
+{
+    return (uint32_t)((table_hash(canon) >> 8) & bucket_mask);
+}
+
+__device__ __forceinline__ uint32_t home_bucket(const DevIndex &ix, uint64_t kmer)
 {
     const uint64_t rc = revcomp(kmer);
-    return (uint32_t)(table_hash(kmer < rc ? kmer : rc) & ix.slot_mask);
+    return home_bucket_of(kmer < rc ? kmer : rc, ix.bucket_mask);
 }
 
 // KMerIndex.map_kmer (_common.pyx:54-97) on the canonical-key table: hit on the
 // canonical key; strand of the query relative to the canonical form decides whether
 // the stored coordinate is returned as is or reverse-complemented (~entry).
-// `slot` = home_slot(ix, kmer), computed (and prefetched) when the k-mer was produced.
-__device__ __forceinline__ Coord map_kmer_at(const DevIndex &ix, uint64_t kmer, uint32_t slot)
+// `bucket` = home_bucket(ix, kmer).  One iteration reads a whole 64-byte bucket with four
+// read-only 16-byte loads; at load <= 0.25 a second bucket is needed ~0.4 % of the time.
+__device__ __forceinline__ Coord map_kmer_at(const DevIndex &ix, uint64_t kmer, uint32_t bucket)
 {
     const uint64_t rc = revcomp(kmer);
     const bool fwd = kmer < rc;
     const uint64_t canon = fwd ? kmer : rc;
-    uint64_t i = slot;
+    uint64_t b = bucket;
     for (;;) {
-        const Slot s = load_slot(ix.table + i);
-        if (s.key == canon) return Coord{fwd ? s.entry : ~s.entry, s.offset};
-        if (s.key == EMPTY_KEY) return coord_invalid();
-        i = (i + 1) & ix.slot_mask;
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ix.table + BUCKET_SLOTS * b);
+        const ulonglong2 s0 = __ldg(p), s1 = __ldg(p + 1), s2 = __ldg(p + 2), s3 = __ldg(p + 3);
+        uint64_t v = 0;
+        bool found = false;
+        if (s0.x == canon) { v = s0.y; found = true; }
+        if (s1.x == canon) { v = s1.y; found = true; }
+        if (s2.x == canon) { v = s2.y; found = true; }
+        if (s3.x == canon) { v = s3.y; found = true; }
+        if (found) {
+            const int32_t entry = (int32_t)(uint32_t)v;
+            return Coord{fwd ? entry : ~entry, (int32_t)(uint32_t)(v >> 32)};
+        }
+        if (s3.x == EMPTY_KEY) return coord_invalid();
+        b = (b + 1) & ix.bucket_mask;
     }
 }
 
 __device__ __forceinline__ Coord map_kmer(const DevIndex &ix, uint64_t kmer)
 {
-    return map_kmer_at(ix, kmer, home_slot(ix, kmer));
+    return map_kmer_at(ix, kmer, home_bucket(ix, kmer));
 }
 
 struct Contig {
@@ -149,6 +153,7 @@ struct Contig {
     uint32_t target_offset;
     int32_t target_count;
     int32_t length;
+    int32_t t[INLINE_TARGETS];  // first 8 target entries
 };
 
 __device__ __forceinline__ Contig load_contig(const DevIndex &ix, int32_t index)
@@ -156,7 +161,11 @@ __device__ __forceinline__ Contig load_contig(const DevIndex &ix, int32_t index)
     const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ix.contigs + index);
     const ulonglong2 a = __ldg(p);
     const ulonglong2 b = __ldg(p + 1);
+    const int4 t0 = __ldg(reinterpret_cast<const int4 *>(p + 2));
+    const int4 t1 = __ldg(reinterpret_cast<const int4 *>(p + 3));
     Contig c;
+    c.t[0] = t0.x; c.t[1] = t0.y; c.t[2] = t0.z; c.t[3] = t0.w;
+    c.t[4] = t1.x; c.t[5] = t1.y; c.t[6] = t1.z; c.t[7] = t1.w;
     c.first_kmer = a.x & KMER_MASK;
     c.last_kmer = a.y & KMER_MASK;
     c.target_count = (int32_t)((a.x >> 50) | ((a.y >> 50) << 14));

@@ -1,0 +1,933 @@
+// The mapping kernel: reads -> equivalence classes against the HBM-resident index.
+//
+// A block is a pool of ITEMS (a unit = read or pair, with the 2-bit codes of the current mate,
+// its two target lists and 80 bytes of state) resident in shared memory, and a set of worker
+// warps.  The reference's per-read state machine is cut at its memory accesses into PHASES:
+//
+//   P_LOAD    take the next unit (mate 0) and stage the packed read into shared memory
+//   P_LOOKUP  KMerIndex.map_kmer (hash + bucket probe) for the one pending k-mer: the first
+//             k-mer of a scan, a contig-junction k-mer, a walk fallback
+//   P_SCAN    _find_first_kmer after its first miss: the next 4 read positions are hashed and
+//             probed together (4 independent bucket loads in flight), first hit wins
+//   P_MAP     contig record + map_contig for the scan hit
+//   P_FILTER  contig record + _filter_on_contig at a junction (or the reload of the first
+//             contig before the right walk)
+//   P_WALK    one head of the left/right contig-walk loops, or the final edge check: jump to
+//             the contig edge, 8-base SIFT4 check (direction-generic), next junction k-mer
+//   P_TALLY   map_read_pair mate intersection, FLD, class dictionary
+//
+// Item (row, lane) is only ever worked on by lane `lane` of some warp, so all of its shared
+// memory ([field][row][lane]) is bank-conflict free.  For each phase and lane a 32-bit mask
+// says which rows are waiting for that phase.  A warp iteration: every lane reads its masks,
+// the warp votes for the phase most of its lanes can serve, each lane claims one waiting row
+// of that phase (atomicAnd), loads the item state (four 16-byte shared loads), runs the phase,
+// stores the state and sets the row's bit in the mask of the phase the item needs next
+// (atomicOr).  With rows >> phases nearly every lane finds work in the voted phase, so each
+// heavy piece of code runs once, fully populated, instead of diverging 32 ways; the address
+// an item will need next is prefetched into L2 when it is queued.
+//
+// Reference semantics restated here (paths under /root/reference/seekmer/):
+//   map_read            _mapper.pyx:151-193      find_first_kmer   :199-216
+//   filter_to_left      _mapper.pyx:222-275      filter_to_right   :281-343
+//   intersect (mates)   _mapper.pyx:350-397      map_read_pair     :111-145
+//   sift4_align_left    _mapper.pyx:404-445      sift4_align_right :452-493
+//   map_contig          _common.pyx:143-179      filter_on_contig  :185-235
+//   get_contig_sequence _common.pyx:103-137      get_tail_kmer     :241-266
+//   batch driver + FLD  _mapper.pyx:73-101       tuple ids         :528-537
+#pragma once
+
+#include "dict.cuh"
+#include "kmer.cuh"
+#include "sift4.cuh"
+
+namespace skm {
+
+#ifndef SKM_LIST_CAP
+#define SKM_LIST_CAP 16
+#endif
+#ifndef SKM_Q_THREADS
+#define SKM_Q_THREADS 512
+#endif
+constexpr int Q_THREADS = SKM_Q_THREADS;  // worker threads per block (one block per SM)
+constexpr int LIST_CAP = SKM_LIST_CAP;    // per-read target list entries kept in shared memory
+constexpr int ALIGN_LENGTH = 8;           // _mapper.pyx:22
+constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
+constexpr int SCAN_WIDTH = 4;             // read positions probed per P_SCAN step
+
+struct MapArgs {
+    const uint64_t *packed;   // [n_reads][words] from pack_reads_kernel
+    const int32_t *lens;      // per-read length, or NULL with fixed_len
+    int32_t fixed_len;
+    int32_t code_words;       // u64 words of 2-bit codes per read (from max read length)
+    int32_t wild_words;       // u64 words of wildcard bits per read
+    int32_t words;            // code_words + wild_words, rounded up to even (16-byte records)
+    int32_t paired;
+    int64_t n_units;
+    int64_t first_unit;
+    int32_t *out_class;
+    int32_t *out_length;
+    int32_t *arena;           // spill space for target lists longer than LIST_CAP
+    uint64_t arena_cap;
+    unsigned long long *cursors;  // [0]=work counter [1]=arena cursor
+};
+
+enum : int { P_LOAD = 0, P_SCAN, P_LOOKUP, P_MAP, P_FILTER, P_WALK, P_TALLY, N_PHASES, P_DEAD = N_PHASES };
+// who asked for the pending lookup / filter operation
+enum : int {
+    C_FIND = 0,  // _find_first_kmer scan (_mapper.pyx:199-216)
+    C_LEFT_J,    // left walk junction (:247-251)
+    C_LEFT_F,    // left walk fallback (:257-261)
+    C_RIGHT_C,   // right walk start: contig of the cached first hit (:283-290)
+    C_RIGHT_J    // right walk junction (:309-313)
+};
+// item flag bits
+enum : uint32_t {
+    F_CTX = 7u, F_DIR = 8u, F_MATE = 16u, F_ATTEMPT = 32u, F_FORWARD = 64u, F_L_ARENA = 128u,
+    F_M1_ARENA = 256u, F_CTG_A0 = 512u, F_WILD = 1024u
+};
+constexpr int STATE_VECS = 5;  // uint4 words of item state
+constexpr int CTG_WORDS = 3;   // contig stash: first_kmer, last_kmer, seq_offset
+
+constexpr size_t map_item_bytes(int code_words)
+{
+    return sizeof(uint64_t) * ((size_t)code_words + CTG_WORDS) + sizeof(int32_t) * 2 * LIST_CAP + 16 * STATE_VECS;
+}
+constexpr size_t map_fixed_bytes() { return sizeof(uint32_t) * (N_PHASES * 32 + SKM_MAX_FRAGMENT_LENGTH) + 16; }
+
+// ---- shared-memory views of one item; ITEMS = rows * 32 is a compile-time constant so every
+// ---- field access is one ld/st.shared with an immediate offset
+template <int ITEMS>
+struct ReadView {
+    const uint64_t *w;     // &codes[0][item]; word k at w[k * ITEMS]
+    const uint64_t *wild;  // global wildcard words of the read, NULL when it has none
+    int len;
+    int wild_words;
+
+    __device__ __forceinline__ uint64_t word(int k) const { return w[k * ITEMS]; }
+    __device__ __forceinline__ uint32_t code(int p) const
+    {
+        return (uint32_t)(word(p >> 5) >> (62 - 2 * (p & 31))) & 3u;
+    }
+    // 25-mer starting at base p (_kmer.pxd:46-68)
+    __device__ __forceinline__ uint64_t kmer(int p) const
+    {
+        const int k = p >> 5, s = p & 31;
+        uint64_t x = word(k) << (2 * s);
+        if (s > 7) x |= word(k + 1) >> (64 - 2 * s);
+        return x >> 14;
+    }
+    // 9 read bases starting at base s >= 0, first base in bits 17:16
+    __device__ __forceinline__ uint32_t codes9(int s) const
+    {
+        const int k = s >> 5, sh = s & 31;
+        uint64_t x = word(k) << (2 * sh);
+        if (sh > 23) x |= word(k + 1) >> (64 - 2 * sh);  // k + 1 <= code_words: in bounds
+        return (uint32_t)(x >> 46);
+    }
+    // wildcard bits (_match_base, _mapper.pyx:500-501) of 9 read bases from s: bit i <-> base s + i
+    __device__ __forceinline__ uint32_t wild9(int s) const
+    {
+        if (!wild) return 0u;
+        const int k = s >> 6, b = s & 63;
+        uint64_t x = __ldg(wild + k) >> b;
+        if (b > 55 && k + 1 < wild_words) x |= __ldg(wild + k + 1) << (64 - b);
+        return (uint32_t)x & 0x1FFu;
+    }
+};
+
+// A target list: shared memory ([entry][item]) or, when longer than LIST_CAP, the arena.
+template <int ITEMS>
+struct List {
+    uint32_t sa;   // shared-window address of element 0, or 0 = arena
+    int32_t *gp;   // arena pointer when sa == 0
+    int n;
+    __device__ __forceinline__ int32_t get(int i) const
+    {
+        if (sa) {
+            int32_t v;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa + 4u * ITEMS * (uint32_t)i));
+            return v;
+        }
+        return gp[i];
+    }
+    __device__ __forceinline__ void set(int i, int32_t v)
+    {
+        if (sa) asm volatile("st.shared.s32 [%0], %1;" ::"r"(sa + 4u * ITEMS * (uint32_t)i), "r"(v) : "memory");
+        else gp[i] = v;
+    }
+};
+
+struct Span {
+    int begin, end;
+    Coord anchor;
+};
+
+template <int ITEMS>
+struct Lane {
+    int st, ctx, dir, mate, attempt;
+    bool forward, ctg_a0, has_wild, m1_dirty;
+    long long unit;
+    int pos, move, len, clen;
+    uint64_t kmer;
+    uint32_t bucket;  // home bucket of `kmer`, prefetched into L2 when the k-mer was produced
+    Coord anchor0;
+    Span sp;
+    List<ITEMS> l;
+    // mate 1 results while mate 2 is mapped
+    int m1_begin, m1_len;
+    Coord m1_anchor;
+    List<ITEMS> m1;
+};
+
+template <int ITEMS>
+struct ItemMem {
+    uint4 *state;      // &state[0][item]; vector v at state[v * ITEMS]
+    uint64_t *codes;   // &codes[0][item]
+    uint64_t *ctg;     // &ctg[0][item]
+    uint32_t list0_sa, list1_sa;
+    int32_t *arena;
+    __device__ __forceinline__ List<ITEMS> fresh_list(int mate) const
+    {
+        return List<ITEMS>{mate ? list1_sa : list0_sa, nullptr, 0};
+    }
+};
+
+__device__ __forceinline__ int sx16(uint32_t v) { return (int)(int16_t)(uint16_t)v; }
+
+template <int ITEMS>
+__device__ __forceinline__ void lane_load(Lane<ITEMS> &L, const ItemMem<ITEMS> &I, bool with_m1)
+{
+    const uint4 v0 = I.state[0], v1 = I.state[ITEMS], v2 = I.state[2 * ITEMS], v3 = I.state[3 * ITEMS];
+    L.unit = (long long)v0.x;
+    const uint32_t f = v0.y;
+    L.ctx = (int)(f & F_CTX);
+    L.dir = (f & F_DIR) ? 1 : 0;
+    L.mate = (f & F_MATE) ? 1 : 0;
+    L.attempt = (f & F_ATTEMPT) ? 1 : 0;
+    L.forward = (f & F_FORWARD) != 0;
+    L.ctg_a0 = (f & F_CTG_A0) != 0;
+    L.has_wild = (f & F_WILD) != 0;
+    L.m1_dirty = false;
+    L.pos = (int)(v0.z & 0xFFFFu);
+    L.len = (int)(v0.z >> 16);
+    L.move = (int)v0.w;
+    L.kmer = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
+    L.bucket = v1.z;
+    L.sp.begin = sx16(v1.w);
+    L.sp.end = sx16(v1.w >> 16);
+    L.anchor0 = Coord{(int32_t)v2.x, (int32_t)v2.y};
+    L.sp.anchor = Coord{(int32_t)v2.z, (int32_t)v2.w};
+    L.l = I.fresh_list(L.mate);
+    L.l.n = (int)(v3.x & 0xFFFFu);
+    if (f & F_L_ARENA) {
+        L.l.sa = 0;
+        L.l.gp = I.arena + v3.z;
+    }
+    L.m1 = I.fresh_list(0);
+    L.m1.n = (int)(v3.x >> 16);
+    if (f & F_M1_ARENA) {
+        L.m1.sa = 0;
+        L.m1.gp = I.arena + v3.w;
+    }
+    L.clen = (int)v3.y;
+    if (with_m1) {
+        const uint4 v4 = I.state[4 * ITEMS];
+        L.m1_begin = sx16(v4.x);
+        L.m1_len = (int)(v4.x >> 16);
+        L.m1_anchor = Coord{(int32_t)v4.y, (int32_t)v4.z};
+    }
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void lane_store(const Lane<ITEMS> &L, const ItemMem<ITEMS> &I)
+{
+    uint4 v0, v1, v2, v3;
+    v0.x = (uint32_t)L.unit;
+    v0.y = (uint32_t)L.ctx | (L.dir ? F_DIR : 0u) | (L.mate ? F_MATE : 0u) | (L.attempt ? F_ATTEMPT : 0u)
+           | (L.forward ? F_FORWARD : 0u) | (L.l.sa ? 0u : F_L_ARENA) | (L.m1.sa ? 0u : F_M1_ARENA)
+           | (L.ctg_a0 ? F_CTG_A0 : 0u) | (L.has_wild ? F_WILD : 0u);
+    v0.z = ((uint32_t)L.pos & 0xFFFFu) | ((uint32_t)L.len << 16);
+    v0.w = (uint32_t)L.move;
+    v1.x = (uint32_t)L.kmer;
+    v1.y = (uint32_t)(L.kmer >> 32);
+    v1.z = L.bucket;
+    v1.w = ((uint32_t)L.sp.begin & 0xFFFFu) | ((uint32_t)L.sp.end << 16);
+    v2.x = (uint32_t)L.anchor0.entry;
+    v2.y = (uint32_t)L.anchor0.offset;
+    v2.z = (uint32_t)L.sp.anchor.entry;
+    v2.w = (uint32_t)L.sp.anchor.offset;
+    v3.x = ((uint32_t)L.l.n & 0xFFFFu) | ((uint32_t)L.m1.n << 16);
+    v3.y = (uint32_t)L.clen;
+    v3.z = L.l.sa ? 0u : (uint32_t)(L.l.gp - I.arena);
+    v3.w = L.m1.sa ? 0u : (uint32_t)(L.m1.gp - I.arena);
+    I.state[0] = v0;
+    I.state[ITEMS] = v1;
+    I.state[2 * ITEMS] = v2;
+    I.state[3 * ITEMS] = v3;
+    if (L.m1_dirty) {
+        uint4 v4;
+        v4.x = ((uint32_t)L.m1_begin & 0xFFFFu) | ((uint32_t)L.m1_len << 16);
+        v4.y = (uint32_t)L.m1_anchor.entry;
+        v4.z = (uint32_t)L.m1_anchor.offset;
+        v4.w = 0;
+        I.state[4 * ITEMS] = v4;
+    }
+}
+
+// ---- index-side helpers ------------------------------------------------------------------
+// get_contig_sequence(coordinate, +-8) as a 16-bit window
+__device__ __forceinline__ uint32_t contig_window(const DevIndex &ix, int64_t seq_offset, Coord a, bool left_edge)
+{
+    const int64_t p = seq_offset + a.offset;
+    if (a.entry >= 0) return seq_window8(ix, left_edge ? p : p + K - ALIGN_LENGTH);
+    return revcomp8(seq_window8(ix, left_edge ? p + K - ALIGN_LENGTH : p));
+}
+
+// 8-base window at a contig EDGE, taken from the record's first/last k-mer instead of the
+// sequence pool: inside the walk loops the anchor always sits on the first or last k-mer of
+// its contig (offset 0 or length-k, _mapper.pyx:229-236,289-295), and first_kmer/last_kmer
+// are the encodings of the contig's first/last 25 bases (_index_builder.pyx:565-567).
+__device__ __forceinline__ uint32_t edge_window(uint64_t first_kmer, uint64_t last_kmer, Coord a, bool left_edge)
+{
+    const uint32_t head = (uint32_t)(first_kmer >> (2 * K - 16)) & 0xFFFFu;  // first 8 bases
+    const uint32_t tail = (uint32_t)last_kmer & 0xFFFFu;                      // last 8 bases
+    if (a.entry >= 0) return left_edge ? head : tail;
+    return revcomp8(left_edge ? tail : head);
+}
+
+struct MapCtx {
+    const DevIndex &ix;
+    const MapArgs &a;
+    uint32_t *status;
+};
+
+// map_contig (_common.pyx:143-179) for an already loaded contig record.  Forward: the
+// contig's targets in order; reverse: reversed order, every entry bit-negated.
+template <int ITEMS>
+__device__ __forceinline__ void map_contig(const MapCtx &cx, const Contig &c, Coord at, List<ITEMS> &l)
+{
+    const bool forward = at.entry >= 0;
+    const int n = c.target_count;
+    const int32_t x = forward ? 0 : -1;
+    if (n <= INLINE_TARGETS) {  // straight-line: the 8 inline entries are already in registers
+#pragma unroll
+        for (int j = 0; j < INLINE_TARGETS; ++j)
+            if (j < n) l.set(forward ? j : n - 1 - j, c.t[j] ^ x);
+        l.n = n;
+        return;
+    }
+    if (n > LIST_CAP) {
+        const unsigned long long off = atomicAdd(&cx.a.cursors[1], (unsigned long long)n);
+        if (off + (unsigned long long)n > cx.a.arena_cap) {
+            atomicOr(cx.status, ST_ARENA_FULL);
+            l.n = 0;
+            return;
+        }
+        l.sa = 0;
+        l.gp = cx.a.arena + off;
+    }
+    const int32_t *t = cx.ix.targets + c.target_offset;
+    for (int i = 0; i < n; ++i) l.set(i, __ldg(t + (forward ? i : n - 1 - i)) ^ x);
+    l.n = n;
+}
+
+// _filter_on_contig (_common.pyx:185-235): direction-aware sorted-merge intersection of the
+// span's list with the contig's list; equal entries pair off one to one; zero matches leave
+// the list intact and return false.
+template <int ITEMS>
+__device__ __forceinline__ bool filter_on_contig(const MapCtx &cx, const Contig &c, Coord at, List<ITEMS> &l)
+{
+    if (l.n == 0) return true;
+    const bool forward = at.entry >= 0;
+    const int length = c.target_count;
+    if (length == 0) return false;
+    const int32_t x = forward ? 0 : -1;
+    if (length <= INLINE_TARGETS) {
+        // Both lists are ascending (targets are sorted per contig, _index_builder.pyx:540, and
+        // map_contig / this filter keep that order), so the merge keeps the r-th occurrence of a
+        // value v in the span's list exactly when the contig's list holds more than r copies of
+        // v.  Counting against 8 registers needs no data-dependent control flow.
+        int32_t t[INLINE_TARGETS];
+#pragma unroll
+        for (int j = 0; j < INLINE_TARGETS; ++j) t[j] = c.t[j] ^ x;
+        int w = 0, run = 0;
+        int32_t prev = 0;
+        const int n = l.n;
+        for (int i = 0; i < n; ++i) {
+            const int32_t v = l.get(i);
+            run = (i > 0 && v == prev) ? run + 1 : 0;
+            prev = v;
+            int copies = 0;
+#pragma unroll
+            for (int j = 0; j < INLINE_TARGETS; ++j) copies += (j < length && t[j] == v) ? 1 : 0;
+            if (run < copies) {
+                l.set(w, v);
+                w += 1;
+            }
+        }
+        if (w == 0) return false;
+        l.n = w;
+        return true;
+    }
+    const int32_t *t = cx.ix.targets + c.target_offset;
+    int read_index = 0, write_index = 0, track = 0;
+    int32_t index_entry = __ldg(t + (forward ? 0 : length - 1)) ^ x;
+    int32_t target_entry = l.get(0);
+    while (true) {
+        if (target_entry == index_entry) {
+            l.set(write_index, target_entry);
+            read_index += 1;
+            write_index += 1;
+            track += 1;
+            if (read_index == l.n || track == length) break;
+            target_entry = l.get(read_index);
+            index_entry = __ldg(t + (forward ? track : length - 1 - track)) ^ x;
+        } else if (target_entry < index_entry) {
+            read_index += 1;
+            if (read_index == l.n) break;
+            target_entry = l.get(read_index);
+        } else {
+            track += 1;
+            if (track == length) break;
+            index_entry = __ldg(t + (forward ? track : length - 1 - track)) ^ x;
+        }
+    }
+    if (write_index == 0) return false;
+    l.n = write_index;
+    return true;
+}
+
+// mate intersection (_mapper.pyx:350-397): list 1 ascending vs list 2 descending, negated
+template <int ITEMS>
+__device__ __forceinline__ bool intersect(List<ITEMS> &l1, const List<ITEMS> &l2)
+{
+    if (l1.n == 0) return true;
+    if (l2.n == 0) return false;
+    int cursor1_read = 0, cursor1_write = 0, cursor2 = l2.n - 1;
+    while (cursor1_read != l1.n && cursor2 != -1) {
+        const int32_t entry1 = l1.get(cursor1_read);
+        const int32_t entry2 = ~l2.get(cursor2);
+        if (entry1 == entry2) {
+            l1.set(cursor1_write, entry1);
+            cursor1_read += 1;
+            cursor1_write += 1;
+            cursor2 -= 1;
+        } else if (entry1 < entry2) {
+            cursor1_read += 1;
+        } else {
+            cursor2 -= 1;
+        }
+    }
+    if (cursor1_write == 0) return false;
+    l1.n = cursor1_write;
+    return true;
+}
+
+// ---- state-machine transitions ------------------------------------------------------------
+template <int ITEMS>
+struct Step {
+    Lane<ITEMS> &L;
+    const ItemMem<ITEMS> &I;
+    const ReadView<ITEMS> &rv;
+    const DevIndex &ix;
+    int paired;
+
+    // Record the next single k-mer to look up and start pulling its home bucket towards L2.
+    __device__ __forceinline__ void want_kmer(uint64_t kmer)
+    {
+        L.kmer = kmer;
+        L.bucket = home_bucket(ix, kmer);
+        prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * L.bucket);
+        L.st = P_LOOKUP;
+    }
+
+    __device__ __forceinline__ void read_done()
+    {
+        if (paired && L.mate == 0) {
+            L.m1_begin = L.sp.begin;
+            L.m1_anchor = L.sp.anchor;
+            L.m1_len = L.len;
+            L.m1 = L.l;
+            L.m1_dirty = true;
+            L.mate = 1;
+            L.st = P_LOAD;
+        } else {
+            L.st = P_TALLY;
+        }
+    }
+
+    __device__ __forceinline__ void after_attempt()  // map_read :177-193
+    {
+        if (L.l.n != 0 || L.attempt == 1) {
+            read_done();
+            return;
+        }
+        L.attempt = 1;
+        L.sp.anchor = coord_invalid();
+        L.sp.begin += K;
+        if (L.sp.begin + K > L.len) L.sp.begin = L.len - K;
+        L.sp.end = L.sp.begin;
+        L.pos = L.sp.begin;
+        L.l = I.fresh_list(L.mate);
+        L.ctx = C_FIND;
+        want_kmer(rv.kmer(L.pos));
+    }
+
+    __device__ __forceinline__ void after_left()  // map_read :174-176
+    {
+        if (L.l.n != 0 && L.sp.end < L.len - K) {
+            if (L.ctg_a0) {
+                // the stash still holds the contig of the first hit (no junction was crossed):
+                // _filter_targets_to_right starts there (:283-295) without another record load
+                L.sp.anchor = L.anchor0;
+                L.forward = L.anchor0.entry >= 0;
+                L.move = L.forward ? L.clen - L.anchor0.offset - K : L.anchor0.offset;
+                L.dir = 1;
+                L.st = P_WALK;
+            } else {
+                prefetch_l2(ix.contigs + (L.anchor0.entry >= 0 ? L.anchor0.entry : ~L.anchor0.entry));
+                L.ctx = C_RIGHT_C;
+                L.st = P_FILTER;
+            }
+        } else {
+            after_attempt();
+        }
+    }
+
+    // _filter_targets_to_left :250-263 when the junction lookup or its filter failed
+    __device__ __forceinline__ void left_junction_failed()
+    {
+        if (L.ctx == C_LEFT_J) {
+            if (L.sp.begin < K) {
+                L.sp.begin = 0;
+                after_left();
+            } else {
+                L.sp.begin -= K;
+                L.ctx = C_LEFT_F;
+                want_kmer(rv.kmer(L.sp.begin));
+            }
+        } else {  // C_LEFT_F
+            L.l.n = 0;
+            after_left();
+        }
+    }
+
+    // a k-mer hit: next comes its contig record
+    __device__ __forceinline__ void hit(Coord h)
+    {
+        L.sp.anchor = h;
+        prefetch_l2(ix.contigs + (h.entry >= 0 ? h.entry : ~h.entry));
+        L.st = L.ctx == C_FIND ? P_MAP : P_FILTER;
+    }
+};
+
+// sift4_align_left(window, read, qoff) for dir == 0, sift4_align_right for dir == 1 (sift4.cuh)
+template <int ITEMS>
+__device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView<ITEMS> &rv, int qoff, int dir)
+{
+    int s = qoff - (1 - dir);  // the left routine may look one base left of its window (:421)
+    const int pad = s < 0 ? 1 : 0;
+    s += pad;
+    uint32_t codes = rv.codes9(s) >> (2 * pad);
+    uint32_t wild = (rv.wild9(s) << pad) & 0x1FFu;
+    if (dir) {
+        wild = reverse_bits(wild, 9);
+    } else {
+        codes = reverse_pairs(codes, 9);
+        ref16 = reverse_pairs(ref16, 8);
+    }
+    return sift4_unified(ref16, codes, wild, 1 - dir, dir ? rv.len - qoff : qoff + 8);
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(Q_THREADS, 1)
+map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
+{
+    constexpr int ITEMS = ROWS * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *sm_state = reinterpret_cast<uint4 *>(smem_raw);                            // [STATE_VECS][ITEMS]
+    uint64_t *sm_codes = reinterpret_cast<uint64_t *>(sm_state + STATE_VECS * ITEMS);  // [code_words][ITEMS]
+    uint64_t *sm_ctg = sm_codes + (size_t)a.code_words * ITEMS;                       // [CTG_WORDS][ITEMS]
+    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + CTG_WORDS * ITEMS);      // [2 * LIST_CAP][ITEMS]
+    uint32_t *sm_masks = reinterpret_cast<uint32_t *>(sm_lists + 2 * LIST_CAP * ITEMS);  // [N_PHASES][32]
+    uint32_t *sm_fld = sm_masks + N_PHASES * 32;                                      // [FLD_BINS]
+    int *sm_live = reinterpret_cast<int *>(sm_fld + SKM_MAX_FRAGMENT_LENGTH);
+
+    for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) sm_fld[i] = 0;
+    for (int i = threadIdx.x; i < N_PHASES * 32; i += blockDim.x)
+        sm_masks[i] = i < 32 ? (ROWS == 32 ? 0xFFFFFFFFu : (1u << ROWS) - 1u) : 0u;  // everything in P_LOAD
+    for (int i = threadIdx.x; i < STATE_VECS * ITEMS; i += blockDim.x) sm_state[i] = make_uint4(0, 0, 0, 0);  // mate 0
+    if (threadIdx.x == 0) *sm_live = ITEMS;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const MapCtx cx{ix, a, dict.status};
+    volatile uint32_t *vmasks = sm_masks;
+    unsigned iter = (unsigned)warp * 5u;
+
+    for (;;) {
+        // ---- vote: the phase most lanes have a waiting row for ---------------------------
+        uint32_t mm = 0;
+        int phase;
+        {
+            uint32_t m[N_PHASES];
+            unsigned best = 0;
+#pragma unroll
+            for (int p = 0; p < N_PHASES; ++p) {
+                m[p] = vmasks[p * 32 + lane];
+                const unsigned c = (unsigned)__popc(__ballot_sync(0xffffffffu, m[p] != 0));
+                const unsigned cand = c ? (c << 3) | (unsigned)p : 0u;
+                best = cand > best ? cand : best;
+            }
+            if (best == 0) {
+                int live = 0;
+                if (lane == 0) live = *reinterpret_cast<volatile int *>(sm_live);
+                live = __shfl_sync(0xffffffffu, live, 0);
+                if (live == 0) break;
+                __nanosleep(200);
+                continue;
+            }
+            phase = (int)(best & 7u);
+#pragma unroll
+            for (int p = 0; p < N_PHASES; ++p)
+                if (p == phase) mm = m[p];
+        }
+        // ---- claim one waiting row of that phase ---------------------------------------------
+        bool mine = false;
+        int row = 0;
+        if (mm) {
+            const unsigned rot = iter & 31u;
+            const uint32_t mr = __funnelshift_r(mm, mm, rot);
+            row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
+            const uint32_t old = atomicAnd(&sm_masks[phase * 32 + lane], ~(1u << row));
+            mine = (old >> row) & 1u;
+        }
+        iter += 1;
+        __threadfence_block();
+        const int item = row * 32 + lane;
+        ItemMem<ITEMS> I;
+        I.state = sm_state + item;
+        I.codes = sm_codes + item;
+        I.ctg = sm_ctg + item;
+        I.list0_sa = (uint32_t)__cvta_generic_to_shared(sm_lists + item);
+        I.list1_sa = I.list0_sa + 4u * LIST_CAP * ITEMS;
+        I.arena = a.arena;
+        Lane<ITEMS> L;
+        L.st = phase;
+        ReadView<ITEMS> rv;
+        rv.w = I.codes;
+        rv.wild = nullptr;
+        rv.wild_words = a.wild_words;
+        Step<ITEMS> S{L, I, rv, ix, a.paired};
+
+        if (phase == P_LOAD) {
+            if (mine) lane_load(L, I, false);
+            // ---- new units for finished items (mate 0): one global atomic per warp -------------
+            const bool need = mine && L.mate == 0;
+            const unsigned nb = __ballot_sync(0xffffffffu, need);
+            if (nb) {
+                long long base = 0;
+                if (lane == 0) base = (long long)atomicAdd(&a.cursors[0], (unsigned long long)__popc(nb));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (need) {
+                    L.unit = base + __popc(nb & ((1u << lane) - 1u));
+                    if (L.unit >= a.n_units) L.st = P_DEAD;
+                }
+            }
+            if (mine && L.st == P_LOAD) {
+                const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
+                const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(a.packed + read_idx * (long long)a.words);
+                uint64_t any_wild = 0;
+                for (int k = 0; k < a.words; k += 2) {  // 16-byte records: words is even
+                    const ulonglong2 v = __ldg(src + (k >> 1));
+                    if (k < a.code_words) I.codes[k * ITEMS] = v.x;
+                    else any_wild |= v.x;  // wildcard words; the padding word is zero
+                    if (k + 1 < a.code_words) I.codes[(k + 1) * ITEMS] = v.y;
+                    else any_wild |= v.y;
+                }
+                int len = a.lens ? __ldg(a.lens + read_idx) : a.fixed_len;
+                const int max_len = a.code_words * 32;
+                if (len > max_len) len = max_len;
+                L.len = len;
+                L.has_wild = any_wild != 0;
+                L.sp = Span{0, 0, coord_invalid()};
+                L.l = I.fresh_list(L.mate);
+                L.attempt = 0;
+                L.pos = 0;
+                L.ctg_a0 = false;
+                L.ctx = C_FIND;
+                if (len >= K) {
+                    S.want_kmer(rv.kmer(0));
+                } else {  // undefined in the reference; reported unaligned and flagged
+                    atomicOr(dict.status, ST_SHORT_READ);
+                    S.read_done();
+                }
+            }
+        } else if (phase == P_LOOKUP) {
+            if (mine) {
+                lane_load(L, I, false);
+                rv.len = L.len;
+                const Coord h = map_kmer_at(ix, L.kmer, L.bucket);
+                if (h.offset >= 0) {
+                    S.hit(h);
+                } else {
+                    L.sp.anchor = h;
+                    if (L.ctx == C_FIND) {
+                        // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
+                        // targets empty and map_read returns (:170-171, :186-187)
+                        L.pos += 1;
+                        if (L.pos + K <= L.len) L.st = P_SCAN;
+                        else S.read_done();
+                    } else if (L.ctx == C_RIGHT_J) {
+                        L.l.n = 0;  // :312-315
+                        S.after_attempt();
+                    } else {
+                        S.left_junction_failed();
+                    }
+                }
+            }
+        } else if (phase == P_SCAN) {
+            if (mine) {
+                lane_load(L, I, false);
+                rv.len = L.len;
+                // positions pos .. pos+3 (while they fit); L.kmer is the k-mer at pos-1
+                uint64_t km[SCAN_WIDTH];
+                uint32_t bk[SCAN_WIDTH];
+                Coord h[SCAN_WIDTH];
+                uint64_t k = L.kmer;
+#pragma unroll
+                for (int j = 0; j < SCAN_WIDTH; ++j) {
+                    const int p = L.pos + j;
+                    h[j] = coord_invalid();
+                    km[j] = k;
+                    bk[j] = 0;
+                    if (p + K <= L.len) {
+                        k = ((k << 2) | rv.code(p + K - 1)) & KMER_MASK;
+                        km[j] = k;
+                        bk[j] = home_bucket(ix, k);
+                        prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * bk[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < SCAN_WIDTH; ++j)
+                    if (L.pos + j + K <= L.len) h[j] = map_kmer_at(ix, km[j], bk[j]);
+                int first = SCAN_WIDTH;
+#pragma unroll
+                for (int j = SCAN_WIDTH - 1; j >= 0; --j)
+                    if (h[j].offset >= 0) first = j;
+                if (first < SCAN_WIDTH) {
+                    L.pos += first;
+                    Coord hh = h[0];
+                    uint64_t kk = km[0];
+#pragma unroll
+                    for (int j = 1; j < SCAN_WIDTH; ++j)
+                        if (j == first) {
+                            hh = h[j];
+                            kk = km[j];
+                        }
+                    L.kmer = kk;
+                    S.hit(hh);
+                } else {
+                    L.sp.anchor = coord_invalid();
+                    const int tried = min(SCAN_WIDTH, L.len - K + 1 - L.pos);
+                    L.pos += tried;
+                    L.kmer = k;
+                    if (L.pos + K <= L.len) L.st = P_SCAN;
+                    else S.read_done();
+                }
+            }
+        } else if (phase == P_MAP || phase == P_FILTER) {
+            if (mine) {
+                lane_load(L, I, false);
+                rv.len = L.len;
+                const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
+                const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
+                I.ctg[0] = c.first_kmer;
+                I.ctg[ITEMS] = c.last_kmer;
+                I.ctg[2 * ITEMS] = (uint64_t)c.seq_offset;
+                L.clen = c.length;
+                L.forward = at.entry >= 0;
+                const int to_start = L.forward ? at.offset : c.length - at.offset - K;
+                const int to_end = L.forward ? c.length - at.offset - K : at.offset;
+                if (phase == P_MAP) {  // ctx == C_FIND
+                    map_contig(cx, c, at, L.l);
+                    L.sp.begin = L.pos;
+                    L.sp.end = L.pos;
+                    L.anchor0 = at;
+                    L.ctg_a0 = true;
+                    if (L.l.n == 0) {
+                        S.read_done();  // `if is_empty(targets): return span`
+                    } else if (L.sp.begin > 0) {
+                        L.move = to_start;
+                        L.dir = 0;
+                        L.st = P_WALK;
+                    } else {
+                        S.after_left();
+                    }
+                } else {
+                    bool ok = true;
+                    if (L.ctx != C_RIGHT_C) {
+                        ok = filter_on_contig(cx, c, at, L.l);
+                        L.ctg_a0 = false;
+                    } else {
+                        L.sp.anchor = at;  // :283-284 — same k-mer as the scan hit, lookup cached
+                        L.ctg_a0 = true;
+                    }
+                    if (L.ctx == C_RIGHT_C || L.ctx == C_RIGHT_J) {
+                        if (ok) {
+                            L.move = to_end;
+                            L.dir = 1;
+                            L.st = P_WALK;
+                        } else {
+                            L.l.n = 0;  // :312-315
+                            S.after_attempt();
+                        }
+                    } else if (ok) {
+                        L.move = to_start;
+                        L.dir = 0;
+                        L.st = P_WALK;
+                    } else {
+                        S.left_junction_failed();
+                    }
+                }
+            }
+        } else if (phase == P_WALK) {
+            if (mine) {
+                lane_load(L, I, false);
+                rv.len = L.len;
+                if (L.has_wild) {
+                    const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
+                    rv.wild = a.packed + read_idx * (long long)a.words + a.code_words;
+                }
+                // heads of the loops of _filter_targets_to_left (:234-275) and _to_right (:293-343)
+                const uint64_t first_kmer = I.ctg[0], last_kmer = I.ctg[ITEMS];
+                const int dir = L.dir;
+                int rem = dir ? L.len - L.sp.end - K : L.sp.begin;  // bases left towards the read end
+                const bool in_loop = rem > L.move;
+                const int step = in_loop ? L.move : rem;
+                const int delta = L.forward ? step : -step;
+                L.sp.anchor.offset += dir ? delta : -delta;
+                uint32_t ref16;
+                int qoff;
+                if (in_loop) {
+                    rem -= L.move;
+                    ref16 = edge_window(first_kmer, last_kmer, L.sp.anchor, dir == 0);
+                    qoff = dir ? L.len - rem - ALIGN_LENGTH : rem;
+                } else {
+                    ref16 = contig_window(ix, (int64_t)I.ctg[2 * ITEMS], L.sp.anchor, dir == 0);
+                    qoff = dir ? L.len - ALIGN_LENGTH : 0;
+                }
+                const int shift = sift4_edge(ref16, rv, qoff, dir);
+                bool finished = true;  // this direction is over (success or failure)
+                if (in_loop) {
+                    if (shift == INVALID_SHIFT || shift + 1 + L.move <= 0) {
+                        L.l.n = 0;
+                    } else {
+                        rem -= shift + 1;
+                        if (rem < 0) rem = 0;  // :244-246 / :306-308, list intact
+                        else finished = false;
+                    }
+                    if (L.l.n != 0) {
+                        if (dir) L.sp.end = L.len - rem - K;
+                        else L.sp.begin = rem;
+                    } else if (!dir) {
+                        L.sp.begin = rem;  // the failed left walk leaves begin where it stopped (:235,241-242)
+                    } else {
+                        L.sp.end = L.len - rem - K;
+                    }
+                    if (!finished) {
+                        uint64_t tail = L.sp.anchor.offset == 0 ? first_kmer : last_kmer;  // get_tail_kmer
+                        if (L.sp.anchor.entry < 0) tail = revcomp(tail);
+                        L.ctx = dir ? C_RIGHT_J : C_LEFT_J;
+                        if (dir) S.want_kmer(((tail << 2) | rv.code(L.sp.end + K - 1)) & KMER_MASK);
+                        else S.want_kmer((tail >> 2) | ((uint64_t)rv.code(L.sp.begin) << (2 * K - 2)));
+                    }
+                } else if (shift == INVALID_SHIFT) {
+                    L.l.n = 0;
+                }
+                if (finished) {
+                    if (dir) S.after_attempt();
+                    else S.after_left();
+                }
+            }
+        } else {  // P_TALLY
+            long long slot = -1;
+            if (mine) {
+                lane_load(L, I, true);
+                int length;
+                if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
+                    int begin1 = L.m1_begin, end1;
+                    if (!intersect(L.m1, L.l)) {
+                        L.m1.n = 0;
+                        begin1 = 0;
+                        end1 = -K;
+                    } else if (L.m1_anchor.entry != ~L.sp.anchor.entry) {
+                        begin1 = 0;
+                        end1 = -K;
+                    } else {
+                        end1 = L.m1_len - K;
+                        int interval = L.sp.anchor.offset - L.m1_anchor.offset;
+                        if (L.m1_anchor.entry < 0) interval = -interval;
+                        end1 += interval + (L.len - K) - L.sp.begin;
+                    }
+                    length = end1 - begin1 + K;
+                    L.l = L.m1;
+                } else {
+                    length = L.sp.end - L.sp.begin + K;
+                }
+                if (a.out_length) a.out_length[L.unit] = length;
+                if (length > 0) {  // _mapper.pyx:90-94
+                    if (length >= SKM_MAX_FRAGMENT_LENGTH) length = SKM_MAX_FRAGMENT_LENGTH - 1;
+                    atomicAdd(&sm_fld[length], 1u);
+                }
+                if (L.l.n > 0) {
+                    const ulonglong2 key = tuple_key(L.l, L.l.n, true);
+                    slot = dict_find_or_insert(dict, key, L.l, L.l.n, true);
+                }
+                if (a.out_class) a.out_class[L.unit] = (int32_t)slot;
+                if (slot >= 0) {
+                    const unsigned long long g = (unsigned long long)(a.first_unit + L.unit);
+                    if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
+                        atomicMin(&dict.first[slot], g);
+                }
+                // the item is free again: mate 0 of a new unit
+                L.mate = 0;
+                L.l = I.fresh_list(0);
+                L.m1 = I.fresh_list(0);
+                L.st = P_LOAD;
+            }
+            __syncwarp();
+            // one count atomic per distinct class per warp (mapper.py:60-75)
+            const unsigned same = __match_any_sync(0xffffffffu, slot);
+            if (slot >= 0 && lane == __ffs(same) - 1)
+                atomicAdd(&dict.counts[slot], (unsigned long long)__popc(same));
+            const unsigned done = __ballot_sync(0xffffffffu, mine);
+            const unsigned mapped = __ballot_sync(0xffffffffu, mine && slot >= 0);
+            if (lane == 0) {
+                const int n_al = __popc(mapped);
+                const int n_un = __popc(done) - n_al;
+                if (n_un) atomicAdd(&dict.scalars[2], (unsigned long long)n_un);
+                if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
+            }
+        }
+        // ---- publish: state first, then the row's bit in the next phase's mask --------------
+        if (mine) {
+            if (L.st == P_DEAD) {
+                atomicSub(sm_live, 1);
+            } else {
+                lane_store(L, I);
+                __threadfence_block();
+                atomicOr(&sm_masks[L.st * 32 + lane], 1u << row);
+            }
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) {
+        const uint32_t v = sm_fld[i];
+        if (v) atomicAdd(&dict.fld[i], (unsigned long long)v);
+    }
+}
+
+}  // namespace skm
