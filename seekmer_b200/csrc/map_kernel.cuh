@@ -295,53 +295,112 @@ __device__ __forceinline__ uint32_t edge_window(uint64_t first_kmer, uint64_t la
     return revcomp8(left_edge ? tail : head);
 }
 
-struct MapCtx {
-    const DevIndex &ix;
-    const MapArgs &a;
-    uint32_t *status;
-};
+// Element access for a list given by value (shared-window address or arena pointer).
+template <int ITEMS>
+__device__ __forceinline__ int32_t list_get(uint32_t sa, const int32_t *gp, int i)
+{
+    return List<ITEMS>{sa, const_cast<int32_t *>(gp), 0}.get(i);
+}
+template <int ITEMS>
+__device__ __forceinline__ void list_set(uint32_t sa, int32_t *gp, int i, int32_t v)
+{
+    List<ITEMS>{sa, gp, 0}.set(i, v);
+}
+
+// map_contig for a contig with more than 8 targets: the full list is read from targets[]; more
+// than LIST_CAP entries spill to the arena.  Out of line (rare) with scalar arguments only, so
+// nothing of the caller's state is forced into local memory.  Returns the arena offset used,
+// -1 when the list went to shared memory, -2 when the arena is exhausted.
+template <int ITEMS>
+__device__ __noinline__ long long map_contig_long(const int32_t *t, int n, int forward, uint32_t sa, int32_t *arena,
+                                                  unsigned long long arena_cap, unsigned long long *cursor,
+                                                  uint32_t *status)
+{
+    const int32_t x = forward ? 0 : -1;
+    long long off = -1;
+    int32_t *gp = nullptr;
+    if (n > LIST_CAP) {
+        off = (long long)atomicAdd(cursor, (unsigned long long)n);
+        if ((unsigned long long)off + (unsigned long long)n > arena_cap) {
+            atomicOr(status, ST_ARENA_FULL);
+            return -2;
+        }
+        sa = 0;
+        gp = arena + off;
+    }
+    for (int i = 0; i < n; ++i) list_set<ITEMS>(sa, gp, i, __ldg(t + (forward ? i : n - 1 - i)) ^ x);
+    return off;
+}
 
 // map_contig (_common.pyx:143-179) for an already loaded contig record.  Forward: the
 // contig's targets in order; reverse: reversed order, every entry bit-negated.
 template <int ITEMS>
-__device__ __forceinline__ void map_contig(const MapCtx &cx, const Contig &c, Coord at, List<ITEMS> &l)
+__device__ __forceinline__ void map_contig(const DevIndex &ix, const MapArgs &a, uint32_t *status, const Contig &c,
+                                           Coord at, List<ITEMS> &l)
 {
     const bool forward = at.entry >= 0;
     const int n = c.target_count;
     const int32_t x = forward ? 0 : -1;
+    l.n = n;
     if (n <= INLINE_TARGETS) {  // straight-line: the 8 inline entries are already in registers
 #pragma unroll
         for (int j = 0; j < INLINE_TARGETS; ++j)
             if (j < n) l.set(forward ? j : n - 1 - j, c.t[j] ^ x);
-        l.n = n;
         return;
     }
-    if (n > LIST_CAP) {
-        const unsigned long long off = atomicAdd(&cx.a.cursors[1], (unsigned long long)n);
-        if (off + (unsigned long long)n > cx.a.arena_cap) {
-            atomicOr(cx.status, ST_ARENA_FULL);
-            l.n = 0;
-            return;
-        }
+    const long long off = map_contig_long<ITEMS>(ix.targets + c.target_offset, n, forward ? 1 : 0, l.sa, a.arena,
+                                                 a.arena_cap, a.cursors + 1, status);
+    if (off == -2) {
+        l.n = 0;
+    } else if (off >= 0) {
         l.sa = 0;
-        l.gp = cx.a.arena + off;
+        l.gp = a.arena + off;
     }
-    const int32_t *t = cx.ix.targets + c.target_offset;
-    for (int i = 0; i < n; ++i) l.set(i, __ldg(t + (forward ? i : n - 1 - i)) ^ x);
-    l.n = n;
+}
+
+// the sorted merge itself, for contigs with more than 8 targets (list read from targets[]);
+// returns the new list length, 0 = no match (list left intact)
+template <int ITEMS>
+__device__ __noinline__ int filter_long(const int32_t *t, int length, int forward, uint32_t sa, int32_t *gp, int n)
+{
+    const int32_t x = forward ? 0 : -1;
+    int read_index = 0, write_index = 0, track = 0;
+    int32_t index_entry = __ldg(t + (forward ? 0 : length - 1)) ^ x;
+    int32_t target_entry = list_get<ITEMS>(sa, gp, 0);
+    while (true) {
+        if (target_entry == index_entry) {
+            list_set<ITEMS>(sa, gp, write_index, target_entry);
+            read_index += 1;
+            write_index += 1;
+            track += 1;
+            if (read_index == n || track == length) break;
+            target_entry = list_get<ITEMS>(sa, gp, read_index);
+            index_entry = __ldg(t + (forward ? track : length - 1 - track)) ^ x;
+        } else if (target_entry < index_entry) {
+            read_index += 1;
+            if (read_index == n) break;
+            target_entry = list_get<ITEMS>(sa, gp, read_index);
+        } else {
+            track += 1;
+            if (track == length) break;
+            index_entry = __ldg(t + (forward ? track : length - 1 - track)) ^ x;
+        }
+    }
+    return write_index;
 }
 
 // _filter_on_contig (_common.pyx:185-235): direction-aware sorted-merge intersection of the
 // span's list with the contig's list; equal entries pair off one to one; zero matches leave
 // the list intact and return false.
 template <int ITEMS>
-__device__ __forceinline__ bool filter_on_contig(const MapCtx &cx, const Contig &c, Coord at, List<ITEMS> &l)
+__device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Contig &c, Coord at, List<ITEMS> &l)
 {
     if (l.n == 0) return true;
     const bool forward = at.entry >= 0;
     const int length = c.target_count;
     if (length == 0) return false;
     const int32_t x = forward ? 0 : -1;
+    int w;
     if (length <= INLINE_TARGETS) {
         // Both lists are ascending (targets are sorted per contig, _index_builder.pyx:540, and
         // map_contig / this filter keep that order), so the merge keeps the r-th occurrence of a
@@ -350,9 +409,10 @@ __device__ __forceinline__ bool filter_on_contig(const MapCtx &cx, const Contig 
         int32_t t[INLINE_TARGETS];
 #pragma unroll
         for (int j = 0; j < INLINE_TARGETS; ++j) t[j] = c.t[j] ^ x;
-        int w = 0, run = 0;
+        int run = 0;
         int32_t prev = 0;
         const int n = l.n;
+        w = 0;
         for (int i = 0; i < n; ++i) {
             const int32_t v = l.get(i);
             run = (i > 0 && v == prev) ? run + 1 : 0;
@@ -365,35 +425,11 @@ __device__ __forceinline__ bool filter_on_contig(const MapCtx &cx, const Contig 
                 w += 1;
             }
         }
-        if (w == 0) return false;
-        l.n = w;
-        return true;
+    } else {
+        w = filter_long<ITEMS>(ix.targets + c.target_offset, length, forward ? 1 : 0, l.sa, l.gp, l.n);
     }
-    const int32_t *t = cx.ix.targets + c.target_offset;
-    int read_index = 0, write_index = 0, track = 0;
-    int32_t index_entry = __ldg(t + (forward ? 0 : length - 1)) ^ x;
-    int32_t target_entry = l.get(0);
-    while (true) {
-        if (target_entry == index_entry) {
-            l.set(write_index, target_entry);
-            read_index += 1;
-            write_index += 1;
-            track += 1;
-            if (read_index == l.n || track == length) break;
-            target_entry = l.get(read_index);
-            index_entry = __ldg(t + (forward ? track : length - 1 - track)) ^ x;
-        } else if (target_entry < index_entry) {
-            read_index += 1;
-            if (read_index == l.n) break;
-            target_entry = l.get(read_index);
-        } else {
-            track += 1;
-            if (track == length) break;
-            index_entry = __ldg(t + (forward ? track : length - 1 - track)) ^ x;
-        }
-    }
-    if (write_index == 0) return false;
-    l.n = write_index;
+    if (w == 0) return false;
+    l.n = w;
     return true;
 }
 
@@ -424,102 +460,38 @@ __device__ __forceinline__ bool intersect(List<ITEMS> &l1, const List<ITEMS> &l2
 }
 
 // ---- state-machine transitions ------------------------------------------------------------
-template <int ITEMS>
-struct Step {
-    Lane<ITEMS> &L;
-    const ItemMem<ITEMS> &I;
-    const ReadView<ITEMS> &rv;
-    const DevIndex &ix;
-    int paired;
-
-    // Record the next single k-mer to look up and start pulling its home bucket towards L2.
-    __device__ __forceinline__ void want_kmer(uint64_t kmer)
-    {
-        L.kmer = kmer;
-        L.bucket = home_bucket(ix, kmer);
-        prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * L.bucket);
-        L.st = P_LOOKUP;
-    }
-
-    __device__ __forceinline__ void read_done()
-    {
-        if (paired && L.mate == 0) {
-            L.m1_begin = L.sp.begin;
-            L.m1_anchor = L.sp.anchor;
-            L.m1_len = L.len;
-            L.m1 = L.l;
-            L.m1_dirty = true;
-            L.mate = 1;
-            L.st = P_LOAD;
-        } else {
-            L.st = P_TALLY;
-        }
-    }
-
-    __device__ __forceinline__ void after_attempt()  // map_read :177-193
-    {
-        if (L.l.n != 0 || L.attempt == 1) {
-            read_done();
-            return;
-        }
-        L.attempt = 1;
-        L.sp.anchor = coord_invalid();
-        L.sp.begin += K;
-        if (L.sp.begin + K > L.len) L.sp.begin = L.len - K;
-        L.sp.end = L.sp.begin;
-        L.pos = L.sp.begin;
-        L.l = I.fresh_list(L.mate);
-        L.ctx = C_FIND;
-        want_kmer(rv.kmer(L.pos));
-    }
-
-    __device__ __forceinline__ void after_left()  // map_read :174-176
-    {
-        if (L.l.n != 0 && L.sp.end < L.len - K) {
-            if (L.ctg_a0) {
-                // the stash still holds the contig of the first hit (no junction was crossed):
-                // _filter_targets_to_right starts there (:283-295) without another record load
-                L.sp.anchor = L.anchor0;
-                L.forward = L.anchor0.entry >= 0;
-                L.move = L.forward ? L.clen - L.anchor0.offset - K : L.anchor0.offset;
-                L.dir = 1;
-                L.st = P_WALK;
-            } else {
-                prefetch_l2(ix.contigs + (L.anchor0.entry >= 0 ? L.anchor0.entry : ~L.anchor0.entry));
-                L.ctx = C_RIGHT_C;
-                L.st = P_FILTER;
-            }
-        } else {
-            after_attempt();
-        }
-    }
-
-    // _filter_targets_to_left :250-263 when the junction lookup or its filter failed
-    __device__ __forceinline__ void left_junction_failed()
-    {
-        if (L.ctx == C_LEFT_J) {
-            if (L.sp.begin < K) {
-                L.sp.begin = 0;
-                after_left();
-            } else {
-                L.sp.begin -= K;
-                L.ctx = C_LEFT_F;
-                want_kmer(rv.kmer(L.sp.begin));
-            }
-        } else {  // C_LEFT_F
-            L.l.n = 0;
-            after_left();
-        }
-    }
-
-    // a k-mer hit: next comes its contig record
-    __device__ __forceinline__ void hit(Coord h)
-    {
-        L.sp.anchor = h;
-        prefetch_l2(ix.contigs + (h.entry >= 0 ? h.entry : ~h.entry));
-        L.st = L.ctx == C_FIND ? P_MAP : P_FILTER;
-    }
+// A phase ends by naming what happens next; the transitions of map_read (:151-193) and of the
+// walk fallbacks are applied once, after the phase switch, by every lane together.
+enum : int {
+    EV_NONE = 0,
+    EV_LEFT_FAILED,    // _filter_targets_to_left :250-263: junction lookup or its filter failed
+    EV_AFTER_LEFT,     // map_read :174-176
+    EV_AFTER_ATTEMPT,  // map_read :177-193
+    EV_READ_DONE
 };
+
+__device__ __noinline__ uint32_t hash_bucket(uint64_t kmer, uint64_t bucket_mask)
+{
+    const uint64_t rc = revcomp(kmer);
+    return home_bucket_of(kmer < rc ? kmer : rc, bucket_mask);
+}
+
+// the bucket probe, packed as entry | offset << 32
+__device__ __noinline__ unsigned long long probe_kmer(const Slot *table, uint64_t bucket_mask, uint64_t kmer,
+                                                      uint32_t bucket)
+{
+    DevIndex ix;
+    ix.table = table;
+    ix.bucket_mask = bucket_mask;
+    const Coord c = map_kmer_at(ix, kmer, bucket);
+    return (unsigned long long)(uint32_t)c.entry | ((unsigned long long)(uint32_t)c.offset << 32);
+}
+
+__device__ __forceinline__ Coord probe_kmer(const DevIndex &ix, uint64_t kmer, uint32_t bucket)
+{
+    const unsigned long long v = probe_kmer(ix.table, ix.bucket_mask, kmer, bucket);
+    return Coord{(int32_t)(uint32_t)v, (int32_t)(uint32_t)(v >> 32)};
+}
 
 // sift4_align_left(window, read, qoff) for dir == 0, sift4_align_right for dir == 1 (sift4.cuh)
 template <int ITEMS>
@@ -561,7 +533,6 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const MapCtx cx{ix, a, dict.status};
     volatile uint32_t *vmasks = sm_masks;
     unsigned iter = (unsigned)warp * 5u;
 
@@ -614,14 +585,27 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
         I.arena = a.arena;
         Lane<ITEMS> L;
         L.st = phase;
+        L.mate = 0;
+        L.unit = 0;
+        L.len = 0;
+        L.has_wild = false;
+        if (mine) lane_load(L, I, phase == P_TALLY);
         ReadView<ITEMS> rv;
         rv.w = I.codes;
-        rv.wild = nullptr;
+        rv.len = L.len;
         rv.wild_words = a.wild_words;
-        Step<ITEMS> S{L, I, rv, ix, a.paired};
+        rv.wild = nullptr;
+        if (L.has_wild) {
+            const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
+            rv.wild = a.packed + read_idx * (long long)a.words + a.code_words;
+        }
+        int ev = EV_NONE;
+        int want_pos = -1;       // look up the read's k-mer at this position next ...
+        bool want = false;       // ... or this explicit k-mer
+        uint64_t want_kmer = 0;
+        long long slot = -1;     // P_TALLY: dictionary slot of the unit's class
 
         if (phase == P_LOAD) {
-            if (mine) lane_load(L, I, false);
             // ---- new units for finished items (mate 0): one global atomic per warp -------------
             const bool need = mine && L.mate == 0;
             const unsigned nb = __ballot_sync(0xffffffffu, need);
@@ -649,6 +633,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 const int max_len = a.code_words * 32;
                 if (len > max_len) len = max_len;
                 L.len = len;
+                rv.len = len;
                 L.has_wild = any_wild != 0;
                 L.sp = Span{0, 0, coord_invalid()};
                 L.l = I.fresh_list(L.mate);
@@ -657,89 +642,78 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 L.ctg_a0 = false;
                 L.ctx = C_FIND;
                 if (len >= K) {
-                    S.want_kmer(rv.kmer(0));
+                    want_pos = 0;
                 } else {  // undefined in the reference; reported unaligned and flagged
                     atomicOr(dict.status, ST_SHORT_READ);
-                    S.read_done();
+                    ev = EV_READ_DONE;
                 }
             }
         } else if (phase == P_LOOKUP) {
             if (mine) {
-                lane_load(L, I, false);
-                rv.len = L.len;
-                const Coord h = map_kmer_at(ix, L.kmer, L.bucket);
+                const Coord h = probe_kmer(ix, L.kmer, L.bucket);
+                L.sp.anchor = h;
                 if (h.offset >= 0) {
-                    S.hit(h);
+                    prefetch_l2(ix.contigs + (h.entry >= 0 ? h.entry : ~h.entry));
+                    L.st = L.ctx == C_FIND ? P_MAP : P_FILTER;
+                } else if (L.ctx == C_FIND) {
+                    // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
+                    // targets empty and map_read returns (:170-171, :186-187)
+                    L.pos += 1;
+                    if (L.pos + K <= L.len) L.st = P_SCAN;
+                    else ev = EV_READ_DONE;
+                } else if (L.ctx == C_RIGHT_J) {
+                    L.l.n = 0;  // :312-315
+                    ev = EV_AFTER_ATTEMPT;
                 } else {
-                    L.sp.anchor = h;
-                    if (L.ctx == C_FIND) {
-                        // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
-                        // targets empty and map_read returns (:170-171, :186-187)
-                        L.pos += 1;
-                        if (L.pos + K <= L.len) L.st = P_SCAN;
-                        else S.read_done();
-                    } else if (L.ctx == C_RIGHT_J) {
-                        L.l.n = 0;  // :312-315
-                        S.after_attempt();
-                    } else {
-                        S.left_junction_failed();
-                    }
+                    ev = EV_LEFT_FAILED;
                 }
             }
         } else if (phase == P_SCAN) {
             if (mine) {
-                lane_load(L, I, false);
-                rv.len = L.len;
                 // positions pos .. pos+3 (while they fit); L.kmer is the k-mer at pos-1
                 uint64_t km[SCAN_WIDTH];
                 uint32_t bk[SCAN_WIDTH];
-                Coord h[SCAN_WIDTH];
                 uint64_t k = L.kmer;
+                const int fit = L.len - K + 1 - L.pos;  // >= 1
 #pragma unroll
                 for (int j = 0; j < SCAN_WIDTH; ++j) {
-                    const int p = L.pos + j;
-                    h[j] = coord_invalid();
                     km[j] = k;
                     bk[j] = 0;
-                    if (p + K <= L.len) {
-                        k = ((k << 2) | rv.code(p + K - 1)) & KMER_MASK;
+                    if (j < fit) {
+                        k = ((k << 2) | rv.code(L.pos + j + K - 1)) & KMER_MASK;
                         km[j] = k;
-                        bk[j] = home_bucket(ix, k);
+                        bk[j] = hash_bucket(k, ix.bucket_mask);
                         prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * bk[j]);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < SCAN_WIDTH; ++j)
-                    if (L.pos + j + K <= L.len) h[j] = map_kmer_at(ix, km[j], bk[j]);
                 int first = SCAN_WIDTH;
+                Coord hh = coord_invalid();
+                uint64_t kk = k;
 #pragma unroll
-                for (int j = SCAN_WIDTH - 1; j >= 0; --j)
-                    if (h[j].offset >= 0) first = j;
-                if (first < SCAN_WIDTH) {
-                    L.pos += first;
-                    Coord hh = h[0];
-                    uint64_t kk = km[0];
-#pragma unroll
-                    for (int j = 1; j < SCAN_WIDTH; ++j)
-                        if (j == first) {
-                            hh = h[j];
+                for (int j = SCAN_WIDTH - 1; j >= 0; --j) {
+                    if (j < fit) {
+                        const Coord h = probe_kmer(ix, km[j], bk[j]);
+                        if (h.offset >= 0) {
+                            first = j;
+                            hh = h;
                             kk = km[j];
                         }
-                    L.kmer = kk;
-                    S.hit(hh);
+                    }
+                }
+                L.sp.anchor = hh;
+                L.kmer = kk;
+                if (first < SCAN_WIDTH) {
+                    L.pos += first;
+                    prefetch_l2(ix.contigs + (hh.entry >= 0 ? hh.entry : ~hh.entry));
+                    L.st = P_MAP;
                 } else {
-                    L.sp.anchor = coord_invalid();
-                    const int tried = min(SCAN_WIDTH, L.len - K + 1 - L.pos);
-                    L.pos += tried;
-                    L.kmer = k;
+                    L.pos += min(SCAN_WIDTH, fit);
                     if (L.pos + K <= L.len) L.st = P_SCAN;
-                    else S.read_done();
+                    else ev = EV_READ_DONE;
                 }
             }
         } else if (phase == P_MAP || phase == P_FILTER) {
             if (mine) {
-                lane_load(L, I, false);
-                rv.len = L.len;
                 const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
                 const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
                 I.ctg[0] = c.first_kmer;
@@ -750,24 +724,24 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 const int to_start = L.forward ? at.offset : c.length - at.offset - K;
                 const int to_end = L.forward ? c.length - at.offset - K : at.offset;
                 if (phase == P_MAP) {  // ctx == C_FIND
-                    map_contig(cx, c, at, L.l);
+                    map_contig(ix, a, dict.status, c, at, L.l);
                     L.sp.begin = L.pos;
                     L.sp.end = L.pos;
                     L.anchor0 = at;
                     L.ctg_a0 = true;
                     if (L.l.n == 0) {
-                        S.read_done();  // `if is_empty(targets): return span`
+                        ev = EV_READ_DONE;  // `if is_empty(targets): return span`
                     } else if (L.sp.begin > 0) {
                         L.move = to_start;
                         L.dir = 0;
                         L.st = P_WALK;
                     } else {
-                        S.after_left();
+                        ev = EV_AFTER_LEFT;
                     }
                 } else {
                     bool ok = true;
                     if (L.ctx != C_RIGHT_C) {
-                        ok = filter_on_contig(cx, c, at, L.l);
+                        ok = filter_on_contig(ix, c, at, L.l);
                         L.ctg_a0 = false;
                     } else {
                         L.sp.anchor = at;  // :283-284 — same k-mer as the scan hit, lookup cached
@@ -780,25 +754,19 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                             L.st = P_WALK;
                         } else {
                             L.l.n = 0;  // :312-315
-                            S.after_attempt();
+                            ev = EV_AFTER_ATTEMPT;
                         }
                     } else if (ok) {
                         L.move = to_start;
                         L.dir = 0;
                         L.st = P_WALK;
                     } else {
-                        S.left_junction_failed();
+                        ev = EV_LEFT_FAILED;
                     }
                 }
             }
         } else if (phase == P_WALK) {
             if (mine) {
-                lane_load(L, I, false);
-                rv.len = L.len;
-                if (L.has_wild) {
-                    const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
-                    rv.wild = a.packed + read_idx * (long long)a.words + a.code_words;
-                }
                 // heads of the loops of _filter_targets_to_left (:234-275) and _to_right (:293-343)
                 const uint64_t first_kmer = I.ctg[0], last_kmer = I.ctg[ITEMS];
                 const int dir = L.dir;
@@ -839,21 +807,17 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                         uint64_t tail = L.sp.anchor.offset == 0 ? first_kmer : last_kmer;  // get_tail_kmer
                         if (L.sp.anchor.entry < 0) tail = revcomp(tail);
                         L.ctx = dir ? C_RIGHT_J : C_LEFT_J;
-                        if (dir) S.want_kmer(((tail << 2) | rv.code(L.sp.end + K - 1)) & KMER_MASK);
-                        else S.want_kmer((tail >> 2) | ((uint64_t)rv.code(L.sp.begin) << (2 * K - 2)));
+                        want = true;
+                        want_kmer = dir ? ((tail << 2) | rv.code(L.sp.end + K - 1)) & KMER_MASK
+                                        : (tail >> 2) | ((uint64_t)rv.code(L.sp.begin) << (2 * K - 2));
                     }
                 } else if (shift == INVALID_SHIFT) {
                     L.l.n = 0;
                 }
-                if (finished) {
-                    if (dir) S.after_attempt();
-                    else S.after_left();
-                }
+                if (finished) ev = dir ? EV_AFTER_ATTEMPT : EV_AFTER_LEFT;
             }
         } else {  // P_TALLY
-            long long slot = -1;
             if (mine) {
-                lane_load(L, I, true);
                 int length;
                 if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
                     int begin1 = L.m1_begin, end1;
@@ -910,8 +874,86 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
             }
         }
-        // ---- publish: state first, then the row's bit in the next phase's mask --------------
+
+        // ---- transitions (one copy, all phases) ------------------------------------------------
         if (mine) {
+            if (ev == EV_LEFT_FAILED) {
+                if (L.ctx == C_LEFT_J) {
+                    if (L.sp.begin < K) {
+                        L.sp.begin = 0;
+                        ev = EV_AFTER_LEFT;
+                    } else {
+                        L.sp.begin -= K;
+                        L.ctx = C_LEFT_F;
+                        want_pos = L.sp.begin;
+                        ev = EV_NONE;
+                    }
+                } else {  // C_LEFT_F
+                    L.l.n = 0;
+                    ev = EV_AFTER_LEFT;
+                }
+            }
+            if (ev == EV_AFTER_LEFT) {
+                if (L.l.n != 0 && L.sp.end < L.len - K) {
+                    if (L.ctg_a0) {
+                        // the stash still holds the contig of the first hit (no junction was
+                        // crossed): _filter_targets_to_right starts there (:283-295) without
+                        // another record load
+                        L.sp.anchor = L.anchor0;
+                        L.forward = L.anchor0.entry >= 0;
+                        L.move = L.forward ? L.clen - L.anchor0.offset - K : L.anchor0.offset;
+                        L.dir = 1;
+                        L.st = P_WALK;
+                    } else {
+                        prefetch_l2(ix.contigs + (L.anchor0.entry >= 0 ? L.anchor0.entry : ~L.anchor0.entry));
+                        L.ctx = C_RIGHT_C;
+                        L.st = P_FILTER;
+                    }
+                    ev = EV_NONE;
+                } else {
+                    ev = EV_AFTER_ATTEMPT;
+                }
+            }
+            if (ev == EV_AFTER_ATTEMPT) {
+                if (L.l.n != 0 || L.attempt == 1) {
+                    ev = EV_READ_DONE;
+                } else {
+                    L.attempt = 1;
+                    L.sp.anchor = coord_invalid();
+                    L.sp.begin += K;
+                    if (L.sp.begin + K > L.len) L.sp.begin = L.len - K;
+                    L.sp.end = L.sp.begin;
+                    L.pos = L.sp.begin;
+                    L.l = I.fresh_list(L.mate);
+                    L.ctx = C_FIND;
+                    want_pos = L.pos;
+                    ev = EV_NONE;
+                }
+            }
+            if (ev == EV_READ_DONE) {
+                if (a.paired && L.mate == 0) {
+                    L.m1_begin = L.sp.begin;
+                    L.m1_anchor = L.sp.anchor;
+                    L.m1_len = L.len;
+                    L.m1 = L.l;
+                    L.m1_dirty = true;
+                    L.mate = 1;
+                    L.st = P_LOAD;
+                } else {
+                    L.st = P_TALLY;
+                }
+            }
+            if (want_pos >= 0) {
+                want = true;
+                want_kmer = rv.kmer(want_pos);
+            }
+            if (want) {  // the next single k-mer: start pulling its home bucket towards L2
+                L.kmer = want_kmer;
+                L.bucket = hash_bucket(want_kmer, ix.bucket_mask);
+                prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * L.bucket);
+                L.st = P_LOOKUP;
+            }
+            // ---- publish: state first, then the row's bit in the next phase's mask ----------
             if (L.st == P_DEAD) {
                 atomicSub(sm_live, 1);
             } else {
