@@ -54,6 +54,16 @@ constexpr int ALIGN_LENGTH = 8;           // _mapper.pyx:22
 constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
 constexpr int SCAN_WIDTH = 4;             // read positions probed per P_SCAN step
 
+// What the mapper leaves behind for one unit: the span length of _mapper.pyx:90 and the ordered
+// target list (signed entries; signs are stripped when the class key is formed, :528-537).
+// Lists longer than REC_IDS live in the arena: ids[0..1] then hold the arena offset.
+constexpr int REC_IDS = 14;
+struct __align__(16) UnitRec {
+    int32_t n;
+    int32_t length;
+    int32_t ids[REC_IDS];
+};
+
 struct MapArgs {
     const uint64_t *packed;   // [n_reads][words] from pack_reads_kernel
     const int32_t *lens;      // per-read length, or NULL with fixed_len
@@ -64,8 +74,7 @@ struct MapArgs {
     int32_t paired;
     int64_t n_units;
     int64_t first_unit;
-    int32_t *out_class;
-    int32_t *out_length;
+    UnitRec *units;           // [n_units] mapping result of every unit, consumed by tally_units_kernel
     int32_t *arena;           // spill space for target lists longer than LIST_CAP
     uint64_t arena_cap;
     unsigned long long *cursors;  // [0]=work counter [1]=arena cursor
@@ -92,7 +101,7 @@ constexpr size_t map_item_bytes(int code_words)
 {
     return sizeof(uint64_t) * ((size_t)code_words + CTG_WORDS) + sizeof(int32_t) * 2 * LIST_CAP + 16 * STATE_VECS;
 }
-constexpr size_t map_fixed_bytes() { return sizeof(uint32_t) * (N_PHASES * 32 + SKM_MAX_FRAGMENT_LENGTH) + 16; }
+constexpr size_t map_fixed_bytes() { return sizeof(uint32_t) * (N_PHASES * 32) + 16; }
 
 // ---- shared-memory views of one item; ITEMS = rows * 32 is a compile-time constant so every
 // ---- field access is one ld/st.shared with an immediate offset
@@ -135,26 +144,17 @@ struct ReadView {
     }
 };
 
-// A target list: shared memory ([entry][item]) or, when longer than LIST_CAP, the arena.
+// A target list: shared memory ([entry][item], element stride ITEMS) or, when longer than
+// LIST_CAP, the arena (dense).  One generic pointer and a stride serve both, so element access
+// is a single load/store without a branch.
 template <int ITEMS>
 struct List {
-    uint32_t sa;   // shared-window address of element 0, or 0 = arena
-    int32_t *gp;   // arena pointer when sa == 0
+    int32_t *p;   // element 0
+    int stride;   // ITEMS (shared memory) or 1 (arena)
     int n;
-    __device__ __forceinline__ int32_t get(int i) const
-    {
-        if (sa) {
-            int32_t v;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(sa + 4u * ITEMS * (uint32_t)i));
-            return v;
-        }
-        return gp[i];
-    }
-    __device__ __forceinline__ void set(int i, int32_t v)
-    {
-        if (sa) asm volatile("st.shared.s32 [%0], %1;" ::"r"(sa + 4u * ITEMS * (uint32_t)i), "r"(v) : "memory");
-        else gp[i] = v;
-    }
+    __device__ __forceinline__ bool in_arena() const { return stride == 1; }
+    __device__ __forceinline__ int32_t get(int i) const { return p[i * stride]; }
+    __device__ __forceinline__ void set(int i, int32_t v) { p[i * stride] = v; }
 };
 
 struct Span {
@@ -184,11 +184,11 @@ struct ItemMem {
     uint4 *state;      // &state[0][item]; vector v at state[v * ITEMS]
     uint64_t *codes;   // &codes[0][item]
     uint64_t *ctg;     // &ctg[0][item]
-    uint32_t list0_sa, list1_sa;
+    int32_t *list0;    // &lists[0][item]; mate 2 uses the second LIST_CAP entries
     int32_t *arena;
     __device__ __forceinline__ List<ITEMS> fresh_list(int mate) const
     {
-        return List<ITEMS>{mate ? list1_sa : list0_sa, nullptr, 0};
+        return List<ITEMS>{list0 + (mate ? LIST_CAP * ITEMS : 0), ITEMS, 0};
     }
 };
 
@@ -219,16 +219,10 @@ __device__ __forceinline__ void lane_load(Lane<ITEMS> &L, const ItemMem<ITEMS> &
     L.sp.anchor = Coord{(int32_t)v2.z, (int32_t)v2.w};
     L.l = I.fresh_list(L.mate);
     L.l.n = (int)(v3.x & 0xFFFFu);
-    if (f & F_L_ARENA) {
-        L.l.sa = 0;
-        L.l.gp = I.arena + v3.z;
-    }
+    if (f & F_L_ARENA) L.l = List<ITEMS>{I.arena + v3.z, 1, L.l.n};
     L.m1 = I.fresh_list(0);
     L.m1.n = (int)(v3.x >> 16);
-    if (f & F_M1_ARENA) {
-        L.m1.sa = 0;
-        L.m1.gp = I.arena + v3.w;
-    }
+    if (f & F_M1_ARENA) L.m1 = List<ITEMS>{I.arena + v3.w, 1, L.m1.n};
     L.clen = (int)v3.y;
     if (with_m1) {
         const uint4 v4 = I.state[4 * ITEMS];
@@ -244,7 +238,7 @@ __device__ __forceinline__ void lane_store(const Lane<ITEMS> &L, const ItemMem<I
     uint4 v0, v1, v2, v3;
     v0.x = (uint32_t)L.unit;
     v0.y = (uint32_t)L.ctx | (L.dir ? F_DIR : 0u) | (L.mate ? F_MATE : 0u) | (L.attempt ? F_ATTEMPT : 0u)
-           | (L.forward ? F_FORWARD : 0u) | (L.l.sa ? 0u : F_L_ARENA) | (L.m1.sa ? 0u : F_M1_ARENA)
+           | (L.forward ? F_FORWARD : 0u) | (L.l.in_arena() ? F_L_ARENA : 0u) | (L.m1.in_arena() ? F_M1_ARENA : 0u)
            | (L.ctg_a0 ? F_CTG_A0 : 0u) | (L.has_wild ? F_WILD : 0u);
     v0.z = ((uint32_t)L.pos & 0xFFFFu) | ((uint32_t)L.len << 16);
     v0.w = (uint32_t)L.move;
@@ -258,8 +252,8 @@ __device__ __forceinline__ void lane_store(const Lane<ITEMS> &L, const ItemMem<I
     v2.w = (uint32_t)L.sp.anchor.offset;
     v3.x = ((uint32_t)L.l.n & 0xFFFFu) | ((uint32_t)L.m1.n << 16);
     v3.y = (uint32_t)L.clen;
-    v3.z = L.l.sa ? 0u : (uint32_t)(L.l.gp - I.arena);
-    v3.w = L.m1.sa ? 0u : (uint32_t)(L.m1.gp - I.arena);
+    v3.z = L.l.in_arena() ? (uint32_t)(L.l.p - I.arena) : 0u;
+    v3.w = L.m1.in_arena() ? (uint32_t)(L.m1.p - I.arena) : 0u;
     I.state[0] = v0;
     I.state[ITEMS] = v1;
     I.state[2 * ITEMS] = v2;
@@ -295,40 +289,27 @@ __device__ __forceinline__ uint32_t edge_window(uint64_t first_kmer, uint64_t la
     return revcomp8(left_edge ? tail : head);
 }
 
-// Element access for a list given by value (shared-window address or arena pointer).
-template <int ITEMS>
-__device__ __forceinline__ int32_t list_get(uint32_t sa, const int32_t *gp, int i)
-{
-    return List<ITEMS>{sa, const_cast<int32_t *>(gp), 0}.get(i);
-}
-template <int ITEMS>
-__device__ __forceinline__ void list_set(uint32_t sa, int32_t *gp, int i, int32_t v)
-{
-    List<ITEMS>{sa, gp, 0}.set(i, v);
-}
-
 // map_contig for a contig with more than 8 targets: the full list is read from targets[]; more
 // than LIST_CAP entries spill to the arena.  Out of line (rare) with scalar arguments only, so
 // nothing of the caller's state is forced into local memory.  Returns the arena offset used,
-// -1 when the list went to shared memory, -2 when the arena is exhausted.
-template <int ITEMS>
-__device__ __noinline__ long long map_contig_long(const int32_t *t, int n, int forward, uint32_t sa, int32_t *arena,
-                                                  unsigned long long arena_cap, unsigned long long *cursor,
-                                                  uint32_t *status)
+// -1 when the list went to the caller's shared-memory list, -2 when the arena is exhausted.
+__device__ __noinline__ long long map_contig_long(const int32_t *t, int n, int forward, int32_t *p, int stride,
+                                                  int32_t *arena, unsigned long long arena_cap,
+                                                  unsigned long long *cursor, uint32_t *status)
 {
     const int32_t x = forward ? 0 : -1;
     long long off = -1;
-    int32_t *gp = nullptr;
     if (n > LIST_CAP) {
         off = (long long)atomicAdd(cursor, (unsigned long long)n);
         if ((unsigned long long)off + (unsigned long long)n > arena_cap) {
             atomicOr(status, ST_ARENA_FULL);
             return -2;
         }
-        sa = 0;
-        gp = arena + off;
+        p = arena + off;
+        stride = 1;
     }
-    for (int i = 0; i < n; ++i) list_set<ITEMS>(sa, gp, i, __ldg(t + (forward ? i : n - 1 - i)) ^ x);
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) p[i * stride] = __ldg(t + (forward ? i : n - 1 - i)) ^ x;
     return off;
 }
 
@@ -348,38 +329,33 @@ __device__ __forceinline__ void map_contig(const DevIndex &ix, const MapArgs &a,
             if (j < n) l.set(forward ? j : n - 1 - j, c.t[j] ^ x);
         return;
     }
-    const long long off = map_contig_long<ITEMS>(ix.targets + c.target_offset, n, forward ? 1 : 0, l.sa, a.arena,
-                                                 a.arena_cap, a.cursors + 1, status);
-    if (off == -2) {
-        l.n = 0;
-    } else if (off >= 0) {
-        l.sa = 0;
-        l.gp = a.arena + off;
-    }
+    const long long off = map_contig_long(ix.targets + c.target_offset, n, forward ? 1 : 0, l.p, l.stride, a.arena,
+                                          a.arena_cap, a.cursors + 1, status);
+    if (off == -2) l.n = 0;
+    else if (off >= 0) l = List<ITEMS>{a.arena + off, 1, n};
 }
 
 // the sorted merge itself, for contigs with more than 8 targets (list read from targets[]);
 // returns the new list length, 0 = no match (list left intact)
-template <int ITEMS>
-__device__ __noinline__ int filter_long(const int32_t *t, int length, int forward, uint32_t sa, int32_t *gp, int n)
+__device__ __noinline__ int filter_long(const int32_t *t, int length, int forward, int32_t *p, int stride, int n)
 {
     const int32_t x = forward ? 0 : -1;
     int read_index = 0, write_index = 0, track = 0;
     int32_t index_entry = __ldg(t + (forward ? 0 : length - 1)) ^ x;
-    int32_t target_entry = list_get<ITEMS>(sa, gp, 0);
+    int32_t target_entry = p[0];
     while (true) {
         if (target_entry == index_entry) {
-            list_set<ITEMS>(sa, gp, write_index, target_entry);
+            p[write_index * stride] = target_entry;
             read_index += 1;
             write_index += 1;
             track += 1;
             if (read_index == n || track == length) break;
-            target_entry = list_get<ITEMS>(sa, gp, read_index);
+            target_entry = p[read_index * stride];
             index_entry = __ldg(t + (forward ? track : length - 1 - track)) ^ x;
         } else if (target_entry < index_entry) {
             read_index += 1;
             if (read_index == n) break;
-            target_entry = list_get<ITEMS>(sa, gp, read_index);
+            target_entry = p[read_index * stride];
         } else {
             track += 1;
             if (track == length) break;
@@ -413,6 +389,7 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
         int32_t prev = 0;
         const int n = l.n;
         w = 0;
+#pragma unroll 1
         for (int i = 0; i < n; ++i) {
             const int32_t v = l.get(i);
             run = (i > 0 && v == prev) ? run + 1 : 0;
@@ -426,7 +403,7 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
             }
         }
     } else {
-        w = filter_long<ITEMS>(ix.targets + c.target_offset, length, forward ? 1 : 0, l.sa, l.gp, l.n);
+        w = filter_long(ix.targets + c.target_offset, length, forward ? 1 : 0, l.p, l.stride, l.n);
     }
     if (w == 0) return false;
     l.n = w;
@@ -440,6 +417,7 @@ __device__ __forceinline__ bool intersect(List<ITEMS> &l1, const List<ITEMS> &l2
     if (l1.n == 0) return true;
     if (l2.n == 0) return false;
     int cursor1_read = 0, cursor1_write = 0, cursor2 = l2.n - 1;
+#pragma unroll 1
     while (cursor1_read != l1.n && cursor2 != -1) {
         const int32_t entry1 = l1.get(cursor1_read);
         const int32_t entry2 = ~l2.get(cursor2);
@@ -493,6 +471,22 @@ __device__ __forceinline__ Coord probe_kmer(const DevIndex &ix, uint64_t kmer, u
     return Coord{(int32_t)(uint32_t)v, (int32_t)(uint32_t)(v >> 32)};
 }
 
+// A final list longer than a unit record: make sure it lives in the arena, return its offset.
+__device__ __noinline__ long long emit_long_list(const int32_t *p, int stride, int n, int32_t *arena,
+                                                 unsigned long long arena_cap, unsigned long long *cursor,
+                                                 uint32_t *status)
+{
+    if (stride == 1) return (long long)(p - arena);
+    const unsigned long long off = atomicAdd(cursor, (unsigned long long)n);
+    if (off + (unsigned long long)n > arena_cap) {
+        atomicOr(status, ST_ARENA_FULL);
+        return 0;
+    }
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) arena[off + i] = p[i * stride];
+    return (long long)off;
+}
+
 // sift4_align_left(window, read, qoff) for dir == 0, sift4_align_right for dir == 1 (sift4.cuh)
 template <int ITEMS>
 __device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView<ITEMS> &rv, int qoff, int dir)
@@ -513,7 +507,7 @@ __device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView<ITEMS> 
 
 template <int ROWS>
 __global__ void __launch_bounds__(Q_THREADS, 1)
-map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
+map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
 {
     constexpr int ITEMS = ROWS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -522,10 +516,8 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
     uint64_t *sm_ctg = sm_codes + (size_t)a.code_words * ITEMS;                       // [CTG_WORDS][ITEMS]
     int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + CTG_WORDS * ITEMS);      // [2 * LIST_CAP][ITEMS]
     uint32_t *sm_masks = reinterpret_cast<uint32_t *>(sm_lists + 2 * LIST_CAP * ITEMS);  // [N_PHASES][32]
-    uint32_t *sm_fld = sm_masks + N_PHASES * 32;                                      // [FLD_BINS]
-    int *sm_live = reinterpret_cast<int *>(sm_fld + SKM_MAX_FRAGMENT_LENGTH);
+    int *sm_live = reinterpret_cast<int *>(sm_masks + N_PHASES * 32);
 
-    for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) sm_fld[i] = 0;
     for (int i = threadIdx.x; i < N_PHASES * 32; i += blockDim.x)
         sm_masks[i] = i < 32 ? (ROWS == 32 ? 0xFFFFFFFFu : (1u << ROWS) - 1u) : 0u;  // everything in P_LOAD
     for (int i = threadIdx.x; i < STATE_VECS * ITEMS; i += blockDim.x) sm_state[i] = make_uint4(0, 0, 0, 0);  // mate 0
@@ -580,8 +572,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
         I.state = sm_state + item;
         I.codes = sm_codes + item;
         I.ctg = sm_ctg + item;
-        I.list0_sa = (uint32_t)__cvta_generic_to_shared(sm_lists + item);
-        I.list1_sa = I.list0_sa + 4u * LIST_CAP * ITEMS;
+        I.list0 = sm_lists + item;
         I.arena = a.arena;
         Lane<ITEMS> L;
         L.st = phase;
@@ -603,7 +594,6 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
         int want_pos = -1;       // look up the read's k-mer at this position next ...
         bool want = false;       // ... or this explicit k-mer
         uint64_t want_kmer = 0;
-        long long slot = -1;     // P_TALLY: dictionary slot of the unit's class
 
         if (phase == P_LOAD) {
             // ---- new units for finished items (mate 0): one global atomic per warp -------------
@@ -644,7 +634,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 if (len >= K) {
                     want_pos = 0;
                 } else {  // undefined in the reference; reported unaligned and flagged
-                    atomicOr(dict.status, ST_SHORT_READ);
+                    atomicOr(status, ST_SHORT_READ);
                     ev = EV_READ_DONE;
                 }
             }
@@ -724,7 +714,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 const int to_start = L.forward ? at.offset : c.length - at.offset - K;
                 const int to_end = L.forward ? c.length - at.offset - K : at.offset;
                 if (phase == P_MAP) {  // ctx == C_FIND
-                    map_contig(ix, a, dict.status, c, at, L.l);
+                    map_contig(ix, a, status, c, at, L.l);
                     L.sp.begin = L.pos;
                     L.sp.end = L.pos;
                     L.anchor0 = at;
@@ -816,7 +806,7 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 }
                 if (finished) ev = dir ? EV_AFTER_ATTEMPT : EV_AFTER_LEFT;
             }
-        } else {  // P_TALLY
+        } else {  // P_TALLY: the unit is mapped; leave its record for tally_units_kernel
             if (mine) {
                 int length;
                 if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
@@ -839,39 +829,21 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
                 } else {
                     length = L.sp.end - L.sp.begin + K;
                 }
-                if (a.out_length) a.out_length[L.unit] = length;
-                if (length > 0) {  // _mapper.pyx:90-94
-                    if (length >= SKM_MAX_FRAGMENT_LENGTH) length = SKM_MAX_FRAGMENT_LENGTH - 1;
-                    atomicAdd(&sm_fld[length], 1u);
-                }
-                if (L.l.n > 0) {
-                    const ulonglong2 key = tuple_key(L.l, L.l.n, true);
-                    slot = dict_find_or_insert(dict, key, L.l, L.l.n, true);
-                }
-                if (a.out_class) a.out_class[L.unit] = (int32_t)slot;
-                if (slot >= 0) {
-                    const unsigned long long g = (unsigned long long)(a.first_unit + L.unit);
-                    if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
-                        atomicMin(&dict.first[slot], g);
+                UnitRec *rec = a.units + L.unit;
+                const int n = L.l.n;
+                *reinterpret_cast<int2 *>(rec) = make_int2(n, length);
+                if (n <= REC_IDS) {
+#pragma unroll 1
+                    for (int i = 0; i < n; ++i) rec->ids[i] = L.l.get(i);
+                } else {
+                    const long long off = emit_long_list(L.l.p, L.l.stride, n, a.arena, a.arena_cap, a.cursors + 1, status);
+                    *reinterpret_cast<long long *>(rec->ids) = off;
                 }
                 // the item is free again: mate 0 of a new unit
                 L.mate = 0;
                 L.l = I.fresh_list(0);
                 L.m1 = I.fresh_list(0);
                 L.st = P_LOAD;
-            }
-            __syncwarp();
-            // one count atomic per distinct class per warp (mapper.py:60-75)
-            const unsigned same = __match_any_sync(0xffffffffu, slot);
-            if (slot >= 0 && lane == __ffs(same) - 1)
-                atomicAdd(&dict.counts[slot], (unsigned long long)__popc(same));
-            const unsigned done = __ballot_sync(0xffffffffu, mine);
-            const unsigned mapped = __ballot_sync(0xffffffffu, mine && slot >= 0);
-            if (lane == 0) {
-                const int n_al = __popc(mapped);
-                const int n_un = __popc(done) - n_al;
-                if (n_un) atomicAdd(&dict.scalars[2], (unsigned long long)n_un);
-                if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
             }
         }
 
@@ -965,6 +937,61 @@ map_reads_kernel(const DevIndex ix, const DictDev dict, const MapArgs a)
         __syncwarp();
     }
 
+}
+
+// Pass 3: tally.  One thread per unit reads the record the mapper left, updates the FLD
+// (_mapper.pyx:90-94, shared-memory histogram flushed once per block), finds or inserts the
+// ordered id tuple in the class dictionary (MapResult.update, mapper.py:60-75; one count atomic
+// per distinct class per warp) and keeps the smallest unit index per class (first-seen order).
+__global__ void __launch_bounds__(256)
+tally_units_kernel(const DictDev dict, const UnitRec *__restrict__ units, const int32_t *__restrict__ arena,
+                   int64_t n_units, int64_t first_unit, int32_t *__restrict__ out_class,
+                   int32_t *__restrict__ out_length)
+{
+    __shared__ uint32_t sm_fld[SKM_MAX_FRAGMENT_LENGTH];
+    for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) sm_fld[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31LL; base < n_units;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t u = base + lane;
+        const bool live = u < n_units;
+        long long slot = -1;
+        if (live) {
+            const int4 *r = reinterpret_cast<const int4 *>(units + u);
+            const int4 q0 = __ldg(r);
+            const int n = q0.x;
+            int length = q0.y;
+            if (out_length) out_length[u] = length;
+            if (length > 0) {
+                if (length >= SKM_MAX_FRAGMENT_LENGTH) length = SKM_MAX_FRAGMENT_LENGTH - 1;
+                atomicAdd(&sm_fld[length], 1u);
+            }
+            if (n > 0) {
+                const long long off = (long long)(uint32_t)q0.z | ((long long)q0.w << 32);
+                const DenseIds view{n <= REC_IDS ? units[u].ids : arena + off};
+                const ulonglong2 key = tuple_key(view, n, true);
+                slot = dict_find_or_insert(dict, key, view, n, true);
+            }
+            if (out_class) out_class[u] = (int32_t)slot;
+            if (slot >= 0) {
+                const unsigned long long g = (unsigned long long)(first_unit + u);
+                if (g < *reinterpret_cast<volatile unsigned long long *>(&dict.first[slot]))
+                    atomicMin(&dict.first[slot], g);
+            }
+        }
+        const unsigned same = __match_any_sync(0xffffffffu, slot);
+        if (slot >= 0 && lane == __ffs(same) - 1)
+            atomicAdd(&dict.counts[slot], (unsigned long long)__popc(same));
+        const unsigned done = __ballot_sync(0xffffffffu, live);
+        const unsigned mapped = __ballot_sync(0xffffffffu, live && slot >= 0);
+        if (lane == 0) {
+            const int n_al = __popc(mapped);
+            const int n_un = __popc(done) - n_al;
+            if (n_un) atomicAdd(&dict.scalars[2], (unsigned long long)n_un);
+            if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
+        }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) {
         const uint32_t v = sm_fld[i];

@@ -165,6 +165,8 @@ struct skm_mapper {
     int threads = Q_THREADS, rows_limit = 0;  // SKM_THREADS / SKM_ROWS override for experiments
     int32_t *d_out = nullptr;
     size_t d_out_cap = 0;
+    UnitRec *d_units = nullptr;    // map_reads_kernel output, tally_units_kernel input
+    size_t d_units_cap = 0;
     uint64_t *d_packed = nullptr;  // pack_reads_kernel output
     size_t d_packed_cap = 0;
     int32_t *d_lens = nullptr;
@@ -209,6 +211,7 @@ SKM_API void skm_mapper_destroy(skm_mapper *m)
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     cudaFree(m->d_out);
     cudaFree(m->d_packed);
+    cudaFree(m->d_units);
     cudaFree(m->d_lens);
     cudaSetDevice(prev);
     delete m;
@@ -310,7 +313,7 @@ static size_t map_smem_bytes(int code_words, int rows)
 }
 
 // map_reads_kernel is instantiated for a few pool sizes; the launch takes the largest that fits
-typedef void (*map_kernel_fn)(const DevIndex, const DictDev, const MapArgs);
+typedef void (*map_kernel_fn)(const DevIndex, const MapArgs, uint32_t *);
 struct MapVariant {
     int rows;
     map_kernel_fn fn;
@@ -357,8 +360,9 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     a.lens = lens;
     a.n_units = n_units;
     a.first_unit = first_unit;
-    a.out_class = d_out_class;
-    a.out_length = d_out_length;
+    rc = ensure((void **)&m->d_units, &m->d_units_cap, sizeof(UnitRec) * (size_t)n_units);
+    if (rc) return rc;
+    a.units = m->d_units;
     SKM_CUDA(cudaMemsetAsync(m->cursors, 0, sizeof(unsigned long long) * 2, st));
     // one block per SM; as many item rows as shared memory holds (at most 32: one mask bit each)
     const MapVariant *var = nullptr;
@@ -374,7 +378,11 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     SKM_CUDA(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t want = (n_units + var->rows * 32 - 1) / (var->rows * 32);
     const int grid = (int)std::min<int64_t>(m->sm_count, std::max<int64_t>(want, 1));
-    var->fn<<<grid, m->threads, smem, st>>>(m->index->d, m->d, a);
+    var->fn<<<grid, m->threads, smem, st>>>(m->index->d, a, m->d.status);
+    SKM_CUDA(cudaGetLastError());
+    const int tally_blocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)m->sm_count * 8);
+    tally_units_kernel<<<tally_blocks, 256, 0, st>>>(m->d, m->d_units, m->arena, n_units, first_unit, d_out_class,
+                                                    d_out_length);
     SKM_CUDA(cudaGetLastError());
     return SKM_OK;
 }
