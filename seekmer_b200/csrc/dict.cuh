@@ -16,7 +16,7 @@ struct DictDev {
     int32_t *pool;                // transcript ids of every class, tuple order
     uint64_t mask;                // slots - 1
     uint64_t pool_cap;
-    unsigned long long *scalars;  // [0]=pool cursor [1]=n_classes [2]=unaligned [3]=aligned
+    unsigned long long *scalars;  // [0]=pool cursor [1]=n_classes [2]=unaligned [3]=aligned [4]=ids stored
     unsigned long long *fld;      // FLD_BINS
     uint32_t *status;
 };
@@ -72,35 +72,24 @@ __device__ __forceinline__ ulonglong2 tuple_key(const Ids &ids, int n, bool stri
     return make_ulonglong2(h1, h2);
 }
 
-// Find-or-insert; returns the slot, or -1 when the table is full.  The winner of the
-// 128-bit CAS copies the tuple into the id pool; nobody reads it before the kernel ends.
-template <typename Ids>
-__device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const Ids &ids, int n,
-                                       bool strip_sign)
+// Find the key's slot or claim an empty one; returns the slot, or -1 when the table is full.
+// `won` tells the caller that it claimed the slot and owes the class its ids in the pool.
+__device__ __forceinline__ int64_t dict_find_or_claim(const DictDev &d, ulonglong2 key, bool &won)
 {
+    won = false;
     uint64_t s = (key.x ^ (key.y >> 17)) & d.mask;
     const ulonglong2 empty = make_ulonglong2(EMPTY_KEY, EMPTY_KEY);
     for (uint64_t probes = 0; probes <= d.mask; ++probes) {
-        // 64-bit halves are individually atomic; only a definite foreign h1 skips the CAS
+        // A slot is written once, by the 128-bit CAS, and never changes.  The 64-bit halves are
+        // read individually (each atomic): a matching h1 followed by a matching h2 is this key
+        // - the common case, no atomic needed; a foreign h1 moves on; anything else (empty, or
+        // h1 seen before h2 became visible) goes through the CAS.
         const uint64_t seen = *reinterpret_cast<volatile const uint64_t *>(&d.keys[s].x);
+        if (seen == key.x && *reinterpret_cast<volatile const uint64_t *>(&d.keys[s].y) == key.y) return (int64_t)s;
         if (seen == EMPTY_KEY || seen == key.x) {
             const ulonglong2 old = cas128(d.keys + s, empty, key);
             if (old.x == EMPTY_KEY && old.y == EMPTY_KEY) {
-                const unsigned long long off = atomicAdd(&d.scalars[0], (unsigned long long)n);
-                if (off + (unsigned long long)n > d.pool_cap) {
-                    atomicOr(d.status, ST_POOL_FULL);
-                    d.pool_off[s] = 0;
-                    d.len[s] = 0;
-                } else {
-                    for (int i = 0; i < n; ++i) {
-                        int32_t e = ids.get(i);
-                        if (strip_sign && e < 0) e = ~e;
-                        d.pool[off + i] = e;
-                    }
-                    d.pool_off[s] = (uint32_t)off;
-                    d.len[s] = (uint32_t)n;
-                }
-                atomicAdd(&d.scalars[1], 1ULL);
+                won = true;
                 return (int64_t)s;
             }
             if (old.x == key.x && old.y == key.y) return (int64_t)s;
@@ -109,6 +98,42 @@ __device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const I
     }
     atomicOr(d.status, ST_DICT_FULL);
     return -1;
+}
+
+// The winner of a slot copies the tuple into the id pool at `off`; nobody reads it before the
+// kernel ends.
+template <typename Ids>
+__device__ __forceinline__ void dict_store_ids(const DictDev &d, int64_t s, unsigned long long off, const Ids &ids,
+                                               int n, bool strip_sign)
+{
+    if (off + (unsigned long long)n > d.pool_cap) {
+        atomicOr(d.status, ST_POOL_FULL);
+        d.pool_off[s] = 0;
+        d.len[s] = 0;
+        return;
+    }
+    for (int i = 0; i < n; ++i) {
+        int32_t e = ids.get(i);
+        if (strip_sign && e < 0) e = ~e;
+        d.pool[off + i] = e;
+    }
+    d.pool_off[s] = (uint32_t)off;
+    d.len[s] = (uint32_t)n;
+}
+
+// Find-or-insert for callers without warp-level aggregation (the merge path).
+template <typename Ids>
+__device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const Ids &ids, int n,
+                                       bool strip_sign)
+{
+    bool won;
+    const int64_t s = dict_find_or_claim(d, key, won);
+    if (won) {
+        dict_store_ids(d, s, atomicAdd(&d.scalars[0], (unsigned long long)n), ids, n, strip_sign);
+        atomicAdd(&d.scalars[1], 1ULL);
+        atomicAdd(&d.scalars[4], (unsigned long long)n);
+    }
+    return s;
 }
 
 }  // namespace skm

@@ -9,9 +9,8 @@
 //             k-mer of a scan, a contig-junction k-mer, a walk fallback
 //   P_SCAN    _find_first_kmer after its first miss: the next 4 read positions are hashed and
 //             probed together (4 independent bucket loads in flight), first hit wins
-//   P_MAP     contig record + map_contig for the scan hit
-//   P_FILTER  contig record + _filter_on_contig at a junction (or the reload of the first
-//             contig before the right walk)
+//   P_CONTIG  contig record of a hit: map_contig for the scan hit, _filter_on_contig at a
+//             junction (or the reload of the first contig before the right walk)
 //   P_WALK    one head of the left/right contig-walk loops, or the final edge check: jump to
 //             the contig edge, 8-base SIFT4 check (direction-generic), next junction k-mer
 //   P_TALLY   map_read_pair mate intersection, FLD, class dictionary
@@ -54,15 +53,13 @@ constexpr int ALIGN_LENGTH = 8;           // _mapper.pyx:22
 constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
 constexpr int SCAN_WIDTH = 4;             // read positions probed per P_SCAN step
 
-// What the mapper leaves behind for one unit: the span length of _mapper.pyx:90 and the ordered
-// target list (signed entries; signs are stripped when the class key is formed, :528-537).
-// Lists longer than REC_IDS live in the arena: ids[0..1] then hold the arena offset.
+// What the mapper leaves behind for one unit, field-major so that tally_units_kernel reads it
+// coalesced: units[0][u] = number of targets, units[1][u] = span length of _mapper.pyx:90,
+// units[2 + k][u] = k-th target (signed entries; signs are stripped when the class key is
+// formed, :528-537).  Lists longer than REC_IDS live in the arena: rows 2 and 3 then hold the
+// low and high half of the arena offset.
 constexpr int REC_IDS = 14;
-struct __align__(16) UnitRec {
-    int32_t n;
-    int32_t length;
-    int32_t ids[REC_IDS];
-};
+constexpr int REC_ROWS = 2 + REC_IDS;
 
 struct MapArgs {
     const uint64_t *packed;   // [n_reads][words] from pack_reads_kernel
@@ -74,13 +71,13 @@ struct MapArgs {
     int32_t paired;
     int64_t n_units;
     int64_t first_unit;
-    UnitRec *units;           // [n_units] mapping result of every unit, consumed by tally_units_kernel
+    int32_t *units;           // [REC_ROWS][n_units] mapping results, consumed by tally_units_kernel
     int32_t *arena;           // spill space for target lists longer than LIST_CAP
     uint64_t arena_cap;
     unsigned long long *cursors;  // [0]=work counter [1]=arena cursor
 };
 
-enum : int { P_LOAD = 0, P_SCAN, P_LOOKUP, P_MAP, P_FILTER, P_WALK, P_TALLY, N_PHASES, P_DEAD = N_PHASES };
+enum : int { P_LOAD = 0, P_SCAN, P_LOOKUP, P_CONTIG, P_WALK, P_TALLY, N_PHASES, P_DEAD = N_PHASES };
 // who asked for the pending lookup / filter operation
 enum : int {
     C_FIND = 0,  // _find_first_kmer scan (_mapper.pyx:199-216)
@@ -313,6 +310,14 @@ __device__ __noinline__ long long map_contig_long(const int32_t *t, int n, int f
     return off;
 }
 
+// entries 8..15 of a contig's target list (zero beyond its end), for lists of 9..16 targets
+__device__ __forceinline__ void load_targets_hi(const DevIndex &ix, const Contig &c, int32_t (&t)[INLINE_TARGETS])
+{
+    const int32_t *src = ix.targets + c.target_offset + INLINE_TARGETS;
+#pragma unroll
+    for (int j = 0; j < INLINE_TARGETS; ++j) t[j] = INLINE_TARGETS + j < c.target_count ? __ldg(src + j) : 0;
+}
+
 // map_contig (_common.pyx:143-179) for an already loaded contig record.  Forward: the
 // contig's targets in order; reverse: reversed order, every entry bit-negated.
 template <int ITEMS>
@@ -323,10 +328,18 @@ __device__ __forceinline__ void map_contig(const DevIndex &ix, const MapArgs &a,
     const int n = c.target_count;
     const int32_t x = forward ? 0 : -1;
     l.n = n;
-    if (n <= INLINE_TARGETS) {  // straight-line: the 8 inline entries are already in registers
+    if (n <= 2 * INLINE_TARGETS && n <= LIST_CAP) {
+        // straight-line: the first 8 entries came with the record, 8 more are fetched if needed
 #pragma unroll
         for (int j = 0; j < INLINE_TARGETS; ++j)
             if (j < n) l.set(forward ? j : n - 1 - j, c.t[j] ^ x);
+        if (n > INLINE_TARGETS) {
+            int32_t t[INLINE_TARGETS];
+            load_targets_hi(ix, c, t);
+#pragma unroll
+            for (int j = 0; j < INLINE_TARGETS; ++j)
+                if (INLINE_TARGETS + j < n) l.set(forward ? INLINE_TARGETS + j : n - 1 - INLINE_TARGETS - j, t[j] ^ x);
+        }
         return;
     }
     const long long off = map_contig_long(ix.targets + c.target_offset, n, forward ? 1 : 0, l.p, l.stride, a.arena,
@@ -377,14 +390,26 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
     if (length == 0) return false;
     const int32_t x = forward ? 0 : -1;
     int w;
-    if (length <= INLINE_TARGETS) {
+    if (length <= 2 * INLINE_TARGETS) {
         // Both lists are ascending (targets are sorted per contig, _index_builder.pyx:540, and
         // map_contig / this filter keep that order), so the merge keeps the r-th occurrence of a
         // value v in the span's list exactly when the contig's list holds more than r copies of
         // v.  Counting against 8 registers needs no data-dependent control flow.
-        int32_t t[INLINE_TARGETS];
+        // An element whose value differs from its predecessor's (no duplicate: nearly always)
+        // only needs to know whether the value occurs at all: 8 compare-and-accumulate
+        // instructions against registers, unused slots holding a copy of entry 0.  Duplicates
+        // take the exact count.
+        int32_t t[INLINE_TARGETS], t2[INLINE_TARGETS];
 #pragma unroll
-        for (int j = 0; j < INLINE_TARGETS; ++j) t[j] = c.t[j] ^ x;
+        for (int j = 0; j < INLINE_TARGETS; ++j) t[j] = (j < length ? c.t[j] : c.t[0]) ^ x;
+        const bool more = length > INLINE_TARGETS;  // 9..16 targets: 8 more from targets[]
+#pragma unroll
+        for (int j = 0; j < INLINE_TARGETS; ++j) t2[j] = t[0];
+        if (more) {
+            load_targets_hi(ix, c, t2);
+#pragma unroll
+            for (int j = 0; j < INLINE_TARGETS; ++j) t2[j] = (INLINE_TARGETS + j < length ? t2[j] : c.t[0]) ^ x;
+        }
         int run = 0;
         int32_t prev = 0;
         const int n = l.n;
@@ -394,10 +419,21 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
             const int32_t v = l.get(i);
             run = (i > 0 && v == prev) ? run + 1 : 0;
             prev = v;
-            int copies = 0;
+            bool keep = false;
 #pragma unroll
-            for (int j = 0; j < INLINE_TARGETS; ++j) copies += (j < length && t[j] == v) ? 1 : 0;
-            if (run < copies) {
+            for (int j = 0; j < INLINE_TARGETS; ++j) keep |= t[j] == v;
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < INLINE_TARGETS; ++j) keep |= t2[j] == v;
+            }
+            if (run > 0 && keep) {  // the r-th copy of v stays iff the contig lists more than r copies
+                int copies = 0;
+#pragma unroll
+                for (int j = 0; j < INLINE_TARGETS; ++j)
+                    copies += (j < length && t[j] == v) + (INLINE_TARGETS + j < length && t2[j] == v);
+                keep = run < copies;
+            }
+            if (keep) {
                 l.set(w, v);
                 w += 1;
             }
@@ -644,7 +680,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 L.sp.anchor = h;
                 if (h.offset >= 0) {
                     prefetch_l2(ix.contigs + (h.entry >= 0 ? h.entry : ~h.entry));
-                    L.st = L.ctx == C_FIND ? P_MAP : P_FILTER;
+                    L.st = P_CONTIG;
                 } else if (L.ctx == C_FIND) {
                     // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
                     // targets empty and map_read returns (:170-171, :186-187)
@@ -695,14 +731,14 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (first < SCAN_WIDTH) {
                     L.pos += first;
                     prefetch_l2(ix.contigs + (hh.entry >= 0 ? hh.entry : ~hh.entry));
-                    L.st = P_MAP;
+                    L.st = P_CONTIG;
                 } else {
                     L.pos += min(SCAN_WIDTH, fit);
                     if (L.pos + K <= L.len) L.st = P_SCAN;
                     else ev = EV_READ_DONE;
                 }
             }
-        } else if (phase == P_MAP || phase == P_FILTER) {
+        } else if (phase == P_CONTIG) {
             if (mine) {
                 const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
                 const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
@@ -713,7 +749,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 L.forward = at.entry >= 0;
                 const int to_start = L.forward ? at.offset : c.length - at.offset - K;
                 const int to_end = L.forward ? c.length - at.offset - K : at.offset;
-                if (phase == P_MAP) {  // ctx == C_FIND
+                if (L.ctx == C_FIND) {
                     map_contig(ix, a, status, c, at, L.l);
                     L.sp.begin = L.pos;
                     L.sp.end = L.pos;
@@ -829,15 +865,18 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 } else {
                     length = L.sp.end - L.sp.begin + K;
                 }
-                UnitRec *rec = a.units + L.unit;
+                int32_t *rec = a.units + L.unit;
                 const int n = L.l.n;
-                *reinterpret_cast<int2 *>(rec) = make_int2(n, length);
+                rec[0] = n;
+                rec[a.n_units] = length;
+                rec += 2 * a.n_units;
                 if (n <= REC_IDS) {
 #pragma unroll 1
-                    for (int i = 0; i < n; ++i) rec->ids[i] = L.l.get(i);
+                    for (int i = 0; i < n; ++i) rec[i * a.n_units] = L.l.get(i);
                 } else {
                     const long long off = emit_long_list(L.l.p, L.l.stride, n, a.arena, a.arena_cap, a.cursors + 1, status);
-                    *reinterpret_cast<long long *>(rec->ids) = off;
+                    rec[0] = (int32_t)(uint32_t)off;
+                    rec[a.n_units] = (int32_t)(off >> 32);
                 }
                 // the item is free again: mate 0 of a new unit
                 L.mate = 0;
@@ -879,7 +918,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     } else {
                         prefetch_l2(ix.contigs + (L.anchor0.entry >= 0 ? L.anchor0.entry : ~L.anchor0.entry));
                         L.ctx = C_RIGHT_C;
-                        L.st = P_FILTER;
+                        L.st = P_CONTIG;
                     }
                     ev = EV_NONE;
                 } else {
@@ -925,6 +964,9 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * L.bucket);
                 L.st = P_LOOKUP;
             }
+        }
+        __syncwarp();
+        if (mine) {
             // ---- publish: state first, then the row's bit in the next phase's mask ----------
             if (L.st == P_DEAD) {
                 atomicSub(sm_live, 1);
@@ -939,39 +981,56 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
 
 }
 
-// Pass 3: tally.  One thread per unit reads the record the mapper left, updates the FLD
-// (_mapper.pyx:90-94, shared-memory histogram flushed once per block), finds or inserts the
-// ordered id tuple in the class dictionary (MapResult.update, mapper.py:60-75; one count atomic
-// per distinct class per warp) and keeps the smallest unit index per class (first-seen order).
+// Pass 3: tally.  One thread per unit reads what the mapper left (coalesced, field-major),
+// updates the FLD (_mapper.pyx:90-94, shared-memory histogram flushed once per block), finds or
+// inserts the ordered id tuple in the class dictionary (MapResult.update, mapper.py:60-75; one
+// count atomic per distinct class per warp) and keeps the smallest unit index per class
+// (first-seen order).
+struct UnitIds {
+    const int32_t *p;  // &units[2][u], or the arena list
+    int64_t stride;    // n_units, or 1
+    __device__ __forceinline__ int32_t get(int i) const { return __ldg(p + i * stride); }
+};
+
+constexpr int POOL_CHUNK = 4096;  // ids a warp takes from the pool cursor at a time
+
 __global__ void __launch_bounds__(256)
-tally_units_kernel(const DictDev dict, const UnitRec *__restrict__ units, const int32_t *__restrict__ arena,
+tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const int32_t *__restrict__ arena,
                    int64_t n_units, int64_t first_unit, int32_t *__restrict__ out_class,
                    int32_t *__restrict__ out_length)
 {
     __shared__ uint32_t sm_fld[SKM_MAX_FRAGMENT_LENGTH];
+    __shared__ unsigned long long sm_totals[4];  // new classes, ids stored, unaligned, aligned
     for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) sm_fld[i] = 0;
+    if (threadIdx.x < 4) sm_totals[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    // every counter that all units share is aggregated: id-pool space per warp in chunks,
+    // class / id / unit totals per block
+    unsigned long long chunk_next = 0, chunk_end = 0;
+    unsigned new_classes = 0, new_ids = 0, n_unaligned = 0, n_aligned = 0;  // lane 0 only
     for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31LL; base < n_units;
          base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t u = base + lane;
         const bool live = u < n_units;
         long long slot = -1;
+        bool won = false;
+        int n = 0;
+        UnitIds view{units + 2 * n_units + u, n_units};
         if (live) {
-            const int4 *r = reinterpret_cast<const int4 *>(units + u);
-            const int4 q0 = __ldg(r);
-            const int n = q0.x;
-            int length = q0.y;
+            n = __ldg(units + u);
+            int length = __ldg(units + n_units + u);
             if (out_length) out_length[u] = length;
             if (length > 0) {
                 if (length >= SKM_MAX_FRAGMENT_LENGTH) length = SKM_MAX_FRAGMENT_LENGTH - 1;
                 atomicAdd(&sm_fld[length], 1u);
             }
             if (n > 0) {
-                const long long off = (long long)(uint32_t)q0.z | ((long long)q0.w << 32);
-                const DenseIds view{n <= REC_IDS ? units[u].ids : arena + off};
-                const ulonglong2 key = tuple_key(view, n, true);
-                slot = dict_find_or_insert(dict, key, view, n, true);
+                if (n > REC_IDS) {
+                    const long long off = (long long)(uint32_t)view.get(0) | ((long long)view.get(1) << 32);
+                    view = UnitIds{arena + off, 1};
+                }
+                slot = dict_find_or_claim(dict, tuple_key(view, n, true), won);
             }
             if (out_class) out_class[u] = (int32_t)slot;
             if (slot >= 0) {
@@ -980,22 +1039,54 @@ tally_units_kernel(const DictDev dict, const UnitRec *__restrict__ units, const 
                     atomicMin(&dict.first[slot], g);
             }
         }
+        __syncwarp();
+        // ---- new classes: pool space for all winners of the warp at once -----------------------
+        const unsigned winners = __ballot_sync(0xffffffffu, won);
+        if (winners) {
+            int incl = won ? n : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const unsigned long long total = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
+            if (chunk_next + total > chunk_end) {
+                const unsigned long long take = total > POOL_CHUNK ? total : POOL_CHUNK;
+                unsigned long long got = 0;
+                if (lane == 0) got = atomicAdd(&dict.scalars[0], take);
+                chunk_next = __shfl_sync(0xffffffffu, got, 0);
+                chunk_end = chunk_next + take;
+            }
+            if (won) dict_store_ids(dict, slot, chunk_next + (unsigned long long)(incl - n), view, n, true);
+            chunk_next += total;
+            new_classes += (unsigned)__popc(winners);
+            new_ids += (unsigned)total;
+        }
+        // ---- one count atomic per distinct class per warp (mapper.py:60-75) -------------------------
         const unsigned same = __match_any_sync(0xffffffffu, slot);
         if (slot >= 0 && lane == __ffs(same) - 1)
             atomicAdd(&dict.counts[slot], (unsigned long long)__popc(same));
         const unsigned done = __ballot_sync(0xffffffffu, live);
         const unsigned mapped = __ballot_sync(0xffffffffu, live && slot >= 0);
-        if (lane == 0) {
-            const int n_al = __popc(mapped);
-            const int n_un = __popc(done) - n_al;
-            if (n_un) atomicAdd(&dict.scalars[2], (unsigned long long)n_un);
-            if (n_al) atomicAdd(&dict.scalars[3], (unsigned long long)n_al);
-        }
+        n_aligned += (unsigned)__popc(mapped);
+        n_unaligned += (unsigned)(__popc(done) - __popc(mapped));
+    }
+    if (lane == 0) {
+        if (new_classes) atomicAdd(&sm_totals[0], (unsigned long long)new_classes);
+        if (new_ids) atomicAdd(&sm_totals[1], (unsigned long long)new_ids);
+        if (n_unaligned) atomicAdd(&sm_totals[2], (unsigned long long)n_unaligned);
+        if (n_aligned) atomicAdd(&sm_totals[3], (unsigned long long)n_aligned);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) {
         const uint32_t v = sm_fld[i];
         if (v) atomicAdd(&dict.fld[i], (unsigned long long)v);
+    }
+    if (threadIdx.x == 0) {
+        if (sm_totals[0]) atomicAdd(&dict.scalars[1], sm_totals[0]);
+        if (sm_totals[1]) atomicAdd(&dict.scalars[4], sm_totals[1]);
+        if (sm_totals[2]) atomicAdd(&dict.scalars[2], sm_totals[2]);
+        if (sm_totals[3]) atomicAdd(&dict.scalars[3], sm_totals[3]);
     }
 }
 

@@ -165,7 +165,7 @@ struct skm_mapper {
     int threads = Q_THREADS, rows_limit = 0;  // SKM_THREADS / SKM_ROWS override for experiments
     int32_t *d_out = nullptr;
     size_t d_out_cap = 0;
-    UnitRec *d_units = nullptr;    // map_reads_kernel output, tally_units_kernel input
+    int32_t *d_units = nullptr;     // map_reads_kernel output, tally_units_kernel input
     size_t d_units_cap = 0;
     uint64_t *d_packed = nullptr;  // pack_reads_kernel output
     size_t d_packed_cap = 0;
@@ -227,7 +227,7 @@ SKM_API int skm_mapper_reset(skm_mapper *m, void *stream)
     SKM_CUDA(cudaMemsetAsync(m->d.first, 0xFF, sizeof(unsigned long long) * (size_t)m->slots, st));
     SKM_CUDA(cudaMemsetAsync(m->d.len, 0, sizeof(uint32_t) * (size_t)m->slots, st));
     SKM_CUDA(cudaMemsetAsync(m->d.pool_off, 0, sizeof(uint32_t) * (size_t)m->slots, st));
-    SKM_CUDA(cudaMemsetAsync(m->d.scalars, 0, sizeof(unsigned long long) * 4, st));
+    SKM_CUDA(cudaMemsetAsync(m->d.scalars, 0, sizeof(unsigned long long) * 8, st));
     SKM_CUDA(cudaMemsetAsync(m->d.fld, 0, sizeof(unsigned long long) * FLD_BINS, st));
     SKM_CUDA(cudaMemsetAsync(m->d.status, 0, sizeof(uint32_t), st));
     return SKM_OK;
@@ -281,7 +281,7 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
     A((void **)&m->d.pool_off, sizeof(uint32_t) * (size_t)slots);
     A((void **)&m->d.len, sizeof(uint32_t) * (size_t)slots);
     A((void **)&m->d.pool, sizeof(int32_t) * (size_t)id_capacity);
-    A((void **)&m->d.scalars, sizeof(unsigned long long) * 4);
+    A((void **)&m->d.scalars, sizeof(unsigned long long) * 8);
     A((void **)&m->d.fld, sizeof(unsigned long long) * FLD_BINS);
     A((void **)&m->d.status, sizeof(uint32_t));
     A((void **)&m->cursors, sizeof(unsigned long long) * 4);
@@ -360,7 +360,7 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     a.lens = lens;
     a.n_units = n_units;
     a.first_unit = first_unit;
-    rc = ensure((void **)&m->d_units, &m->d_units_cap, sizeof(UnitRec) * (size_t)n_units);
+    rc = ensure((void **)&m->d_units, &m->d_units_cap, sizeof(int32_t) * REC_ROWS * (size_t)n_units);
     if (rc) return rc;
     a.units = m->d_units;
     SKM_CUDA(cudaMemsetAsync(m->cursors, 0, sizeof(unsigned long long) * 2, st));
@@ -380,7 +380,7 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     const int grid = (int)std::min<int64_t>(m->sm_count, std::max<int64_t>(want, 1));
     var->fn<<<grid, m->threads, smem, st>>>(m->index->d, a, m->d.status);
     SKM_CUDA(cudaGetLastError());
-    const int tally_blocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)m->sm_count * 8);
+    const int tally_blocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)m->sm_count * 32);
     tally_units_kernel<<<tally_blocks, 256, 0, st>>>(m->d, m->d_units, m->arena, n_units, first_unit, d_out_class,
                                                     d_out_length);
     SKM_CUDA(cudaGetLastError());
@@ -484,13 +484,13 @@ SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[6], void *stream)
     if (!m || !sizes) return fail(SKM_ERR_INVALID, "skm_classes_size: NULL argument");
     SKM_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long sc[4];
+    unsigned long long sc[5];
     uint32_t status = 0;
     SKM_CUDA(cudaMemcpyAsync(sc, m->d.scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
     SKM_CUDA(cudaMemcpyAsync(&status, m->d.status, sizeof(status), cudaMemcpyDeviceToHost, st));
     SKM_CUDA(cudaStreamSynchronize(st));
     sizes[0] = (int64_t)sc[1];
-    sizes[1] = (int64_t)sc[0];
+    sizes[1] = (int64_t)sc[4];  // ids stored (the pool cursor sc[0] also counts unused chunk tails)
     sizes[2] = (int64_t)sc[2];
     sizes[3] = (int64_t)sc[3];
     sizes[4] = m->slots / 2;
