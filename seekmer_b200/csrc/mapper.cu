@@ -15,79 +15,102 @@ namespace skm {
 
 constexpr int FLD_BINS = SKM_MAX_FRAGMENT_LENGTH;
 
-__device__ __forceinline__ uint32_t lut_entry(uint32_t b)
+// ---- pass 1: ASCII reads -> packed reads ----------------------------------------------------
+// Four ASCII bases in one 32-bit word -> their 2-bit codes (first base in bits 7:6) and their
+// wildcard bits (bit k <-> base k).  Codes follow _kmer.pxd:253-273 (A=0 C=1 G=2 T=3, case
+// folded, every other byte 0); a wildcard is any byte that is not one of upper-case "ACGT"
+// (_mapper.pyx:500-501).  Branch-free SWAR: with y = fold(x) ^ 0x40 the four letters are
+// y = 0x01, 0x03, 0x07, 0x14; everything is a boolean function of bits 0,1,2,4 of each byte
+// once bits 7,6,3 are known to be clear.
+__device__ __forceinline__ void convert4(uint32_t x, uint32_t &codes8, uint32_t &wild4)
 {
-    // bits 1:0 = 2-bit code (_kmer.pxd:253-273), bit 2 = "not one of ACGT" (_mapper.pyx:501)
-    const uint32_t u = b & 0xDFu;
-    const uint32_t code = u == 'T' ? 3u : u == 'G' ? 2u : u == 'C' ? 1u : 0u;
-    const bool upper = b == 'A' || b == 'C' || b == 'G' || b == 'T';
-    return code | (upper ? 0u : 4u);
+    const uint32_t m = 0x01010101u;
+    const uint32_t y = (x & 0xDFDFDFDFu) ^ 0x40404040u;
+    const uint32_t bad = (y >> 7) | (y >> 6) | (y >> 3);
+    const uint32_t b1 = y >> 1, b2 = y >> 2, b4 = y >> 4;
+    const uint32_t acg = y & (b1 | ~b2);       // A, C or G (given b4 clear)
+    const uint32_t t = b2 & ~b1 & ~y;          // T (given b4 set)
+    const uint32_t letter = ((b4 & t) | (~b4 & acg)) & ~bad & m;  // 1 per valid byte
+    const uint32_t c0 = (b4 | (b1 & ~b2)) & m;  // C or T
+    const uint32_t c1 = (b4 | b2) & m;          // G or T
+    const uint32_t codes = (c0 | (c1 << 1)) & (letter * 3u);
+    codes8 = (codes * 0x40100401u) >> 24;       // byte j -> bits 7-2j:6-2j, no carries (disjoint fields)
+    const uint32_t wild = ~(letter & ~(x >> 5)) & m;  // not an upper-case letter of the four
+    wild4 = (wild * 0x10204080u) >> 28;         // byte j -> bit j
 }
 
-// Pass 1: ASCII reads -> packed reads (2-bit codes, first base in the top bits of each u64,
-// followed by one wildcard bit per base).  Fully convergent streaming kernel; the byte ->
-// (code, wildcard) table lives in shared memory.
+// One thread per 32 bases = one 64-bit code word and half a wildcard word of the packed record
+// [code_words | wild_words | pad to even].  Consecutive threads convert consecutive 32-byte
+// pieces of the input, so loads and stores are coalesced whatever the read length; the piece is
+// fetched with three aligned 16-byte loads and shifted into place.
 __global__ void __launch_bounds__(256)
 pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ offsets,
-                  int32_t fixed_len, int32_t code_words, int32_t words, int64_t n_reads,
+                  int32_t fixed_len, int32_t code_words, int32_t wild_words, int32_t words, int64_t n_reads,
                   uint64_t *__restrict__ packed, int32_t *__restrict__ lens)
 {
-    __shared__ uint8_t sm_lut[256];
-    sm_lut[threadIdx.x] = (uint8_t)lut_entry(threadIdx.x);
-    __syncthreads();
-    const int64_t read = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const int64_t read = idx <= 0xFFFFFFFFULL ? (int64_t)((uint32_t)idx / (uint32_t)code_words)
+                                              : (int64_t)(idx / (uint32_t)code_words);
+    const int w = (int)(idx - (uint64_t)read * (uint32_t)code_words);
     if (read >= n_reads) return;
     int64_t off;
     int len;
     if (offsets) {
-        off = offsets[read];
-        len = (int)(offsets[read + 1] - off);
+        off = __ldg(offsets + read);
+        len = (int)(__ldg(offsets + read + 1) - off);
     } else {
         off = read * (int64_t)fixed_len;
         len = fixed_len;
     }
-    if (lens) lens[read] = len;
+    uint64_t *out = packed + read * (int64_t)words;
+    if (w == 0) {
+        if (lens) lens[read] = len;
+        if (code_words + wild_words < words) out[words - 1] = 0;  // padding word
+    }
     const int max_len = code_words * 32;
     if (len > max_len) len = max_len;  // the host sizes code_words from the longest read
-    const uint8_t *src = bases + off;
-    uint64_t *out = packed + read * (int64_t)words;
-    uint64_t acc = 0, wacc = 0;
-    int cw = 0, ww = code_words;
-    int j = 0;
-    auto push = [&](uint32_t byte) {
-        const uint32_t v = sm_lut[byte];
-        acc = (acc << 2) | (v & 3u);
-        wacc |= (uint64_t)(v >> 2) << (j & 63);
-        if ((j & 31) == 31) {
-            out[cw] = acc;
-            cw += 1;
-            acc = 0;
-            if ((j & 63) == 63) {
-                out[ww] = wacc;
-                ww += 1;
-                wacc = 0;
-            }
-        }
-        j += 1;
-    };
-    while (j < len && (reinterpret_cast<uintptr_t>(src + j) & 7)) push(__ldg(src + j));
-    while (j + 8 <= len) {
-        const uint64_t w8 = __ldg(reinterpret_cast<const unsigned long long *>(src + j));
+    const int nb = min(32, len - 32 * w);  // bases of this piece
+    uint64_t codes = 0;
+    uint32_t wild = 0;
+    if (nb > 0) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(bases) + (uintptr_t)off + 32u * (uintptr_t)w;
+        const uint4 *q = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+        const int sh = (int)(addr & 15);
+        // three aligned chunks cover the 32 bytes from any alignment; a chunk is read only if it
+        // holds bytes of this piece (so nothing outside the caller's allocation granule is touched)
+        uint32_t x[13];
+        const uint4 q0 = __ldg(q);
+        const uint4 q1 = sh + nb > 16 ? __ldg(q + 1) : make_uint4(0, 0, 0, 0);
+        const uint4 q2 = sh + nb > 32 ? __ldg(q + 2) : make_uint4(0, 0, 0, 0);
+        x[0] = q0.x; x[1] = q0.y; x[2] = q0.z; x[3] = q0.w;
+        x[4] = q1.x; x[5] = q1.y; x[6] = q1.z; x[7] = q1.w;
+        x[8] = q2.x; x[9] = q2.y; x[10] = q2.z; x[11] = q2.w;
+        x[12] = 0;
+        if (sh & 8) {
 #pragma unroll
-        for (int b = 0; b < 8; ++b) push((uint32_t)(w8 >> (8 * b)) & 0xFFu);
+            for (int i = 0; i < 11; ++i) x[i] = x[i + 2];
+        }
+        if (sh & 4) {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) x[i] = x[i + 1];
+        }
+        const int bs = 8 * (sh & 3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t c8, w4;
+            convert4(__funnelshift_r(x[i], x[i + 1], bs), c8, w4);
+            codes |= (uint64_t)c8 << (56 - 8 * i);
+            wild |= w4 << (4 * i);
+        }
+        if (nb < 32) {  // bases past the end of the read are zero codes, no wildcards
+            codes &= ~0ULL << (64 - 2 * nb);
+            wild &= (1u << nb) - 1u;
+        }
     }
-    while (j < len) push(__ldg(src + j));
-    if (len & 31) {
-        out[cw] = acc << (2 * (32 - (len & 31)));
-        cw += 1;
-    }
-    if (len & 63) {
-        out[ww] = wacc;
-        ww += 1;
-    }
-    // the mapper reads whole records: no stale words behind short reads
-    for (; cw < code_words; ++cw) out[cw] = 0;
-    for (; ww < words; ++ww) out[ww] = 0;
+    out[w] = codes;
+    uint32_t *wout = reinterpret_cast<uint32_t *>(out + code_words) + w;
+    *wout = wild;
+    if (w == code_words - 1 && !(w & 1)) wout[1] = 0;  // upper half of the last wildcard word
 }
 
 // ---- export / merge -------------------------------------------------------------------
@@ -353,8 +376,10 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
         if (rc) return rc;
         lens = m->d_lens;
     }
-    pack_reads_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_bases, d_offsets, a.fixed_len, a.code_words,
-                                                                        a.words, n_reads, m->d_packed, lens);
+    const int64_t pack_threads = n_reads * a.code_words;
+    if (pack_threads >= (1LL << 31) * 256) return fail(SKM_ERR_INVALID, "skm_map_batch: batch too large for one launch");
+    pack_reads_kernel<<<(unsigned)((pack_threads + 255) / 256), 256, 0, st>>>(
+        d_bases, d_offsets, a.fixed_len, a.code_words, a.wild_words, a.words, n_reads, m->d_packed, lens);
     SKM_CUDA(cudaGetLastError());
     a.packed = m->d_packed;
     a.lens = lens;
