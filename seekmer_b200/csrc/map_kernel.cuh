@@ -45,13 +45,17 @@ namespace skm {
 #define SKM_LIST_CAP 16
 #endif
 #ifndef SKM_Q_THREADS
-#define SKM_Q_THREADS 512
+#define SKM_Q_THREADS 640
 #endif
 constexpr int Q_THREADS = SKM_Q_THREADS;  // worker threads per block (one block per SM)
 constexpr int LIST_CAP = SKM_LIST_CAP;    // per-read target list entries kept in shared memory
 constexpr int ALIGN_LENGTH = 8;           // _mapper.pyx:22
 constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
 constexpr int SCAN_WIDTH = 4;             // read positions probed per P_SCAN step
+#ifndef SKM_STICKY_LANES
+#define SKM_STICKY_LANES 16
+#endif
+constexpr int STICKY_LANES = SKM_STICKY_LANES;  // a phase repeats while this many lanes still have rows for it
 
 // What the mapper leaves behind for one unit, field-major so that tally_units_kernel reads it
 // coalesced: units[0][u] = number of targets, units[1][u] = span length of _mapper.pyx:90,
@@ -563,12 +567,19 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     volatile uint32_t *vmasks = sm_masks;
     unsigned iter = (unsigned)warp * 5u;
+    int phase = -1;
 
     for (;;) {
         // ---- vote: the phase most lanes have a waiting row for ---------------------------
+        // ... unless the phase just run still has rows for most lanes: then it runs again (its
+        // code is hot in the instruction cache and the full vote is skipped)
         uint32_t mm = 0;
-        int phase;
-        {
+        bool again = false;
+        if (phase >= 0) {
+            mm = vmasks[phase * 32 + lane];
+            again = __popc(__ballot_sync(0xffffffffu, mm != 0)) >= STICKY_LANES;
+        }
+        if (!again) {
             uint32_t m[N_PHASES];
             unsigned best = 0;
 #pragma unroll
@@ -584,6 +595,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 live = __shfl_sync(0xffffffffu, live, 0);
                 if (live == 0) break;
                 __nanosleep(200);
+                phase = -1;
                 continue;
             }
             phase = (int)(best & 7u);
