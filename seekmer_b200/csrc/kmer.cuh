@@ -98,7 +98,9 @@ __host__ __device__ __forceinline__ uint64_t reference_hash(uint64_t m)
 
 __device__ __forceinline__ void prefetch_l2(const void *p)
 {
+#ifndef SKM_NO_PREFETCH
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
 }
 
 // Home bucket of a k-mer in the device table.
@@ -116,16 +118,14 @@ __device__ __forceinline__ uint32_t home_bucket(const DevIndex &ix, uint64_t kme
 // KMerIndex.map_kmer (_common.pyx:54-97) on the canonical-key table: hit on the
 // canonical key; strand of the query relative to the canonical form decides whether
 // the stored coordinate is returned as is or reverse-complemented (~entry).
-// `bucket` = home_bucket(ix, kmer).  One iteration reads a whole 64-byte bucket with four
-// read-only 16-byte loads; at load <= 0.25 a second bucket is needed ~0.4 % of the time.
-__device__ __forceinline__ Coord map_kmer_at(const DevIndex &ix, uint64_t kmer, uint32_t bucket)
+// One iteration reads a whole 64-byte bucket with four read-only 16-byte loads; at load
+// <= 0.25 a second bucket is needed ~0.4 % of the time.
+__device__ __forceinline__ Coord probe_canonical(const Slot *table, uint64_t bucket_mask, uint64_t canon, bool fwd,
+                                                 uint32_t bucket)
 {
-    const uint64_t rc = revcomp(kmer);
-    const bool fwd = kmer < rc;
-    const uint64_t canon = fwd ? kmer : rc;
     uint64_t b = bucket;
     for (;;) {
-        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ix.table + BUCKET_SLOTS * b);
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(table + BUCKET_SLOTS * b);
         const ulonglong2 s0 = __ldg(p), s1 = __ldg(p + 1), s2 = __ldg(p + 2), s3 = __ldg(p + 3);
         uint64_t v = 0;
         bool found = false;
@@ -138,13 +138,16 @@ __device__ __forceinline__ Coord map_kmer_at(const DevIndex &ix, uint64_t kmer, 
             return Coord{fwd ? entry : ~entry, (int32_t)(uint32_t)(v >> 32)};
         }
         if (s3.x == EMPTY_KEY) return coord_invalid();
-        b = (b + 1) & ix.bucket_mask;
+        b = (b + 1) & bucket_mask;
     }
 }
 
 __device__ __forceinline__ Coord map_kmer(const DevIndex &ix, uint64_t kmer)
 {
-    return map_kmer_at(ix, kmer, home_bucket(ix, kmer));
+    const uint64_t rc = revcomp(kmer);
+    const bool fwd = kmer < rc;
+    const uint64_t canon = fwd ? kmer : rc;
+    return probe_canonical(ix.table, ix.bucket_mask, canon, fwd, home_bucket_of(canon, ix.bucket_mask));
 }
 
 struct Contig {

@@ -170,7 +170,6 @@ struct Lane {
     long long unit;
     int pos, move, len, clen;
     uint64_t kmer;
-    uint32_t bucket;  // home bucket of `kmer`, prefetched into L2 when the k-mer was produced
     Coord anchor0;
     Span sp;
     List<ITEMS> l;
@@ -213,7 +212,6 @@ __device__ __forceinline__ void lane_load(Lane<ITEMS> &L, const ItemMem<ITEMS> &
     L.len = (int)(v0.z >> 16);
     L.move = (int)v0.w;
     L.kmer = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
-    L.bucket = v1.z;
     L.sp.begin = sx16(v1.w);
     L.sp.end = sx16(v1.w >> 16);
     L.anchor0 = Coord{(int32_t)v2.x, (int32_t)v2.y};
@@ -245,7 +243,7 @@ __device__ __forceinline__ void lane_store(const Lane<ITEMS> &L, const ItemMem<I
     v0.w = (uint32_t)L.move;
     v1.x = (uint32_t)L.kmer;
     v1.y = (uint32_t)(L.kmer >> 32);
-    v1.z = L.bucket;
+    v1.z = 0;
     v1.w = ((uint32_t)L.sp.begin & 0xFFFFu) | ((uint32_t)L.sp.end << 16);
     v2.x = (uint32_t)L.anchor0.entry;
     v2.y = (uint32_t)L.anchor0.offset;
@@ -488,26 +486,34 @@ enum : int {
     EV_READ_DONE
 };
 
-__device__ __noinline__ uint32_t hash_bucket(uint64_t kmer, uint64_t bucket_mask)
+// One k-mer lookup, out of line so that P_LOOKUP and the four probes of P_SCAN share one copy
+// of the code; the result is packed as entry | offset << 32.
+__device__ __noinline__ unsigned long long lookup_packed(const Slot *table, uint64_t bucket_mask, uint64_t canon,
+                                                         int fwd, uint32_t bucket)
 {
-    const uint64_t rc = revcomp(kmer);
-    return home_bucket_of(kmer < rc ? kmer : rc, bucket_mask);
-}
-
-// the bucket probe, packed as entry | offset << 32
-__device__ __noinline__ unsigned long long probe_kmer(const Slot *table, uint64_t bucket_mask, uint64_t kmer,
-                                                      uint32_t bucket)
-{
-    DevIndex ix;
-    ix.table = table;
-    ix.bucket_mask = bucket_mask;
-    const Coord c = map_kmer_at(ix, kmer, bucket);
+    const Coord c = probe_canonical(table, bucket_mask, canon, fwd != 0, bucket);
     return (unsigned long long)(uint32_t)c.entry | ((unsigned long long)(uint32_t)c.offset << 32);
 }
 
-__device__ __forceinline__ Coord probe_kmer(const DevIndex &ix, uint64_t kmer, uint32_t bucket)
+struct Probe {
+    uint64_t canon;
+    uint32_t bucket;
+    bool fwd;
+};
+
+__device__ __forceinline__ Probe prepare_probe(uint64_t kmer, uint64_t bucket_mask)
 {
-    const unsigned long long v = probe_kmer(ix.table, ix.bucket_mask, kmer, bucket);
+    const uint64_t rc = revcomp(kmer);
+    Probe p;
+    p.fwd = kmer < rc;
+    p.canon = p.fwd ? kmer : rc;
+    p.bucket = home_bucket_of(p.canon, bucket_mask);
+    return p;
+}
+
+__device__ __forceinline__ Coord run_probe(const DevIndex &ix, const Probe &p)
+{
+    const unsigned long long v = lookup_packed(ix.table, ix.bucket_mask, p.canon, p.fwd ? 1 : 0, p.bucket);
     return Coord{(int32_t)(uint32_t)v, (int32_t)(uint32_t)(v >> 32)};
 }
 
@@ -688,10 +694,9 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
         } else if (phase == P_LOOKUP) {
             if (mine) {
-                const Coord h = probe_kmer(ix, L.kmer, L.bucket);
+                const Coord h = run_probe(ix, prepare_probe(L.kmer, ix.bucket_mask));
                 L.sp.anchor = h;
                 if (h.offset >= 0) {
-                    prefetch_l2(ix.contigs + (h.entry >= 0 ? h.entry : ~h.entry));
                     L.st = P_CONTIG;
                 } else if (L.ctx == C_FIND) {
                     // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
@@ -710,19 +715,14 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             if (mine) {
                 // positions pos .. pos+3 (while they fit); L.kmer is the k-mer at pos-1
                 uint64_t km[SCAN_WIDTH];
-                uint32_t bk[SCAN_WIDTH];
+                Probe pr[SCAN_WIDTH];
                 uint64_t k = L.kmer;
                 const int fit = L.len - K + 1 - L.pos;  // >= 1
 #pragma unroll
                 for (int j = 0; j < SCAN_WIDTH; ++j) {
+                    if (j < fit) k = ((k << 2) | rv.code(L.pos + j + K - 1)) & KMER_MASK;
                     km[j] = k;
-                    bk[j] = 0;
-                    if (j < fit) {
-                        k = ((k << 2) | rv.code(L.pos + j + K - 1)) & KMER_MASK;
-                        km[j] = k;
-                        bk[j] = hash_bucket(k, ix.bucket_mask);
-                        prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * bk[j]);
-                    }
+                    pr[j] = prepare_probe(k, ix.bucket_mask);
                 }
                 int first = SCAN_WIDTH;
                 Coord hh = coord_invalid();
@@ -730,7 +730,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
 #pragma unroll
                 for (int j = SCAN_WIDTH - 1; j >= 0; --j) {
                     if (j < fit) {
-                        const Coord h = probe_kmer(ix, km[j], bk[j]);
+                        const Coord h = run_probe(ix, pr[j]);
                         if (h.offset >= 0) {
                             first = j;
                             hh = h;
@@ -742,7 +742,6 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 L.kmer = kk;
                 if (first < SCAN_WIDTH) {
                     L.pos += first;
-                    prefetch_l2(ix.contigs + (hh.entry >= 0 ? hh.entry : ~hh.entry));
                     L.st = P_CONTIG;
                 } else {
                     L.pos += min(SCAN_WIDTH, fit);
@@ -928,7 +927,6 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                         L.dir = 1;
                         L.st = P_WALK;
                     } else {
-                        prefetch_l2(ix.contigs + (L.anchor0.entry >= 0 ? L.anchor0.entry : ~L.anchor0.entry));
                         L.ctx = C_RIGHT_C;
                         L.st = P_CONTIG;
                     }
@@ -970,10 +968,8 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 want = true;
                 want_kmer = rv.kmer(want_pos);
             }
-            if (want) {  // the next single k-mer: start pulling its home bucket towards L2
+            if (want) {  // the next single k-mer; P_LOOKUP hashes it, with all its lanes together
                 L.kmer = want_kmer;
-                L.bucket = hash_bucket(want_kmer, ix.bucket_mask);
-                prefetch_l2(ix.table + (uint64_t)BUCKET_SLOTS * L.bucket);
                 L.st = P_LOOKUP;
             }
         }

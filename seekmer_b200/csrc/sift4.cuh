@@ -101,9 +101,11 @@ __host__ __device__ inline int sift4_unified(uint32_t ref16, uint32_t q18, uint3
     // match(r, q) for q - r in {-1, 0, 1}
 #define SKM_M(r, q) ((((q) == (r) ? m_0 : ((q) > (r) ? m_hi : m_lo)) >> (14 - 2 * (r))) & 1u)
     // The common case: all 8 bases match on the main diagonal.  From q0 = 0 the loop walks it
-    // straight to r = q = 8; from q0 = 1 a mismatch of (r 0, q 1) re-aligns to r = q = 1 at no
-    // cost (the probe of (1, 1) matches, :427-436) and the walk ends the same way.  Either way 0.
-    if (m_0 == 0x5555u && (q0 == 0 || !(m_hi & 0x4000u))) return 0;
+    // straight to r = q = 8: shift 0.  From q0 = 1 the walk starts on the diagonal above; at its
+    // first mismatch (r = k, q = k + 1) the cursors re-align to r = q = k + 1, the probe of that
+    // cell matches at no cost (:427-436) and the main diagonal leads to r = q = 8: shift 0 -
+    // unless the upper diagonal matches for r = 0..6, when q reaches 8 with r = 7: shift 1.
+    if (m_0 == 0x5555u) return (q0 != 0 && (m_hi & 0x5554u) == 0x5554u) ? 1 : 0;
     int r = 0, q = q0, distance = 0;
     while (r < 8 && q < 8) {
         if (SKM_M(r, q)) {
