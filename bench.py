@@ -194,16 +194,18 @@ def run_ours(args):
 
     launches = {'n': 0}
 
-    def step_device(timing=None):
+    kernel_times = []
+
+    def step_device(timed=False):
         mp.reset()
-        if timing is not None:
-            timing[0].record()
         mp.map_batch(d_bases, None, n_pairs, True, first_unit=first_unit, fixed_len=READ_LEN)
-        if timing is not None:
-            timing[1].record()
-        launches['n'] += 1
+        launches['n'] += 3  # pack_reads_kernel, map_reads_kernel, tally_units_kernel
         table = mp.export_torch()
-        launches['n'] += 2
+        launches['n'] += 2  # dict_export_kernel, set_i64_kernel
+        if timed:
+            # CUDA events the library records around each kernel on the launch stream; the
+            # export above has already synchronised that stream
+            kernel_times.append(mp.kernel_ms())
         if world > 1:
             table = sdist.merge_class_tables(table)
         return table
@@ -216,20 +218,19 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local)
-    kernel_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                     for _ in range(args.steps)]
     barrier()
     sampler.start()
     launches['n'] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        table = step_device(kernel_events[k])
+        table = step_device(timed=True)
     e1.record()
     barrier()
     clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
-    kernel_ms = float(numpy.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    kernel_ms = float(numpy.mean([k['map_reads_kernel'] for k in kernel_times]))
+    kernels_ms = {name: round(float(numpy.mean([k[name] for k in kernel_times])), 3) for name in kernel_times[0]}
     gpu_launches = launches['n']
     t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -332,10 +333,23 @@ def run_ours(args):
             pass
         peak = float(peaks.get('hbm_gbs', 6650.0))
         achieved = n_pairs * b_pair / (kernel_ms_max / 1e3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of map_reads_kernel from the committed
+        # ncu --set full capture (profiles/): bytes per pair there x the pairs of one launch here
+        traffic, traffic_src = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'map_reads_kernel_traffic.json')))
+            traffic = round(tr['dram_bytes_per_pair'] * n_pairs)
+            traffic_src = tr['source']
+        except Exception:
+            pass
         roofline = {'bound': 'hbm', 'kernel': 'map_reads_kernel', 'achieved': round(achieved, 2), 'peak': peak,
-                    'peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback', 'unit': 'GB/s',
-                    'frac': round(achieved / peak, 4), 'traffic': None, 'algorithmic_bytes_per_pair': round(b_pair, 1),
-                    'kernel_ms': round(kernel_ms_max, 3), 'per_read_accesses': per_read}
+                    'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs, burst)' if 'hbm_gbs' in peaks
+                    else 'fallback (B200_PROFILING.md)', 'unit': 'GB/s',
+                    'frac': round(achieved / peak, 4), 'traffic': traffic, 'traffic_source': traffic_src,
+                    'algorithmic_bytes_per_pair': round(b_pair, 1), 'pairs_per_launch': n_pairs,
+                    'kernel_ms': round(kernel_ms_max, 3), 'step_kernels_ms': kernels_ms,
+                    'kernel_share_of_step': round(kernel_ms_max / ms_per_step, 3),
+                    'per_read_accesses': per_read}
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             offs = numpy.arange(2 * sample + 1, dtype='i8') * READ_LEN

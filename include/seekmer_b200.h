@@ -134,6 +134,11 @@ int skm_map_batch(skm_mapper *mapper, const uint8_t *bases, const int64_t *read_
                   int64_t first_unit, int buffers_on_device, int32_t *out_class,
                   int32_t *out_length, void *stream);
 
+/* Measurement support: device durations (ms, CUDA events on the launch stream) of the three
+ * kernels of the most recent chunk mapped by skm_map_batch: ms[0] = pack_reads_kernel,
+ * ms[1] = map_reads_kernel, ms[2] = tally_units_kernel.  Blocks until that chunk is done. */
+int skm_mapper_kernel_ms(skm_mapper *mapper, double ms[3]);
+
 /* sizes[0]=n_classes, [1]=total ids, [2]=unaligned units, [3]=aligned units,
  * [4]=class slots capacity, [5]=status flags raised on device (0 = none) */
 int skm_classes_size(skm_mapper *mapper, int64_t sizes[6], void *stream);

@@ -24,7 +24,7 @@ TARGET_DTYPE = numpy.dtype([('entry', '<i4'), ('offset', '<i4')])
 EXPORTS = (
     'skm_last_error', 'skm_device_count', 'skm_version', 'skm_index_create', 'skm_index_destroy',
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
-    'skm_mapper_reset', 'skm_map_batch', 'skm_classes_size', 'skm_classes_export',
+    'skm_mapper_reset', 'skm_map_batch', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_effective_lengths', 'skm_em', 'skm_multinomial', 'skm_synth_reads',
     'skm_build_kmer_table',
 )
@@ -72,6 +72,8 @@ def load():
     L.skm_mapper_reset.argtypes = [vp, vp]
     L.skm_map_batch.restype = ci
     L.skm_map_batch.argtypes = [vp, vp, vp, i32, i32, i64, ci, i64, ci, vp, vp, vp]
+    L.skm_mapper_kernel_ms.restype = ci
+    L.skm_mapper_kernel_ms.argtypes = [vp, vp]
     L.skm_classes_size.restype = ci
     L.skm_classes_size.argtypes = [vp, vp, vp]
     L.skm_classes_export.restype = ci
@@ -240,6 +242,12 @@ class DeviceMapper:
                                    int(max_len), int(n_units), int(bool(paired)), int(first_unit),
                                    int(on_device), _ptr(out_class), _ptr(out_length), stream))
         return out_class, out_length
+
+    def kernel_ms(self):
+        """Device durations (ms) of pack / map / tally kernels of the last mapped chunk."""
+        a = numpy.zeros(3, dtype='f8')
+        check(load().skm_mapper_kernel_ms(self._h, _np_ptr(a)))
+        return dict(zip(('pack_reads_kernel', 'map_reads_kernel', 'tally_units_kernel'), a.tolist()))
 
     def sizes(self, stream=None):
         a = numpy.zeros(6, dtype='i8')

@@ -1000,7 +1000,7 @@ struct UnitIds {
     __device__ __forceinline__ int32_t get(int i) const { return __ldg(p + i * stride); }
 };
 
-constexpr int POOL_CHUNK = 4096;  // ids a warp takes from the pool cursor at a time
+constexpr int POOL_CHUNK = 256;  // ids a warp takes from the pool cursor at a time (unused tails stay unused)
 
 __global__ void __launch_bounds__(256)
 tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const int32_t *__restrict__ arena,

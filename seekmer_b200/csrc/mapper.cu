@@ -188,6 +188,8 @@ struct skm_mapper {
     int threads = Q_THREADS, rows_limit = 0;  // SKM_THREADS / SKM_ROWS override for experiments
     int32_t *d_out = nullptr;
     size_t d_out_cap = 0;
+    cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr};  // around pack | map | tally of the last chunk
+    bool timed = false;
     int32_t *d_units = nullptr;     // map_reads_kernel output, tally_units_kernel input
     size_t d_units_cap = 0;
     uint64_t *d_packed = nullptr;  // pack_reads_kernel output
@@ -231,6 +233,8 @@ SKM_API void skm_mapper_destroy(skm_mapper *m)
         if (m->ev_copy[i]) cudaEventDestroy(m->ev_copy[i]);
         if (m->ev_compute[i]) cudaEventDestroy(m->ev_compute[i]);
     }
+    for (cudaEvent_t e : m->ev_kernel)
+        if (e) cudaEventDestroy(e);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     cudaFree(m->d_out);
     cudaFree(m->d_packed);
@@ -263,14 +267,6 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
     *out = nullptr;
     if (!index) return fail(SKM_ERR_INVALID, "skm_mapper_create: NULL index");
     SKM_CUDA(cudaSetDevice(index->device));
-    // Random 16/32-byte probes dominate the traffic: ask L2 to fetch single 32-byte sectors from
-    // DRAM instead of the default 64 bytes (a hint; SKM_L2_FETCH overrides for experiments).
-    {
-        const char *g = getenv("SKM_L2_FETCH");
-        const size_t gran = g ? (size_t)atoi(g) : 32;
-        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-        cudaGetLastError();
-    }
     if (class_capacity <= 0) class_capacity = 1LL << 22;
     int64_t slots = 1024;
     while (slots < 2 * class_capacity) slots <<= 1;
@@ -314,6 +310,7 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
         e = cudaEventCreateWithFlags(&m->ev_copy[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_compute[i], cudaEventDisableTiming);
     }
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&m->ev_kernel[i]);
     if (e != cudaSuccess) {
         skm_mapper_destroy(m);
         return fail(SKM_ERR_OOM, std::string("skm_mapper_create: ") + cudaGetErrorString(e));
@@ -376,11 +373,13 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
         if (rc) return rc;
         lens = m->d_lens;
     }
+    SKM_CUDA(cudaEventRecord(m->ev_kernel[0], st));
     const int64_t pack_threads = n_reads * a.code_words;
     if (pack_threads >= (1LL << 31) * 256) return fail(SKM_ERR_INVALID, "skm_map_batch: batch too large for one launch");
     pack_reads_kernel<<<(unsigned)((pack_threads + 255) / 256), 256, 0, st>>>(
         d_bases, d_offsets, a.fixed_len, a.code_words, a.wild_words, a.words, n_reads, m->d_packed, lens);
     SKM_CUDA(cudaGetLastError());
+    SKM_CUDA(cudaEventRecord(m->ev_kernel[1], st));
     a.packed = m->d_packed;
     a.lens = lens;
     a.n_units = n_units;
@@ -403,11 +402,16 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     SKM_CUDA(cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t want = (n_units + var->rows * 32 - 1) / (var->rows * 32);
     const int grid = (int)std::min<int64_t>(m->sm_count, std::max<int64_t>(want, 1));
+    // the three kernels are bracketed by events on their own stream (skm_mapper_kernel_ms); the
+    // work-counter memset above sits between events 1 and 2 with the map kernel
     var->fn<<<grid, m->threads, smem, st>>>(m->index->d, a, m->d.status);
     SKM_CUDA(cudaGetLastError());
-    const int tally_blocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)m->sm_count * 32);
+    SKM_CUDA(cudaEventRecord(m->ev_kernel[2], st));
+    const int tally_blocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)m->sm_count * 8);
     tally_units_kernel<<<tally_blocks, 256, 0, st>>>(m->d, m->d_units, m->arena, n_units, first_unit, d_out_class,
                                                     d_out_length);
+    SKM_CUDA(cudaEventRecord(m->ev_kernel[3], st));
+    m->timed = true;
     SKM_CUDA(cudaGetLastError());
     return SKM_OK;
 }
@@ -502,6 +506,20 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     if (out_length)
         SKM_CUDA(cudaMemcpyAsync(out_length, d_length, sizeof(int32_t) * (size_t)n_units, cudaMemcpyDeviceToHost, st));
     return check_status(m, st, "skm_map_batch");
+}
+
+SKM_API int skm_mapper_kernel_ms(skm_mapper *m, double ms[3])
+{
+    if (!m || !ms) return fail(SKM_ERR_INVALID, "skm_mapper_kernel_ms: NULL argument");
+    if (!m->timed) return fail(SKM_ERR_INVALID, "skm_mapper_kernel_ms: nothing has been mapped yet");
+    SKM_CUDA(cudaSetDevice(m->device));
+    SKM_CUDA(cudaEventSynchronize(m->ev_kernel[3]));
+    for (int i = 0; i < 3; ++i) {
+        float t = 0.f;
+        SKM_CUDA(cudaEventElapsedTime(&t, m->ev_kernel[i], m->ev_kernel[i + 1]));
+        ms[i] = (double)t;
+    }
+    return SKM_OK;
 }
 
 SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[6], void *stream)
