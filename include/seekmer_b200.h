@@ -186,6 +186,19 @@ int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicat
                     int64_t first_replicate, uint64_t seed, int64_t *out,
                     int buffers_on_device, int device, void *stream);
 
+/* Replaces: the bootstrap loop of infer.run (infer.py:79-82), i.e. n_replicates times
+ * quantify(results, x0=main, bootstrap=True): resample the integer class counts (as
+ * skm_multinomial, same counters), run the EM for every replicate from the one normalised
+ * guess x0[n_transcripts] and, when `tpm` != 0, apply the TPM post-processing of
+ * infer.py:127-129 - all on the device; the resampled counts never cross PCIe.
+ * out_x is [n_replicates][n_transcripts]. */
+int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes,
+                     int64_t nnz, const int64_t *counts, const double *eff_len,
+                     int64_t n_transcripts, const double *x0, int64_t n_replicates,
+                     int64_t first_replicate, uint64_t seed, int64_t max_iters, int tpm,
+                     double *out_x, int32_t *out_iters, int buffers_on_device, int device,
+                     void *stream);
+
 /* Workload generation twin of seekmer_b200/synth.py (bench/test support, not
  * part of the reference surface): fills `bases` (device) with ASCII reads for
  * global units [first_unit, first_unit+n_units). */

@@ -10,6 +10,9 @@
 // coalesced 256-byte access and every replicate's sum runs in the reference's order
 // (numpy.bincount accumulates sequentially in nnz order).
 #include <algorithm>
+#include <cstdlib>
+#include <ctime>
+#include <mutex>
 #include <vector>
 #include <cub/cub.cuh>
 
@@ -80,6 +83,55 @@ __global__ void sum_counts_kernel(const double *__restrict__ counts_cr, int64_t 
         __syncthreads();
     }
     if (threadIdx.x == 0) n_out[r] = sm[0];
+}
+
+// x[t][r] = x0[t] for every replicate
+__global__ void broadcast_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n, int R)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n * R) dst[i] = src[i / R];
+}
+
+// resampled integer counts [R][C] -> fp64 [C][R]
+__global__ void counts_to_f64_kernel(const unsigned long long *__restrict__ src, double *__restrict__ dst,
+                                     int64_t n_classes, int R)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_classes * R) return;
+    const int64_t c = i / R;
+    const int r = (int)(i - c * R);
+    dst[i] = (double)src[(int64_t)r * n_classes + c];
+}
+
+// TPM post-processing of infer.py:127-129 for every replicate (one block each), x in [R][T]:
+// x /= sum(x) / 1e6;  x[x < 0.001] = 0;  x /= sum(x) / 1e6
+__device__ double block_sum(double v, double *sm)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double total = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += sm[w];
+    return total;
+}
+
+__global__ void tpm_finish_kernel(double *__restrict__ x, int64_t n_tx)
+{
+    __shared__ double sm[32];
+    double *row = x + (int64_t)blockIdx.x * n_tx;
+    double local = 0.0;
+    for (int64_t t = threadIdx.x; t < n_tx; t += blockDim.x) local += row[t];
+    const double scale1 = __ddiv_rn(block_sum(local, sm), 1000000.0);
+    local = 0.0;
+    for (int64_t t = threadIdx.x; t < n_tx; t += blockDim.x) {
+        double v = __ddiv_rn(row[t], scale1);
+        if (v < 0.001) v = 0.0;  // NaN (an all-zero replicate) compares false and stays NaN, as in numpy
+        row[t] = v;
+        local += v;
+    }
+    const double scale2 = __ddiv_rn(block_sum(local, sm), 1000000.0);
+    for (int64_t t = threadIdx.x; t < n_tx; t += blockDim.x) row[t] = __ddiv_rn(row[t], scale2);
 }
 
 struct EmState {
@@ -301,10 +353,75 @@ __global__ void multinomial_kernel(const unsigned long long *__restrict__ cum, i
     }
 }
 
+// Scratch memory: blocks from cudaMalloc are kept in a per-device cache when a call is done
+// and handed out again to the next call (cudaMalloc / cudaFree cost milliseconds per GB-sized
+// buffer and cudaFree synchronises the device; the stream-ordered pool was measured to stall
+// for hundreds of ms on these sizes).  All users run on one stream at a time per device and
+// synchronise it before returning, so a cached block is never still in use.
+struct BlockCache {
+    struct Block {
+        void *p;
+        size_t bytes;
+    };
+    std::mutex mu;
+    std::vector<Block> free_blocks[64];
+    cudaError_t take(int device, size_t bytes, void **out, size_t *got)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            auto &v = free_blocks[device & 63];
+            int best = -1;
+            for (int i = 0; i < (int)v.size(); ++i)
+                if (v[i].bytes >= bytes && v[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || v[i].bytes < v[best].bytes))
+                    best = i;
+            if (best >= 0) {
+                *out = v[best].p;
+                *got = v[best].bytes;
+                v.erase(v.begin() + best);
+                return cudaSuccess;
+            }
+        }
+        *got = bytes;
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+            cudaGetLastError();
+            trim(device);
+            e = cudaMalloc(out, bytes);
+        }
+        return e;
+    }
+    void give(int device, void *p, size_t bytes)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        free_blocks[device & 63].push_back(Block{p, bytes});
+    }
+    void trim(int device)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (Block &b : free_blocks[device & 63]) cudaFree(b.p);
+        free_blocks[device & 63].clear();
+    }
+};
+static BlockCache g_blocks;
+
+static void keep_pool_memory(int) {}
+
 struct DeviceBuf {
     void *p = nullptr;
-    ~DeviceBuf() { cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+    size_t bytes = 0;
+    int device = 0;
+    ~DeviceBuf() { release(); }
+    void release()
+    {
+        if (p) g_blocks.give(device, p, bytes);
+        p = nullptr;
+    }
+    cudaError_t alloc(size_t want, cudaStream_t = nullptr)
+    {
+        release();
+        cudaGetDevice(&device);
+        return g_blocks.take(device, std::max<size_t>(want, 256), &p, &bytes);
+    }
     template <typename T>
     T *as() { return reinterpret_cast<T *>(p); }
 };
@@ -312,6 +429,31 @@ struct DeviceBuf {
 }  // namespace skm
 
 using namespace skm;
+
+// SKM_TRACE=1: wall-clock stage times on stderr (each mark synchronises the stream)
+struct Trace {
+    bool on;
+    cudaStream_t st;
+    double t0;
+    static double now()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit Trace(cudaStream_t s) : on(getenv("SKM_TRACE") != nullptr), st(s), t0(0)
+    {
+        if (on) t0 = now();
+    }
+    void mark(const char *what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double t = now();
+        fprintf(stderr, "[skm trace] %-28s %9.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
 
 #define EM_TRY(expr)                                                                            \
     do {                                                                                        \
@@ -355,75 +497,53 @@ SKM_API int skm_effective_lengths(const int64_t *fld, const double *lengths, int
     return SKM_OK;
 }
 
-SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
-                   const double *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
-                   int64_t n_replicates, int64_t max_iters, double *out_x, int32_t *out_iters,
-                   int buffers_on_device, int device, void *stream)
+struct EmInputs {
+    const int64_t *d_ptr;      // CSR by class (device)
+    const int32_t *d_tx;
+    const double *d_len;       // effective lengths [T]
+    int64_t C, nnz, T;
+    int R;
+    int64_t max_iters;
+    const double *counts_rc;   // class counts [R][C] (ABI layout), or
+    const double *counts_cr;   // ... already in kernel layout [C][R]
+    const double *x_rt;        // initial guess [R][T] (ABI layout), or
+    const double *x_t;         // ... one guess [T] shared by all replicates
+};
+
+// The EM proper on device-resident inputs; d_out [R][T], d_iters [R] (device).
+static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStream_t st)
 {
-    if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
-        return fail(SKM_ERR_INVALID, "skm_em: NULL argument");
-    if (n_classes <= 0 || nnz <= 0 || n_transcripts <= 0 || n_replicates <= 0)
-        return fail(SKM_ERR_INVALID, "skm_em: empty problem");
-    if (nnz >= (1LL << 31) || n_classes >= (1LL << 31) || n_transcripts >= (1LL << 31))
-        return fail(SKM_ERR_INVALID, "skm_em: structure too large for int32 indices");
-    if (skm_device_count() <= device || device < 0)
-        return fail(SKM_ERR_CUDA, "skm_em: no such CUDA device (there is no CPU fallback)");
-    EM_TRY(cudaSetDevice(device));
-    cudaStream_t st = (cudaStream_t)stream;
-    const int R = (int)n_replicates;
-    const int64_t C = n_classes, T = n_transcripts;
-    if (max_iters <= 0) max_iters = 1000000;
-
-    // ---- inputs on the device
-    DeviceBuf b_ptr, b_tx, b_cnt_in, b_len, b_x_in, b_out_rt;
-    const int64_t *d_ptr = class_ptr;
-    const int32_t *d_tx = class_tx;
-    const double *d_cnt_in = counts, *d_len = eff_len, *d_x_in = x0;
-    if (!buffers_on_device) {
-        EM_TRY(b_ptr.alloc(sizeof(int64_t) * (size_t)(C + 1)));
-        EM_TRY(b_tx.alloc(sizeof(int32_t) * (size_t)nnz));
-        EM_TRY(b_cnt_in.alloc(sizeof(double) * (size_t)(C * R)));
-        EM_TRY(b_len.alloc(sizeof(double) * (size_t)T));
-        EM_TRY(b_x_in.alloc(sizeof(double) * (size_t)(T * R)));
-        EM_TRY(cudaMemcpyAsync(b_ptr.p, class_ptr, sizeof(int64_t) * (size_t)(C + 1), cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_tx.p, class_tx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_cnt_in.p, counts, sizeof(double) * (size_t)(C * R), cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_len.p, eff_len, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_x_in.p, x0, sizeof(double) * (size_t)(T * R), cudaMemcpyHostToDevice, st));
-        d_ptr = b_ptr.as<int64_t>();
-        d_tx = b_tx.as<int32_t>();
-        d_cnt_in = b_cnt_in.as<double>();
-        d_len = b_len.as<double>();
-        d_x_in = b_x_in.as<double>();
-    }
-
+    const int64_t C = in.C, T = in.T, nnz = in.nnz;
+    const int R = in.R;
+    const int64_t max_iters = in.max_iters > 0 ? in.max_iters : 1000000;
+    Trace trace(st);
     // ---- CSC by transcript: stable radix sort of (transcript, nnz index)
     DeviceBuf b_rowof, b_idx, b_keys_out, b_idx_out, b_txclass, b_hist, b_txptr, b_tmp, b_bad;
-    EM_TRY(b_rowof.alloc(sizeof(int32_t) * (size_t)nnz));
-    EM_TRY(b_idx.alloc(sizeof(int32_t) * (size_t)nnz));
-    EM_TRY(b_keys_out.alloc(sizeof(int32_t) * (size_t)nnz));
-    EM_TRY(b_idx_out.alloc(sizeof(int32_t) * (size_t)nnz));
-    EM_TRY(b_txclass.alloc(sizeof(int32_t) * (size_t)nnz));
-    EM_TRY(b_hist.alloc(sizeof(unsigned long long) * (size_t)(T + 1)));
-    EM_TRY(b_txptr.alloc(sizeof(int64_t) * (size_t)(T + 1)));
-    EM_TRY(b_bad.alloc(sizeof(unsigned int)));
+    EM_TRY(b_rowof.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_idx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_keys_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_idx_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_txclass.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_hist.alloc(sizeof(unsigned long long) * (size_t)(T + 1), st));
+    EM_TRY(b_txptr.alloc(sizeof(int64_t) * (size_t)(T + 1), st));
+    EM_TRY(b_bad.alloc(sizeof(unsigned int), st));
     EM_TRY(cudaMemsetAsync(b_hist.p, 0, sizeof(unsigned long long) * (size_t)(T + 1), st));
     EM_TRY(cudaMemsetAsync(b_bad.p, 0, sizeof(unsigned int), st));
-    expand_rows_kernel<<<blocks_for(C, 256), 256, 0, st>>>(d_ptr, C, b_rowof.as<int32_t>());
+    expand_rows_kernel<<<blocks_for(C, 256), 256, 0, st>>>(in.d_ptr, C, b_rowof.as<int32_t>());
     iota_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_idx.as<int32_t>(), nnz);
-    histogram_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(d_tx, nnz, T, b_hist.as<unsigned long long>(),
+    histogram_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(in.d_tx, nnz, T, b_hist.as<unsigned long long>(),
                                                           b_bad.as<unsigned int>());
     {
         size_t tmp_sort = 0, tmp_scan = 0;
         int end_bit = 1;
         while ((1LL << end_bit) < T) ++end_bit;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, d_tx, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, in.d_tx, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
                                         b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st);
         cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, b_hist.as<unsigned long long>(),
                                       b_txptr.as<unsigned long long>(), (int)(T + 1), st);
-        EM_TRY(b_tmp.alloc(std::max(tmp_sort, tmp_scan)));
+        EM_TRY(b_tmp.alloc(std::max(tmp_sort, tmp_scan), st));
         size_t tmp = std::max(tmp_sort, tmp_scan);
-        EM_TRY(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp, d_tx, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
+        EM_TRY(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp, in.d_tx, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
                                                b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st));
         tmp = std::max(tmp_sort, tmp_scan);
         EM_TRY(cub::DeviceScan::InclusiveSum(b_tmp.p, tmp, b_hist.as<unsigned long long>(),
@@ -439,25 +559,29 @@ SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_
         if (bad) return fail(SKM_ERR_INVALID, "skm_em: transcript index out of range in class_tx");
     }
 
+    trace.mark("em: CSC build");
     // ---- state in kernel layout
     DeviceBuf b_cnt, b_xa, b_xb, b_inner, b_n, b_maxd, b_active, b_iters, b_nactive;
-    EM_TRY(b_xa.alloc(sizeof(double) * (size_t)(T * R)));
-    EM_TRY(b_xb.alloc(sizeof(double) * (size_t)(T * R)));
-    EM_TRY(b_inner.alloc(sizeof(double) * (size_t)(C * R)));
-    EM_TRY(b_n.alloc(sizeof(double) * (size_t)R));
-    EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * (size_t)R));
-    EM_TRY(b_active.alloc(sizeof(int32_t) * (size_t)R));
-    EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R));
-    EM_TRY(b_nactive.alloc(sizeof(int32_t)));
-    const double *d_cnt = d_cnt_in;
-    if (R > 1) {
-        EM_TRY(b_cnt.alloc(sizeof(double) * (size_t)(C * R)));
-        transpose_kernel<<<blocks_for(C * R, 256), 256, 0, st>>>(d_cnt_in, b_cnt.as<double>(), R, C);
-        transpose_kernel<<<blocks_for(T * R, 256), 256, 0, st>>>(d_x_in, b_xa.as<double>(), R, T);
-        d_cnt = b_cnt.as<double>();
-    } else {
-        EM_TRY(cudaMemcpyAsync(b_xa.p, d_x_in, sizeof(double) * (size_t)T, cudaMemcpyDeviceToDevice, st));
+    EM_TRY(b_xa.alloc(sizeof(double) * (size_t)(T * R), st));
+    EM_TRY(b_xb.alloc(sizeof(double) * (size_t)(T * R), st));
+    EM_TRY(b_inner.alloc(sizeof(double) * (size_t)(C * R), st));
+    EM_TRY(b_n.alloc(sizeof(double) * (size_t)R, st));
+    EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * (size_t)R, st));
+    EM_TRY(b_active.alloc(sizeof(int32_t) * (size_t)R, st));
+    EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R, st));
+    EM_TRY(b_nactive.alloc(sizeof(int32_t), st));
+    const double *d_cnt = in.counts_cr;
+    if (!d_cnt) {
+        d_cnt = in.counts_rc;  // [R][C]; the same thing as [C][R] for one replicate
+        if (R > 1) {
+            EM_TRY(b_cnt.alloc(sizeof(double) * (size_t)(C * R), st));
+            transpose_kernel<<<blocks_for(C * R, 256), 256, 0, st>>>(in.counts_rc, b_cnt.as<double>(), R, C);
+            d_cnt = b_cnt.as<double>();
+        }
     }
+    if (in.x_t) broadcast_kernel<<<blocks_for(T * R, 256), 256, 0, st>>>(in.x_t, b_xa.as<double>(), T, R);
+    else if (R > 1) transpose_kernel<<<blocks_for(T * R, 256), 256, 0, st>>>(in.x_rt, b_xa.as<double>(), R, T);
+    else EM_TRY(cudaMemcpyAsync(b_xa.p, in.x_rt, sizeof(double) * (size_t)T, cudaMemcpyDeviceToDevice, st));
     sum_counts_kernel<<<R, EM_BLOCK, 0, st>>>(d_cnt, C, R, b_n.as<double>());
     EM_TRY(cudaMemsetAsync(b_maxd.p, 0, sizeof(unsigned long long) * (size_t)R, st));
     EM_TRY(cudaMemsetAsync(b_iters.p, 0, sizeof(int32_t) * (size_t)R, st));
@@ -465,12 +589,12 @@ SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_
     fill_i32_kernel<<<1, 32, 0, st>>>(b_nactive.as<int32_t>(), 1, R);
 
     EmState s{};
-    s.class_ptr = d_ptr;
-    s.class_tx = d_tx;
+    s.class_ptr = in.d_ptr;
+    s.class_tx = in.d_tx;
     s.tx_ptr = b_txptr.as<int64_t>();
     s.tx_class = b_txclass.as<int32_t>();
     s.counts = d_cnt;
-    s.eff_len = d_len;
+    s.eff_len = in.d_len;
     s.n = b_n.as<double>();
     s.inner = b_inner.as<double>();
     s.maxd = b_maxd.as<unsigned long long>();
@@ -481,6 +605,7 @@ SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_
     s.n_tx = T;
     s.R = R;
 
+    trace.mark("em: state setup");
     double *cur = b_xa.as<double>(), *nxt = b_xb.as<double>();
     // Iterations are enqueued in groups; once every replicate has met the stop condition the
     // remaining launches of a group are no-ops (they test *n_active first), so the executed
@@ -520,52 +645,80 @@ SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_
         cur = (executed & 1) ? b_xb.as<double>() : b_xa.as<double>();
     }
 
-    // ---- outputs in ABI layout
-    double *d_out = out_x;
-    if (!buffers_on_device) {
-        EM_TRY(b_out_rt.alloc(sizeof(double) * (size_t)(T * R)));
-        d_out = b_out_rt.as<double>();
-    }
+    trace.mark("em: iterations");
     if (R > 1) transpose_kernel<<<blocks_for(T * R, 256), 256, 0, st>>>(cur, d_out, T, R);
     else EM_TRY(cudaMemcpyAsync(d_out, cur, sizeof(double) * (size_t)T, cudaMemcpyDeviceToDevice, st));
     EM_TRY(cudaGetLastError());
-    if (!buffers_on_device) {
-        EM_TRY(cudaMemcpyAsync(out_x, d_out, sizeof(double) * (size_t)(T * R), cudaMemcpyDeviceToHost, st));
-        if (out_iters) EM_TRY(cudaMemcpyAsync(out_iters, s.iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
-    } else if (out_iters) {
-        EM_TRY(cudaMemcpyAsync(out_iters, s.iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToDevice, st));
-    }
-    EM_TRY(cudaStreamSynchronize(st));
+    if (d_iters) EM_TRY(cudaMemcpyAsync(d_iters, s.iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToDevice, st));
+    EM_TRY(cudaStreamSynchronize(st));  // scratch buffers are released in stream order after this
     return SKM_OK;
 }
 
-SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicates,
-                            int64_t first_replicate, uint64_t seed, int64_t *out, int buffers_on_device,
-                            int device, void *stream)
+SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
+                   const double *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
+                   int64_t n_replicates, int64_t max_iters, double *out_x, int32_t *out_iters,
+                   int buffers_on_device, int device, void *stream)
 {
-    if (!counts || !out) return fail(SKM_ERR_INVALID, "skm_multinomial: NULL argument");
-    if (n_classes <= 0 || n_replicates <= 0) return fail(SKM_ERR_INVALID, "skm_multinomial: empty problem");
-    if (n_classes >= (1LL << 31)) return fail(SKM_ERR_INVALID, "skm_multinomial: too many classes");
+    if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
+        return fail(SKM_ERR_INVALID, "skm_em: NULL argument");
+    if (n_classes <= 0 || nnz <= 0 || n_transcripts <= 0 || n_replicates <= 0)
+        return fail(SKM_ERR_INVALID, "skm_em: empty problem");
+    if (nnz >= (1LL << 31) || n_classes >= (1LL << 31) || n_transcripts >= (1LL << 31))
+        return fail(SKM_ERR_INVALID, "skm_em: structure too large for int32 indices");
     if (skm_device_count() <= device || device < 0)
-        return fail(SKM_ERR_CUDA, "skm_multinomial: no such CUDA device (there is no CPU fallback)");
+        return fail(SKM_ERR_CUDA, "skm_em: no such CUDA device (there is no CPU fallback)");
     EM_TRY(cudaSetDevice(device));
+    keep_pool_memory(device);
     cudaStream_t st = (cudaStream_t)stream;
-    DeviceBuf b_counts, b_cum, b_lo, b_tmp, b_out;
-    const int64_t *d_counts = counts;
-    int64_t *d_out = out;
+    const int R = (int)n_replicates;
+    const int64_t C = n_classes, T = n_transcripts;
+
+    DeviceBuf b_ptr, b_tx, b_cnt_in, b_len, b_x_in, b_out, b_iters;
+    EmInputs in{class_ptr, class_tx, eff_len, C, nnz, T, R, max_iters, counts, nullptr, x0, nullptr};
+    double *d_out = out_x;
+    int32_t *d_iters = out_iters;
     if (!buffers_on_device) {
-        EM_TRY(b_counts.alloc(sizeof(int64_t) * (size_t)n_classes));
-        EM_TRY(b_out.alloc(sizeof(int64_t) * (size_t)(n_classes * n_replicates)));
-        EM_TRY(cudaMemcpyAsync(b_counts.p, counts, sizeof(int64_t) * (size_t)n_classes, cudaMemcpyHostToDevice, st));
-        d_counts = b_counts.as<int64_t>();
-        d_out = b_out.as<int64_t>();
+        EM_TRY(b_ptr.alloc(sizeof(int64_t) * (size_t)(C + 1), st));
+        EM_TRY(b_tx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+        EM_TRY(b_cnt_in.alloc(sizeof(double) * (size_t)(C * R), st));
+        EM_TRY(b_len.alloc(sizeof(double) * (size_t)T, st));
+        EM_TRY(b_x_in.alloc(sizeof(double) * (size_t)(T * R), st));
+        EM_TRY(b_out.alloc(sizeof(double) * (size_t)(T * R), st));
+        EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R, st));
+        EM_TRY(cudaMemcpyAsync(b_ptr.p, class_ptr, sizeof(int64_t) * (size_t)(C + 1), cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_tx.p, class_tx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_cnt_in.p, counts, sizeof(double) * (size_t)(C * R), cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_len.p, eff_len, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_x_in.p, x0, sizeof(double) * (size_t)(T * R), cudaMemcpyHostToDevice, st));
+        in.d_ptr = b_ptr.as<int64_t>();
+        in.d_tx = b_tx.as<int32_t>();
+        in.counts_rc = b_cnt_in.as<double>();
+        in.d_len = b_len.as<double>();
+        in.x_rt = b_x_in.as<double>();
+        d_out = b_out.as<double>();
+        d_iters = b_iters.as<int32_t>();
     }
-    EM_TRY(b_cum.alloc(sizeof(unsigned long long) * (size_t)n_classes));
-    EM_TRY(b_lo.alloc(sizeof(int32_t) * 65537));
+    const int rc = em_core(in, d_out, d_iters, st);
+    if (rc) return rc;
+    if (!buffers_on_device) {
+        EM_TRY(cudaMemcpyAsync(out_x, d_out, sizeof(double) * (size_t)(T * R), cudaMemcpyDeviceToHost, st));
+        if (out_iters) EM_TRY(cudaMemcpyAsync(out_iters, d_iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaStreamSynchronize(st));
+    }
+    return SKM_OK;
+}
+
+// Resample n = sum(counts) reads with replacement, n_replicates times, on device buffers.
+static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t n_replicates, int64_t first_replicate,
+                            uint64_t seed, int64_t *d_out, int device, cudaStream_t st)
+{
+    DeviceBuf b_cum, b_lo, b_tmp;
+    EM_TRY(b_cum.alloc(sizeof(unsigned long long) * (size_t)n_classes, st));
+    EM_TRY(b_lo.alloc(sizeof(int32_t) * 65537, st));
     size_t tmp = 0;
     cub::DeviceScan::InclusiveSum(nullptr, tmp, reinterpret_cast<const unsigned long long *>(d_counts),
                                   b_cum.as<unsigned long long>(), (int)n_classes, st);
-    EM_TRY(b_tmp.alloc(tmp));
+    EM_TRY(b_tmp.alloc(tmp, st));
     EM_TRY(cub::DeviceScan::InclusiveSum(b_tmp.p, tmp, reinterpret_cast<const unsigned long long *>(d_counts),
                                          b_cum.as<unsigned long long>(), (int)n_classes, st));
     unsigned long long n = 0;
@@ -584,8 +737,112 @@ SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_
                                                 reinterpret_cast<unsigned long long *>(d_out));
     }
     EM_TRY(cudaGetLastError());
-    if (!buffers_on_device)
-        EM_TRY(cudaMemcpyAsync(out, d_out, sizeof(int64_t) * (size_t)(n_classes * n_replicates), cudaMemcpyDeviceToHost, st));
     EM_TRY(cudaStreamSynchronize(st));
+    return SKM_OK;
+}
+
+SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicates,
+                            int64_t first_replicate, uint64_t seed, int64_t *out, int buffers_on_device,
+                            int device, void *stream)
+{
+    if (!counts || !out) return fail(SKM_ERR_INVALID, "skm_multinomial: NULL argument");
+    if (n_classes <= 0 || n_replicates <= 0) return fail(SKM_ERR_INVALID, "skm_multinomial: empty problem");
+    if (n_classes >= (1LL << 31)) return fail(SKM_ERR_INVALID, "skm_multinomial: too many classes");
+    if (skm_device_count() <= device || device < 0)
+        return fail(SKM_ERR_CUDA, "skm_multinomial: no such CUDA device (there is no CPU fallback)");
+    EM_TRY(cudaSetDevice(device));
+    keep_pool_memory(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceBuf b_counts, b_out;
+    const int64_t *d_counts = counts;
+    int64_t *d_out = out;
+    if (!buffers_on_device) {
+        EM_TRY(b_counts.alloc(sizeof(int64_t) * (size_t)n_classes, st));
+        EM_TRY(b_out.alloc(sizeof(int64_t) * (size_t)(n_classes * n_replicates), st));
+        EM_TRY(cudaMemcpyAsync(b_counts.p, counts, sizeof(int64_t) * (size_t)n_classes, cudaMemcpyHostToDevice, st));
+        d_counts = b_counts.as<int64_t>();
+        d_out = b_out.as<int64_t>();
+    }
+    const int rc = multinomial_core(d_counts, n_classes, n_replicates, first_replicate, seed, d_out, device, st);
+    if (rc) return rc;
+    if (!buffers_on_device) {
+        EM_TRY(cudaMemcpyAsync(out, d_out, sizeof(int64_t) * (size_t)(n_classes * n_replicates), cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaStreamSynchronize(st));
+    }
+    return SKM_OK;
+}
+
+SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
+                             const int64_t *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
+                             int64_t n_replicates, int64_t first_replicate, uint64_t seed, int64_t max_iters,
+                             int tpm, double *out_x, int32_t *out_iters, int buffers_on_device, int device,
+                             void *stream)
+{
+    if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
+        return fail(SKM_ERR_INVALID, "skm_em_bootstrap: NULL argument");
+    if (n_classes <= 0 || nnz <= 0 || n_transcripts <= 0 || n_replicates <= 0)
+        return fail(SKM_ERR_INVALID, "skm_em_bootstrap: empty problem");
+    if (nnz >= (1LL << 31) || n_classes >= (1LL << 31) || n_transcripts >= (1LL << 31))
+        return fail(SKM_ERR_INVALID, "skm_em_bootstrap: structure too large for int32 indices");
+    if (skm_device_count() <= device || device < 0)
+        return fail(SKM_ERR_CUDA, "skm_em_bootstrap: no such CUDA device (there is no CPU fallback)");
+    EM_TRY(cudaSetDevice(device));
+    keep_pool_memory(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = (int)n_replicates;
+    const int64_t C = n_classes, T = n_transcripts;
+
+    DeviceBuf b_ptr, b_tx, b_counts, b_len, b_x, b_out, b_iters, b_draws, b_cr;
+    EmInputs in{class_ptr, class_tx, eff_len, C, nnz, T, R, max_iters, nullptr, nullptr, nullptr, x0};
+    const int64_t *d_counts = counts;
+    double *d_out = out_x;
+    int32_t *d_iters = out_iters;
+    if (!buffers_on_device) {
+        EM_TRY(b_ptr.alloc(sizeof(int64_t) * (size_t)(C + 1), st));
+        EM_TRY(b_tx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+        EM_TRY(b_counts.alloc(sizeof(int64_t) * (size_t)C, st));
+        EM_TRY(b_len.alloc(sizeof(double) * (size_t)T, st));
+        EM_TRY(b_x.alloc(sizeof(double) * (size_t)T, st));
+        EM_TRY(b_out.alloc(sizeof(double) * (size_t)(T * R), st));
+        EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R, st));
+        EM_TRY(cudaMemcpyAsync(b_ptr.p, class_ptr, sizeof(int64_t) * (size_t)(C + 1), cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_tx.p, class_tx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_counts.p, counts, sizeof(int64_t) * (size_t)C, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_len.p, eff_len, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_x.p, x0, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, st));
+        in.d_ptr = b_ptr.as<int64_t>();
+        in.d_tx = b_tx.as<int32_t>();
+        in.d_len = b_len.as<double>();
+        in.x_t = b_x.as<double>();
+        d_counts = b_counts.as<int64_t>();
+        d_out = b_out.as<double>();
+        d_iters = b_iters.as<int32_t>();
+    }
+    Trace trace(st);
+    trace.mark("bootstrap: inputs to device");
+    // resample on the device, then straight into the EM's [class][replicate] fp64 layout
+    EM_TRY(b_draws.alloc(sizeof(int64_t) * (size_t)(C * R), st));
+    int rc = multinomial_core(d_counts, C, R, first_replicate, seed, b_draws.as<int64_t>(), device, st);
+    if (rc) return rc;
+    EM_TRY(b_cr.alloc(sizeof(double) * (size_t)(C * R), st));
+    counts_to_f64_kernel<<<blocks_for(C * R, 256), 256, 0, st>>>(b_draws.as<unsigned long long>(), b_cr.as<double>(), C, R);
+    EM_TRY(cudaGetLastError());
+    b_draws.release();
+    trace.mark("bootstrap: resample");
+    in.counts_cr = b_cr.as<double>();
+    rc = em_core(in, d_out, d_iters, st);
+    if (rc) return rc;
+    trace.mark("bootstrap: em_core");
+    if (tpm) {
+        tpm_finish_kernel<<<R, 1024, 0, st>>>(d_out, T);
+        EM_TRY(cudaGetLastError());
+    }
+    trace.mark("bootstrap: tpm");
+    if (!buffers_on_device) {
+        EM_TRY(cudaMemcpyAsync(out_x, d_out, sizeof(double) * (size_t)(T * R), cudaMemcpyDeviceToHost, st));
+        if (out_iters) EM_TRY(cudaMemcpyAsync(out_iters, d_iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
+    }
+    EM_TRY(cudaStreamSynchronize(st));
+    trace.mark("bootstrap: results to host");
     return SKM_OK;
 }

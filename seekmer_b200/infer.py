@@ -155,12 +155,21 @@ def quantify_bootstraps(results, x0, n_replicates, seed=None, return_iters=False
         return (z, numpy.zeros(n_replicates, dtype='i4')) if return_iters else z
     if seed is None:
         seed = _draw_seed()
-    counts = _resample(results.class_count, n_replicates, seed, first_replicate).astype('f8')
-    x = x0.copy()
+    counts = numpy.ascontiguousarray(results.class_count, dtype='i8')
+    if not (counts == results.class_count).all():
+        raise ValueError('bootstrap needs integral class counts')
+    x = numpy.ascontiguousarray(x0, dtype='f8').copy()
     x /= x.sum()
-    xs, iters = _em_device(numpy.tile(x, (n_replicates, 1)), transcript_length, results.class_map,
-                           counts)
-    out = [_finish(xs[i].copy()) for i in range(n_replicates)]
+    ptr, tx = _csr_from_class_map(results.class_map, counts.shape[0])
+    xs = numpy.zeros((n_replicates, x.shape[0]), dtype='f8')
+    iters = numpy.zeros(n_replicates, dtype='i4')
+    _lib.require_device()
+    # resample + EM for all replicates in one device-resident call
+    _lib.check(_lib.load().skm_em_bootstrap(
+        _lib._np_ptr(ptr), _lib._np_ptr(tx), counts.shape[0], tx.shape[0], _lib._np_ptr(counts),
+        _lib._np_ptr(transcript_length), x.shape[0], _lib._np_ptr(x), n_replicates, first_replicate,
+        int(seed) & (2 ** 64 - 1), 0, 1, _lib._np_ptr(xs), _lib._np_ptr(iters), 0, 0, None))
+    out = list(xs)  # TPM post-processing (`infer.py:127-129`) already applied on the device
     return (out, iters) if return_iters else out
 
 
