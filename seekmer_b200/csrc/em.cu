@@ -134,12 +134,35 @@ __global__ void tpm_finish_kernel(double *__restrict__ x, int64_t n_tx)
     for (int64_t t = threadIdx.x; t < n_tx; t += blockDim.x) row[t] = __ddiv_rn(row[t], scale2);
 }
 
+// keep the columns map[0..R_new) of a [rows][R_old] matrix: dst is [rows][R_new]
+__global__ void compact_cols_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t rows,
+                                    int R_old, int R_new, const int32_t *__restrict__ map)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows * R_new) return;
+    const int64_t row = i / R_new;
+    const int j = (int)(i - row * R_new);
+    dst[i] = src[row * R_old + map[j]];
+}
+
+// columns cols[j] of x [rows][R_old] -> rows origs[j] of out [.][rows] (the ABI layout)
+__global__ void extract_cols_kernel(const double *__restrict__ src, int64_t rows, int R_old, int n_cols,
+                                    const int32_t *__restrict__ cols, const int32_t *__restrict__ origs,
+                                    double *__restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows * n_cols) return;
+    const int64_t t = i / n_cols;
+    const int j = (int)(i - t * n_cols);
+    out[(int64_t)origs[j] * rows + t] = src[t * R_old + cols[j]];
+}
+
 struct EmState {
     const int64_t *class_ptr;   // CSR by class
     const int32_t *class_tx;
     const int64_t *tx_ptr;      // CSC by transcript (entries in nnz order)
     const int32_t *tx_class;
-    const double *counts;       // [C][R]
+    const double *counts;       // [C][R] (R = live replicate columns)
     const double *eff_len;      // [T]
     const double *n;            // [R]
     double *inner;              // [C][R]
@@ -610,13 +633,33 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     // Iterations are enqueued in groups; once every replicate has met the stop condition the
     // remaining launches of a group are no-ops (they test *n_active first), so the executed
     // iteration count is exact while the host only synchronises once per group.
+    //
+    // Replicates stop at very different iteration counts (bootstraps: mean ~40, max > 100), so
+    // whenever at most half of the live columns are still running the finished ones are written
+    // to the output and the state is compacted to the running columns: the work of an
+    // iteration follows the number of replicates that still need it.
     const int GROUP = 8;
     int64_t done = 0;
     int32_t n_active = R;
-    const dim3 grid_c((unsigned)((C + EM_BLOCK / 32 - 1) / (EM_BLOCK / 32)), (unsigned)((R + 31) / 32));
-    const dim3 grid_t((unsigned)((T + EM_BLOCK / 32 - 1) / (EM_BLOCK / 32)), (unsigned)((R + 31) / 32));
+    int Rc = R;                          // live columns
+    std::vector<int32_t> orig((size_t)R);  // original replicate of each live column
+    for (int r = 0; r < R; ++r) orig[(size_t)r] = r;
+    std::vector<int32_t> final_iters((size_t)R, 0);
+    std::vector<int32_t> h_active((size_t)R), h_iters((size_t)R), h_map;
+    std::vector<double> h_n((size_t)R);
+    DeviceBuf b_map;
+    EM_TRY(b_map.alloc(sizeof(int32_t) * 2 * (size_t)R, st));
+    const bool may_compact = R > 1 && (in.counts_cr != nullptr || b_cnt.p != nullptr);  // counts buffer is scratch
+    double *counts_buf = const_cast<double *>(d_cnt), *inner_buf = b_inner.as<double>();
+    double *group_cur = cur, *group_nxt = nxt;
+    int64_t group_base = 0;
     while (n_active > 0 && done < max_iters) {
         const int g = (int)std::min<int64_t>(GROUP, max_iters - done);
+        const dim3 grid_c((unsigned)((C + EM_BLOCK / 32 - 1) / (EM_BLOCK / 32)), (unsigned)((Rc + 31) / 32));
+        const dim3 grid_t((unsigned)((T + EM_BLOCK / 32 - 1) / (EM_BLOCK / 32)), (unsigned)((Rc + 31) / 32));
+        group_cur = cur;
+        group_nxt = nxt;
+        group_base = done;
         for (int k = 0; k < g; ++k) {
             if (R == 1) {
                 em_class_kernel_r1<<<blocks_for(C, EM_BLOCK), EM_BLOCK, 0, st>>>(s, cur);
@@ -632,24 +675,80 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
         EM_TRY(cudaGetLastError());
         EM_TRY(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
-    }
-    // Kernels of a group enqueued after the last replicate stopped are no-ops, so the device
-    // stopped ping-ponging while the host kept swapping.  The buffer written by the last
-    // EXECUTED iteration (xb for odd counts, xa for even) holds every replicate's final x:
-    // replicates that stopped earlier are copied through on each later iteration.
-    {
-        std::vector<int32_t> h_iters((size_t)R);
-        EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
+        if (!may_compact || n_active <= 0 || 2 * n_active > Rc || Rc <= 8 || done >= max_iters) continue;
+        // ---- compact to the running columns (every iteration of this group did execute) --------
+        EM_TRY(cudaMemcpyAsync(h_active.data(), s.active, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaMemcpyAsync(h_n.data(), s.n, sizeof(double) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
-        const int32_t executed = *std::max_element(h_iters.begin(), h_iters.end());
-        cur = (executed & 1) ? b_xb.as<double>() : b_xa.as<double>();
+        std::vector<int32_t> keep, drop_cols, drop_orig, keep_orig;
+        std::vector<int32_t> keep_iters;
+        std::vector<double> keep_n;
+        for (int c = 0; c < Rc; ++c) {
+            if (h_active[(size_t)c]) {
+                keep.push_back(c);
+                keep_orig.push_back(orig[(size_t)c]);
+                keep_iters.push_back(h_iters[(size_t)c]);
+                keep_n.push_back(h_n[(size_t)c]);
+            } else {
+                drop_cols.push_back(c);
+                drop_orig.push_back(orig[(size_t)c]);
+                final_iters[(size_t)orig[(size_t)c]] = h_iters[(size_t)c];
+            }
+        }
+        const int n_keep = (int)keep.size(), n_drop = (int)drop_cols.size();
+        int32_t *d_map = b_map.as<int32_t>();
+        // finished columns -> output rows
+        EM_TRY(cudaMemcpyAsync(d_map, drop_cols.data(), sizeof(int32_t) * (size_t)n_drop, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(d_map + R, drop_orig.data(), sizeof(int32_t) * (size_t)n_drop, cudaMemcpyHostToDevice, st));
+        extract_cols_kernel<<<blocks_for(T * n_drop, 256), 256, 0, st>>>(cur, T, Rc, n_drop, d_map, d_map + R, d_out);
+        EM_TRY(cudaStreamSynchronize(st));  // the map buffer is reused just below
+        // running columns: x (cur -> nxt, swap), counts (-> the inner buffer, swap), n, iters, active
+        EM_TRY(cudaMemcpyAsync(d_map, keep.data(), sizeof(int32_t) * (size_t)n_keep, cudaMemcpyHostToDevice, st));
+        compact_cols_kernel<<<blocks_for(T * n_keep, 256), 256, 0, st>>>(cur, nxt, T, Rc, n_keep, d_map);
+        std::swap(cur, nxt);
+        compact_cols_kernel<<<blocks_for(C * n_keep, 256), 256, 0, st>>>(counts_buf, inner_buf, C, Rc, n_keep, d_map);
+        std::swap(counts_buf, inner_buf);
+        s.counts = counts_buf;
+        s.inner = inner_buf;
+        EM_TRY(cudaMemcpyAsync(const_cast<double *>(s.n), keep_n.data(), sizeof(double) * (size_t)n_keep, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(s.iters, keep_iters.data(), sizeof(int32_t) * (size_t)n_keep, cudaMemcpyHostToDevice, st));
+        fill_i32_kernel<<<blocks_for(n_keep, 256), 256, 0, st>>>(s.active, n_keep, 1);
+        EM_TRY(cudaMemsetAsync(s.maxd, 0, sizeof(unsigned long long) * (size_t)n_keep, st));
+        EM_TRY(cudaGetLastError());
+        EM_TRY(cudaStreamSynchronize(st));  // host vectors above go out of scope
+        orig = keep_orig;
+        Rc = n_keep;
+        s.R = Rc;
+    }
+    // Kernels of the last group enqueued after the last replicate stopped are no-ops, so the
+    // device stopped ping-ponging while the host kept swapping.  The buffer written by the last
+    // EXECUTED iteration holds every live column's final x: columns that stopped earlier are
+    // copied through on each later iteration.
+    {
+        EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaStreamSynchronize(st));
+        const int64_t executed = *std::max_element(h_iters.begin(), h_iters.begin() + Rc);
+        const int64_t in_group = executed - group_base;  // iterations the last group really ran
+        cur = (in_group & 1) ? group_nxt : group_cur;
+        for (int c = 0; c < Rc; ++c) final_iters[(size_t)orig[(size_t)c]] = h_iters[(size_t)c];
     }
 
     trace.mark("em: iterations");
-    if (R > 1) transpose_kernel<<<blocks_for(T * R, 256), 256, 0, st>>>(cur, d_out, T, R);
-    else EM_TRY(cudaMemcpyAsync(d_out, cur, sizeof(double) * (size_t)T, cudaMemcpyDeviceToDevice, st));
+    if (R > 1) {
+        std::vector<int32_t> cols((size_t)Rc);
+        for (int c = 0; c < Rc; ++c) cols[(size_t)c] = c;
+        int32_t *d_map = b_map.as<int32_t>();
+        EM_TRY(cudaMemcpyAsync(d_map, cols.data(), sizeof(int32_t) * (size_t)Rc, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(d_map + R, orig.data(), sizeof(int32_t) * (size_t)Rc, cudaMemcpyHostToDevice, st));
+        extract_cols_kernel<<<blocks_for(T * Rc, 256), 256, 0, st>>>(cur, T, Rc, Rc, d_map, d_map + R, d_out);
+        EM_TRY(cudaStreamSynchronize(st));
+    } else {
+        EM_TRY(cudaMemcpyAsync(d_out, cur, sizeof(double) * (size_t)T, cudaMemcpyDeviceToDevice, st));
+    }
     EM_TRY(cudaGetLastError());
-    if (d_iters) EM_TRY(cudaMemcpyAsync(d_iters, s.iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToDevice, st));
+    if (d_iters)
+        EM_TRY(cudaMemcpyAsync(d_iters, final_iters.data(), sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, st));
     EM_TRY(cudaStreamSynchronize(st));  // scratch buffers are released in stream order after this
     return SKM_OK;
 }
