@@ -134,6 +134,18 @@ int skm_map_batch(skm_mapper *mapper, const uint8_t *bases, const int64_t *read_
                   int64_t first_unit, int buffers_on_device, int32_t *out_class,
                   int32_t *out_length, void *stream);
 
+/* Replaces: the line loops of common.feed_single_ended_reads / feed_pair_ended_reads
+ * (common.py:126-197) plus skm_map_batch: maps the reads of raw FASTQ TEXT.  text1 (and text2
+ * for mates; NULL = single-ended) must start at a record boundary; as many whole 4-line records
+ * as both chunks hold are parsed on the device (newline scan; line 4r+1 = sequence of record r,
+ * blanks stripped at both ends), packed straight out of the text and mapped.  consumedN = bytes
+ * of textN that were used: the caller prepends the rest to the next chunk.  Chunks < 2 GiB.
+ * out_class / out_length as in skm_map_batch (sized for the units the chunks can hold). */
+int skm_map_fastq(skm_mapper *mapper, const uint8_t *text1, int64_t n1, const uint8_t *text2,
+                  int64_t n2, int64_t first_unit, int buffers_on_device, int64_t *consumed1,
+                  int64_t *consumed2, int64_t *n_units, int32_t *out_class, int32_t *out_length,
+                  void *stream);
+
 /* Measurement support: device durations (ms, CUDA events on the launch stream) of the three
  * kernels of the most recent chunk mapped by skm_map_batch: ms[0] = pack_reads_kernel,
  * ms[1] = map_reads_kernel, ms[2] = tally_units_kernel.  Blocks until that chunk is done. */

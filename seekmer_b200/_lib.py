@@ -24,7 +24,7 @@ TARGET_DTYPE = numpy.dtype([('entry', '<i4'), ('offset', '<i4')])
 EXPORTS = (
     'skm_last_error', 'skm_device_count', 'skm_version', 'skm_index_create', 'skm_index_destroy',
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
-    'skm_mapper_reset', 'skm_map_batch', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
+    'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_effective_lengths', 'skm_em', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
     'skm_build_kmer_table',
 )
@@ -72,6 +72,8 @@ def load():
     L.skm_mapper_reset.argtypes = [vp, vp]
     L.skm_map_batch.restype = ci
     L.skm_map_batch.argtypes = [vp, vp, vp, i32, i32, i64, ci, i64, ci, vp, vp, vp]
+    L.skm_map_fastq.restype = ci
+    L.skm_map_fastq.argtypes = [vp, vp, i64, vp, i64, i64, ci, vp, vp, vp, vp, vp, vp]
     L.skm_mapper_kernel_ms.restype = ci
     L.skm_mapper_kernel_ms.argtypes = [vp, vp]
     L.skm_classes_size.restype = ci
@@ -244,6 +246,16 @@ class DeviceMapper:
                                    int(max_len), int(n_units), int(bool(paired)), int(first_unit),
                                    int(on_device), _ptr(out_class), _ptr(out_length), stream))
         return out_class, out_length
+
+    def map_fastq(self, text1, n1, text2=None, n2=0, first_unit=0, stream=None):
+        """Map the whole records of raw FASTQ text (uint8 numpy arrays, host).  Returns
+        (n_units, consumed1, consumed2)."""
+        out = numpy.zeros(3, dtype='i8')
+        base = out.ctypes.data
+        check(load().skm_map_fastq(self._h, _ptr(text1), int(n1), _ptr(text2), int(n2), int(first_unit), 0,
+                                   ctypes.c_void_p(base), ctypes.c_void_p(base + 8) if text2 is not None else None,
+                                   ctypes.c_void_p(base + 16), None, None, stream))
+        return int(out[2]), int(out[0]), int(out[1])
 
     def kernel_ms(self):
         """Device durations (ms) of pack / map / tally kernels of the last mapped chunk."""

@@ -173,7 +173,133 @@ def _fastq_records(handle):
             yield name, line.strip()
 
 
+class FastqSource:
+    """What `feed_single_ended_reads` / `feed_pair_ended_reads` return: iterating it yields the
+    reference's `(count, names, reads)` batches (`common.py:126-197`), and it remembers the
+    file paths, so that `ReadMapper` can instead hand the raw FASTQ text to the GPU
+    (`skm_map_fastq`) when nobody needs the read names."""
+
+    def __init__(self, paths, paired):
+        self.paths = [pathlib.Path(p) for p in paths]
+        self.paired = paired
+        if paired and len(self.paths) % 2 != 0:
+            raise ValueError('cannot process odd numbers of pair-ended files')
+
+    def __iter__(self):
+        return (_iterate_pair_ended if self.paired else _iterate_single_ended)(*self.paths)
+
+    def __next__(self):  # the reference's feeders are generators: next(feeder) must work
+        if getattr(self, '_gen', None) is None:
+            self._gen = iter(self)
+        return next(self._gen)
+
+    def text_chunks(self, chunk_bytes):
+        """Yield `(buf1, n1, buf2, n2, eof)`: raw text of the file (pair) in reusable uint8
+        buffers, each call handing over `chunk_bytes` more per file.  The consumer reports how
+        much it used through `.consumed(c1, c2)` before asking for the next chunk; the rest is
+        kept in front of the new data."""
+        files = iterate_by_group(self.paths, 2) if self.paired else [(p,) for p in self.paths]
+        for group in files:
+            with contextlib.ExitStack() as stack:
+                handles = [stack.enter_context(decompress_and_open(p)) for p in group]
+                carries = [_Carry(chunk_bytes, p.stat().st_size if p.suffix not in _EXTERNAL else None)
+                           for p in group]
+                self._carries = carries
+                while True:
+                    for c, h in zip(carries, handles):
+                        c.fill(h)
+                    eof = all(c.eof for c in carries)
+                    if eof:
+                        for c in carries:
+                            c.finish()
+                    yield tuple(x for c in carries for x in (c.buf, c.n)) + (eof,)
+                    if eof:
+                        break
+
+    def consumed(self, *used):
+        for c, u in zip(self._carries, used):
+            c.drop(u)
+
+
+class _Carry:
+    """A growing text window over one FASTQ stream: unread tail + freshly read bytes."""
+
+    def __init__(self, chunk_bytes, size_hint=None):
+        if size_hint is not None:  # a regular file: no need for more than it holds
+            chunk_bytes = max(min(chunk_bytes, size_hint + 16), 1 << 16)
+        self.chunk = chunk_bytes
+        self.buf = _pinned_bytes(2 * chunk_bytes + 64)
+        self.n = 0
+        self.eof = False
+
+    def fill(self, handle):
+        if self.eof:
+            return
+        if self.n + self.chunk > self.buf.shape[0]:  # a record longer than a chunk: grow
+            grown = _pinned_bytes(2 * (self.n + self.chunk) + 64)
+            grown[:self.n] = self.buf[:self.n]
+            self.buf = grown
+        want = self.chunk
+        view = memoryview(self.buf)[self.n:self.n + want]
+        got = 0
+        while got < want:
+            k = handle.readinto(view[got:])
+            if not k:
+                self.eof = True
+                break
+            got += k
+        self.n += got
+
+    def finish(self):
+        """End of stream: terminate the last line, and complete a trailing partial record that
+        has its sequence line (the reference's line-index logic yields it, `common.py:137-138`)."""
+        if self.n and self.buf[self.n - 1] != 10:
+            self.buf[self.n] = 10
+            self.n += 1
+        lines = int(numpy.count_nonzero(self.buf[:self.n] == 10))
+        extra = (-lines) % 4
+        if extra in (1, 2):  # 3 or 2 lines of the last record are there: header + sequence (+ '+')
+            self.buf[self.n:self.n + extra] = 10
+            self.n += extra
+        elif extra == 3:  # a lone header line: no read
+            nl = numpy.flatnonzero(self.buf[:self.n - 1] == 10)
+            self.n = int(nl[-1]) + 1 if nl.size else 0
+
+    def drop(self, used):
+        rest = self.n - used
+        if used and rest:
+            self.buf[:rest] = self.buf[used:self.n].copy()
+        self.n = rest
+
+
+def _pinned_bytes(n):
+    """uint8 host buffer, page-locked when torch can provide it (faster H2D copies)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+            a = t.numpy()
+            _PINNED_KEEPALIVE.append(t)
+            return a
+    except Exception:
+        pass
+    return numpy.empty(n, dtype='u1')
+
+
+_PINNED_KEEPALIVE = []
+
+
 def feed_single_ended_reads(*paths):
+    """Single-ended FASTQ file(s) as one sample (`common.py:126-158`)."""
+    return FastqSource(paths, paired=False)
+
+
+def feed_pair_ended_reads(*paths):
+    """Pair-ended FASTQ file pairs as one sample, mates interleaved (`common.py:161-197`)."""
+    return FastqSource(paths, paired=True)
+
+
+def _iterate_single_ended(*paths):
     """Yield `(count, names, reads)` batches of up to BUFFER_SIZE reads; all files form one
     sample."""
     names, reads = [], []
@@ -190,7 +316,7 @@ def feed_single_ended_reads(*paths):
     _LOG.debug('Finished reading sequence file(s)')
 
 
-def feed_pair_ended_reads(*paths):
+def _iterate_pair_ended(*paths):
     """Yield `(pair_count, names, reads)` with mates interleaved (2i, 2i+1)."""
     if len(paths) % 2 != 0:
         raise ValueError('cannot process odd numbers of pair-ended files')

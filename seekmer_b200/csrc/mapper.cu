@@ -7,7 +7,10 @@
 // transcript-id tuple into a device-resident class dictionary (dict.cuh).  The fragment-length
 // histogram is accumulated in shared memory and flushed once per block.
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
+
+#include <cub/cub.cuh>
 
 #include "map_kernel.cuh"
 
@@ -44,9 +47,9 @@ __device__ __forceinline__ void convert4(uint32_t x, uint32_t &codes8, uint32_t 
 // pieces of the input, so loads and stores are coalesced whatever the read length; the piece is
 // fetched with three aligned 16-byte loads and shifted into place.
 __global__ void __launch_bounds__(256)
-pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ offsets,
-                  int32_t fixed_len, int32_t code_words, int32_t wild_words, int32_t words, int64_t n_reads,
-                  uint64_t *__restrict__ packed, int32_t *__restrict__ lens)
+pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__ starts,
+                  const int64_t *__restrict__ ends, int32_t fixed_len, int32_t code_words, int32_t wild_words,
+                  int32_t words, int64_t n_reads, uint64_t *__restrict__ packed, int32_t *__restrict__ lens)
 {
     const uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const int64_t read = idx <= 0xFFFFFFFFULL ? (int64_t)((uint32_t)idx / (uint32_t)code_words)
@@ -55,9 +58,9 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__
     if (read >= n_reads) return;
     int64_t off;
     int len;
-    if (offsets) {
-        off = __ldg(offsets + read);
-        len = (int)(__ldg(offsets + read + 1) - off);
+    if (starts) {  // read i = bases[starts[i], ends[i]); a CSR offsets array is starts = o, ends = o + 1
+        off = __ldg(starts + read);
+        len = (int)(__ldg(ends + read) - off);
     } else {
         off = read * (int64_t)fixed_len;
         len = fixed_len;
@@ -111,6 +114,101 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__
     uint32_t *wout = reinterpret_cast<uint32_t *>(out + code_words) + w;
     *wout = wild;
     if (w == code_words - 1 && !(w & 1)) wout[1] = 0;  // upper half of the last wildcard word
+}
+
+// ---- FASTQ text on the device (replaces the line loop of common.feed_*_reads) -----------------
+// A chunk of FASTQ text that starts at a record boundary is parsed where it lies: newline
+// positions are compacted (count per 4 KB block, scan, write), line 4r+1 of the chunk is the
+// sequence of record r, and the pack kernel reads the bases straight out of the text.
+constexpr int NL_BLOCK_BYTES = 4096;
+constexpr int NL_THREADS = 256;  // 16 bytes per thread
+
+__device__ __forceinline__ unsigned newline_mask16(const uint8_t *text, int64_t n, int64_t at)
+{
+    unsigned mask = 0;
+    if (at + 16 <= n && (reinterpret_cast<uintptr_t>(text + at) & 15) == 0) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + at));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t z = w[k] ^ 0x0A0A0A0Au;  // zero byte <=> newline
+            const uint32_t hit = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u;
+            mask |= (((hit >> 7) & 1u) | ((hit >> 14) & 2u) | ((hit >> 21) & 4u) | ((hit >> 28) & 8u)) << (4 * k);
+        }
+    } else {
+        for (int k = 0; k < 16; ++k)
+            if (at + k < n && text[at + k] == '\n') mask |= 1u << k;
+    }
+    return mask;
+}
+
+__global__ void __launch_bounds__(NL_THREADS)
+count_newlines_kernel(const uint8_t *__restrict__ text, int64_t n, unsigned long long *__restrict__ block_counts)
+{
+    const int64_t at = blockIdx.x * (int64_t)NL_BLOCK_BYTES + threadIdx.x * 16;
+    const int c = at < n ? __popc(newline_mask16(text, n, at)) : 0;
+    __shared__ int warp_sums[NL_THREADS / 32];
+    int v = c;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < NL_THREADS / 32; ++w) t += warp_sums[w];
+        block_counts[blockIdx.x] = (unsigned long long)t;
+    }
+}
+
+// block_base = exclusive scan of block_counts; positions are relative to `text`
+__global__ void __launch_bounds__(NL_THREADS)
+write_newlines_kernel(const uint8_t *__restrict__ text, int64_t n, const unsigned long long *__restrict__ block_base,
+                      int64_t *__restrict__ positions)
+{
+    const int64_t at = blockIdx.x * (int64_t)NL_BLOCK_BYTES + threadIdx.x * 16;
+    const unsigned mask = at < n ? newline_mask16(text, n, at) : 0u;
+    const int c = __popc(mask);
+    // exclusive prefix of c over the block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ int warp_sums[NL_THREADS / 32];
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int before = incl - c;
+    for (int w = 0; w < warp; ++w) before += warp_sums[w];
+    int64_t *out = positions + block_base[blockIdx.x] + before;
+    unsigned m = mask;
+    while (m) {
+        const int k = __ffs((int)m) - 1;
+        m &= m - 1;
+        *out++ = at + k;
+    }
+}
+
+// Sequence line of record u in each file: [start, end) offsets into the device text buffer,
+// stripped of blanks at both ends like bytes.strip() (common.py:137-138); mates interleaved.
+__global__ void fastq_units_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ nl1,
+                                   const int64_t *__restrict__ nl2, int64_t base2, int64_t n_units, int paired,
+                                   int64_t *__restrict__ starts, int64_t *__restrict__ ends, int *__restrict__ len_range)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n_reads = paired ? 2 * n_units : n_units;
+    if (i >= n_reads) return;
+    const int64_t u = paired ? i >> 1 : i;
+    const bool second = paired && (i & 1);
+    const int64_t *nl = second ? nl2 : nl1;
+    const int64_t base = second ? base2 : 0;
+    int64_t b = base + nl[4 * u] + 1, e = base + nl[4 * u + 1];
+    while (e > b && text[e - 1] <= ' ') --e;
+    while (b < e && text[b] <= ' ') ++b;
+    starts[i] = b;
+    ends[i] = e;
+    const int len = (int)(e - b);
+    atomicMax(&len_range[0], len);
+    atomicMin(&len_range[1], len);
 }
 
 // ---- export / merge -------------------------------------------------------------------
@@ -196,6 +294,18 @@ struct skm_mapper {
     size_t d_packed_cap = 0;
     int32_t *d_lens = nullptr;
     size_t d_lens_cap = 0;
+    // skm_map_fastq
+    uint8_t *d_text = nullptr;
+    size_t d_text_cap = 0;
+    int64_t *d_nl[2] = {nullptr, nullptr};
+    size_t d_nl_cap[2] = {0, 0};
+    unsigned long long *d_blk = nullptr;  // per-block newline counts / bases
+    size_t d_blk_cap = 0;
+    int64_t *d_bounds = nullptr;  // starts | ends of the reads of a FASTQ chunk
+    size_t d_bounds_cap = 0;
+    void *d_scan_tmp = nullptr;
+    size_t d_scan_tmp_cap = 0;
+    int *d_len_range = nullptr;
 };
 
 static int ensure(void **p, size_t *cap, size_t need)
@@ -239,6 +349,13 @@ SKM_API void skm_mapper_destroy(skm_mapper *m)
     cudaFree(m->d_out);
     cudaFree(m->d_packed);
     cudaFree(m->d_units);
+    cudaFree(m->d_text);
+    cudaFree(m->d_nl[0]);
+    cudaFree(m->d_nl[1]);
+    cudaFree(m->d_blk);
+    cudaFree(m->d_bounds);
+    cudaFree(m->d_scan_tmp);
+    cudaFree(m->d_len_range);
     cudaFree(m->d_lens);
     cudaSetDevice(prev);
     delete m;
@@ -360,15 +477,14 @@ static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
 }
 
 // pack + map of one device-resident chunk on stream `st`
-static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_offsets, MapArgs a,
-                        int64_t n_units, int64_t first_unit, int32_t *d_out_class, int32_t *d_out_length,
-                        cudaStream_t st)
+int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_starts, const int64_t *d_ends, MapArgs a,
+                 int64_t n_units, int64_t first_unit, int32_t *d_out_class, int32_t *d_out_length, cudaStream_t st)
 {
     const int64_t n_reads = a.paired ? 2 * n_units : n_units;
     int rc = ensure((void **)&m->d_packed, &m->d_packed_cap, sizeof(uint64_t) * (size_t)n_reads * a.words);
     if (rc) return rc;
     int32_t *lens = nullptr;
-    if (d_offsets) {
+    if (d_starts) {
         rc = ensure((void **)&m->d_lens, &m->d_lens_cap, sizeof(int32_t) * (size_t)n_reads);
         if (rc) return rc;
         lens = m->d_lens;
@@ -377,7 +493,7 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     const int64_t pack_threads = n_reads * a.code_words;
     if (pack_threads >= (1LL << 31) * 256) return fail(SKM_ERR_INVALID, "skm_map_batch: batch too large for one launch");
     pack_reads_kernel<<<(unsigned)((pack_threads + 255) / 256), 256, 0, st>>>(
-        d_bases, d_offsets, a.fixed_len, a.code_words, a.wild_words, a.words, n_reads, m->d_packed, lens);
+        d_bases, d_starts, d_ends, a.fixed_len, a.code_words, a.wild_words, a.words, n_reads, m->d_packed, lens);
     SKM_CUDA(cudaGetLastError());
     SKM_CUDA(cudaEventRecord(m->ev_kernel[1], st));
     a.packed = m->d_packed;
@@ -456,7 +572,8 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     a.cursors = m->cursors;
 
     if (buffers_on_device)
-        return launch_chunk(m, bases, read_offsets, a, n_units, first_unit, out_class, out_length, st);
+        return launch_chunk(m, bases, read_offsets, read_offsets ? read_offsets + 1 : nullptr, a, n_units, first_unit,
+                            out_class, out_length, st);
 
     // ---- host buffers: double-buffered H2D copies overlapped with pack + map --------------
     int32_t *d_class = nullptr, *d_length = nullptr;
@@ -496,7 +613,8 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
         // the kernels index reads from 0 within the chunk; explicit offsets keep their global
         // byte values, so only then is the base pointer shifted back by b0
         rc = launch_chunk(m, read_offsets ? m->d_bases[slot] - b0 : m->d_bases[slot],
-                          read_offsets ? m->d_offsets[slot] : nullptr, a, nu,
+                          read_offsets ? m->d_offsets[slot] : nullptr,
+                          read_offsets ? m->d_offsets[slot] + 1 : nullptr, a, nu,
                           first_unit + u0, d_class ? d_class + u0 : nullptr, d_length ? d_length + u0 : nullptr, st);
         if (rc) return rc;
         SKM_CUDA(cudaEventRecord(m->ev_compute[slot], st));
@@ -506,6 +624,120 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     if (out_length)
         SKM_CUDA(cudaMemcpyAsync(out_length, d_length, sizeof(int32_t) * (size_t)n_units, cudaMemcpyDeviceToHost, st));
     return check_status(m, st, "skm_map_batch");
+}
+
+// Newline positions of text[0, n) on the device; returns their number.
+static int find_newlines(skm_mapper *m, const uint8_t *d_text, int64_t n, int which, int64_t *count, cudaStream_t st)
+{
+    *count = 0;
+    if (n <= 0) return SKM_OK;
+    const int64_t blocks = (n + NL_BLOCK_BYTES - 1) / NL_BLOCK_BYTES;
+    int rc = ensure((void **)&m->d_blk, &m->d_blk_cap, sizeof(unsigned long long) * (size_t)(2 * (blocks + 1)));
+    if (rc) return rc;
+    unsigned long long *cnt = m->d_blk, *base = m->d_blk + blocks + 1;
+    SKM_CUDA(cudaMemsetAsync(cnt + blocks, 0, sizeof(unsigned long long), st));
+    count_newlines_kernel<<<(unsigned)blocks, NL_THREADS, 0, st>>>(d_text, n, cnt);
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, cnt, base, (int)(blocks + 1), st);
+    rc = ensure(&m->d_scan_tmp, &m->d_scan_tmp_cap, tmp);
+    if (rc) return rc;
+    SKM_CUDA(cub::DeviceScan::ExclusiveSum(m->d_scan_tmp, tmp, cnt, base, (int)(blocks + 1), st));
+    unsigned long long total = 0;
+    SKM_CUDA(cudaMemcpyAsync(&total, base + blocks, sizeof(total), cudaMemcpyDeviceToHost, st));
+    SKM_CUDA(cudaStreamSynchronize(st));
+    *count = (int64_t)total;
+    if (total == 0) return SKM_OK;
+    rc = ensure((void **)&m->d_nl[which], &m->d_nl_cap[which], sizeof(int64_t) * (size_t)total);
+    if (rc) return rc;
+    write_newlines_kernel<<<(unsigned)blocks, NL_THREADS, 0, st>>>(d_text, n, base, m->d_nl[which]);
+    SKM_CUDA(cudaGetLastError());
+    // the scratch (m->d_blk) is reused by the next call on the same stream: ordered
+    return SKM_OK;
+}
+
+SKM_API int skm_map_fastq(skm_mapper *m, const uint8_t *text1, int64_t n1, const uint8_t *text2, int64_t n2,
+                          int64_t first_unit, int buffers_on_device, int64_t *consumed1, int64_t *consumed2,
+                          int64_t *n_units_out, int32_t *out_class, int32_t *out_length, void *stream)
+{
+    if (!m || !text1 || !consumed1 || !n_units_out) return fail(SKM_ERR_INVALID, "skm_map_fastq: NULL argument");
+    if (n1 < 0 || n2 < 0 || (text2 && !consumed2)) return fail(SKM_ERR_INVALID, "skm_map_fastq: bad argument");
+    if (n1 >= (1LL << 31) || n2 >= (1LL << 31))
+        return fail(SKM_ERR_INVALID, "skm_map_fastq: chunks of 2 GiB or more are not supported");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int paired = text2 != nullptr;
+    *consumed1 = 0;
+    if (consumed2) *consumed2 = 0;
+    *n_units_out = 0;
+    // ---- the text in one device buffer: file 1 at 0, file 2 at base2 (16-byte aligned) ---------
+    const int64_t base2 = (n1 + 15) & ~15LL;
+    const uint8_t *d_text = text1;
+    if (!buffers_on_device || paired) {
+        int rc = ensure((void **)&m->d_text, &m->d_text_cap, (size_t)(base2 + n2 + 64));
+        if (rc) return rc;
+        const cudaMemcpyKind kind = buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        SKM_CUDA(cudaMemcpyAsync(m->d_text, text1, (size_t)n1, kind, st));
+        if (paired && n2 > 0) SKM_CUDA(cudaMemcpyAsync(m->d_text + base2, text2, (size_t)n2, kind, st));
+        d_text = m->d_text;
+    }
+    // ---- lines, records, units --------------------------------------------------------------------
+    int64_t lines1 = 0, lines2 = 0;
+    int rc = find_newlines(m, d_text, n1, 0, &lines1, st);
+    if (rc) return rc;
+    if (paired) {
+        rc = find_newlines(m, d_text + base2, n2, 1, &lines2, st);
+        if (rc) return rc;
+    }
+    const int64_t n_units = paired ? std::min(lines1, lines2) / 4 : lines1 / 4;
+    if (n_units == 0) return SKM_OK;
+    const int64_t n_reads = paired ? 2 * n_units : n_units;
+    rc = ensure((void **)&m->d_bounds, &m->d_bounds_cap, sizeof(int64_t) * 2 * (size_t)n_reads);
+    if (rc) return rc;
+    if (!m->d_len_range) SKM_CUDA(cudaMalloc(&m->d_len_range, 2 * sizeof(int)));
+    const int init_range[2] = {0, INT32_MAX};
+    SKM_CUDA(cudaMemcpyAsync(m->d_len_range, init_range, sizeof(init_range), cudaMemcpyHostToDevice, st));
+    int64_t *d_starts = m->d_bounds, *d_ends = m->d_bounds + n_reads;
+    fastq_units_kernel<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_text, m->d_nl[0], m->d_nl[1], base2, n_units,
+                                                                         paired, d_starts, d_ends, m->d_len_range);
+    SKM_CUDA(cudaGetLastError());
+    int len_range[2] = {0, 0};
+    int64_t last1 = 0, last2 = 0;
+    SKM_CUDA(cudaMemcpyAsync(len_range, m->d_len_range, sizeof(len_range), cudaMemcpyDeviceToHost, st));
+    SKM_CUDA(cudaMemcpyAsync(&last1, m->d_nl[0] + (4 * n_units - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (paired)
+        SKM_CUDA(cudaMemcpyAsync(&last2, m->d_nl[1] + (4 * n_units - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SKM_CUDA(cudaStreamSynchronize(st));
+    if (len_range[1] < K)
+        return fail(SKM_ERR_INVALID, "skm_map_fastq: read shorter than k=25 (undefined in the reference)");
+    if (len_range[0] > 4096) return fail(SKM_ERR_INVALID, "skm_map_fastq: reads longer than 4096 bases are not supported");
+    MapArgs a{};
+    a.fixed_len = 0;
+    a.code_words = (len_range[0] + 31) / 32;
+    a.wild_words = (len_range[0] + 63) / 64;
+    a.words = (a.code_words + a.wild_words + 1) & ~1;
+    a.paired = paired;
+    a.arena = m->arena;
+    a.arena_cap = m->arena_cap;
+    a.cursors = m->cursors;
+    int32_t *d_class = out_class, *d_length = out_length;
+    if (!buffers_on_device && (out_class || out_length)) {
+        rc = ensure((void **)&m->d_out, &m->d_out_cap, sizeof(int32_t) * 2 * (size_t)n_units);
+        if (rc) return rc;
+        d_class = out_class ? m->d_out : nullptr;
+        d_length = out_length ? m->d_out + n_units : nullptr;
+    }
+    rc = launch_chunk(m, d_text, d_starts, d_ends, a, n_units, first_unit, d_class, d_length, st);
+    if (rc) return rc;
+    if (!buffers_on_device) {
+        if (out_class)
+            SKM_CUDA(cudaMemcpyAsync(out_class, d_class, sizeof(int32_t) * (size_t)n_units, cudaMemcpyDeviceToHost, st));
+        if (out_length)
+            SKM_CUDA(cudaMemcpyAsync(out_length, d_length, sizeof(int32_t) * (size_t)n_units, cudaMemcpyDeviceToHost, st));
+    }
+    *consumed1 = last1 + 1;
+    if (paired) *consumed2 = last2 + 1;
+    *n_units_out = n_units;
+    return check_status(m, st, "skm_map_fastq");  // synchronises: the text buffers may be reused
 }
 
 SKM_API int skm_mapper_kernel_ms(skm_mapper *m, double ms[3])

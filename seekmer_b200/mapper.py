@@ -17,7 +17,7 @@ import threading
 
 import numpy
 
-from . import _lib
+from . import _lib, common
 from ._log import Logger
 
 __all__ = ('MAX_FRAGMENT_LENGTH', 'MapResult', 'ReadMapper', 'SummarizedResult', 'map_reads',
@@ -151,6 +151,9 @@ def summarize_table(table, map_result):
         effective_lengths=map_result.effective_lengths)
 
 
+FASTQ_CHUNK_BYTES = 128 << 20  # raw text handed to the GPU per file and call
+
+
 def _device_of(index):
     return getattr(index, 'default_device', 0)
 
@@ -192,6 +195,23 @@ class ReadMapper:
         want_reads = self.map_result.readmap is not None
         try:
             first_unit = 0
+            if isinstance(reads_iterator, common.FastqSource) and not want_reads:
+                # nobody needs the read names: the raw FASTQ text goes to the GPU and is parsed
+                # there (skm_map_fastq) instead of line by line in Python
+                for chunk in reads_iterator.text_chunks(FASTQ_CHUNK_BYTES):
+                    if reads_iterator.paired:
+                        b1, n1, b2, n2, eof = chunk
+                        units, c1, c2 = mapper.map_fastq(b1, n1, b2, n2, first_unit=first_unit)
+                        reads_iterator.consumed(c1, c2)
+                        if eof and (c1 < n1 or c2 < n2):
+                            _LOG.debug('Mate files differ in length; surplus reads ignored (zip semantics).')
+                    else:
+                        b1, n1, eof = chunk
+                        units, c1, _ = mapper.map_fastq(b1, n1, first_unit=first_unit)
+                        reads_iterator.consumed(c1)
+                    first_unit += units
+                    _LOG.debug('Mapped {} reads.', units)
+                reads_iterator = ()
             for read_count, read_names, reads in reads_iterator:
                 single_ended = read_count == len(reads)  # `_mapper.pyx:75`
                 bases, offsets, fixed_len, max_len = _pack_batch(reads)
