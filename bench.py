@@ -184,7 +184,7 @@ def run_ours(args):
     built, sim, lengths = make_workload(args, rank, world, device)
     index = _lib.DeviceIndex(built.kmers, built.contigs, built.sequences, built.targets, built.n_transcripts)
     info = index.info()
-    mp = _lib.DeviceMapper(index, class_capacity=1 << 23, id_capacity=1 << 27)
+    mp = _lib.DeviceMapper(index, class_capacity=1 << 22, id_capacity=1 << 26)  # ~4x the classes of this workload
 
     n_pairs = args.pairs
     first_unit = rank * n_pairs
@@ -200,14 +200,17 @@ def run_ours(args):
         mp.reset()
         mp.map_batch(d_bases, None, n_pairs, True, first_unit=first_unit, fixed_len=READ_LEN)
         launches['n'] += 3  # pack_reads_kernel, map_reads_kernel, tally_units_kernel
-        table = mp.export_torch()
-        launches['n'] += 2  # dict_export_kernel, set_i64_kernel
+        if world > 1:
+            # one all-gather of the exported dictionaries, peers merged on the device
+            table = sdist.merge_mappers(mp)
+            launches['n'] += 4 + 2 * (world - 1)  # 2 exports (2 kernels each) + merge + FLD add per peer
+        else:
+            table = mp.export_torch()
+            launches['n'] += 2  # dict_export_kernel, set_i64_kernel
         if timed:
             # CUDA events the library records around each kernel on the launch stream; the
             # export above has already synchronised that stream
             kernel_times.append(mp.kernel_ms())
-        if world > 1:
-            table = sdist.merge_class_tables(table)
         return table
 
     def barrier():
@@ -253,9 +256,7 @@ def run_ours(args):
             n = min(batch, n_pairs - s)
             mp.map_batch(h_np[s * 2 * READ_LEN:(s + n) * 2 * READ_LEN], None, n, True, first_unit=first_unit + s,
                          fixed_len=READ_LEN)
-        tab = mp.export_torch()
-        if world > 1:
-            tab = sdist.merge_class_tables(tab)
+        tab = sdist.merge_mappers(mp) if world > 1 else mp.export_torch()
         return sdist.table_to_host(tab)
 
     e2e_steps = max(1, min(args.steps, 2))

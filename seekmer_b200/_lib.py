@@ -325,6 +325,34 @@ class DeviceMapper:
                     fld=fld, scalars=torch.tensor([sz['unaligned'], sz['aligned']], dtype=torch.int64,
                                                   device=dev))
 
+    def export_raw_torch(self, stream=None):
+        """Dictionary as torch tensors on the mapper's GPU in table order (unsorted): the cheap
+        form for shipping to other ranks."""
+        import torch
+        dev = torch.device('cuda', self.index.device)
+        if stream is None:
+            stream = current_stream_ptr(dev)
+        sz = self.sizes(stream)
+        n, n_ids = sz['n_classes'], sz['n_ids']
+        off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        ids = torch.zeros(max(n_ids, 1), dtype=torch.int32, device=dev)
+        counts = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+        first = torch.zeros(max(n, 1), dtype=torch.int64, device=dev)
+        fld = torch.zeros(MAX_FRAGMENT_LENGTH, dtype=torch.int64, device=dev)
+        check(load().skm_classes_export(self._h, _ptr(off), _ptr(ids), _ptr(counts), _ptr(first), None,
+                                        _ptr(fld), 1, stream))
+        return dict(key_offsets=off, key_ids=ids[:n_ids], counts=counts[:n], first_unit=first[:n], fld=fld,
+                    unaligned=sz['unaligned'], aligned=sz['aligned'])
+
+    def merge_device(self, key_offsets, key_ids, counts, first_unit, fld, unaligned, stream=None):
+        """Add another rank's exported classes (torch tensors on this GPU) to the dictionary."""
+        if stream is None:
+            stream = current_stream_ptr(key_ids.device)
+        n = int(counts.shape[0])
+        check(load().skm_classes_merge(self._h, _ptr(key_offsets), _ptr(key_ids) if key_ids.numel() else None,
+                                       _ptr(counts) if n else None, _ptr(first_unit) if n else None, n,
+                                       _ptr(fld), int(unaligned), 1, stream))
+
     def merge(self, key_offsets, key_ids, counts, first_unit, fld=None, unaligned=0, stream=None):
         key_offsets = numpy.ascontiguousarray(key_offsets, dtype='i8')
         key_ids = numpy.ascontiguousarray(key_ids, dtype='i4')

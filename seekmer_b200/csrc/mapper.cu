@@ -243,17 +243,24 @@ __global__ void dict_merge_kernel(const DictDev d, const int64_t *key_offsets, c
                                   const int64_t *counts, const int64_t *first_unit, int64_t n_classes)
 {
     const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= n_classes) return;
-    const int64_t start = key_offsets[c];
-    const int n = (int)(key_offsets[c + 1] - start);
-    if (n <= 0) return;
-    const DenseIds ids{key_ids + start};
-    const ulonglong2 key = tuple_key(ids, n, false);
-    const int64_t slot = dict_find_or_insert(d, key, ids, n, false);
-    if (slot < 0) return;
-    atomicAdd(&d.counts[slot], (unsigned long long)counts[c]);
-    atomicMin(&d.first[slot], (unsigned long long)first_unit[c]);
-    atomicAdd(&d.scalars[3], (unsigned long long)counts[c]);
+    unsigned long long added = 0;
+    if (c < n_classes) {
+        const int64_t start = key_offsets[c];
+        const int n = (int)(key_offsets[c + 1] - start);
+        if (n > 0) {
+            const DenseIds ids{key_ids + start};
+            const ulonglong2 key = tuple_key(ids, n, false);
+            const int64_t slot = dict_find_or_insert(d, key, ids, n, false);
+            if (slot >= 0) {
+                added = (unsigned long long)counts[c];
+                atomicAdd(&d.counts[slot], added);
+                atomicMin(&d.first[slot], (unsigned long long)first_unit[c]);
+            }
+        }
+    }
+    // the aligned total is one address for everybody: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) added += __shfl_down_sync(0xffffffffu, added, o);
+    if ((threadIdx.x & 31) == 0 && added) atomicAdd(&d.scalars[3], added);
 }
 
 __global__ void add_i64_kernel(unsigned long long *dst, const int64_t *src, int n)

@@ -139,6 +139,52 @@ def merge_class_tables(table, group=None):
                 scalars=dense[n_global + MAX_FRAGMENT_LENGTH:].clone())
 
 
+def merge_mappers(mp, group=None):
+    """Collective, CUDA only: make every rank's device dictionary the global one and return the
+    global table (same shape and order as `merge_class_tables`).
+
+    One exchange step: every rank ships its exported dictionary (CSR keys, counts, first-seen
+    units, FLD, unaligned count; ~30 MB) in ONE all-gather over NVLink, then inserts the other
+    ranks' classes into its own device dictionary with the library's merge kernel
+    (`skm_classes_merge`: same 128-bit tuple hash, counts added with atomics, first-seen unit
+    by atomicMin).  All ranks end with the same dictionary, exported in first-seen order."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return mp.export_torch()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    t = mp.export_raw_torch()
+    dev = t['fld'].device
+    n, n_ids = int(t['counts'].shape[0]), int(t['key_ids'].shape[0])
+    ids64 = torch.zeros((n_ids + 1) // 2, dtype=torch.int64, device=dev)
+    ids64.view(torch.int32)[:n_ids] = t['key_ids']
+    head = torch.tensor([n, n_ids, t['unaligned']], dtype=torch.int64, device=dev)
+    packed = torch.cat([head, t['fld'], t['key_offsets'], t['counts'], t['first_unit'], ids64])
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([packed.shape[0]], dtype=torch.int64, device=dev), group=group)
+    cap = max(int(s.item()) for s in sizes)
+    mine = torch.zeros(cap, dtype=torch.int64, device=dev)
+    mine[:packed.shape[0]] = packed
+    gathered = torch.zeros(world * cap, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    heads = gathered.view(world, cap)[:, :3].cpu().tolist()
+    for r in range(world):
+        if r == rank:
+            continue
+        buf = gathered[r * cap:(r + 1) * cap]
+        rn, rids, run = (int(v) for v in heads[r])
+        o = 3
+        fld = buf[o:o + MAX_FRAGMENT_LENGTH]
+        o += MAX_FRAGMENT_LENGTH
+        off = buf[o:o + rn + 1]
+        o += rn + 1
+        cnt = buf[o:o + rn]
+        o += rn
+        first = buf[o:o + rn]
+        o += rn
+        ids = buf[o:o + (rids + 1) // 2].view(torch.int32)[:rids]
+        mp.merge_device(off, ids, cnt, first, fld, run)
+    return mp.export_torch()
+
+
 def table_to_host(table):
     """Torch table -> the numpy dict shape of `_lib.DeviceMapper.export()`."""
     sc = table['scalars'].cpu().tolist()

@@ -211,6 +211,32 @@ def test_merge_equals_single_mapper(golden_synth, small_tx):
     assert ta['unaligned'] == tw['unaligned'] and ta['aligned'] == tw['aligned']
 
 
+def test_merge_on_device_matches_single_mapper(golden_synth, small_tx):
+    """The multi-GPU exchange path (`dist.merge_mappers`): a peer's raw export, shipped as torch
+    tensors, merged into the local dictionary on the device == one mapper over everything."""
+    g = golden_synth
+    kw = SYNTH_CASES['pe100']
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **kw)
+    n = 3000
+    bases, _ = sim.generate(0, n)
+    ix = _lib.DeviceIndex(*g.index_arrays(), 60)
+    whole = _lib.DeviceMapper(ix)
+    whole.map_batch(bases, None, n, True, fixed_len=100)
+    parts = [_lib.DeviceMapper(ix) for _ in range(3)]
+    bounds = [0, 900, 2100, n]
+    for p, lo, hi in zip(parts, bounds[:-1], bounds[1:]):
+        p.map_batch(bases[lo * 200:hi * 200], None, hi - lo, True, first_unit=lo, fixed_len=100)
+    for peer in parts[1:]:
+        t = peer.export_raw_torch()
+        parts[0].merge_device(t['key_offsets'], t['key_ids'], t['counts'], t['first_unit'], t['fld'], t['unaligned'])
+    ta, tw = parts[0].export(), whole.export()
+    for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
+        assert (ta[k] == tw[k]).all(), k
+    assert ta['unaligned'] == tw['unaligned'] and ta['aligned'] == tw['aligned']
+    tt = parts[0].export_torch()
+    assert (tt['counts'].cpu().numpy() == tw['counts']).all()
+
+
 def test_synth_reads_device_twin(small_tx):
     import ctypes
     import torch
