@@ -45,13 +45,16 @@ namespace skm {
 #define SKM_LIST_CAP 16
 #endif
 #ifndef SKM_Q_THREADS
-#define SKM_Q_THREADS 640
+#define SKM_Q_THREADS 768
 #endif
 constexpr int Q_THREADS = SKM_Q_THREADS;  // worker threads per block (one block per SM)
 constexpr int LIST_CAP = SKM_LIST_CAP;    // per-read target list entries kept in shared memory
 constexpr int ALIGN_LENGTH = 8;           // _mapper.pyx:22
 constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
-constexpr int SCAN_WIDTH = 4;             // read positions probed per P_SCAN step
+#ifndef SKM_SCAN_WIDTH
+#define SKM_SCAN_WIDTH 3
+#endif
+constexpr int SCAN_WIDTH = SKM_SCAN_WIDTH;  // read positions probed per P_SCAN step
 #ifndef SKM_STICKY_LANES
 #define SKM_STICKY_LANES 16
 #endif
