@@ -192,7 +192,8 @@ int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes,
 
 /* Replaces: scipy.stats.multinomial(n, p).rvs() at infer.py:108-111 — resample
  * n = sum(counts) reads with replacement, n_replicates times.  Integer-exact,
- * counter-based (Philox4x32-10 keyed by seed, replicate, draw). out is
+ * counter-based (Philox4x32-10 keyed by seed; counter = (draw pair, replicate); one block
+ * of four words yields two 64-bit draws). out is
  * int64[n_replicates * n_classes]; replicate ids start at first_replicate. */
 int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicates,
                     int64_t first_replicate, uint64_t seed, int64_t *out,

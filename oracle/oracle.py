@@ -361,9 +361,10 @@ def bootstrap_counts(class_count, n_replicates, seed):
     """Resample reads with replacement: counts ~ Multinomial(n, class_count / n).
 
     Same distribution as `scipy.stats.multinomial(n, p).rvs()` at `infer.py:108-111`, realised
-    as n i.i.d. categorical draws with integer arithmetic only: draw d of replicate r takes
-    Philox(counter=(d_lo, d_hi, r, 0), key=(seed_lo, seed_hi)) -> 64-bit word w = (x1<<32)|x0,
-    u = (w * n) >> 64 (uniform in [0, n)), class = upper_bound(cumsum(count), u).
+    as n i.i.d. categorical draws with integer arithmetic only: draws 2j and 2j+1 of replicate r
+    take Philox(counter=(j_lo, j_hi, r, 0), key=(seed_lo, seed_hi)) -> 64-bit words
+    w = (x1<<32)|x0 and (x3<<32)|x2, u = (w * n) >> 64 (uniform in [0, n)),
+    class = upper_bound(cumsum(count), u).
     Bit-exact with the device resampler for the same (seed, replicate).
     """
     cc = numpy.asarray(class_count)
@@ -374,10 +375,13 @@ def bootstrap_counts(class_count, n_replicates, seed):
     out = numpy.zeros((n_replicates, counts_i.shape[0]), dtype='i8')
     if n == 0:
         return out
-    d = numpy.arange(n, dtype='u8')
+    j = numpy.arange((n + 1) // 2, dtype='u8')
     for r in range(n_replicates):
-        x0, x1, _, _ = philox4x32(d & 0xFFFFFFFF, d >> 32, r, 0, seed & 0xFFFFFFFF, seed >> 32)
-        w = (x1.astype('u8') << numpy.uint64(32)) | x0.astype('u8')
+        x0, x1, x2, x3 = philox4x32(j & 0xFFFFFFFF, j >> 32, r, 0, seed & 0xFFFFFFFF, seed >> 32)
+        w = numpy.empty(2 * j.shape[0], dtype='u8')
+        w[0::2] = (x1.astype('u8') << numpy.uint64(32)) | x0.astype('u8')
+        w[1::2] = (x3.astype('u8') << numpy.uint64(32)) | x2.astype('u8')
+        w = w[:n]
         # (w * n) >> 64 with 64-bit pieces
         n_lo, n_hi = n & 0xFFFFFFFF, n >> 32
         w_lo, w_hi = w & 0xFFFFFFFF, w >> 32

@@ -185,17 +185,22 @@ __global__ void em_class_kernel_r1(const EmState s, const double *__restrict__ x
     s.inner[c] = __ddiv_rn(sum, s.counts[c]);
 }
 
+// R > 1: one thread per (class, replicate), replicates fastest: consecutive lanes read consecutive
+// replicates of the same rows (coalesced), and every lane has work whatever R is (the state is
+// compacted to the running replicates as they finish, so R shrinks during a run).
 __global__ void em_class_kernel(const EmState s, const double *__restrict__ x)
 {
     if (*s.n_active == 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t c = blockIdx.x * (int64_t)(EM_BLOCK / 32) + warp;
-    const int r = blockIdx.y * 32 + lane;
-    if (c >= s.n_classes || r >= s.R || !s.active[r]) return;
-    double sum = 0.0;
-    const int64_t b = s.class_ptr[c], e = s.class_ptr[c + 1];
-    for (int64_t j = b; j < e; ++j) sum = __dadd_rn(sum, x[(int64_t)s.class_tx[j] * s.R + r]);
-    s.inner[c * s.R + r] = __ddiv_rn(sum, s.counts[c * s.R + r]);
+    const int64_t total = s.n_classes * s.R;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = e / s.R;
+        const int r = (int)(e - c * s.R);
+        if (!s.active[r]) continue;
+        double sum = 0.0;
+        const int64_t b = s.class_ptr[c], en = s.class_ptr[c + 1];
+        for (int64_t j = b; j < en; ++j) sum = __dadd_rn(sum, x[(int64_t)s.class_tx[j] * s.R + r]);
+        s.inner[e] = __ddiv_rn(sum, s.counts[e]);
+    }
 }
 
 __device__ __forceinline__ void note_change(const EmState &s, int r, double xn, double xo)
@@ -235,23 +240,24 @@ __global__ void em_tx_kernel_r1(const EmState s, const double *__restrict__ x, d
 __global__ void em_tx_kernel(const EmState s, const double *__restrict__ x, double *__restrict__ xn_out)
 {
     if (*s.n_active == 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t t = blockIdx.x * (int64_t)(EM_BLOCK / 32) + warp;
-    const int r = blockIdx.y * 32 + lane;
-    if (t >= s.n_tx || r >= s.R) return;
-    const double xt = x[t * s.R + r];
-    if (!s.active[r]) {
-        xn_out[t * s.R + r] = xt;
-        return;
+    const int64_t total = s.n_tx * s.R;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = e / s.R;
+        const int r = (int)(e - t * s.R);
+        const double xt = x[e];
+        if (!s.active[r]) {
+            xn_out[e] = xt;
+            continue;
+        }
+        double acc = 0.0;
+        const int64_t b = s.tx_ptr[t], en = s.tx_ptr[t + 1];
+        for (int64_t j = b; j < en; ++j)
+            acc = __dadd_rn(acc, __ddiv_rn(xt, s.inner[(int64_t)s.tx_class[j] * s.R + r]));
+        double v = __ddiv_rn(__ddiv_rn(acc, s.eff_len[t]), s.n[r]);
+        if (v != v) v = 0.0;
+        note_change(s, r, v, xt);
+        xn_out[e] = v;
     }
-    double acc = 0.0;
-    const int64_t b = s.tx_ptr[t], e = s.tx_ptr[t + 1];
-    for (int64_t j = b; j < e; ++j)
-        acc = __dadd_rn(acc, __ddiv_rn(xt, s.inner[(int64_t)s.tx_class[j] * s.R + r]));
-    double v = __ddiv_rn(__ddiv_rn(acc, s.eff_len[t]), s.n[r]);
-    if (v != v) v = 0.0;
-    note_change(s, r, v, xt);
-    xn_out[t * s.R + r] = v;
 }
 
 // Loop condition of infer.py:160 evaluated per replicate after each update.
@@ -358,21 +364,27 @@ __global__ void multinomial_kernel(const unsigned long long *__restrict__ cum, i
     const int64_t r = blockIdx.y;
     unsigned long long *dst = out + r * n_classes;
     const uint32_t rep = (uint32_t)(first_replicate + r);
-    for (unsigned long long d = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; d < n;
-         d += (unsigned long long)gridDim.x * blockDim.x) {
+    // one Philox block = two draws: words (x0, x1) -> draw 2j, (x2, x3) -> draw 2j + 1
+    const unsigned long long n_blocks = (n + 1) >> 1;
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < n_blocks;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t x[4];
-        philox4x32((uint32_t)d, (uint32_t)(d >> 32), rep, 0u, seed_lo, seed_hi, x);
-        const unsigned long long w = ((unsigned long long)x[1] << 32) | x[0];
-        const unsigned long long u = __umul64hi(w, n);
-        const uint32_t b = (uint32_t)(w >> 48);
-        int64_t a = lo[b], z = (int64_t)lo[b + 1] + 1;
-        if (z > n_classes) z = n_classes;
-        while (a < z) {
-            const int64_t m = (a + z) >> 1;
-            if (cum[m] > u) z = m;
-            else a = m + 1;
+        philox4x32((uint32_t)j, (uint32_t)(j >> 32), rep, 0u, seed_lo, seed_hi, x);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (2 * j + h >= n) break;
+            const unsigned long long w = ((unsigned long long)x[2 * h + 1] << 32) | x[2 * h];
+            const unsigned long long u = __umul64hi(w, n);
+            const uint32_t b = (uint32_t)(w >> 48);
+            int64_t a = lo[b], z = (int64_t)lo[b + 1] + 1;
+            if (z > n_classes) z = n_classes;
+            while (a < z) {
+                const int64_t m = (a + z) >> 1;
+                if (cum[m] > u) z = m;
+                else a = m + 1;
+            }
+            atomicAdd(&dst[a], 1ULL);
         }
-        atomicAdd(&dst[a], 1ULL);
     }
 }
 
@@ -655,8 +667,8 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     int64_t group_base = 0;
     while (n_active > 0 && done < max_iters) {
         const int g = (int)std::min<int64_t>(GROUP, max_iters - done);
-        const dim3 grid_c((unsigned)((C + EM_BLOCK / 32 - 1) / (EM_BLOCK / 32)), (unsigned)((Rc + 31) / 32));
-        const dim3 grid_t((unsigned)((T + EM_BLOCK / 32 - 1) / (EM_BLOCK / 32)), (unsigned)((Rc + 31) / 32));
+        const unsigned grid_c = (unsigned)std::min<int64_t>((C * Rc + EM_BLOCK - 1) / EM_BLOCK, 1 << 20);
+        const unsigned grid_t = (unsigned)std::min<int64_t>((T * Rc + EM_BLOCK - 1) / EM_BLOCK, 1 << 20);
         group_cur = cur;
         group_nxt = nxt;
         group_base = done;
@@ -829,7 +841,7 @@ static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t 
                                                                        b_lo.as<int32_t>());
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        const unsigned gx = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)sms * 8);
+        const unsigned gx = (unsigned)std::min<unsigned long long>((n / 2 + 256) / 256, (unsigned long long)sms * 8);
         const dim3 grid(gx, (unsigned)n_replicates);
         multinomial_kernel<<<grid, 256, 0, st>>>(b_cum.as<unsigned long long>(), n_classes, n, b_lo.as<int32_t>(),
                                                 first_replicate, (uint32_t)seed, (uint32_t)(seed >> 32),

@@ -263,6 +263,8 @@ __global__ void dict_merge_kernel(const DictDev d, const int64_t *key_offsets, c
     if ((threadIdx.x & 31) == 0 && added) atomicAdd(&d.scalars[3], added);
 }
 
+__global__ void add_value_kernel(unsigned long long *dst, unsigned long long v) { *dst += v; }
+
 __global__ void add_i64_kernel(unsigned long long *dst, const int64_t *src, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -886,14 +888,8 @@ SKM_API int skm_classes_merge(skm_mapper *m, const int64_t *key_offsets, const i
         e = cudaGetLastError();
     }
     if (e == cudaSuccess && unaligned > 0) {
-        int64_t *d_un = nullptr;
-        e = cudaMalloc((void **)&d_un, sizeof(int64_t));
-        if (e == cudaSuccess) {
-            cudaMemcpyAsync(d_un, &unaligned, sizeof(int64_t), cudaMemcpyHostToDevice, st);
-            add_i64_kernel<<<1, 32, 0, st>>>(m->d.scalars + 2, d_un, 1);
-            cudaStreamSynchronize(st);
-            cudaFree(d_un);
-        }
+        add_value_kernel<<<1, 1, 0, st>>>(m->d.scalars + 2, (unsigned long long)unaligned);
+        e = cudaGetLastError();
     }
     int rc = SKM_OK;
     if (e == cudaSuccess) rc = check_status(m, st, "skm_classes_merge");
