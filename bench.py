@@ -360,12 +360,23 @@ def run_ours(args):
             cpu_baseline = {'value': round(sample / cpu_s, 1), 'unit': UNIT, 'cores': cores, 'kind': 'port',
                             'sample': '%d of the same 2x%d pairs, C oracle (OpenMP), index resident in RAM'
                                       % (sample, READ_LEN)}
-            # parity on the sample: FLD and aligned count from an independent GPU pass
+            # parity on the sample, from an independent GPU pass with per-unit outputs: FLD, aligned
+            # count, every unit's span length, and the partition of units into classes (two units
+            # share a GPU dictionary slot exactly when the oracle gives them the same id tuple)
             mp.reset()
-            mp.map_batch(d_bases[:sample * 2 * READ_LEN], None, sample, True, first_unit=0, fixed_len=READ_LEN)
+            g_cls, g_len = mp.map_batch(d_bases[:sample * 2 * READ_LEN], None, sample, True, first_unit=0,
+                                        fixed_len=READ_LEN, per_read=True)
             chk = mp.export()
+            g_cls, g_len = g_cls.cpu().numpy().astype('i8'), g_len.cpu().numpy()
+            o_key = numpy.where(cnt > 0, h, numpy.uint64(0)).astype('u8')  # unaligned units: one class
+            g_key = numpy.where(g_cls >= 0, g_cls + 1, 0)
+            pairs_seen = numpy.unique(numpy.stack([g_key.astype('u8'), o_key]), axis=1)
+            one_to_one = (numpy.unique(pairs_seen[0]).size == pairs_seen.shape[1]
+                          and numpy.unique(pairs_seen[1]).size == pairs_seen.shape[1])
             parity = {'sample_pairs': sample, 'fld_equal': bool((chk['fld'] == fld).all()),
-                      'aligned_equal': bool(chk['aligned'] == aligned)}
+                      'aligned_equal': bool(chk['aligned'] == aligned),
+                      'unit_lengths_equal': bool((g_len == length).all()),
+                      'unit_classes_equal': bool(one_to_one and ((g_cls >= 0) == (cnt > 0)).all())}
     except Exception as exc:  # the oracle is optional infrastructure for the bench line
         log('oracle leg skipped: %r' % (exc,))
 

@@ -398,43 +398,54 @@ struct BlockCache {
         void *p;
         size_t bytes;
     };
+    static constexpr size_t SLAB = 256u << 20;  // small blocks are carved out of slabs: few cudaMalloc calls
     std::mutex mu;
     std::vector<Block> free_blocks[64];
+    std::vector<void *> slabs[64];
+    char *slab_next[64] = {};
+    size_t slab_left[64] = {};
     cudaError_t take(int device, size_t bytes, void **out, size_t *got)
     {
-        {
-            std::lock_guard<std::mutex> lock(mu);
-            auto &v = free_blocks[device & 63];
-            int best = -1;
-            for (int i = 0; i < (int)v.size(); ++i)
-                if (v[i].bytes >= bytes && v[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || v[i].bytes < v[best].bytes))
-                    best = i;
-            if (best >= 0) {
-                *out = v[best].p;
-                *got = v[best].bytes;
-                v.erase(v.begin() + best);
-                return cudaSuccess;
-            }
+        const int d = device & 63;
+        bytes = (bytes + 255) & ~(size_t)255;
+        std::lock_guard<std::mutex> lock(mu);
+        auto &v = free_blocks[d];
+        int best = -1;
+        for (int i = 0; i < (int)v.size(); ++i)
+            if (v[i].bytes >= bytes && v[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || v[i].bytes < v[best].bytes))
+                best = i;
+        if (best >= 0) {
+            *out = v[best].p;
+            *got = v[best].bytes;
+            v.erase(v.begin() + best);
+            return cudaSuccess;
         }
         *got = bytes;
-        cudaError_t e = cudaMalloc(out, bytes);
-        if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
-            cudaGetLastError();
-            trim(device);
-            e = cudaMalloc(out, bytes);
+        if (bytes <= SLAB / 4) {
+            if (slab_left[d] < bytes) {
+                void *slab = nullptr;
+                const cudaError_t e = cudaMalloc(&slab, SLAB);
+                if (e != cudaSuccess) return e;
+                slabs[d].push_back(slab);
+                slab_next[d] = static_cast<char *>(slab);
+                slab_left[d] = SLAB;
+            }
+            *out = slab_next[d];
+            slab_next[d] += bytes;
+            slab_left[d] -= bytes;
+            return cudaSuccess;
         }
-        return e;
+        void *p = nullptr;
+        const cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return e;
+        slabs[d].push_back(p);
+        *out = p;
+        return cudaSuccess;
     }
     void give(int device, void *p, size_t bytes)
     {
         std::lock_guard<std::mutex> lock(mu);
         free_blocks[device & 63].push_back(Block{p, bytes});
-    }
-    void trim(int device)
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        for (Block &b : free_blocks[device & 63]) cudaFree(b.p);
-        free_blocks[device & 63].clear();
     }
 };
 static BlockCache g_blocks;
