@@ -38,8 +38,13 @@ struct __align__(16) Slot {
     int32_t offset;
 };
 
-// 64-byte contig record = one DRAM burst: header plus the first 8 entries of the contig's
-// target list (most lists fit; longer ones continue in targets[]).
+// 128-byte contig record.  First 64 bytes (one DRAM burst, what P_CONTIG reads): header plus
+// the first 8 entries of the contig's target list (most lists fit; longer ones continue in
+// targets[]).  Second 64 bytes: the graph LINKS of the contig - the coordinates map_kmer returns
+// for the 4 k-mers that extend its last k-mer to the right and the 4 that extend its first k-mer
+// to the left, probed once when the index is laid out.  A contig walk that crosses a junction
+// reads the next coordinate here (8 bytes, L2-resident) instead of hashing and probing the
+// 4 GB k-mer table; the other strand follows from map_kmer(rc(x)) = {~entry, offset}.
 //   w0 = first_kmer | (target_count low 14 bits  << 50)
 //   w1 = last_kmer  | (target_count high 14 bits << 50)
 constexpr int INLINE_TARGETS = 8;
@@ -50,6 +55,8 @@ struct __align__(64) ContigRec {
     uint32_t target_offset;  // into targets[]
     uint32_t length;         // contig length in bases
     int32_t inline_targets[INLINE_TARGETS];  // targets[target_offset .. +8), zero padded
+    int2 right_of_last[4];   // map_kmer(append(last_kmer, b)),   b = A C G T; {entry, offset}
+    int2 left_of_first[4];   // map_kmer(prepend(first_kmer, b))
 };
 
 // The k-mer table is probed by BUCKET: 4 consecutive 16-byte slots = 64 bytes = one DRAM burst.

@@ -96,6 +96,22 @@ __global__ void relayout_contigs_kernel(const skm_contig_entry *__restrict__ src
     atomicMax(max_tc, (unsigned long long)tc);
 }
 
+// Graph links (common.cuh): 8 probes of the finished device table per contig.
+__global__ void contig_links_kernel(const DevIndex ix, ContigRec *__restrict__ recs, int64_t n_contigs)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_contigs * 8) return;
+    const int64_t c = i >> 3;
+    const int k = (int)(i & 7);
+    const uint64_t b = (uint64_t)(k & 3);
+    const uint64_t first = recs[c].w0 & KMER_MASK, last = recs[c].w1 & KMER_MASK;
+    const uint64_t query = k < 4 ? ((last << 2) | b) & KMER_MASK              // append(last_kmer, b), _kmer.pxd:71-86
+                                 : (first >> 2) | (b << (2 * K - 2));          // prepend(first_kmer, b), :89-106
+    const Coord hit = map_kmer(ix, query);
+    int2 *dst = k < 4 ? recs[c].right_of_last : recs[c].left_of_first;
+    dst[k & 3] = make_int2(hit.entry, hit.offset);
+}
+
 __device__ __forceinline__ uint32_t code_of(uint8_t b)  // _kmer.pxd:253-273
 {
     const uint8_t u = b & 0xDF;
@@ -359,6 +375,11 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
     ix->d.n_contigs = n_contigs;
     ix->d.n_bases = n_bases;
     ix->d.n_targets = n_targets;
+    contig_links_kernel<<<(unsigned)((n_contigs * 8 + 255) / 256), 256, 0, st>>>(ix->d, ix->contigs, n_contigs);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        skm_index_destroy(ix);
+        return fail(SKM_ERR_CUDA, "skm_index_create: contig link kernel failed");
+    }
     *out = ix;
     return SKM_OK;
 }

@@ -178,6 +178,24 @@ __device__ __forceinline__ Contig load_contig(const DevIndex &ix, int32_t index)
     return c;
 }
 
+// The coordinate of the k-mer that continues a contig walk across the junction at the anchor's
+// contig edge with read base `b` (what _filter_targets_to_left/right look up at
+// _mapper.pyx:247-249,309-311), from the contig's links.  Walking right (dir 1) along a forward
+// anchor, or left along a reverse one, leaves through the contig's last k-mer; the other two
+// cases through its first.  On the reverse strand the query is the reverse complement of a
+// stored one: complement the base, bit-negate the entry.
+__device__ __forceinline__ Coord contig_link(const DevIndex &ix, Coord anchor, int dir, uint32_t b)
+{
+    const bool forward = anchor.entry >= 0;
+    const ContigRec *rec = ix.contigs + (forward ? anchor.entry : ~anchor.entry);
+    const bool via_last = (dir != 0) == forward;
+    const int2 *links = via_last ? rec->right_of_last : rec->left_of_first;
+    const bool direct = (dir != 0) == via_last;  // stored queries: append to last, prepend to first
+    const int2 v = __ldg(links + (direct ? b : 3u - b));
+    if (v.y < 0) return Coord{v.x, v.y};  // a miss: the caller does the real lookup
+    return Coord{direct ? v.x : ~v.x, v.y};
+}
+
 // 8 bases starting at absolute base position p of the packed contig pool, as 16 bits
 // (first base in the top two bits).
 __device__ __forceinline__ uint32_t seq_window8(const DevIndex &ix, int64_t p)

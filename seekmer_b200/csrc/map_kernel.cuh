@@ -844,12 +844,21 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                         L.sp.end = L.len - rem - K;
                     }
                     if (!finished) {
-                        uint64_t tail = L.sp.anchor.offset == 0 ? first_kmer : last_kmer;  // get_tail_kmer
-                        if (L.sp.anchor.entry < 0) tail = revcomp(tail);
+                        // the junction k-mer is the contig's edge k-mer shifted by one read base
+                        // (:247-249, :309-311); where it lives is a link of the contig record
+                        const uint32_t base = rv.code(dir ? L.sp.end + K - 1 : L.sp.begin);
                         L.ctx = dir ? C_RIGHT_J : C_LEFT_J;
-                        want = true;
-                        want_kmer = dir ? ((tail << 2) | rv.code(L.sp.end + K - 1)) & KMER_MASK
-                                        : (tail >> 2) | ((uint64_t)rv.code(L.sp.begin) << (2 * K - 2));
+                        const Coord next = contig_link(ix, L.sp.anchor, dir, base);
+                        if (next.offset >= 0) {
+                            L.sp.anchor = next;
+                            L.st = P_CONTIG;
+                        } else {  // not a hit (or a degenerate slot): the table lookup decides
+                            uint64_t tail = L.sp.anchor.offset == 0 ? first_kmer : last_kmer;  // get_tail_kmer
+                            if (L.sp.anchor.entry < 0) tail = revcomp(tail);
+                            want = true;
+                            want_kmer = dir ? ((tail << 2) | base) & KMER_MASK
+                                            : (tail >> 2) | ((uint64_t)base << (2 * K - 2));
+                        }
                     }
                 } else if (shift == INVALID_SHIFT) {
                     L.l.n = 0;
