@@ -75,8 +75,9 @@ const char *skm_version(void);
 
 /* Replaces: KMerIndex.__init__ / KMerIndex.load (_common.pyx:21-48,287-313).
  * Re-lays the index out for the GPU once: canonical-key open-addressing table
- * (load <= 0.25, 16-byte slots), 32-byte contig records, 2-bit packed contig
- * sequences, entry-only int32 target lists.  `inputs_on_device` != 0 means the
+ * (load <= 0.25, 16-byte slots in 64-byte buckets), 128-byte contig records
+ * (header, 8 inline targets, graph links), 2-bit packed contig sequences,
+ * entry-only int32 target lists.  `inputs_on_device` != 0 means the
  * four arrays are device pointers on `device` (reference layout); they are
  * only read. */
 int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,

@@ -450,8 +450,6 @@ struct BlockCache {
 };
 static BlockCache g_blocks;
 
-static void keep_pool_memory(int) {}
-
 struct DeviceBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -790,7 +788,6 @@ SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_
     if (skm_device_count() <= device || device < 0)
         return fail(SKM_ERR_CUDA, "skm_em: no such CUDA device (there is no CPU fallback)");
     EM_TRY(cudaSetDevice(device));
-    keep_pool_memory(device);
     cudaStream_t st = (cudaStream_t)stream;
     const int R = (int)n_replicates;
     const int64_t C = n_classes, T = n_transcripts;
@@ -873,7 +870,6 @@ SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_
     if (skm_device_count() <= device || device < 0)
         return fail(SKM_ERR_CUDA, "skm_multinomial: no such CUDA device (there is no CPU fallback)");
     EM_TRY(cudaSetDevice(device));
-    keep_pool_memory(device);
     cudaStream_t st = (cudaStream_t)stream;
     DeviceBuf b_counts, b_out;
     const int64_t *d_counts = counts;
@@ -909,7 +905,6 @@ SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, 
     if (skm_device_count() <= device || device < 0)
         return fail(SKM_ERR_CUDA, "skm_em_bootstrap: no such CUDA device (there is no CPU fallback)");
     EM_TRY(cudaSetDevice(device));
-    keep_pool_memory(device);
     cudaStream_t st = (cudaStream_t)stream;
     const int R = (int)n_replicates;
     const int64_t C = n_classes, T = n_transcripts;

@@ -1,7 +1,8 @@
 // Index upload and re-layout: KMerIndex arrays (reference layout) -> HBM-resident
-// canonical-key hash table + 32-byte contig records + 2-bit sequence pool + entry-only
-// target lists.  Replaces KMerIndex.__init__/load on the device side
-// (_common.pyx:21-48,287-313) and KMerIndex.map_kmer for vectors of k-mers.
+// canonical-key hash table in 4-slot buckets + 128-byte contig records (header, 8 inline
+// targets, graph links) + 2-bit sequence pool + entry-only target lists.  Replaces
+// KMerIndex.__init__/load on the device side (_common.pyx:21-48,287-313) and KMerIndex.map_kmer
+// for vectors of k-mers.
 #include <mutex>
 
 #include "kmer.cuh"

@@ -109,12 +109,6 @@ __host__ __device__ __forceinline__ uint32_t home_bucket_of(uint64_t canon, uint
     return (uint32_t)((table_hash(canon) >> 8) & bucket_mask);
 }
 
-__device__ __forceinline__ uint32_t home_bucket(const DevIndex &ix, uint64_t kmer)
-{
-    const uint64_t rc = revcomp(kmer);
-    return home_bucket_of(kmer < rc ? kmer : rc, ix.bucket_mask);
-}
-
 // KMerIndex.map_kmer (_common.pyx:54-97) on the canonical-key table: hit on the
 // canonical key; strand of the query relative to the canonical form decides whether
 // the stored coordinate is returned as is or reverse-complemented (~entry).

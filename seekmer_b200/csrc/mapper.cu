@@ -486,7 +486,7 @@ static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
 }
 
 // pack + map of one device-resident chunk on stream `st`
-int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_starts, const int64_t *d_ends, MapArgs a,
+static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_starts, const int64_t *d_ends, MapArgs a,
                  int64_t n_units, int64_t first_unit, int32_t *d_out_class, int32_t *d_out_length, cudaStream_t st)
 {
     const int64_t n_reads = a.paired ? 2 * n_units : n_units;
