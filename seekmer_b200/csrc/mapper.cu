@@ -22,24 +22,24 @@ constexpr int FLD_BINS = SKM_MAX_FRAGMENT_LENGTH;
 // Four ASCII bases in one 32-bit word -> their 2-bit codes (first base in bits 7:6) and their
 // wildcard bits (bit k <-> base k).  Codes follow _kmer.pxd:253-273 (A=0 C=1 G=2 T=3, case
 // folded, every other byte 0); a wildcard is any byte that is not one of upper-case "ACGT"
-// (_mapper.pyx:500-501).  Branch-free SWAR: with y = fold(x) ^ 0x40 the four letters are
-// y = 0x01, 0x03, 0x07, 0x14; everything is a boolean function of bits 0,1,2,4 of each byte
-// once bits 7,6,3 are known to be clear.
+// (_mapper.pyx:500-501).  Branch-free, 4 bytes at a time.
 __device__ __forceinline__ void convert4(uint32_t x, uint32_t &codes8, uint32_t &wild4)
 {
-    const uint32_t m = 0x01010101u;
-    const uint32_t y = (x & 0xDFDFDFDFu) ^ 0x40404040u;
-    const uint32_t bad = (y >> 7) | (y >> 6) | (y >> 3);
-    const uint32_t b1 = y >> 1, b2 = y >> 2, b4 = y >> 4;
-    const uint32_t acg = y & (b1 | ~b2);       // A, C or G (given b4 clear)
-    const uint32_t t = b2 & ~b1 & ~y;          // T (given b4 set)
-    const uint32_t letter = ((b4 & t) | (~b4 & acg)) & ~bad & m;  // 1 per valid byte
-    const uint32_t c0 = (b4 | (b1 & ~b2)) & m;  // C or T
-    const uint32_t c1 = (b4 | b2) & m;          // G or T
-    const uint32_t codes = (c0 | (c1 << 1)) & (letter * 3u);
+    // The low 3 bits of the case-folded byte tell the four letters apart (A 1, C 3, G 7, T 4); two
+    // byte permutes use them as indexes into 8-entry tables: the 2-bit code, and what bits 7..3 of
+    // the byte must be for it to really be that letter (0x41,0x43,0x47 >> 3 = 8, 0x54 >> 3 = 10).
+    const uint32_t u = x & 0xDFDFDFDFu;
+    const uint32_t lo3 = u & 0x07070707u;
+    const uint32_t t = lo3 | (lo3 >> 4);
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420u);             // nibble j = low 3 bits of byte j
+    const uint32_t code = __byte_perm(0x01000000u, 0x02000003u, sel);  // [1]=A 0 [3]=C 1 [7]=G 2 [4]=T 3
+    const uint32_t want = __byte_perm(0x08FF08FFu, 0x08FFFF0Au, sel);  // bits 7..3 of that letter, FF = none
+    const uint32_t z = ((u >> 3) & 0x1F1F1F1Fu) ^ want;                   // zero byte <=> the byte is the letter
+    const uint32_t letter = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u;  // 0x80 per letter
+    const uint32_t codes = code & ((letter >> 7) | (letter >> 6));
     codes8 = (codes * 0x40100401u) >> 24;       // byte j -> bits 7-2j:6-2j, no carries (disjoint fields)
-    const uint32_t wild = ~(letter & ~(x >> 5)) & m;  // not an upper-case letter of the four
-    wild4 = (wild * 0x10204080u) >> 28;         // byte j -> bit j
+    const uint32_t wild = ~(letter & ~(x << 2)) & 0x80808080u;  // not an upper-case letter of the four
+    wild4 = ((wild >> 7) * 0x10204080u) >> 28;  // byte j -> bit j
 }
 
 // One thread per 32 bases = one 64-bit code word and half a wildcard word of the packed record
