@@ -139,6 +139,20 @@ def test_medium_vs_oracle(orc, medium, L, mu, sd, paired, sub):
     check_against_oracle(orc, arrays, bases, sim.offsets(n), n, paired, batches=2)
 
 
+def test_arbitrary_bytes_vs_oracle(orc, medium):
+    """Every byte value can turn up in a read: anything but ACGTacgt encodes as 'A' and anything
+    but upper-case ACGT is a wildcard for the edge checks (_kmer.pxd:253-273, _mapper.pyx:500-501)."""
+    tx, arrays = medium
+    sim = synth.ReadSimulator(tx, synth.make_expression(tx.n_transcripts), 100, 250, 30, sub_rate=0.005, seed=31)
+    n = 30000
+    bases, _ = sim.generate(0, n)
+    bases = bases.copy()
+    rng = numpy.random.Generator(numpy.random.PCG64(17))
+    hit = rng.random(bases.shape[0]) < 0.01
+    bases[hit] = rng.integers(0, 256, size=int(hit.sum()), dtype='u1')
+    check_against_oracle(orc, arrays, bases, sim.offsets(n), n, True, batches=2)
+
+
 def test_long_target_lists_spill_to_arena(orc, ref):
     """Contigs shared by more than LIST_CAP=16 transcripts exercise the arena path."""
     tx = synth.make_transcriptome(400, seed=5, max_isoforms=40, mean_exons=8)
