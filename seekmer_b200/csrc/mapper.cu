@@ -216,15 +216,38 @@ __global__ void fastq_units_kernel(const uint8_t *__restrict__ text, const int64
 // (high 24 bits) and the id start (low 40 bits) together, so starts are monotone in the
 // class index and key_offsets is a proper CSR row pointer.  Class order is arbitrary;
 // callers sort by first_unit for the reference's insertion order.
-__global__ void dict_export_kernel(const DictDev d, int64_t slots, unsigned long long *cursor,
-                                   int64_t *key_offsets, int32_t *key_ids, int64_t *counts,
-                                   int64_t *first_unit, int32_t *slot_ids)
+__global__ void __launch_bounds__(256)
+dict_export_kernel(const DictDev d, int64_t slots, unsigned long long *cursor, int64_t *key_offsets,
+                   int32_t *key_ids, int64_t *counts, int64_t *first_unit, int32_t *slot_ids)
 {
+    // one atomic per BLOCK on the shared cursor (class index in the high 24 bits, id start in the
+    // low 40): a block-wide exclusive scan of (1, n ids) hands every occupied slot its place
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= slots) return;
-    if (d.keys[s].x == EMPTY_KEY && d.keys[s].y == EMPTY_KEY) return;
-    const uint32_t n = d.len[s];
-    const unsigned long long old = atomicAdd(cursor, (1ULL << 40) | (unsigned long long)n);
+    const bool live = s < slots && !(d.keys[s].x == EMPTY_KEY && d.keys[s].y == EMPTY_KEY);
+    const uint32_t n = live ? d.len[s] : 0u;
+    const unsigned long long mine = live ? ((1ULL << 40) | (unsigned long long)n) : 0ULL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __shared__ unsigned long long warp_total[8];
+    __shared__ unsigned long long block_base;
+    if (lane == 31) warp_total[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long total = 0;
+        for (int w = 0; w < 8; ++w) {
+            const unsigned long long t = warp_total[w];
+            warp_total[w] = total;
+            total += t;
+        }
+        block_base = total ? atomicAdd(cursor, total) : 0ULL;
+    }
+    __syncthreads();
+    if (!live) return;
+    const unsigned long long old = block_base + warp_total[warp] + (incl - mine);
     const unsigned long long c = old >> 40;
     const unsigned long long p = old & ((1ULL << 40) - 1);
     if (key_offsets) key_offsets[c] = (int64_t)p;
