@@ -172,6 +172,13 @@ int skm_classes_merge(skm_mapper *mapper, const int64_t *key_offsets, const int3
                       const int64_t *fld, int64_t unaligned, int buffers_on_device,
                       void *stream);
 
+/* The same for every peer of a multi-GPU exchange at once (device buffer): `gathered` is the
+ * all-gather of one packed export per rank, words_per_rank int64 words apart, each laid out as
+ * [n_classes, n_ids, unaligned | fld[2000] | key_offsets[n+1] | counts[n] | first_unit[n] |
+ * key_ids (int32)]; the block of `rank` itself is skipped. */
+int skm_classes_merge_packed(skm_mapper *mapper, const int64_t *gathered, int64_t words_per_rank,
+                             int world, int rank, void *stream);
+
 /* Replaces: MapResult.effective_lengths (mapper.py:134-141), fp64, same
  * accumulation order. */
 int skm_effective_lengths(const int64_t *fld, const double *lengths, int64_t n_transcripts,

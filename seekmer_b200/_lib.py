@@ -25,7 +25,7 @@ EXPORTS = (
     'skm_last_error', 'skm_device_count', 'skm_version', 'skm_index_create', 'skm_index_destroy',
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
     'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
-    'skm_classes_merge', 'skm_effective_lengths', 'skm_em', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
+    'skm_classes_merge', 'skm_classes_merge_packed', 'skm_effective_lengths', 'skm_em', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
     'skm_build_kmer_table',
 )
 
@@ -82,6 +82,8 @@ def load():
     L.skm_classes_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, vp]
     L.skm_classes_merge.restype = ci
     L.skm_classes_merge.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, ci, vp]
+    L.skm_classes_merge_packed.restype = ci
+    L.skm_classes_merge_packed.argtypes = [vp, vp, i64, ci, ci, vp]
     L.skm_effective_lengths.restype = ci
     L.skm_effective_lengths.argtypes = [vp, vp, i64, vp, ci, ci, vp]
     L.skm_em.restype = ci
@@ -352,6 +354,25 @@ class DeviceMapper:
         check(load().skm_classes_merge(self._h, _ptr(key_offsets), _ptr(key_ids) if key_ids.numel() else None,
                                        _ptr(counts) if n else None, _ptr(first_unit) if n else None, n,
                                        _ptr(fld), int(unaligned), 1, stream))
+
+    def pack_raw_torch(self, stream=None):
+        """The raw export as ONE int64 tensor on the GPU, in the layout `skm_classes_merge_packed`
+        reads: [n_classes, n_ids, unaligned | fld | key_offsets | counts | first_unit | key_ids]."""
+        import torch
+        t = self.export_raw_torch(stream)
+        dev = t['fld'].device
+        n_ids = int(t['key_ids'].shape[0])
+        ids64 = torch.zeros((n_ids + 1) // 2, dtype=torch.int64, device=dev)
+        ids64.view(torch.int32)[:n_ids] = t['key_ids']
+        head = torch.tensor([int(t['counts'].shape[0]), n_ids, t['unaligned']], dtype=torch.int64, device=dev)
+        return torch.cat([head, t['fld'], t['key_offsets'], t['counts'], t['first_unit'], ids64])
+
+    def merge_packed(self, gathered, words_per_rank, world, rank, stream=None):
+        """Insert every other rank's packed export (`pack_raw_torch`, all-gathered) at once."""
+        if stream is None:
+            stream = current_stream_ptr(gathered.device)
+        check(load().skm_classes_merge_packed(self._h, _ptr(gathered), int(words_per_rank), int(world), int(rank),
+                                              stream))
 
     def merge(self, key_offsets, key_ids, counts, first_unit, fld=None, unaligned=0, stream=None):
         key_offsets = numpy.ascontiguousarray(key_offsets, dtype='i8')

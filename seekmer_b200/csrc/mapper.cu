@@ -286,6 +286,47 @@ __global__ void dict_merge_kernel(const DictDev d, const int64_t *key_offsets, c
     if ((threadIdx.x & 31) == 0 && added) atomicAdd(&d.scalars[3], added);
 }
 
+// All peers of a multi-GPU exchange in one launch.  `gathered` holds one packed export per rank
+// (blockIdx.y), `cap` int64 words apart: [n_classes, n_ids, unaligned | fld[2000] |
+// key_offsets[n+1] | counts[n] | first_unit[n] | key_ids as int32]; the rank's own block is skipped.
+__global__ void dict_merge_packed_kernel(const DictDev d, const int64_t *__restrict__ gathered, int64_t cap, int rank)
+{
+    const int peer = blockIdx.y;
+    if (peer == rank) return;
+    const int64_t *buf = gathered + (int64_t)peer * cap;
+    const int64_t n_classes = buf[0];
+    const int64_t *fld = buf + 3;
+    const int64_t *key_offsets = fld + SKM_MAX_FRAGMENT_LENGTH;
+    const int64_t *counts = key_offsets + n_classes + 1;
+    const int64_t *first_unit = counts + n_classes;
+    const int32_t *key_ids = reinterpret_cast<const int32_t *>(first_unit + n_classes);
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x)
+            if (fld[i]) atomicAdd(&d.fld[i], (unsigned long long)fld[i]);
+        if (threadIdx.x == 0 && buf[2]) atomicAdd(&d.scalars[2], (unsigned long long)buf[2]);
+    }
+    const int64_t rounds = (n_classes + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
+    for (int64_t k = 0; k < rounds; ++k) {  // whole warps stay together for the shuffle below
+        const int64_t c = (k * gridDim.x + blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
+        unsigned long long added = 0;
+        if (c < n_classes) {
+            const int64_t start = key_offsets[c];
+            const int n = (int)(key_offsets[c + 1] - start);
+            if (n > 0) {
+                const DenseIds ids{key_ids + start};
+                const int64_t slot = dict_find_or_insert(d, tuple_key(ids, n, false), ids, n, false);
+                if (slot >= 0) {
+                    added = (unsigned long long)counts[c];
+                    atomicAdd(&d.counts[slot], added);
+                    atomicMin(&d.first[slot], (unsigned long long)first_unit[c]);
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) added += __shfl_down_sync(0xffffffffu, added, o);
+        if ((threadIdx.x & 31) == 0 && added) atomicAdd(&d.scalars[3], added);
+    }
+}
+
 __global__ void add_value_kernel(unsigned long long *dst, unsigned long long v) { *dst += v; }
 
 __global__ void add_i64_kernel(unsigned long long *dst, const int64_t *src, int n)
@@ -770,6 +811,22 @@ SKM_API int skm_map_fastq(skm_mapper *m, const uint8_t *text1, int64_t n1, const
     if (paired) *consumed2 = last2 + 1;
     *n_units_out = n_units;
     return check_status(m, st, "skm_map_fastq");  // synchronises: the text buffers may be reused
+}
+
+SKM_API int skm_classes_merge_packed(skm_mapper *m, const int64_t *gathered, int64_t words_per_rank, int world,
+                                     int rank, void *stream)
+{
+    if (!m || !gathered) return fail(SKM_ERR_INVALID, "skm_classes_merge_packed: NULL argument");
+    if (world < 1 || rank < 0 || rank >= world || words_per_rank < 3 + SKM_MAX_FRAGMENT_LENGTH)
+        return fail(SKM_ERR_INVALID, "skm_classes_merge_packed: bad layout");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (world > 1) {
+        const dim3 grid((unsigned)(m->sm_count * 4), (unsigned)world);
+        dict_merge_packed_kernel<<<grid, 128, 0, st>>>(m->d, gathered, words_per_rank, rank);
+        SKM_CUDA(cudaGetLastError());
+    }
+    return check_status(m, st, "skm_classes_merge_packed");
 }
 
 SKM_API int skm_mapper_kernel_ms(skm_mapper *m, double ms[3])

@@ -151,37 +151,16 @@ def merge_mappers(mp, group=None):
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return mp.export_torch()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    t = mp.export_raw_torch()
-    dev = t['fld'].device
-    n, n_ids = int(t['counts'].shape[0]), int(t['key_ids'].shape[0])
-    ids64 = torch.zeros((n_ids + 1) // 2, dtype=torch.int64, device=dev)
-    ids64.view(torch.int32)[:n_ids] = t['key_ids']
-    head = torch.tensor([n, n_ids, t['unaligned']], dtype=torch.int64, device=dev)
-    packed = torch.cat([head, t['fld'], t['key_offsets'], t['counts'], t['first_unit'], ids64])
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([packed.shape[0]], dtype=torch.int64, device=dev), group=group)
-    cap = max(int(s.item()) for s in sizes)
+    packed = mp.pack_raw_torch()
+    dev = packed.device
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, torch.tensor([packed.shape[0]], dtype=torch.int64, device=dev), group=group)
+    cap = int(sizes.max().item())
     mine = torch.zeros(cap, dtype=torch.int64, device=dev)
     mine[:packed.shape[0]] = packed
     gathered = torch.zeros(world * cap, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(gathered, mine, group=group)
-    heads = gathered.view(world, cap)[:, :3].cpu().tolist()
-    for r in range(world):
-        if r == rank:
-            continue
-        buf = gathered[r * cap:(r + 1) * cap]
-        rn, rids, run = (int(v) for v in heads[r])
-        o = 3
-        fld = buf[o:o + MAX_FRAGMENT_LENGTH]
-        o += MAX_FRAGMENT_LENGTH
-        off = buf[o:o + rn + 1]
-        o += rn + 1
-        cnt = buf[o:o + rn]
-        o += rn
-        first = buf[o:o + rn]
-        o += rn
-        ids = buf[o:o + (rids + 1) // 2].view(torch.int32)[:rids]
-        mp.merge_device(off, ids, cnt, first, fld, run)
+    mp.merge_packed(gathered, cap, world, rank)
     return mp.export_torch()
 
 

@@ -249,6 +249,21 @@ def test_merge_on_device_matches_single_mapper(golden_synth, small_tx):
     assert ta['unaligned'] == tw['unaligned'] and ta['aligned'] == tw['aligned']
     tt = parts[0].export_torch()
     assert (tt['counts'].cpu().numpy() == tw['counts']).all()
+    # the same through the packed all-gather layout, all peers in one launch
+    import torch
+    parts = [_lib.DeviceMapper(ix) for _ in range(3)]
+    for p, lo, hi in zip(parts, bounds[:-1], bounds[1:]):
+        p.map_batch(bases[lo * 200:hi * 200], None, hi - lo, True, first_unit=lo, fixed_len=100)
+    packed = [p.pack_raw_torch() for p in parts]
+    cap = max(int(t.shape[0]) for t in packed)
+    gathered = torch.zeros(3 * cap, dtype=torch.int64, device='cuda')
+    for r, t in enumerate(packed):
+        gathered[r * cap:r * cap + t.shape[0]] = t
+    parts[1].merge_packed(gathered, cap, 3, 1)
+    tb = parts[1].export()
+    for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
+        assert (tb[k] == tw[k]).all(), k
+    assert tb['unaligned'] == tw['unaligned'] and tb['aligned'] == tw['aligned']
 
 
 def test_synth_reads_device_twin(small_tx):
