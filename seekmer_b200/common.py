@@ -110,6 +110,8 @@ class KMerIndex:
             return cls(*parts)
         try:
             import tables
+            if not hasattr(tables, '__version__'):  # a stand-in module without HDF5 behind it
+                raise ImportError('not PyTables')
         except ImportError as exc:
             raise RuntimeError('reading an HDF5 index needs PyTables, which is not installed; '
                                'convert the index to ".npz" where it is') from exc

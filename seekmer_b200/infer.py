@@ -248,6 +248,8 @@ def _output_hdf5(output_path, index, results, run_info, est_counts, bootstrapped
         arrays['bootstrap/bs{}'.format(i)] = bootstrap
     try:
         import tables
+        if not hasattr(tables, '__version__'):  # a stand-in module without HDF5 behind it
+            raise ImportError('not PyTables')
     except ImportError:
         _LOG.warn('PyTables is not installed: writing abundance.npz instead of abundance.h5')
         numpy.savez(str(output_path / 'abundance.npz'),
