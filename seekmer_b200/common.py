@@ -76,7 +76,7 @@ class KMerIndex:
                 import tables
             except ImportError:
                 tables = None
-            if tables is not None:
+            if tables is not None and hasattr(tables, '__version__'):
                 filters = tables.Filters(complib='blosc', complevel=9, fletcher32=True)
                 with tables.open_file(str(path), 'w', filters=filters) as f:
                     f.root._v_attrs['seekmer_version'] = _INDEX_VERSION
