@@ -61,23 +61,32 @@ class ClockSampler:
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
-        self.rows = []
+        self.rows = []   # (host time, csv line)
         self.proc = None
         self.gpu = gpu_index
+        self.window = [None, None]
 
     def start(self):
+        """Started BEFORE the warm-up steps (nvidia-smi needs a few 100 ms to come up and a timed
+        region of 3 steps is ~0.1 s); samples are time-stamped on arrival."""
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.window[0] = time.time()
+
+    def mark_end(self):
+        self.window[1] = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -89,7 +98,14 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        t0, t1 = self.window
+        timed = [r for t, r in self.rows if t0 is not None and t1 is not None and t0 <= t <= t1 + 0.02]
+        # a timed region shorter than the sampling period: fall back to the samples taken while the
+        # identical warm-up steps ran just before it
+        near = [r for t, r in self.rows if t0 is not None and t1 is not None and t0 - 0.25 <= t <= t1 + 0.05]
+        rows = timed or near or [r for _, r in self.rows]
+        self.in_timed_region = len(timed)
+        for r in rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 7:
                 continue
@@ -102,7 +118,8 @@ class ClockSampler:
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(numpy.median(sm)) if sm else None,
-                'sm_max_mhz': float(max(mx)) if mx else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+                'sm_max_mhz': float(max(mx)) if mx else None, 'samples': len(sm),
+                'samples_in_timed_region': self.in_timed_region, 'reasons': sorted(reasons)}
 
 
 # ------------------------------------------------------------------ workload
@@ -218,11 +235,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
     sampler = ClockSampler(local)
-    barrier()
     sampler.start()
+    step_device()  # first step also warms nvidia-smi up
+    time.sleep(0.3)
+    for _ in range(max(args.warmup - 1, 0)):
+        step_device()
+    barrier()
+    sampler.mark_begin()
     launches['n'] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -230,6 +250,7 @@ def run_ours(args):
         table = step_device(timed=True)
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     total_ms = e0.elapsed_time(e1)
     kernel_ms = float(numpy.mean([k['map_reads_kernel'] for k in kernel_times]))
