@@ -96,13 +96,6 @@ __host__ __device__ __forceinline__ uint64_t reference_hash(uint64_t m)
     return (v0 ^ v1) ^ (v2 ^ v3);
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-#ifndef SKM_NO_PREFETCH
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
-
 // Home bucket of a k-mer in the device table.
 __host__ __device__ __forceinline__ uint32_t home_bucket_of(uint64_t canon, uint64_t bucket_mask)
 {

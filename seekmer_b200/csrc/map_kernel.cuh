@@ -5,15 +5,17 @@
 // warps.  The reference's per-read state machine is cut at its memory accesses into PHASES:
 //
 //   P_LOAD    take the next unit (mate 0) and stage the packed read into shared memory
-//   P_LOOKUP  KMerIndex.map_kmer (hash + bucket probe) for the one pending k-mer: the first
-//             k-mer of a scan, a contig-junction k-mer, a walk fallback
-//   P_SCAN    _find_first_kmer after its first miss: the next 4 read positions are hashed and
-//             probed together (4 independent bucket loads in flight), first hit wins
+//   P_LOOKUP  KMerIndex.map_kmer (canonical form, hash, bucket probe) for the one pending k-mer:
+//             the first k-mer of a scan, a walk fallback, a junction k-mer without a stored link
+//   P_SCAN    _find_first_kmer after its first miss: the next SCAN_WIDTH read positions are
+//             hashed and probed together (independent bucket loads in flight), first hit wins
 //   P_CONTIG  contig record of a hit: map_contig for the scan hit, _filter_on_contig at a
 //             junction (or the reload of the first contig before the right walk)
 //   P_WALK    one head of the left/right contig-walk loops, or the final edge check: jump to
-//             the contig edge, 8-base SIFT4 check (direction-generic), next junction k-mer
-//   P_TALLY   map_read_pair mate intersection, FLD, class dictionary
+//             the contig edge, 8-base SIFT4 check (direction-generic); at a junction the next
+//             contig comes from the record's graph link for the next read base
+//   P_TALLY   map_read_pair mate intersection, span length; the unit's record goes to
+//             tally_units_kernel (FLD, class dictionary)
 //
 // Item (row, lane) is only ever worked on by lane `lane` of some warp, so all of its shared
 // memory ([field][row][lane]) is bank-conflict free.  For each phase and lane a 32-bit mask
@@ -21,9 +23,11 @@
 // the warp votes for the phase most of its lanes can serve, each lane claims one waiting row
 // of that phase (atomicAnd), loads the item state (four 16-byte shared loads), runs the phase,
 // stores the state and sets the row's bit in the mask of the phase the item needs next
-// (atomicOr).  With rows >> phases nearly every lane finds work in the voted phase, so each
-// heavy piece of code runs once, fully populated, instead of diverging 32 ways; the address
-// an item will need next is prefetched into L2 when it is queued.
+// (atomicOr).  Each heavy piece of code therefore exists once and runs with most lanes
+// populated, instead of diverging 32 ways; a phase that still has rows for half the lanes runs
+// again without a vote.  The kernel text is kept near the 32 KB the SM's instruction cache
+// holds (the dictionary lives in its own kernel, slow paths are out of line): at 50+ KB this
+// kernel was bound by instruction fetch.
 //
 // Reference semantics restated here (paths under /root/reference/seekmer/):
 //   map_read            _mapper.pyx:151-193      find_first_kmer   :199-216
