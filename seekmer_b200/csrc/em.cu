@@ -338,15 +338,16 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 // ---- bootstrap resampling --------------------------------------------------------------------
 // bucket b (top 16 bits of the 64-bit uniform) starts its search at lo[b]
 __global__ void multinomial_buckets_kernel(const unsigned long long *__restrict__ cum, int64_t n_classes,
-                                           unsigned long long n, int32_t *__restrict__ lo)
+                                           unsigned long long n, int bits, int32_t *__restrict__ lo)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > 65536) return;
-    if (b == 65536) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n_buckets = 1LL << bits;
+    if (b > n_buckets) return;
+    if (b == n_buckets) {
         lo[b] = (int32_t)(n_classes - 1);
         return;
     }
-    const unsigned long long u = __umul64hi((unsigned long long)b << 48, n);
+    const unsigned long long u = __umul64hi((unsigned long long)b << (64 - bits), n);
     int64_t a = 0, z = n_classes;  // first index with cum > u
     while (a < z) {
         const int64_t m = (a + z) >> 1;
@@ -357,7 +358,7 @@ __global__ void multinomial_buckets_kernel(const unsigned long long *__restrict_
 }
 
 __global__ void multinomial_kernel(const unsigned long long *__restrict__ cum, int64_t n_classes,
-                                   unsigned long long n, const int32_t *__restrict__ lo,
+                                   unsigned long long n, int bits, const int32_t *__restrict__ lo,
                                    int64_t first_replicate, uint32_t seed_lo, uint32_t seed_hi,
                                    unsigned long long *__restrict__ out)
 {
@@ -375,7 +376,7 @@ __global__ void multinomial_kernel(const unsigned long long *__restrict__ cum, i
             if (2 * j + h >= n) break;
             const unsigned long long w = ((unsigned long long)x[2 * h + 1] << 32) | x[2 * h];
             const unsigned long long u = __umul64hi(w, n);
-            const uint32_t b = (uint32_t)(w >> 48);
+            const uint32_t b = (uint32_t)(w >> (64 - bits));
             int64_t a = lo[b], z = (int64_t)lo[b + 1] + 1;
             if (z > n_classes) z = n_classes;
             while (a < z) {
@@ -833,7 +834,10 @@ static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t 
 {
     DeviceBuf b_cum, b_lo, b_tmp;
     EM_TRY(b_cum.alloc(sizeof(unsigned long long) * (size_t)n_classes, st));
-    EM_TRY(b_lo.alloc(sizeof(int32_t) * 65537, st));
+    // about two buckets per class: the search that follows the bucket lookup is then 0-1 steps
+    int bits = 16;
+    while (bits < 22 && (1LL << bits) < 2 * n_classes) ++bits;
+    EM_TRY(b_lo.alloc(sizeof(int32_t) * ((size_t)(1LL << bits) + 1), st));
     size_t tmp = 0;
     cub::DeviceScan::InclusiveSum(nullptr, tmp, reinterpret_cast<const unsigned long long *>(d_counts),
                                   b_cum.as<unsigned long long>(), (int)n_classes, st);
@@ -845,13 +849,13 @@ static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t 
     EM_TRY(cudaStreamSynchronize(st));
     EM_TRY(cudaMemsetAsync(d_out, 0, sizeof(int64_t) * (size_t)(n_classes * n_replicates), st));
     if (n > 0) {
-        multinomial_buckets_kernel<<<(65537 + 255) / 256, 256, 0, st>>>(b_cum.as<unsigned long long>(), n_classes, n,
-                                                                       b_lo.as<int32_t>());
+        multinomial_buckets_kernel<<<(unsigned)(((1LL << bits) + 256) / 256), 256, 0, st>>>(
+            b_cum.as<unsigned long long>(), n_classes, n, bits, b_lo.as<int32_t>());
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const unsigned gx = (unsigned)std::min<unsigned long long>((n / 2 + 256) / 256, (unsigned long long)sms * 8);
         const dim3 grid(gx, (unsigned)n_replicates);
-        multinomial_kernel<<<grid, 256, 0, st>>>(b_cum.as<unsigned long long>(), n_classes, n, b_lo.as<int32_t>(),
+        multinomial_kernel<<<grid, 256, 0, st>>>(b_cum.as<unsigned long long>(), n_classes, n, bits, b_lo.as<int32_t>(),
                                                 first_replicate, (uint32_t)seed, (uint32_t)(seed >> 32),
                                                 reinterpret_cast<unsigned long long *>(d_out));
     }
