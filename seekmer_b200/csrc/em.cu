@@ -657,7 +657,7 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     // iteration count is exact while the host only synchronises once per group.
     //
     // Replicates stop at very different iteration counts (bootstraps: mean ~40, max > 100), so
-    // whenever at most half of the live columns are still running the finished ones are written
+    // whenever at most three quarters of the live columns are still running the finished ones are written
     // to the output and the state is compacted to the running columns: the work of an
     // iteration follows the number of replicates that still need it.
     const int GROUP = 8;
@@ -697,7 +697,7 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
         EM_TRY(cudaGetLastError());
         EM_TRY(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
-        if (!may_compact || n_active <= 0 || 2 * n_active > Rc || Rc <= 8 || done >= max_iters) continue;
+        if (!may_compact || n_active <= 0 || 4 * n_active > 3 * Rc || Rc <= 8 || done >= max_iters) continue;
         // ---- compact to the running columns (every iteration of this group did execute) --------
         EM_TRY(cudaMemcpyAsync(h_active.data(), s.active, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
