@@ -266,6 +266,46 @@ def test_merge_on_device_matches_single_mapper(golden_synth, small_tx):
     assert tb['unaligned'] == tw['unaligned'] and tb['aligned'] == tw['aligned']
 
 
+def test_size_independent_properties_on_a_large_batch(medium):
+    """2 M pairs generated on the device (too many for the CPU oracle in a test): every unit lands
+    in exactly one class or in `unaligned`; the FLD holds exactly the units with a positive span;
+    mapping the same batch again doubles every count and adds no class; two shards merged equal
+    the whole."""
+    import torch
+    tx, arrays = medium
+    n = 2_000_000
+    sim = synth.ReadSimulator(tx, synth.make_expression(tx.n_transcripts), 100, 250, 30, seed=77)
+    codes = torch.from_numpy(tx.codes).cuda()
+    offs = torch.from_numpy(tx.offsets).cuda()
+    cum = torch.from_numpy(sim.cum_weights.view('i8')).cuda()
+    d = torch.empty(n * 200, dtype=torch.uint8, device='cuda')
+    L = _lib.load()
+    _lib.check(L.skm_synth_reads(_lib._ptr(codes), _lib._ptr(offs), tx.n_transcripts, _lib._ptr(cum), sim.total_weight,
+                                 sim.L, sim.mu, sim.sd, sim.sub_thresh, sim.n_thresh, sim.random_pct, sim.seed, 1, 0, n,
+                                 _lib._ptr(d), 0, _lib.current_stream_ptr()))
+    ix = _lib.DeviceIndex(*arrays, tx.n_transcripts)
+    whole = _lib.DeviceMapper(ix)
+    cls, length = whole.map_batch(d, None, n, True, fixed_len=100, per_read=True)
+    t1 = whole.export()
+    assert int(t1['counts'].sum()) == t1['aligned'] and t1['aligned'] + t1['unaligned'] == n
+    assert int((cls >= 0).sum()) == t1['aligned']
+    assert int(t1['fld'].sum()) == int((length > 0).sum())
+    assert t1['aligned'] > 0.9 * n and len(t1['counts']) > 100
+    whole.map_batch(d, None, n, True, first_unit=n, fixed_len=100)
+    t2 = whole.export()
+    assert (t2['key_ids'] == t1['key_ids']).all() and (t2['counts'] == 2 * t1['counts']).all()
+    assert (t2['fld'] == 2 * t1['fld']).all() and (t2['first_unit'] == t1['first_unit']).all()
+    a, b = _lib.DeviceMapper(ix), _lib.DeviceMapper(ix)
+    h = n // 3
+    a.map_batch(d[:h * 200], None, h, True, first_unit=0, fixed_len=100)
+    b.map_batch(d[h * 200:], None, n - h, True, first_unit=h, fixed_len=100)
+    tb = b.export_raw_torch()
+    a.merge_device(tb['key_offsets'], tb['key_ids'], tb['counts'], tb['first_unit'], tb['fld'], tb['unaligned'])
+    ta = a.export()
+    for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
+        assert (ta[k] == t1[k]).all(), k
+
+
 def test_synth_reads_device_twin(small_tx):
     import ctypes
     import torch
