@@ -105,7 +105,7 @@ __host__ __device__ __forceinline__ uint32_t home_bucket_of(uint64_t canon, uint
 // KMerIndex.map_kmer (_common.pyx:54-97) on the canonical-key table: hit on the
 // canonical key; strand of the query relative to the canonical form decides whether
 // the stored coordinate is returned as is or reverse-complemented (~entry).
-// One iteration reads a whole 64-byte bucket with four read-only 16-byte loads; at load
+// One iteration reads a whole 64-byte bucket with four 16-byte loads; at load
 // <= 0.25 a second bucket is needed ~0.4 % of the time.
 __device__ __forceinline__ Coord probe_canonical(const Slot *table, uint64_t bucket_mask, uint64_t canon, bool fwd,
                                                  uint32_t bucket)
@@ -113,7 +113,8 @@ __device__ __forceinline__ Coord probe_canonical(const Slot *table, uint64_t buc
     uint64_t b = bucket;
     for (;;) {
         const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(table + BUCKET_SLOTS * b);
-        const ulonglong2 s0 = __ldg(p), s1 = __ldg(p + 1), s2 = __ldg(p + 2), s3 = __ldg(p + 3);
+        // streaming loads: a bucket is used once, it should not push the read's own lines out of L1
+        const ulonglong2 s0 = __ldcs(p), s1 = __ldcs(p + 1), s2 = __ldcs(p + 2), s3 = __ldcs(p + 3);
         uint64_t v = 0;
         bool found = false;
         if (s0.x == canon) { v = s0.y; found = true; }

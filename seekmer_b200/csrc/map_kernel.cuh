@@ -59,6 +59,9 @@ constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
 #define SKM_SCAN_WIDTH 3
 #endif
 constexpr int SCAN_WIDTH = SKM_SCAN_WIDTH;  // read positions probed per P_SCAN step
+#ifndef SKM_IDLE_NS
+#define SKM_IDLE_NS 200
+#endif
 #ifndef SKM_STICKY_LANES
 #define SKM_STICKY_LANES 16
 #endif
@@ -607,7 +610,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (lane == 0) live = *reinterpret_cast<volatile int *>(sm_live);
                 live = __shfl_sync(0xffffffffu, live, 0);
                 if (live == 0) break;
-                __nanosleep(200);
+                __nanosleep(SKM_IDLE_NS);
                 phase = -1;
                 continue;
             }
