@@ -553,6 +553,7 @@ static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
 static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_starts, const int64_t *d_ends, MapArgs a,
                  int64_t n_units, int64_t first_unit, int32_t *d_out_class, int32_t *d_out_length, cudaStream_t st)
 {
+    if (n_units >= (1LL << 32)) return fail(SKM_ERR_INVALID, "skm_map_batch: more than 2^32 units in one chunk");
     const int64_t n_reads = a.paired ? 2 * n_units : n_units;
     int rc = ensure((void **)&m->d_packed, &m->d_packed_cap, sizeof(uint64_t) * (size_t)n_reads * a.words);
     if (rc) return rc;
