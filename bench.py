@@ -96,15 +96,21 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             pass
+        return self.summarize(self.rows, self.window)
+
+    @staticmethod
+    def summarize(stamped_rows, window):
+        """Reduce time-stamped nvidia-smi csv lines to the `clocks` object of the bench line.
+        Only the samples that arrived inside `window` count when there are any."""
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        t0, t1 = self.window
-        timed = [r for t, r in self.rows if t0 is not None and t1 is not None and t0 <= t <= t1 + 0.02]
+        t0, t1 = window
+        timed = [r for t, r in stamped_rows if t0 is not None and t1 is not None and t0 <= t <= t1 + 0.02]
         # a timed region shorter than the sampling period: fall back to the samples taken while the
         # identical warm-up steps ran just before it
-        near = [r for t, r in self.rows if t0 is not None and t1 is not None and t0 - 0.25 <= t <= t1 + 0.05]
-        rows = timed or near or [r for _, r in self.rows]
-        self.in_timed_region = len(timed)
+        near = [r for t, r in stamped_rows
+                if t0 is not None and t1 is not None and t0 - 0.25 <= t <= t1 + 0.05]
+        rows = timed or near or [r for _, r in stamped_rows]
         for r in rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 7:
@@ -119,7 +125,7 @@ class ClockSampler:
                     reasons.add(name)
         return {'sm_mhz': float(numpy.median(sm)) if sm else None,
                 'sm_max_mhz': float(max(mx)) if mx else None, 'samples': len(sm),
-                'samples_in_timed_region': self.in_timed_region, 'reasons': sorted(reasons)}
+                'samples_in_timed_region': len(timed), 'reasons': sorted(reasons)}
 
 
 # ------------------------------------------------------------------ workload
