@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
-"""`seekmer` command line (`__main__.py:13-71`): only the `infer` sub-command is served by this
-package; `index` and `impute` stay with the reference (out of scope)."""
+"""`seekmer` command line (`__main__.py:13-71`): the `infer` and `impute` sub-commands are
+served by this package; `index` stays with the reference (out of scope)."""
 import argparse
 import sys
 
+from . import impute
 from . import infer
 from ._log import StderrHandler
 
@@ -15,11 +16,14 @@ def main(argv=None):
     parser.add_argument('--debug', action='store_true', help='enable debugging messages')
     subparsers = parser.add_subparsers(title='subcommand', dest='subcommand')
     infer.add_subcommand_parser(subparsers)
+    impute.add_subcommand_parser(subparsers)
     opts = vars(parser.parse_args(argv))
     handler = StderrHandler(level='DEBUG' if opts['debug'] else 'INFO')
     with handler.applicationbound():
         if opts['subcommand'] == 'infer':
             infer.run(**opts)
+        elif opts['subcommand'] == 'impute':
+            impute.run(**opts)
         else:
             parser.print_help()
     return 0

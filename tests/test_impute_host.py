@@ -1,0 +1,113 @@
+"""Host side of the `impute` workflow against the reference's own outputs
+(tests/golden/impute_small.npz, made by tests/golden/make_golden_impute.py).  No GPU needed:
+cell weights, blending and the gene table are host logic; the batched EM is in
+tests/test_gpu_impute.py."""
+import numpy
+import pytest
+
+from conftest import GOLDEN, Golden
+from seekmer_b200 import impute, mapper
+
+
+@pytest.fixture(scope='module')
+def gi():
+    return Golden(GOLDEN / 'impute_small.npz')
+
+
+class _Index:
+    def __init__(self, transcripts):
+        self.transcripts = transcripts
+
+
+def _index(gi, golden_synth):
+    tab = golden_synth['transcripts'].copy()
+    tab['gene_id'] = gi['gene_id']
+    return _Index(tab)
+
+
+def _first_round_results(gi):
+    """SummarizedResult objects as the reference had them before blending."""
+    ptr, nnz = gi['class_ptr'], numpy.concatenate([[0], numpy.cumsum(gi['class_nnz'])])
+    out = []
+    for c in range(len(ptr) - 1):
+        counts = gi['class_count'][ptr[c]:ptr[c + 1]].copy()
+        cmap = gi['class_map'][:, nnz[c]:nnz[c + 1]].copy()
+        out.append(mapper.SummarizedResult(int(counts.sum()), 0, int(counts.sum()), cmap, counts,
+                                           gi['fld'], gi['eff_lengths']))
+    return out
+
+
+def test_cell_weights_match_reference(gi, golden_synth, tmp_path):
+    w = impute._calculate_cell_weights(_index(gi, golden_synth), gi['base'], tmp_path)
+    assert ((w != 0) == (gi['weight'] != 0)).all()
+    assert numpy.allclose(w, gi['weight'], rtol=1e-13, atol=0)
+    assert (tmp_path / 'initial_gene_table.csv').read_bytes() == gi['gene_table_csv'].tobytes()
+    assert (tmp_path / 'weight.csv').exists()
+
+
+def test_blend_matches_reference(gi):
+    cells = _first_round_results(gi)
+    impute._blend_mapping_results(cells, gi['weight'] ** int(gi['power']))
+    assert all(c.class_map is cells[0].class_map for c in cells)
+    assert (cells[0].class_map == gi['blended_map']).all()
+    assert numpy.allclose(cells[0].class_count, gi['blended_count_first'], rtol=1e-13, atol=0)
+    assert numpy.allclose(cells[-1].class_count, gi['blended_count_last'], rtol=1e-13, atol=0)
+    # class mass of a cell is preserved up to the weights: row i sums to total_i * sum_j w_ij
+    totals = [gi['class_count'][gi['class_ptr'][c]:gi['class_ptr'][c + 1]].sum() for c in range(len(cells))]
+    w = gi['weight'] ** int(gi['power'])
+    for i, c in enumerate(cells):
+        assert c.class_count.sum() == pytest.approx(totals[i] * w[i].sum(), rel=1e-12)
+
+
+def test_merge_fragment_lengths_shares_one_array():
+    class R:
+        def __init__(self, k):
+            self.fragment_length_counts = numpy.zeros(mapper.MAX_FRAGMENT_LENGTH, dtype='i8')
+            self.fragment_length_counts[k] = k
+    rs = [R(3), R(5), R(5)]
+    impute._merge_fragment_lengths(rs)
+    assert all(r.fragment_length_counts is rs[0].fragment_length_counts for r in rs)
+    assert rs[0].fragment_length_counts[3] == 3 and rs[0].fragment_length_counts[5] == 10
+    assert rs[0].fragment_length_counts.sum() == 13
+
+
+def test_two_means_is_the_optimal_split():
+    rng = numpy.random.default_rng(5)
+    for _ in range(50):
+        v = rng.normal(size=rng.integers(2, 12))
+        lo, hi = impute._two_means(v)
+        s = numpy.sort(v)
+        best = min(((s[:k] - s[:k].mean()) ** 2).sum() + ((s[k:] - s[k:].mean()) ** 2).sum()
+                   for k in range(1, len(s)))
+        assign_hi = numpy.abs(v - hi) < numpy.abs(v - lo)
+        assert 0 < assign_hi.sum() < len(v)
+        cost = ((v[assign_hi] - hi) ** 2).sum() + ((v[~assign_hi] - lo) ** 2).sum()
+        assert cost == pytest.approx(best, rel=1e-9, abs=1e-12)
+    with pytest.raises(ValueError):
+        impute._two_means([0.5])
+
+
+def test_gene_matrix_truncates_like_the_reference(gi, golden_synth):
+    idx = _index(gi, golden_synth)
+    m, names = impute._gene_matrix(idx, gi['base'])
+    assert m.dtype == numpy.dtype('i8') and b'' not in set(names.tolist())
+    genes = numpy.unique(idx.transcripts['gene_id'])
+    assert m.shape == (gi['base'].shape[0], len(genes) - 1)
+    g0 = idx.transcripts['gene_id'] == names[0]
+    assert (m[:, 0] == numpy.trunc(gi['base'][:, g0].sum(axis=1))).all()
+
+
+def test_cli_lists_impute():
+    import argparse
+    sub = argparse.ArgumentParser().add_subparsers(dest='subcommand')
+    impute.add_subcommand_parser(sub)
+    ns = sub.choices['impute'].parse_args(['i.npz', 'out', 'a.fq', 'b.fq', '-s', '-p', '4'])
+    assert ns.single_ended and ns.power == 4 and ns.job_count == 1 and len(ns.fastq_paths) == 2
+
+
+def test_oracle_em_on_blended_counts_is_pinned(gi, orc):
+    """The oracle's EM on the reference's blended (fractional, mostly zero) class counts
+    reproduces the reference's second-round TPM: the GPU test may then use it as the checker."""
+    for counts, want in ((gi['blended_count_first'], gi['tpm'][0]), (gi['blended_count_last'], gi['tpm'][-1])):
+        got = orc.quantify(gi['eff_lengths'], gi['blended_map'], counts)
+        assert numpy.allclose(got, want, rtol=1e-12, atol=0)
