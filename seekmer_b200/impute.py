@@ -7,11 +7,13 @@ _blend_mapping_results — same arguments, same files in the output folder
 
 What changes underneath:
   * every cell is mapped by the GPU mapper (`mapper.map_multiple_samples`);
-  * the second-round quantification is ONE batched EM.  After blending, all cells share one
+  * the second-round quantification is a batched EM.  After blending, all cells share one
     class structure (the concatenation of every cell's classes, `impute.py:238-246`) and
     differ only in their class counts, which is exactly the replicate layout `skm_em` runs
     (`[n_classes][n_cells]`, replicate fastest).  The reference loops `infer.quantify` over
-    the cells, N EMs over N-times-larger inputs (`impute.py:110-115`);
+    the cells, N EMs over N-times-larger inputs (`impute.py:110-115`).  Cells drawing on the
+    same set of cells are batched into one call over just those cells' classes
+    (`_quantify_weighted`); zero-count classes add exactly 0 to the EM sums;
   * the two-cluster split of the correlation values is solved exactly (sorted prefix sums)
     instead of by sklearn's randomly initialised Lloyd iteration (`impute.py:213-214`, no
     random_state): deterministic, and equal to what the reference converges to whenever its
@@ -101,10 +103,8 @@ def impute_cells(index, map_results, power=16, output_path=None, return_stages=F
         return (base, base, None) if return_stages else base
     _LOG.info('Weighting cells.')
     weight = _calculate_cell_weights(index, base, output_path)
-    blended = weight ** power
-    _blend_mapping_results(summarized, blended)
     _LOG.info('Second round quantification...')
-    tpm = _quantify_blended(summarized)
+    tpm = _quantify_weighted(summarized, weight ** power)
     return (tpm, base, weight) if return_stages else tpm
 
 
@@ -126,8 +126,17 @@ def _gene_matrix(index, base_matrix):
     gene_of = numpy.asarray(gene_of).reshape(-1)
     base_matrix = numpy.asarray(base_matrix, dtype='f8')
     sums = numpy.zeros((base_matrix.shape[0], len(genes)), dtype='f8')
-    for g in range(len(genes)):  # the reference's own summation: numpy pairwise over the mask
-        sums[:, g] = base_matrix[:, gene_of == g].sum(axis=1)
+    # The reference sums `base_matrix[:, gene_of == g]` gene by gene (genes x transcripts work).
+    # Same sums, same rounding: genes with equally many transcripts are gathered into one
+    # (cells, genes, k) block and reduced over the contiguous last axis, which is the
+    # summation numpy applies to each gene's (cells, k) block.
+    order = numpy.argsort(gene_of, kind='stable')          # transcripts of a gene, ascending
+    sizes = numpy.bincount(gene_of, minlength=len(genes))
+    first = numpy.concatenate([[0], numpy.cumsum(sizes)[:-1]])
+    for k in numpy.unique(sizes):
+        which = numpy.flatnonzero(sizes == k)
+        members = order[first[which][:, None] + numpy.arange(k)[None, :]]
+        sums[:, which] = base_matrix[:, members].sum(axis=2)
     named = genes != b''
     return sums.astype('i8')[:, named], genes[named]
 
@@ -192,32 +201,109 @@ def _blend_mapping_results(map_results, weight):
         result.class_map = shared
 
 
-def _quantify_blended(map_results):
+def _support_groups(weight):
+    """Cells grouped by which cells they draw counts from (the non-zero pattern of their weight
+    row): cells of one group have zero counts on the same blocks of the blended classes."""
+    groups = {}
+    for i, row in enumerate(numpy.asarray(weight)):
+        groups.setdefault((row != 0).tobytes(), []).append(i)
+    return list(groups.values())
+
+
+def _blended_group(map_results, weight, group):
+    """What `_blend_mapping_results` + `_prune_classes` give for the cells of one support group,
+    built directly: (class_map over the supporting cells' classes, counts[len(group)][classes]).
+    The blocks a group gives no weight to are never materialised, so memory is
+    cells-in-group x supported classes instead of cells x all classes per cell."""
+    support = numpy.flatnonzero(numpy.asarray(weight)[group[0]] != 0)
+    maps, first = [], 0
+    for j in support:
+        block = numpy.array(map_results[j].class_map, dtype='i8')
+        block[0] += first
+        first = block[0].max() + 1
+        maps.append(block)
+    class_map = numpy.concatenate(maps, axis=1)
+    sums = [map_results[j].class_count.sum() for j in support]
+    counts = numpy.empty((len(group), int(first)), dtype='f8')
+    for row, i in enumerate(group):
+        total = map_results[i].class_count.sum()
+        with numpy.errstate(all='ignore'):  # same operation order as `impute.py:249-251`
+            counts[row] = numpy.concatenate(
+                [map_results[j].class_count * weight[i, j] * total / s for j, s in zip(support, sums)])
+    return class_map, counts
+
+
+def _quantify_weighted(map_results, weight):
+    """Blend + second-round quantification of `impute.py:108-115` without building the
+    cells x (all cells' classes) count matrix: one batched device EM per support group."""
+    n_tx = map_results[0].effective_lengths.size if map_results else 0
+    out = numpy.zeros((len(map_results), n_tx), dtype='f8')
+    if not map_results:
+        return out
+    lengths = map_results[0].effective_lengths.astype('f8')
+    x0 = numpy.ones(n_tx, dtype='f8') / lengths
+    x0 /= x0.sum()
+    for group in _support_groups(weight):
+        if not (numpy.asarray(weight)[group[0]] != 0).any():
+            raise ValueError('a cell without any weighted cell cannot be quantified')
+        class_map, counts = _blended_group(map_results, weight, group)
+        per_call = max(1, _EM_BATCH_BYTES // max(8 * counts.shape[1], 1))
+        for start in range(0, len(group), per_call):
+            rows = slice(start, start + per_call)
+            x, _ = infer._em_device(numpy.tile(x0, (len(group[rows]), 1)), lengths, class_map,
+                                    counts[rows])
+            for row in x:
+                infer._finish(row)
+            out[group[rows]] = x
+    return out
+
+
+def _prune_classes(class_map, counts):
+    """Drop the classes whose count is zero in every row of `counts` (cells x classes) and
+    renumber the rest.  A zero-count class adds exactly 0 to every sum of the EM update
+    (`infer.py:153-157`: its `class_inner` is +inf, or NaN where all its transcripts are already
+    0 and stay 0), so the fixed point and the iterates are the same without it."""
+    active = (counts != 0).any(axis=0)
+    if active.all() or not active.any():
+        return class_map, counts
+    new_id = numpy.cumsum(active) - 1
+    rows = numpy.asarray(class_map[0], dtype='i8')
+    keep = active[rows]
+    pruned = numpy.stack([new_id[rows[keep]], numpy.asarray(class_map[1], dtype='i8')[keep]])
+    return pruned, numpy.ascontiguousarray(counts[:, active])
+
+
+def _quantify_blended(map_results, groups=None):
     """`[infer.quantify(r) for r in map_results]` (`impute.py:110-115`) for results that share
-    one class_map: one batched device EM (cells are the replicates), then the TPM step."""
+    one class_map: batched device EMs with the cells as replicates, then the TPM step.
+    `groups` (lists of cell indices, default: one group) are quantified separately, each over
+    only the classes that have a count in at least one of its cells."""
     if not map_results:
         return numpy.zeros((0, 0), dtype='f8')
     shared = map_results[0].class_map
     n_tx = map_results[0].effective_lengths.size
-    if shared.size == 0:
-        return numpy.zeros((len(map_results), n_tx), dtype='f8')
     out = numpy.zeros((len(map_results), n_tx), dtype='f8')
+    if shared.size == 0:
+        return out
+    lengths = map_results[0].effective_lengths.astype('f8')
+    for c in map_results:
+        if c.class_map is not shared or not numpy.array_equal(c.effective_lengths,
+                                                              map_results[0].effective_lengths):
+            raise ValueError('_quantify_blended needs results blended by _blend_mapping_results')
+    x0 = numpy.ones(n_tx, dtype='f8') / lengths
+    x0 /= x0.sum()
     n_classes = map_results[0].class_count.size
     per_call = max(1, _EM_BATCH_BYTES // max(8 * n_classes, 1))
-    start = 0
-    while start < len(map_results):
-        cells = map_results[start:start + per_call]
-        same_lengths = all(numpy.array_equal(c.effective_lengths, cells[0].effective_lengths)
-                           for c in cells)
-        if not same_lengths or any(c.class_map is not shared for c in cells):
-            raise ValueError('_quantify_blended needs results blended by _blend_mapping_results')
-        lengths = cells[0].effective_lengths.astype('f8')
-        x0 = numpy.ones(n_tx, dtype='f8') / lengths
-        x0 /= x0.sum()
-        counts = numpy.stack([numpy.asarray(c.class_count, dtype='f8') for c in cells])
-        x, _ = infer._em_device(numpy.tile(x0, (len(cells), 1)), lengths, shared, counts)
-        for row in x:
-            infer._finish(row)
-        out[start:start + len(cells)] = x
-        start += len(cells)
+    if groups is None:
+        groups = [list(range(len(map_results)))]
+    for group in groups:
+        for start in range(0, len(group), per_call):
+            cells = group[start:start + per_call]
+            counts = numpy.stack([numpy.asarray(map_results[i].class_count, dtype='f8')
+                                  for i in cells])
+            class_map, counts = _prune_classes(shared, counts)
+            x, _ = infer._em_device(numpy.tile(x0, (len(cells), 1)), lengths, class_map, counts)
+            for row in x:
+                infer._finish(row)
+            out[cells] = x
     return out

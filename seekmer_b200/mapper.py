@@ -180,18 +180,26 @@ class ReadMapper:
     the reference's, an instance is used by one thread at a time.
     """
 
-    def __init__(self, index, map_result, device=None, class_capacity=0, id_capacity=0):
+    def __init__(self, index, map_result, device=None, class_capacity=0, id_capacity=0,
+                 device_mapper=None):
         self.index = index
         self.map_result = map_result
         self.device = _device_of(index) if device is None else device
         self._class_capacity = class_capacity
         self._id_capacity = id_capacity
+        # a caller-owned handle to run on (reset, used, left open): creating the class
+        # dictionary costs far more than mapping a small sample (`map_multiple_samples`)
+        self._shared = device_mapper
         self.fragment_length_counts = numpy.zeros(MAX_FRAGMENT_LENGTH, dtype='i8')
 
     def __call__(self, reads_iterator):
         """Run the mapping loop over `(read_count, read_names, reads)` batches."""
-        dev_index = self.index.device_index(self.device)
-        mapper = _lib.DeviceMapper(dev_index, self._class_capacity, self._id_capacity)
+        if self._shared is not None:
+            mapper = self._shared
+            mapper.reset()
+        else:
+            dev_index = self.index.device_index(self.device)
+            mapper = _lib.DeviceMapper(dev_index, self._class_capacity, self._id_capacity)
         want_reads = self.map_result.readmap is not None
         try:
             first_unit = 0
@@ -228,7 +236,8 @@ class ReadMapper:
                 _LOG.debug('Mapped {} reads.', read_count)
             table = mapper.export()
         finally:
-            mapper.close()
+            if self._shared is None:
+                mapper.close()
         classes = _class_tuples(table)
         with self.map_result.lock:
             fresh = not self.map_result.counter
@@ -279,10 +288,19 @@ def map_reads(index, read_feeder, job_count=1, readmap=None, debug=False):
 
 
 def map_multiple_samples(index, read_feeders, job_count=1, debug=False):
-    """One `MapResult` per sample (`mapper.py:196-234`)."""
+    """One `MapResult` per sample (`mapper.py:196-234`).  The samples go through one device
+    mapper, reset in between: a cell of a single-cell run maps in under a millisecond, while
+    allocating a class dictionary takes tens."""
     map_results = []
-    for read_feeder in read_feeders:
-        result = MapResult(index)
-        map_results.append(result)
-        ReadMapper(index, result)(read_feeder)
+    shared = None
+    try:
+        for read_feeder in read_feeders:
+            result = MapResult(index)
+            map_results.append(result)
+            if shared is None:
+                shared = _lib.DeviceMapper(index.device_index(_device_of(index)), 0, 0)
+            ReadMapper(index, result, device_mapper=shared)(read_feeder)
+    finally:
+        if shared is not None:
+            shared.close()
     return map_results

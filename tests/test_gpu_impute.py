@@ -51,6 +51,12 @@ def test_batched_second_round_vs_oracle_and_chunking(gi, orc, monkeypatch):
         want = orc.quantify(gi['eff_lengths'], cell.class_map, cell.class_count)
         assert numpy.allclose(whole[i], want, rtol=TOL, atol=0)
     assert numpy.allclose(whole, gi['tpm'], rtol=TOL, atol=0)
+    # the path impute_cells takes: per support group, unsupported blocks never built
+    grouped = impute._quantify_weighted(_first_round_results(gi), gi['weight'] ** ic.POWER)
+    assert numpy.allclose(grouped, gi['tpm'], rtol=TOL, atol=0)
+    assert numpy.allclose(grouped, whole, rtol=1e-9, atol=0)
+    by_group = impute._quantify_blended(cells, groups=impute._support_groups(gi['weight']))
+    assert numpy.allclose(by_group, grouped, rtol=1e-12, atol=0)
     # three cells per device call: same answers
     monkeypatch.setattr(impute, '_EM_BATCH_BYTES', 3 * 8 * cells[0].class_count.size)
     assert (impute._quantify_blended(cells) == whole).all()

@@ -111,3 +111,68 @@ def test_oracle_em_on_blended_counts_is_pinned(gi, orc):
     for counts, want in ((gi['blended_count_first'], gi['tpm'][0]), (gi['blended_count_last'], gi['tpm'][-1])):
         got = orc.quantify(gi['eff_lengths'], gi['blended_map'], counts)
         assert numpy.allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_gene_sums_equal_the_per_gene_masked_sums():
+    """Bit-for-bit the reference's `base_matrix[:, gene_mask].sum(axis=1)` (`impute.py:200-202`),
+    including genes large enough for numpy's pairwise summation."""
+    rng = numpy.random.default_rng(11)
+    sizes = numpy.concatenate([rng.integers(1, 7, 40), [8, 9, 33, 130, 200]])
+    gene_of = rng.permutation(numpy.repeat(numpy.arange(len(sizes)), sizes))
+    tab = numpy.zeros(len(gene_of), dtype=[('transcript_id', 'S8'), ('gene_id', 'S8'), ('length', 'f8')])
+    tab['gene_id'] = [b'g%04d' % g if g else b'' for g in gene_of]
+    base = rng.lognormal(3, 3, size=(7, len(gene_of)))
+    got, names = impute._gene_matrix(_Index(tab), base)
+    genes, inverse = numpy.unique(tab['gene_id'], return_inverse=True)
+    want = numpy.zeros((7, len(genes)), dtype='i8')
+    for g in range(len(genes)):
+        want[:, g] = base[:, inverse == g].sum(axis=1)
+    assert (got == want[:, genes != b'']).all() and (names == genes[genes != b'']).all()
+    exact = numpy.zeros((7, len(genes)))
+    for g in range(len(genes)):
+        exact[:, g] = base[:, inverse == g].sum(axis=1)
+    sums = numpy.zeros_like(exact)   # the float sums themselves, before truncation
+    order = numpy.argsort(inverse, kind='stable')
+    pos = 0
+    for g, k in enumerate(numpy.bincount(inverse)):
+        sums[:, g] = base[:, order[pos:pos + k]][:, None, :].sum(axis=2)[:, 0]
+        pos += k
+    assert (sums == exact).all()
+
+
+def test_prune_and_support_groups(gi):
+    cells = _first_round_results(gi)
+    w = gi['weight'] ** int(gi['power'])
+    impute._blend_mapping_results(cells, w)
+    groups = impute._support_groups(w)
+    assert sorted(map(tuple, groups)) == [(0, 2, 4, 6), (1, 3, 5, 7)]
+    counts = numpy.stack([cells[i].class_count for i in groups[0]])
+    cmap, pruned = impute._prune_classes(cells[0].class_map, counts)
+    ptr = gi['class_ptr']
+    kept = sum(int(ptr[c + 1] - ptr[c]) for c in groups[0])
+    assert pruned.shape == (4, kept) and (pruned != 0).any(axis=0).all()
+    assert cmap[0].max() == kept - 1 and (numpy.diff(cmap[0]) >= 0).all()
+    # the surviving classes keep their transcripts, in order
+    full = cells[0].class_map
+    active = (counts != 0).any(axis=0)
+    assert (cmap[1] == full[1][active[full[0]]]).all()
+    assert pruned.sum() == pytest.approx(counts.sum(), rel=1e-15)
+    # nothing to drop / everything zero: returned untouched
+    same_map, same = impute._prune_classes(full, numpy.ones((2, counts.shape[1])))
+    assert same_map is full and same.shape == (2, counts.shape[1])
+
+
+def test_blended_group_equals_blend_then_prune(gi):
+    w = gi['weight'] ** int(gi['power'])
+    dense = _first_round_results(gi)
+    impute._blend_mapping_results(dense, w)
+    cells = _first_round_results(gi)
+    for group in impute._support_groups(w):
+        class_map, counts = impute._blended_group(cells, w, group)
+        want_map, want = impute._prune_classes(dense[0].class_map,
+                                               numpy.stack([dense[i].class_count for i in group]))
+        assert (class_map == want_map).all() and class_map.dtype == want_map.dtype
+        assert (counts == want).all()
+    # the inputs are left as they were (the reference's blend renumbers them in place)
+    fresh = _first_round_results(gi)
+    assert all((a.class_map == b.class_map).all() for a, b in zip(cells, fresh))
