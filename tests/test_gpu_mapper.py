@@ -356,3 +356,67 @@ def test_pipelined_host_chunks_match_single_pass(orc, medium, ragged):
     for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
         assert (th[k] == td[k]).all(), k
     assert th['unaligned'] == td['unaligned'] and th['aligned'] == td['aligned']
+
+
+@pytest.fixture(scope='module')
+def long_tx(ref):
+    """Transcripts of 8-18 kb (60 exons) indexed by the reference assembler."""
+    tx = synth.make_transcriptome(40, seed=13, mean_exons=60, median_exon=200, max_isoforms=6)
+    return tx, ref.ref_build_index(tx.sequences())
+
+
+@pytest.mark.parametrize('paired', [True, False])
+def test_maximum_read_length(orc, long_tx, paired):
+    """Reads up to the 4096-base limit of the shared-memory staging (128 code words per read:
+    the kernel variant with the fewest item rows), ragged, 1 % substitutions: walks over ~35
+    contigs per read."""
+    tx, arrays = long_tx
+    sim = synth.ReadSimulator(tx, synth.make_expression(tx.n_transcripts, seed=3), 4096, 6000, 600,
+                              sub_rate=0.01, seed=43)
+    n = 400
+    raw = sim.generate(0, n)[0].tobytes()
+    rng = numpy.random.Generator(numpy.random.PCG64(44))
+    reads = []
+    for i in range(2 * n):
+        length = 4096 if i < 8 else int(rng.integers(1000, 4097))
+        reads.append(raw[i * 4096:i * 4096 + length])
+    bases, offs = orc.pack_reads(reads)
+    units = n if paired else 2 * n
+    table = check_against_oracle(orc, arrays, bases, offs, units, paired, batches=2)
+    assert table['aligned'] > units // 2
+
+
+def test_empty_oversized_and_unmappable_inputs(golden_synth):
+    from seekmer_b200 import common, infer, mapper
+    g = golden_synth
+    ix = _lib.DeviceIndex(*g.index_arrays(), 60)
+    mp = _lib.DeviceMapper(ix)
+    # an empty batch is a no-op and an empty dictionary exports cleanly
+    mp.map_batch(numpy.zeros(0, dtype='u1'), numpy.zeros(1, dtype='i8'), 0, True)
+    table = mp.export()
+    assert table['counts'].shape[0] == 0 and table['key_ids'].shape[0] == 0
+    assert table['aligned'] == 0 and table['unaligned'] == 0 and int(table['fld'].sum()) == 0
+    # one base more than the limit is refused, not truncated
+    with pytest.raises(_lib.SeekmerCudaError, match='4096'):
+        mp.map_batch(numpy.full(4097, ord('A'), dtype='u1'), numpy.asarray([0, 4097], dtype='i8'), 1, False)
+    # reads that hit nothing: all N, and a homopolymer run the index does not contain
+    junk = [b'N' * 100, b'N' * 100, b'A' * 80, b'C' * 80] * 50
+    bases = numpy.frombuffer(b''.join(junk), dtype='u1')
+    offs = numpy.concatenate([[0], numpy.cumsum([len(r) for r in junk])]).astype('i8')
+    cls, lens = mp.map_batch(bases, offs, 100, True, max_len=100, per_read=True)
+    table = mp.export()
+    assert (cls == -1).all() and table['unaligned'] == 100 and table['aligned'] == 0
+    assert table['counts'].shape[0] == 0 and int(table['fld'].sum()) == 0
+    mp.close()
+    ix.close()
+    # the same through the reference-facing API: nothing mapped -> zero abundances
+    index = common.KMerIndex(*g.index_arrays(), g['transcripts'], None)
+    for feeder in ([], [(100, [b'r%d' % i for i in range(100)], junk)]):
+        res = mapper.map_reads(index, iter(feeder))
+        s = res.summarize()
+        assert s.aligned == 0 and s.class_map.size == 0 and s.class_count.size == 0
+        assert s.unaligned == (100 if feeder else 0) and s.total == s.unaligned
+        tpm = infer.quantify(s)                                   # `infer.py:104-105`
+        assert tpm.shape == (60,) and (tpm == 0).all()
+        assert infer.quantify_bootstraps(s, tpm, 2)[1].shape == (60,)
+    index.release_device()
