@@ -31,6 +31,8 @@ def main():
     ap.add_argument('--pairs', type=int, default=50000)
     ap.add_argument('--power', type=int, default=16)
     ap.add_argument('--oracle-cells', type=int, default=2)
+    ap.add_argument('--fastq', action='store_true',
+                    help='also write every cell as FASTQ files and time `impute.run` end to end')
     args = ap.parse_args()
 
     import torch
@@ -51,6 +53,33 @@ def main():
     index._device[0] = dev_index
 
     programmes = [synth.make_expression(n_tx, seed=3 + p) for p in range(4)]
+    fastq_dir = None
+    fastq_paths = []
+    if args.fastq:
+        import tempfile
+        fastq_dir = tempfile.mkdtemp(dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
+
+    def write_fastq(cell, reads):
+        # fixed-width records written as one byte matrix: '@c<cell>.<pair>/<mate>', bases, '+', qualities
+        n, length = reads.shape[0], READ_LEN
+        idx = numpy.arange(n)
+        for mate in (0, 1):
+            rec = numpy.empty((n, 2 * length + 16), dtype='u1')
+            rec[:, 0] = ord('@')
+            for k in range(8):
+                rec[:, 8 - k] = 48 + (idx // 10 ** k) % 10
+            rec[:, 9] = ord('/')
+            rec[:, 10] = ord('1') + mate
+            rec[:, 11] = 10
+            rec[:, 12:12 + length] = reads[:, mate, :]
+            rec[:, 12 + length] = 10
+            rec[:, 13 + length] = ord('+')
+            rec[:, 14 + length] = 10
+            rec[:, 15 + length:15 + 2 * length] = ord('I')
+            rec[:, 15 + 2 * length] = 10
+            path = os.path.join(fastq_dir, 'cell%04d_%d.fastq' % (cell, mate + 1))
+            rec.tofile(path)
+            fastq_paths.append(path)
     d_bases = torch.empty(args.pairs * 2 * READ_LEN, dtype=torch.uint8, device=device)
     L = _lib.load()
 
@@ -65,6 +94,8 @@ def main():
             _lib._ptr(codes), _lib._ptr(offsets), n_tx, _lib._ptr(d_cum), int(cum[-1]), READ_LEN, FRAG_MEAN,
             FRAG_SD, int(round(0.01 * 65536)), int(round(0.001 * 65536)), 1, 1000 + cell, 1, 0, args.pairs,
             d_bases.data_ptr(), 0, _lib.current_stream_ptr()))
+        if fastq_dir is not None:
+            write_fastq(cell, d_bases.cpu().numpy().reshape(args.pairs, 2, READ_LEN))
         mp.reset()   # one device mapper for all cells, as mapper.map_multiple_samples does
         mp.map_batch(d_bases, None, args.pairs, True, first_unit=0, fixed_len=READ_LEN)
         table = mp.export()
@@ -119,6 +150,25 @@ def main():
     t['oracle_s_per_cell'] = (time.time() - t0) / max(k, 1)
     oracle_close = all(bool(numpy.allclose(tpm[i], want[i], rtol=1e-6, atol=0)) for i in range(k))
 
+    end_to_end = None
+    if fastq_dir is not None:
+        import pathlib
+        import shutil
+        host_index = common.KMerIndex(*built.numpy_arrays(), index.transcripts, None)
+        index_path = pathlib.Path(fastq_dir) / 'index.npz'
+        host_index.save(index_path)
+        out_dir = pathlib.Path(fastq_dir) / 'out'
+        t0 = time.time()
+        impute.run(index_path, out_dir, [pathlib.Path(p) for p in fastq_paths], job_count=1,
+                   single_ended=False, debug=False, power=args.power)
+        seconds = time.time() - t0
+        rows = [l.rstrip('\n').split(',') for l in open(str(out_dir / 'tpm.csv'))]
+        table = numpy.asarray([[float(v) for v in r[1:]] for r in rows[1:]]).T
+        end_to_end = {'impute_run_s': round(seconds, 3), 'cells_per_s': round(args.cells / seconds, 2),
+                      'fastq_gb': round(sum(os.path.getsize(p) for p in fastq_paths) / 1e9, 3),
+                      'tpm_csv_equals_in_memory_1e-9': bool(numpy.allclose(table, grouped, rtol=1e-9, atol=0))}
+        shutil.rmtree(fastq_dir, ignore_errors=True)
+
     shared = summarized[0].class_map
     line = {
         'workload': '%d cells x %d 2x%d pairs, %d transcripts, power %d' %
@@ -127,6 +177,7 @@ def main():
         'blended_classes': int(summarized[0].class_count.size), 'blended_nnz': int(shared.shape[1]),
         'weights_kept_per_cell_mean': float((weight != 0).sum(axis=1).mean()),
         'stages': {k_: round(v, 4) for k_, v in t.items()},
+        'from_fastq_files': end_to_end,
         'support_groups': len(impute._support_groups(powered)),
         'second_round_speedup_vs_per_cell_calls':
             round(t['second_round_one_call_per_cell_s'] / t['second_round_grouped_s'], 2),
