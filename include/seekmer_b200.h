@@ -220,6 +220,24 @@ int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, int64_t 
                      double *out_x, int32_t *out_iters, int buffers_on_device, int device,
                      void *stream);
 
+/* Replaces: `[infer.quantify(r) for r in map_results]` of the single-cell workflow
+ * (impute.py:101, mapper.py:196-234 samples) - n_samples independent EMs (infer.py:133-168),
+ * each with its OWN class structure, in one set of launches.  The samples' structures are
+ * laid end to end:
+ *   class_ptr[n_classes+1], class_tx[nnz]   CSR by class over all samples; class_tx holds the
+ *                                            transcript index within the class's own sample
+ *   sample_class_ptr[n_samples+1]           first class of every sample (0 ... n_classes)
+ *   counts[n_classes]                       fp64 class counts
+ *   eff_len, x0, out_x                      [n_samples][n_transcripts]
+ *   out_iters[n_samples]                    EM iterations each sample executed
+ * Every sample stops by its own convergence test and is then carried through unchanged;
+ * results are bit-identical to one skm_em call per sample. */
+int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx,
+                   const int64_t *sample_class_ptr, int64_t n_samples, int64_t n_classes,
+                   int64_t nnz, const double *counts, const double *eff_len,
+                   int64_t n_transcripts, const double *x0, int64_t max_iters, double *out_x,
+                   int32_t *out_iters, int buffers_on_device, int device, void *stream);
+
 /* Workload generation twin of seekmer_b200/synth.py (bench/test support, not
  * part of the reference surface): fills `bases` (device) with ASCII reads for
  * global units [first_unit, first_unit+n_units). */

@@ -25,7 +25,7 @@ EXPORTS = (
     'skm_last_error', 'skm_device_count', 'skm_version', 'skm_index_create', 'skm_index_destroy',
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
     'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
-    'skm_classes_merge', 'skm_classes_merge_packed', 'skm_effective_lengths', 'skm_em', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
+    'skm_classes_merge', 'skm_classes_merge_packed', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
     'skm_build_kmer_table',
 )
 
@@ -88,6 +88,8 @@ def load():
     L.skm_effective_lengths.argtypes = [vp, vp, i64, vp, ci, ci, vp]
     L.skm_em.restype = ci
     L.skm_em.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, vp, vp, ci, ci, vp]
+    L.skm_em_samples.restype = ci
+    L.skm_em_samples.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, ci, ci, vp]
     L.skm_em_bootstrap.restype = ci
     L.skm_em_bootstrap.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u64, i64, ci, vp, vp, ci, ci, vp]
     L.skm_multinomial.restype = ci

@@ -172,6 +172,9 @@ struct EmState {
     int32_t *n_active;          // scalar
     int64_t n_classes, n_tx;
     int R;
+    // many-samples variant (skm_em_samples): R counts samples, rows belong to one sample each
+    const int32_t *class_sample;  // [C] sample of a class
+    int64_t tx_per_sample;        // transcript rows are [sample][transcript]
 };
 
 // ---- E step: inner_c = (sum_{j in c} x[t_j]) / count_c  (infer.py:155-156,162-163) ----------
@@ -278,6 +281,88 @@ __global__ void em_decide_kernel(const EmState s)
     }
     __syncthreads();
     if (threadIdx.x == 0) *s.n_active = still;
+}
+
+// ---- many samples with their own class structures (skm_em_samples) ---------------------------
+// The samples' structures are laid end to end (classes, and transcript rows [sample][transcript],
+// class_tx already holding the global row), so one launch serves every sample that still runs.
+// Per row the arithmetic is that of the R == 1 kernels above, with the sample's own n, stop
+// flag and change maximum: results are bit-identical to one skm_em call per sample.
+__global__ void global_tx_kernel(const int32_t *__restrict__ class_tx, const int32_t *__restrict__ class_of,
+                                 const int32_t *__restrict__ class_sample, int64_t nnz, int64_t tx_per_sample,
+                                 int32_t *__restrict__ out, unsigned int *bad)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    const int32_t t = class_tx[j];
+    if (t < 0 || t >= tx_per_sample) {
+        atomicOr(bad, 1u);
+        out[j] = 0;
+        return;
+    }
+    out[j] = (int32_t)((int64_t)class_sample[class_of[j]] * tx_per_sample + t);
+}
+
+__global__ void sum_counts_samples_kernel(const double *__restrict__ counts, const int64_t *__restrict__ sample_class_ptr,
+                                          double *__restrict__ n_out)
+{
+    // one block per sample, the partition and tree of sum_counts_kernel over the sample's classes
+    const int64_t first = sample_class_ptr[blockIdx.x], last = sample_class_ptr[blockIdx.x + 1];
+    double local = 0.0;
+    for (int64_t c = first + threadIdx.x; c < last; c += blockDim.x) local += counts[c];
+    __shared__ double sm[EM_BLOCK];
+    sm[threadIdx.x] = local;
+    __syncthreads();
+    for (int s = EM_BLOCK / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_out[blockIdx.x] = sm[0];
+}
+
+__global__ void em_class_kernel_samples(const EmState s, const double *__restrict__ x)
+{
+    if (*s.n_active == 0) return;
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= s.n_classes) return;
+    if (!s.active[s.class_sample[c]]) return;
+    double sum = 0.0;
+    for (int64_t j = s.class_ptr[c]; j < s.class_ptr[c + 1]; ++j) sum = __dadd_rn(sum, x[s.class_tx[j]]);
+    s.inner[c] = __ddiv_rn(sum, s.counts[c]);
+}
+
+__global__ void em_tx_kernel_samples(const EmState s, const double *__restrict__ x, double *__restrict__ xn_out)
+{
+    if (*s.n_active == 0) return;
+    const int sub = threadIdx.x & 7;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+    const bool ok = g < s.n_tx;
+    int sample = 0;
+    bool live = false;
+    double acc = 0.0;
+    double xt = 0.0;
+    if (ok) {
+        sample = (int)(g / s.tx_per_sample);
+        live = s.active[sample] != 0;
+        xt = x[g];
+        if (live) {
+            const int64_t b = s.tx_ptr[g], e = s.tx_ptr[g + 1];
+            for (int64_t j = b + sub; j < e; j += 8) acc = __dadd_rn(acc, __ddiv_rn(xt, s.inner[s.tx_class[j]]));
+        }
+    }
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+    if (ok && sub == 0) {
+        if (!live) {
+            xn_out[g] = xt;  // a finished sample is carried through the ping-pong unchanged
+            return;
+        }
+        double v = __ddiv_rn(__ddiv_rn(acc, s.eff_len[g]), s.n[sample]);
+        if (v != v) v = 0.0;
+        note_change(s, sample, v, xt);
+        xn_out[g] = v;
+    }
 }
 
 __global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
@@ -825,6 +910,186 @@ SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_
         if (out_iters) EM_TRY(cudaMemcpyAsync(out_iters, d_iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
     }
+    return SKM_OK;
+}
+
+SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, const int64_t *sample_class_ptr,
+                           int64_t n_samples, int64_t n_classes, int64_t nnz, const double *counts,
+                           const double *eff_len, int64_t n_transcripts, const double *x0, int64_t max_iters,
+                           double *out_x, int32_t *out_iters, int buffers_on_device, int device, void *stream)
+{
+    if (!class_ptr || !class_tx || !sample_class_ptr || !counts || !eff_len || !x0 || !out_x)
+        return fail(SKM_ERR_INVALID, "skm_em_samples: NULL argument");
+    if (n_samples <= 0 || n_classes <= 0 || nnz <= 0 || n_transcripts <= 0)
+        return fail(SKM_ERR_INVALID, "skm_em_samples: empty problem");
+    const int64_t P = n_samples, C = n_classes, T = n_transcripts;
+    if (nnz >= (1LL << 31) || C >= (1LL << 31) || T >= (1LL << 31) || P >= (1LL << 31) / T)
+        return fail(SKM_ERR_INVALID, "skm_em_samples: structure too large for int32 indices");
+    if (skm_device_count() <= device || device < 0)
+        return fail(SKM_ERR_CUDA, "skm_em_samples: no such CUDA device (there is no CPU fallback)");
+    EM_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows = P * T;
+    if (max_iters <= 0) max_iters = 1000000;
+
+    // ---- inputs on the device --------------------------------------------------------------
+    DeviceBuf b_ptr, b_tx, b_sptr, b_cnt, b_len, b_xa, b_xb, b_iters_out;
+    std::vector<int64_t> h_sptr((size_t)P + 1);
+    EM_TRY(b_xa.alloc(sizeof(double) * (size_t)rows, st));
+    EM_TRY(b_xb.alloc(sizeof(double) * (size_t)rows, st));
+    const int64_t *d_ptr = class_ptr, *d_sptr = sample_class_ptr;
+    const int32_t *d_tx_local = class_tx;
+    const double *d_cnt = counts, *d_len = eff_len;
+    if (!buffers_on_device) {
+        EM_TRY(b_ptr.alloc(sizeof(int64_t) * (size_t)(C + 1), st));
+        EM_TRY(b_tx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+        EM_TRY(b_sptr.alloc(sizeof(int64_t) * (size_t)(P + 1), st));
+        EM_TRY(b_cnt.alloc(sizeof(double) * (size_t)C, st));
+        EM_TRY(b_len.alloc(sizeof(double) * (size_t)rows, st));
+        EM_TRY(cudaMemcpyAsync(b_ptr.p, class_ptr, sizeof(int64_t) * (size_t)(C + 1), cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_tx.p, class_tx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_sptr.p, sample_class_ptr, sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_cnt.p, counts, sizeof(double) * (size_t)C, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_len.p, eff_len, sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_xa.p, x0, sizeof(double) * (size_t)rows, cudaMemcpyHostToDevice, st));
+        d_ptr = b_ptr.as<int64_t>();
+        d_tx_local = b_tx.as<int32_t>();
+        d_sptr = b_sptr.as<int64_t>();
+        d_cnt = b_cnt.as<double>();
+        d_len = b_len.as<double>();
+        std::copy(sample_class_ptr, sample_class_ptr + P + 1, h_sptr.begin());
+    } else {
+        EM_TRY(cudaMemcpyAsync(b_xa.p, x0, sizeof(double) * (size_t)rows, cudaMemcpyDeviceToDevice, st));
+        EM_TRY(cudaMemcpyAsync(h_sptr.data(), sample_class_ptr, sizeof(int64_t) * (size_t)(P + 1),
+                               cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaStreamSynchronize(st));
+    }
+    if (h_sptr[0] != 0 || h_sptr[(size_t)P] != C)
+        return fail(SKM_ERR_INVALID, "skm_em_samples: sample_class_ptr must run from 0 to n_classes");
+    for (int64_t p = 0; p < P; ++p)
+        if (h_sptr[(size_t)p + 1] < h_sptr[(size_t)p])
+            return fail(SKM_ERR_INVALID, "skm_em_samples: sample_class_ptr is not monotone");
+
+    // ---- global rows, CSC by (sample, transcript): stable radix sort of (row, nnz index) ------
+    DeviceBuf b_csample, b_rowof, b_gtx, b_idx, b_keys_out, b_idx_out, b_txclass, b_hist, b_txptr, b_tmp, b_bad;
+    EM_TRY(b_csample.alloc(sizeof(int32_t) * (size_t)C, st));
+    EM_TRY(b_rowof.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_gtx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_idx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_keys_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_idx_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_txclass.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_hist.alloc(sizeof(unsigned long long) * (size_t)(rows + 1), st));
+    EM_TRY(b_txptr.alloc(sizeof(int64_t) * (size_t)(rows + 1), st));
+    EM_TRY(b_bad.alloc(sizeof(unsigned int), st));
+    EM_TRY(cudaMemsetAsync(b_hist.p, 0, sizeof(unsigned long long) * (size_t)(rows + 1), st));
+    EM_TRY(cudaMemsetAsync(b_bad.p, 0, sizeof(unsigned int), st));
+    expand_rows_kernel<<<blocks_for(P, 256), 256, 0, st>>>(d_sptr, P, b_csample.as<int32_t>());
+    expand_rows_kernel<<<blocks_for(C, 256), 256, 0, st>>>(d_ptr, C, b_rowof.as<int32_t>());
+    global_tx_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(d_tx_local, b_rowof.as<int32_t>(), b_csample.as<int32_t>(),
+                                                          nnz, T, b_gtx.as<int32_t>(), b_bad.as<unsigned int>());
+    iota_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_idx.as<int32_t>(), nnz);
+    histogram_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_gtx.as<int32_t>(), nnz, rows,
+                                                          b_hist.as<unsigned long long>(), b_bad.as<unsigned int>());
+    {
+        size_t tmp_sort = 0, tmp_scan = 0;
+        int end_bit = 1;
+        while ((1LL << end_bit) < rows) ++end_bit;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, b_gtx.as<int32_t>(), b_keys_out.as<int32_t>(),
+                                        b_idx.as<int32_t>(), b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st);
+        cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, b_hist.as<unsigned long long>(),
+                                      b_txptr.as<unsigned long long>(), (int)(rows + 1), st);
+        EM_TRY(b_tmp.alloc(std::max(tmp_sort, tmp_scan), st));
+        size_t tmp = std::max(tmp_sort, tmp_scan);
+        EM_TRY(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp, b_gtx.as<int32_t>(), b_keys_out.as<int32_t>(),
+                                               b_idx.as<int32_t>(), b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st));
+        tmp = std::max(tmp_sort, tmp_scan);
+        EM_TRY(cub::DeviceScan::InclusiveSum(b_tmp.p, tmp, b_hist.as<unsigned long long>(),
+                                             b_txptr.as<unsigned long long>(), (int)(rows + 1), st));
+    }
+    gather_i32_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_rowof.as<int32_t>(), b_idx_out.as<int32_t>(), nnz,
+                                                           b_txclass.as<int32_t>());
+    EM_TRY(cudaGetLastError());
+    {
+        unsigned int bad = 0;
+        EM_TRY(cudaMemcpyAsync(&bad, b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaStreamSynchronize(st));
+        if (bad) return fail(SKM_ERR_INVALID, "skm_em_samples: transcript index out of range in class_tx");
+    }
+
+    // ---- per-sample state ------------------------------------------------------------------
+    DeviceBuf b_inner, b_n, b_maxd, b_active, b_iters, b_nactive;
+    EM_TRY(b_inner.alloc(sizeof(double) * (size_t)C, st));
+    EM_TRY(b_n.alloc(sizeof(double) * (size_t)P, st));
+    EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * (size_t)P, st));
+    EM_TRY(b_active.alloc(sizeof(int32_t) * (size_t)P, st));
+    EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)P, st));
+    EM_TRY(b_nactive.alloc(sizeof(int32_t), st));
+    sum_counts_samples_kernel<<<(unsigned)P, EM_BLOCK, 0, st>>>(d_cnt, d_sptr, b_n.as<double>());
+    EM_TRY(cudaMemsetAsync(b_maxd.p, 0, sizeof(unsigned long long) * (size_t)P, st));
+    EM_TRY(cudaMemsetAsync(b_iters.p, 0, sizeof(int32_t) * (size_t)P, st));
+    fill_i32_kernel<<<blocks_for(P, 256), 256, 0, st>>>(b_active.as<int32_t>(), P, 1);
+    fill_i32_kernel<<<1, 32, 0, st>>>(b_nactive.as<int32_t>(), 1, (int32_t)P);
+
+    EmState s{};
+    s.class_ptr = d_ptr;
+    s.class_tx = b_gtx.as<int32_t>();
+    s.tx_ptr = b_txptr.as<int64_t>();
+    s.tx_class = b_txclass.as<int32_t>();
+    s.counts = d_cnt;
+    s.eff_len = d_len;
+    s.n = b_n.as<double>();
+    s.inner = b_inner.as<double>();
+    s.maxd = b_maxd.as<unsigned long long>();
+    s.active = b_active.as<int32_t>();
+    s.iters = b_iters.as<int32_t>();
+    s.n_active = b_nactive.as<int32_t>();
+    s.n_classes = C;
+    s.n_tx = rows;
+    s.R = (int)P;
+    s.class_sample = b_csample.as<int32_t>();
+    s.tx_per_sample = T;
+
+    // ---- iterations in groups, as em_core: launches after the last sample stopped are no-ops ----
+    const int GROUP = 8;
+    double *cur = b_xa.as<double>(), *nxt = b_xb.as<double>();
+    double *group_cur = cur, *group_nxt = nxt;
+    int64_t done = 0, group_base = 0;
+    int32_t n_active = (int32_t)P;
+    while (n_active > 0 && done < max_iters) {
+        const int g = (int)std::min<int64_t>(GROUP, max_iters - done);
+        group_cur = cur;
+        group_nxt = nxt;
+        group_base = done;
+        for (int k = 0; k < g; ++k) {
+            em_class_kernel_samples<<<blocks_for(C, EM_BLOCK), EM_BLOCK, 0, st>>>(s, cur);
+            em_tx_kernel_samples<<<blocks_for(rows * 8, EM_BLOCK), EM_BLOCK, 0, st>>>(s, cur, nxt);
+            em_decide_kernel<<<1, 128, 0, st>>>(s);
+            std::swap(cur, nxt);
+        }
+        done += g;
+        EM_TRY(cudaGetLastError());
+        EM_TRY(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaStreamSynchronize(st));
+    }
+    std::vector<int32_t> h_iters((size_t)P);
+    EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, st));
+    EM_TRY(cudaStreamSynchronize(st));
+    {
+        // the buffer written by the last EXECUTED iteration holds every sample's final x
+        const int64_t executed = *std::max_element(h_iters.begin(), h_iters.end());
+        const int64_t in_group = executed - group_base;
+        cur = (in_group & 1) ? group_nxt : group_cur;
+    }
+    EM_TRY(cudaMemcpyAsync(out_x, cur, sizeof(double) * (size_t)rows,
+                           buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (out_iters) {
+        if (buffers_on_device)
+            EM_TRY(cudaMemcpyAsync(out_iters, s.iters, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToDevice, st));
+        else
+            std::copy(h_iters.begin(), h_iters.end(), out_iters);
+    }
+    EM_TRY(cudaStreamSynchronize(st));  // scratch buffers are released after this
     return SKM_OK;
 }
 

@@ -98,7 +98,7 @@ def impute_cells(index, map_results, power=16, output_path=None, return_stages=F
     _merge_fragment_lengths(map_results)
     summarized = [r.summarize() for r in map_results]
     _LOG.info('First round quantification...')
-    base = numpy.asarray([infer.quantify(r) for r in summarized])
+    base = infer.quantify_samples(summarized)
     if power is None:
         return (base, base, None) if return_stages else base
     _LOG.info('Weighting cells.')

@@ -22,7 +22,7 @@ from . import common
 from . import mapper
 from ._log import Logger
 
-__all__ = ['run', 'quantify', 'quantify_bootstraps', 'em', 'output_results',
+__all__ = ['run', 'quantify', 'quantify_bootstraps', 'quantify_samples', 'em', 'output_results',
            'add_subcommand_parser']
 
 _LOG = Logger(__name__)
@@ -170,6 +170,53 @@ def quantify_bootstraps(results, x0, n_replicates, seed=None, return_iters=False
         _lib._np_ptr(transcript_length), x.shape[0], _lib._np_ptr(x), n_replicates, first_replicate,
         int(seed) & (2 ** 64 - 1), 0, 1, _lib._np_ptr(xs), _lib._np_ptr(iters), 0, 0, None))
     out = list(xs)  # TPM post-processing (`infer.py:127-129`) already applied on the device
+    return (out, iters) if return_iters else out
+
+
+def quantify_samples(results_list, return_iters=False, device=0):
+    """`[quantify(r) for r in results_list]` for samples that share the transcript set (the first
+    round of `impute.py:101`): every sample keeps its own class structure, counts, effective
+    lengths and stopping point, but all of them iterate in the same launches
+    (`skm_em_samples`).  Bit-identical to the loop."""
+    n_tx = results_list[0].effective_lengths.size if results_list else 0
+    out = numpy.zeros((len(results_list), n_tx), dtype='f8')
+    iters = numpy.zeros(len(results_list), dtype='i4')
+    live = [i for i, r in enumerate(results_list) if r.class_map.size]  # `infer.py:104-105`
+    if live:
+        ptrs, txs, counts, lengths, x0 = [], [], [], [], []
+        first_class = numpy.zeros(len(live) + 1, dtype='i8')
+        nnz = 0
+        for k, i in enumerate(live):
+            r = results_list[i]
+            if r.effective_lengths.size != n_tx:
+                raise ValueError('quantify_samples: samples must share the transcript set')
+            count = numpy.ascontiguousarray(r.class_count, dtype='f8')
+            ptr, tx = _csr_from_class_map(r.class_map, count.shape[0])
+            ptrs.append(ptr[:-1] + nnz)
+            nnz += int(ptr[-1])
+            txs.append(tx)
+            counts.append(count)
+            first_class[k + 1] = first_class[k] + count.shape[0]
+            length = r.effective_lengths.astype('f8')
+            x = numpy.ones(n_tx, dtype='f8') / length
+            x /= x.sum()
+            lengths.append(length)
+            x0.append(x)
+        ptr = numpy.ascontiguousarray(numpy.concatenate(ptrs + [numpy.asarray([nnz], dtype='i8')]), dtype='i8')
+        tx = numpy.ascontiguousarray(numpy.concatenate(txs), dtype='i4')
+        counts = numpy.ascontiguousarray(numpy.concatenate(counts), dtype='f8')
+        lengths = numpy.ascontiguousarray(numpy.stack(lengths), dtype='f8')
+        x0 = numpy.ascontiguousarray(numpy.stack(x0), dtype='f8')
+        xs = numpy.zeros_like(x0)
+        its = numpy.zeros(len(live), dtype='i4')
+        _lib.require_device()
+        _lib.check(_lib.load().skm_em_samples(
+            _lib._np_ptr(ptr), _lib._np_ptr(tx), _lib._np_ptr(first_class), len(live), counts.shape[0],
+            tx.shape[0], _lib._np_ptr(counts), _lib._np_ptr(lengths), n_tx, _lib._np_ptr(x0), 0,
+            _lib._np_ptr(xs), _lib._np_ptr(its), 0, device, None))
+        for k, i in enumerate(live):
+            out[i] = _finish(xs[k])
+            iters[i] = its[k]
     return (out, iters) if return_iters else out
 
 

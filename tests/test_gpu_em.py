@@ -118,3 +118,40 @@ def test_effective_lengths_bit_exact(orc):
     mr = mapper.MapResult(FakeIndex(lengths))
     mr.fragment_length_counts = fld
     assert (mr.effective_lengths == orc.effective_lengths(fld, lengths)).all()
+
+
+def test_em_samples_bit_identical_to_one_call_per_sample(golden_synth):
+    """`skm_em_samples`: samples with different class structures, counts, effective lengths and
+    iteration counts in one set of launches == `infer.quantify` sample by sample (bit for bit),
+    and == the reference's first-round results of the impute fixture (1e-6)."""
+    from conftest import GOLDEN, Golden
+    from test_impute_host import _first_round_results
+    gi = Golden(GOLDEN / 'impute_small.npz')
+    g = golden_synth
+    cells = _first_round_results(gi)                                   # 8 structures, shared lengths
+    bulk = [summarized(g, case + '_', g['transcripts']['length']) for case in sorted(SYNTH_CASES)]
+    empty = mapper.SummarizedResult(0, 5, 5, numpy.asarray([]).T, numpy.zeros(0), g['pe100_fld'],
+                                    bulk[0].effective_lengths)
+    samples = cells[:3] + [empty] + bulk + cells[3:]
+    got, iters = infer.quantify_samples(samples, return_iters=True)
+    assert got.shape == (len(samples), 60)
+    for i, r in enumerate(samples):
+        want = infer.quantify(r)
+        assert (got[i] == want).all(), i
+        if r.class_map.size:
+            eff = r.effective_lengths.astype('f8')
+            x0 = numpy.ones(eff.size) / eff
+            x0 /= x0.sum()
+            assert iters[i] == infer.em(x0, eff, r.class_map, r.class_count, return_iters=True)[1]
+    assert len(set(iters.tolist())) > 3          # the samples do stop at different iterations
+    assert (got[3] == 0).all() and iters[3] == 0
+    for k, case in enumerate(sorted(SYNTH_CASES)):
+        assert iters[4 + k] == int(g[case + '_em_iters'])
+        assert rel_close(got[4 + k], g[case + '_tpm'])
+    base = numpy.concatenate([got[:3], got[7:]])
+    assert rel_close(base, gi['base'])
+    # error behaviour: a transcript index outside the sample's range is refused
+    bad = mapper.SummarizedResult(10, 0, 10, numpy.asarray([[0, 0], [1, 60]]), numpy.asarray([10.0]),
+                                  g['pe100_fld'], bulk[0].effective_lengths)
+    with pytest.raises(_lib.SeekmerCudaError, match='out of range'):
+        infer.quantify_samples([cells[0], bad])
