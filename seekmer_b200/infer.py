@@ -31,7 +31,7 @@ _LOG = Logger(__name__)
 def run(index_path, output_path, fastq_paths, job_count, save_readmap, single_ended, bootstrap,
         debug, **__):
     """The entrypoint of the inference module (`infer.py:27-85`)."""
-    start_time = datetime.datetime.utcnow()
+    start_time = datetime.datetime.now(datetime.timezone.utc).replace(tzinfo=None)  # utcnow() of `infer.py:48`
     try:
         output_path.mkdir(parents=True)
     except FileExistsError:
