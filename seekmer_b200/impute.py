@@ -245,7 +245,10 @@ def _quantify_weighted(map_results, weight):
     x0 /= x0.sum()
     for group in _support_groups(weight):
         if not (numpy.asarray(weight)[group[0]] != 0).any():
-            raise ValueError('a cell without any weighted cell cannot be quantified')
+            # no gene table to correlate (e.g. nothing mapped): the reference fails on such a
+            # cell (`impute.py:240`, indexing its empty class_map); here it is reported as zeros
+            _LOG.warn('{} cell(s) without any weighted cell: abundances left at zero', len(group))
+            continue
         class_map, counts = _blended_group(map_results, weight, group)
         per_call = max(1, _EM_BATCH_BYTES // max(8 * counts.shape[1], 1))
         for start in range(0, len(group), per_call):

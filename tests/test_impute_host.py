@@ -176,3 +176,9 @@ def test_blended_group_equals_blend_then_prune(gi):
     # the inputs are left as they were (the reference's blend renumbers them in place)
     fresh = _first_round_results(gi)
     assert all((a.class_map == b.class_map).all() for a, b in zip(cells, fresh))
+
+
+def test_cells_without_support_are_reported_as_zeros(gi):
+    cells = _first_round_results(gi)[:2]
+    out = impute._quantify_weighted(cells, numpy.zeros((2, 2)))   # no device work to do
+    assert out.shape == (2, 60) and (out == 0).all()
