@@ -14,10 +14,11 @@ What changes underneath:
     the cells, N EMs over N-times-larger inputs (`impute.py:110-115`).  Cells drawing on the
     same set of cells are batched into one call over just those cells' classes
     (`_quantify_weighted`); zero-count classes add exactly 0 to the EM sums;
-  * the two-cluster split of the correlation values is solved exactly (sorted prefix sums)
-    instead of by sklearn's randomly initialised Lloyd iteration (`impute.py:213-214`, no
-    random_state): deterministic, and equal to what the reference converges to whenever its
-    iteration is not trapped in a worse local optimum.
+  * the two-cluster split of the correlation values is, by default, the reference's own
+    scikit-learn call (`impute.py:213-214`: `KMeans(2)`, unseeded, stopped by tolerance) so
+    that a seeded run reproduces the reference's weights entry for entry; `CLUSTERING =
+    'exact'` switches to the optimal split by sorted prefix sums (deterministic; differs from
+    the iterative result only for values within ~0.01 of the threshold).
 `_calculate_uniquely_mapped_counts` (`impute.py:144-179`) has no caller in the reference and
 is not reproduced.  There is no CPU EM fallback.
 """
@@ -36,6 +37,9 @@ _LOG = Logger(__name__)
 
 # class-count matrix handed to one skm_em call (fp64, cells x blended classes)
 _EM_BATCH_BYTES = 2 << 30
+
+# how the cell-cell correlations are split in two (`_high_cluster`): 'reference' or 'exact'
+CLUSTERING = 'reference'
 
 
 def add_subcommand_parser(subparsers):
@@ -89,7 +93,8 @@ def run(index_path, output_path, fastq_paths, job_count, single_ended, debug, po
     table.to_csv(output_path / 'tpm.csv')
 
 
-def impute_cells(index, map_results, power=16, output_path=None, return_stages=False):
+def impute_cells(index, map_results, power=16, output_path=None, return_stages=False,
+                 clustering=None):
     """Everything of `impute.run` between mapping and the final table (`impute.py:99-122`):
     merge the fragment lengths, quantify every cell, weight the cells by the correlation of
     their gene tables, blend the class counts and quantify again.  Returns the cell-by-
@@ -102,7 +107,7 @@ def impute_cells(index, map_results, power=16, output_path=None, return_stages=F
     if power is None:
         return (base, base, None) if return_stages else base
     _LOG.info('Weighting cells.')
-    weight = _calculate_cell_weights(index, base, output_path)
+    weight = _calculate_cell_weights(index, base, output_path, clustering)
     _LOG.info('Second round quantification...')
     tpm = _quantify_weighted(summarized, weight ** power)
     return (tpm, base, weight) if return_stages else tpm
@@ -158,10 +163,33 @@ def _two_means(values):
     return low_sum[best] / k[best], high_sum[best] / (n - k[best])
 
 
-def _calculate_cell_weights(index, base_matrix, output_path):
+def _high_cluster(values, matrix, clustering):
+    """Which entries of `matrix` fall into the higher of the two clusters of `values`.
+
+    'reference': the reference's own procedure (`impute.py:213-218`) — scikit-learn's
+    `KMeans(2)` with its defaults, initialised from numpy's global RNG and stopped by its
+    tolerance, labels from `predict`.  Seeding numpy reproduces the reference's weights entry
+    for entry; unseeded, boundary values can land on either side from run to run, exactly as
+    they do in the reference.
+    'exact': the optimal split (`_two_means`), deterministic; never a worse clustering than
+    the iterative one and the same labels except for values within ~0.01 of the threshold."""
+    if clustering == 'exact':
+        low, high = _two_means(values)
+        return numpy.abs(matrix - high) < numpy.abs(matrix - low)
+    if clustering != 'reference':
+        raise ValueError(f'unknown clustering: {clustering!r}')
+    import sklearn.cluster
+    model = sklearn.cluster.KMeans(2)
+    model.fit(numpy.asarray(values, dtype='f8').reshape(-1, 1))
+    labels = model.predict(matrix.reshape(-1, 1)).reshape(matrix.shape)
+    return labels == int(numpy.argmax(model.cluster_centers_.ravel()))
+
+
+def _calculate_cell_weights(index, base_matrix, output_path, clustering=None):
     """Cell-by-cell weights (`impute.py:182-224`): Pearson correlation of the integer gene
     tables; the correlations other than NaN and exactly 1.0 are split into two clusters and only
-    pairs falling nearer the higher centre keep their weight."""
+    pairs falling into the higher one keep their weight.  `clustering`: see `_high_cluster`
+    (default: module constant `CLUSTERING`)."""
     gene_matrix, names = _gene_matrix(index, base_matrix)
     if output_path is not None:
         import pandas
@@ -170,9 +198,9 @@ def _calculate_cell_weights(index, base_matrix, output_path):
     with numpy.errstate(all='ignore'):
         weights = numpy.atleast_2d(numpy.corrcoef(gene_matrix))
     valid = ~numpy.isnan(weights)
-    low, high = _two_means(weights[valid & (weights != 1.0)])
+    values = weights[valid & (weights != 1.0)]
     weights[~valid] = 0.0
-    keep = numpy.abs(weights - high) < numpy.abs(weights - low)
+    keep = _high_cluster(values, weights, CLUSTERING if clustering is None else clustering)
     weights = numpy.where(keep, weights, 0.0)
     if output_path is not None:
         import pandas

@@ -30,6 +30,7 @@ def test_impute_cells_matches_reference(gi, golden_synth, small_tx, tmp_path):
     index = _index(gi, golden_synth)
     feeders = [iter(ic.cell_batches(small_tx, c, batch=600)) for c in range(ic.N_CELLS)]
     results = mapper.map_multiple_samples(index, feeders, job_count=3)
+    numpy.random.seed(1)   # the reference draws its KMeans initialisation from numpy's global RNG
     tpm, base, weight = impute.impute_cells(index, results, power=ic.POWER, output_path=tmp_path,
                                             return_stages=True)
     assert (results[0].fragment_length_counts == gi['fld']).all()
