@@ -6,8 +6,9 @@ output folder (run_info.json, abundance.tsv, abundance.h5, optional readmap.txt)
 What changes underneath: `em` runs as fp64 segmented-reduction kernels (`skm_em`); the
 bootstrap resampling of `quantify(..., bootstrap=True)` is an on-device multinomial
 (`skm_multinomial`); and `run` batches all bootstrap replicates through one EM call
-(`quantify_bootstraps`) instead of the reference's serial loop (`infer.py:79-82`).
-There is no CPU EM fallback.
+(`quantify_bootstraps`) instead of the reference's serial loop (`infer.py:79-82`);
+`quantify_samples` does the same for many samples with their own class structures
+(`skm_em_samples`, used by `impute`).  There is no CPU EM fallback.
 """
 import datetime
 import json
@@ -173,6 +174,11 @@ def quantify_bootstraps(results, x0, n_replicates, seed=None, return_iters=False
     return (out, iters) if return_iters else out
 
 
+# transcript rows (samples x transcripts) handed to one skm_em_samples call: ~40 B of device
+# memory per row, and row indices are 32-bit
+_SAMPLE_ROWS_PER_CALL = 1 << 27
+
+
 def quantify_samples(results_list, return_iters=False, device=0):
     """`[quantify(r) for r in results_list]` for samples that share the transcript set (the first
     round of `impute.py:101`): every sample keeps its own class structure, counts, effective
@@ -182,42 +188,50 @@ def quantify_samples(results_list, return_iters=False, device=0):
     out = numpy.zeros((len(results_list), n_tx), dtype='f8')
     iters = numpy.zeros(len(results_list), dtype='i4')
     live = [i for i, r in enumerate(results_list) if r.class_map.size]  # `infer.py:104-105`
-    if live:
-        ptrs, txs, counts, lengths, x0 = [], [], [], [], []
-        first_class = numpy.zeros(len(live) + 1, dtype='i8')
-        nnz = 0
-        for k, i in enumerate(live):
-            r = results_list[i]
-            if r.effective_lengths.size != n_tx:
-                raise ValueError('quantify_samples: samples must share the transcript set')
-            count = numpy.ascontiguousarray(r.class_count, dtype='f8')
-            ptr, tx = _csr_from_class_map(r.class_map, count.shape[0])
-            ptrs.append(ptr[:-1] + nnz)
-            nnz += int(ptr[-1])
-            txs.append(tx)
-            counts.append(count)
-            first_class[k + 1] = first_class[k] + count.shape[0]
-            length = r.effective_lengths.astype('f8')
-            x = numpy.ones(n_tx, dtype='f8') / length
-            x /= x.sum()
-            lengths.append(length)
-            x0.append(x)
-        ptr = numpy.ascontiguousarray(numpy.concatenate(ptrs + [numpy.asarray([nnz], dtype='i8')]), dtype='i8')
-        tx = numpy.ascontiguousarray(numpy.concatenate(txs), dtype='i4')
-        counts = numpy.ascontiguousarray(numpy.concatenate(counts), dtype='f8')
-        lengths = numpy.ascontiguousarray(numpy.stack(lengths), dtype='f8')
-        x0 = numpy.ascontiguousarray(numpy.stack(x0), dtype='f8')
-        xs = numpy.zeros_like(x0)
-        its = numpy.zeros(len(live), dtype='i4')
-        _lib.require_device()
-        _lib.check(_lib.load().skm_em_samples(
-            _lib._np_ptr(ptr), _lib._np_ptr(tx), _lib._np_ptr(first_class), len(live), counts.shape[0],
-            tx.shape[0], _lib._np_ptr(counts), _lib._np_ptr(lengths), n_tx, _lib._np_ptr(x0), 0,
-            _lib._np_ptr(xs), _lib._np_ptr(its), 0, device, None))
-        for k, i in enumerate(live):
+    per_call = max(1, _SAMPLE_ROWS_PER_CALL // max(n_tx, 1))
+    for start in range(0, len(live), per_call):
+        chunk = live[start:start + per_call]
+        xs, its = _em_samples_device([results_list[i] for i in chunk], n_tx, device)
+        for k, i in enumerate(chunk):
             out[i] = _finish(xs[k])
             iters[i] = its[k]
     return (out, iters) if return_iters else out
+
+
+def _em_samples_device(samples, n_tx, device=0):
+    """One `skm_em_samples` call: the samples' class structures laid end to end.  Returns the
+    EM results (samples x transcripts, before the TPM step) and the iteration counts."""
+    ptrs, txs, counts, lengths, x0 = [], [], [], [], []
+    first_class = numpy.zeros(len(samples) + 1, dtype='i8')
+    nnz = 0
+    for k, r in enumerate(samples):
+        if r.effective_lengths.size != n_tx:
+            raise ValueError('quantify_samples: samples must share the transcript set')
+        count = numpy.ascontiguousarray(r.class_count, dtype='f8')
+        ptr, tx = _csr_from_class_map(r.class_map, count.shape[0])
+        ptrs.append(ptr[:-1] + nnz)
+        nnz += int(ptr[-1])
+        txs.append(tx)
+        counts.append(count)
+        first_class[k + 1] = first_class[k] + count.shape[0]
+        length = r.effective_lengths.astype('f8')
+        x = numpy.ones(n_tx, dtype='f8') / length
+        x /= x.sum()
+        lengths.append(length)
+        x0.append(x)
+    ptr = numpy.ascontiguousarray(numpy.concatenate(ptrs + [numpy.asarray([nnz], dtype='i8')]), dtype='i8')
+    tx = numpy.ascontiguousarray(numpy.concatenate(txs), dtype='i4')
+    counts = numpy.ascontiguousarray(numpy.concatenate(counts), dtype='f8')
+    lengths = numpy.ascontiguousarray(numpy.stack(lengths), dtype='f8')
+    x0 = numpy.ascontiguousarray(numpy.stack(x0), dtype='f8')
+    xs = numpy.zeros_like(x0)
+    its = numpy.zeros(len(samples), dtype='i4')
+    _lib.require_device()
+    _lib.check(_lib.load().skm_em_samples(
+        _lib._np_ptr(ptr), _lib._np_ptr(tx), _lib._np_ptr(first_class), len(samples), counts.shape[0],
+        tx.shape[0], _lib._np_ptr(counts), _lib._np_ptr(lengths), n_tx, _lib._np_ptr(x0), 0,
+        _lib._np_ptr(xs), _lib._np_ptr(its), 0, device, None))
+    return xs, its
 
 
 # ---- writers (`infer.py:171-325`) -------------------------------------------------------------

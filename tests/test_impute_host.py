@@ -189,3 +189,34 @@ def test_cells_without_support_are_reported_as_zeros(gi):
     cells = _first_round_results(gi)[:2]
     out = impute._quantify_weighted(cells, numpy.zeros((2, 2)))   # no device work to do
     assert out.shape == (2, 60) and (out == 0).all()
+
+
+def test_quantify_samples_chunks_keep_their_places(gi, orc, monkeypatch):
+    """Host bookkeeping of `infer.quantify_samples` (which samples go into which device call,
+    where their rows land, empty samples), with the device call replaced by the oracle's EM."""
+    from seekmer_b200 import infer
+    calls = []
+
+    def fake_call(samples, n_tx, device=0):
+        calls.append(len(samples))
+        xs, its = [], []
+        for r in samples:
+            eff = r.effective_lengths.astype('f8')
+            x0 = numpy.ones(n_tx) / eff
+            x0 /= x0.sum()
+            x, it = orc.em(x0, eff, r.class_map, r.class_count, return_iters=True)
+            xs.append(x)
+            its.append(it)
+        return numpy.stack(xs), numpy.asarray(its, dtype='i4')
+
+    monkeypatch.setattr(infer, '_em_samples_device', fake_call)
+    monkeypatch.setattr(infer, '_SAMPLE_ROWS_PER_CALL', 3 * 60)          # three samples per call
+    cells = _first_round_results(gi)
+    empty = mapper.SummarizedResult(0, 2, 2, numpy.asarray([]).T, numpy.zeros(0), gi['fld'], gi['eff_lengths'])
+    samples = [empty] + cells[:4] + [empty] + cells[4:]
+    got, iters = infer.quantify_samples(samples, return_iters=True)
+    assert calls == [3, 3, 2]
+    live = [i for i in range(len(samples)) if i not in (0, 5)]
+    assert numpy.allclose(got[live], gi['base'], rtol=1e-12, atol=0)
+    assert (got[[0, 5]] == 0).all() and (iters[[0, 5]] == 0).all() and (iters[live] > 0).all()
+    assert infer.quantify_samples([]).shape == (0, 0)
