@@ -126,9 +126,10 @@ int skm_mapper_reset(skm_mapper *mapper, void *stream);
  *   out_class     optional int32[n_units]: dictionary slot of the unit's class,
  *                 -1 = unaligned  (for -m readmap and per-read parity tests)
  *   out_length    optional int32[n_units]: span.end - span.begin + k (:90)
- * Reads shorter than k are undefined in the reference; here the call fails
- * with SKM_ERR_INVALID when read_offsets are on the host, and such reads are
- * reported unaligned when they are on the device.
+ * Reads shorter than k are undefined in the reference (_kmer.pxd:46-68 reads past
+ * their end).  Here they are legal input (trimmed FASTQ): a unit with such a read is
+ * reported unaligned with span length 0, and the reads are counted (skm_classes_size).
+ * Reads longer than 4096 bases are refused with SKM_ERR_INVALID.
  */
 int skm_map_batch(skm_mapper *mapper, const uint8_t *bases, const int64_t *read_offsets,
                   int32_t fixed_read_len, int32_t max_read_len, int64_t n_units, int paired,
@@ -153,8 +154,9 @@ int skm_map_fastq(skm_mapper *mapper, const uint8_t *text1, int64_t n1, const ui
 int skm_mapper_kernel_ms(skm_mapper *mapper, double ms[3]);
 
 /* sizes[0]=n_classes, [1]=total ids, [2]=unaligned units, [3]=aligned units,
- * [4]=class slots capacity, [5]=status flags raised on device (0 = none) */
-int skm_classes_size(skm_mapper *mapper, int64_t sizes[6], void *stream);
+ * [4]=class slots capacity, [5]=status flags raised on device (0 = none),
+ * [6]=reads shorter than k seen (their units are part of [2]), [7]=id-pool cursor */
+int skm_classes_size(skm_mapper *mapper, int64_t sizes[8], void *stream);
 
 /* Replaces: reading MapResult.counter / fragment_length_counts
  * (mapper.py:54-58) — the dictionary compacted to CSR.  Classes come out in
@@ -178,6 +180,13 @@ int skm_classes_merge(skm_mapper *mapper, const int64_t *key_offsets, const int3
  * key_ids (int32)]; the block of `rank` itself is skipped. */
 int skm_classes_merge_packed(skm_mapper *mapper, const int64_t *gathered, int64_t words_per_rank,
                              int world, int rank, void *stream);
+
+/* The EM entry points keep their large scratch blocks cached per device between calls (a
+ * cudaMalloc/cudaFree pair per call cost more than the EM); at most 8 GiB stay idle, and the
+ * cache is emptied before an allocation is reported as failed.  This gives every idle cached
+ * block back to the driver (e.g. before another library needs the memory); *freed_bytes may
+ * be NULL.  No reference counterpart (the reference's scratch is malloc/free inside the call). */
+int skm_release_cache(int device, int64_t *freed_bytes);
 
 /* Replaces: MapResult.effective_lengths (mapper.py:134-141), fp64, same
  * accumulation order. */

@@ -168,8 +168,6 @@ def map_batch(index, bases, offsets, paired, counters=False):
     bases = numpy.ascontiguousarray(bases, dtype='u1')
     offsets = numpy.ascontiguousarray(offsets, dtype='i8')
     n_reads = offsets.shape[0] - 1
-    if n_reads and int((offsets[1:] - offsets[:-1]).min()) < K:
-        raise ValueError('reads shorter than k=25 are undefined in the reference')
     n_units = n_reads // 2 if paired else n_reads
     out = MapOutput()
     out.ptr = numpy.zeros(n_units + 1, dtype='i8')

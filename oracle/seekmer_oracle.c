@@ -23,7 +23,8 @@
  *   - 64-bit arithmetic where the reference truncates int64 contig offsets to
  *     C int (_common.pyx:124,165-166); identical below 2 GiB of pooled sequence.
  *   - reads shorter than k=25 are undefined behaviour in the reference
- *     (_kmer.pxd:65 reads past the buffer); here they are rejected by the caller.
+ *     (_kmer.pxd:65 reads past the buffer); here a unit with such a read is
+ *     DEFINED to be unaligned with span length 0 (map_unit below).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -593,6 +594,26 @@ static skmo_span map_read_pair(const skmo_index *ix, skmo_seq read1, skmo_seq re
  * out_ptr[n_units + 1]; out_ids capacity out_cap; returns total ids, or
  * -(needed) if out_cap was too small (ptr/len/fld are still complete).
  */
+/* A read shorter than k is undefined behaviour in the reference (_kmer.pxd:46-68 reads past its
+ * end).  The behaviour is DEFINED here, for the oracle and the CUDA path alike: a unit with such
+ * a read is unaligned (empty tuple) with span length 0, whatever its mate maps to. */
+static skmo_span map_unit(const skmo_index *ix, const char *bases, const int64_t *offsets, int64_t i, int paired)
+{
+    if (!paired) {
+        skmo_seq r = {(int)(offsets[i + 1] - offsets[i]), bases + offsets[i]};
+        if (r.length >= SKMO_K) return map_read(ix, r);
+    } else {
+        skmo_seq r1 = {(int)(offsets[2 * i + 1] - offsets[2 * i]), bases + offsets[2 * i]};
+        skmo_seq r2 = {(int)(offsets[2 * i + 2] - offsets[2 * i + 1]), bases + offsets[2 * i + 1]};
+        if (r1.length >= SKMO_K && r2.length >= SKMO_K) return map_read_pair(ix, r1, r2);
+    }
+    skmo_span span;
+    memset(&span, 0, sizeof(span));
+    span.begin = 0;
+    span.end = -SKMO_K;
+    return span;
+}
+
 int64_t skmo_map_batch(const skmo_index *ix, const char *bases, const int64_t *offsets,
                        int64_t n_units, int paired, int64_t *out_ptr, int32_t *out_ids,
                        int64_t out_cap, int32_t *out_length, int64_t *fld, skmo_counters *counters)
@@ -601,15 +622,7 @@ int64_t skmo_map_batch(const skmo_index *ix, const char *bases, const int64_t *o
     g_cnt = counters;
     out_ptr[0] = 0;
     for (int64_t i = 0; i < n_units; ++i) {
-        skmo_span span;
-        if (!paired) {
-            skmo_seq r = {(int)(offsets[i + 1] - offsets[i]), bases + offsets[i]};
-            span = map_read(ix, r);
-        } else {
-            skmo_seq r1 = {(int)(offsets[2 * i + 1] - offsets[2 * i]), bases + offsets[2 * i]};
-            skmo_seq r2 = {(int)(offsets[2 * i + 2] - offsets[2 * i + 1]), bases + offsets[2 * i + 1]};
-            span = map_read_pair(ix, r1, r2);
-        }
+        skmo_span span = map_unit(ix, bases, offsets, i, paired);
         int length = span.end - span.begin + SKMO_K;
         if (out_length) out_length[i] = length;
         if (length > 0) {
@@ -656,15 +669,7 @@ int64_t skmo_map_batch_mt(const skmo_index *ix, const char *bases, const int64_t
         memset(local_fld, 0, sizeof(local_fld));
 #pragma omp for schedule(dynamic, 4096)
         for (int64_t i = 0; i < n_units; ++i) {
-            skmo_span span;
-            if (!paired) {
-                skmo_seq r = {(int)(offsets[i + 1] - offsets[i]), bases + offsets[i]};
-                span = map_read(ix, r);
-            } else {
-                skmo_seq r1 = {(int)(offsets[2 * i + 1] - offsets[2 * i]), bases + offsets[2 * i]};
-                skmo_seq r2 = {(int)(offsets[2 * i + 2] - offsets[2 * i + 1]), bases + offsets[2 * i + 1]};
-                span = map_read_pair(ix, r1, r2);
-            }
+            skmo_span span = map_unit(ix, bases, offsets, i, paired);
             int length = span.end - span.begin + SKMO_K;
             if (out_length) out_length[i] = length;
             if (length > 0) {

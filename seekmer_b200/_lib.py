@@ -25,7 +25,7 @@ EXPORTS = (
     'skm_last_error', 'skm_device_count', 'skm_version', 'skm_index_create', 'skm_index_destroy',
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
     'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
-    'skm_classes_merge', 'skm_classes_merge_packed', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
+    'skm_classes_merge', 'skm_classes_merge_packed', 'skm_release_cache', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
     'skm_build_kmer_table',
 )
 
@@ -84,6 +84,8 @@ def load():
     L.skm_classes_merge.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, ci, vp]
     L.skm_classes_merge_packed.restype = ci
     L.skm_classes_merge_packed.argtypes = [vp, vp, i64, ci, ci, vp]
+    L.skm_release_cache.restype = ci
+    L.skm_release_cache.argtypes = [ci, vp]
     L.skm_effective_lengths.restype = ci
     L.skm_effective_lengths.argtypes = [vp, vp, i64, vp, ci, ci, vp]
     L.skm_em.restype = ci
@@ -268,9 +270,9 @@ class DeviceMapper:
         return dict(zip(('pack_reads_kernel', 'map_reads_kernel', 'tally_units_kernel'), a.tolist()))
 
     def sizes(self, stream=None):
-        a = numpy.zeros(6, dtype='i8')
+        a = numpy.zeros(8, dtype='i8')
         check(load().skm_classes_size(self._h, _np_ptr(a), stream))
-        keys = ('n_classes', 'n_ids', 'unaligned', 'aligned', 'capacity', 'status')
+        keys = ('n_classes', 'n_ids', 'unaligned', 'aligned', 'capacity', 'status', 'short_reads', 'pool_cursor')
         return dict(zip(keys, a.tolist()))
 
     def export(self, with_slots=False, stream=None):
@@ -297,7 +299,7 @@ class DeviceMapper:
                       + numpy.arange(n_ids, dtype='i8'))
             ids = ids[gather]
         out = dict(key_offsets=new_off, key_ids=ids, counts=counts[order], first_unit=first[order],
-                   fld=fld, unaligned=sz['unaligned'], aligned=sz['aligned'])
+                   fld=fld, unaligned=sz['unaligned'], aligned=sz['aligned'], short_reads=sz['short_reads'])
         if with_slots:
             out['slots'] = slots[order]
         return out

@@ -73,6 +73,11 @@ struct DevIndex {
     int64_t n_contigs;
     int64_t n_bases;
     int64_t n_targets;
+    // L2 cache policies (createpolicy values, made once per index by make_policies_kernel):
+    // `pol_hot` goes with every load of contig records, links, sequences and targets, `pol_stream`
+    // with the loads of table buckets and packed reads, which are used once
+    uint64_t pol_hot;
+    uint64_t pol_stream;
 };
 
 // status bits raised by kernels (checked by the host after each batch)
@@ -89,6 +94,8 @@ struct skm_index {
     int device = 0;
     skm::DevIndex d{};
     skm::Slot *table = nullptr;
+    unsigned char *hot = nullptr;  // one block: contigs | seq2 | targets (the L2-resident part of the index)
+    int64_t hot_bytes = 0;
     skm::ContigRec *contigs = nullptr;
     uint32_t *seq2 = nullptr;
     int32_t *targets = nullptr;

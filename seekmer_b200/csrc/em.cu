@@ -483,13 +483,45 @@ struct BlockCache {
     struct Block {
         void *p;
         size_t bytes;
+        bool own;  // a cudaMalloc of its own (can be given back to the driver), not a piece of a slab
     };
     static constexpr size_t SLAB = 256u << 20;  // small blocks are carved out of slabs: few cudaMalloc calls
+    static constexpr size_t KEEP = 8ull << 30;  // own blocks kept idle per device; the largest go first beyond it
     std::mutex mu;
     std::vector<Block> free_blocks[64];
     std::vector<void *> slabs[64];
     char *slab_next[64] = {};
     size_t slab_left[64] = {};
+    // give idle own blocks back to the driver until at most `keep` bytes of them stay cached
+    // (mu held; cudaFree synchronises the device, so this only runs on pressure or on request)
+    size_t trim_locked(int d, size_t keep)
+    {
+        auto &v = free_blocks[d];
+        size_t idle = 0, freed = 0;
+        for (const Block &b : v)
+            if (b.own) idle += b.bytes;
+        while (idle > keep) {
+            int big = -1;
+            for (int i = 0; i < (int)v.size(); ++i)
+                if (v[i].own && (big < 0 || v[i].bytes > v[big].bytes)) big = i;
+            if (big < 0) break;
+            cudaFree(v[big].p);
+            idle -= v[big].bytes;
+            freed += v[big].bytes;
+            v.erase(v.begin() + big);
+        }
+        return freed;
+    }
+    size_t trim(int device, size_t keep)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        const size_t freed = trim_locked(device & 63, keep);
+        cudaSetDevice(prev);
+        return freed;
+    }
     cudaError_t take(int device, size_t bytes, void **out, size_t *got)
     {
         const int d = device & 63;
@@ -510,7 +542,11 @@ struct BlockCache {
         if (bytes <= SLAB / 4) {
             if (slab_left[d] < bytes) {
                 void *slab = nullptr;
-                const cudaError_t e = cudaMalloc(&slab, SLAB);
+                cudaError_t e = cudaMalloc(&slab, SLAB);
+                if (e == cudaErrorMemoryAllocation && trim_locked(d, 0) > 0) {  // our own idle blocks first
+                    cudaGetLastError();
+                    e = cudaMalloc(&slab, SLAB);
+                }
                 if (e != cudaSuccess) return e;
                 slabs[d].push_back(slab);
                 slab_next[d] = static_cast<char *>(slab);
@@ -522,16 +558,21 @@ struct BlockCache {
             return cudaSuccess;
         }
         void *p = nullptr;
-        const cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaErrorMemoryAllocation && trim_locked(d, 0) > 0) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+        }
         if (e != cudaSuccess) return e;
-        slabs[d].push_back(p);
         *out = p;
         return cudaSuccess;
     }
     void give(int device, void *p, size_t bytes)
     {
         std::lock_guard<std::mutex> lock(mu);
-        free_blocks[device & 63].push_back(Block{p, bytes});
+        const int d = device & 63;
+        free_blocks[d].push_back(Block{p, bytes, bytes > SLAB / 4});
+        trim_locked(d, KEEP);
     }
 };
 static BlockCache g_blocks;
@@ -594,6 +635,16 @@ struct Trace {
     } while (0)
 
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)std::max<int64_t>((n + per - 1) / per, 1); }
+
+SKM_API int skm_release_cache(int device, int64_t *freed_bytes)
+{
+    if (freed_bytes) *freed_bytes = 0;
+    if (skm_device_count() <= device || device < 0)
+        return fail(SKM_ERR_CUDA, "skm_release_cache: no such CUDA device");
+    const size_t freed = g_blocks.trim(device, 0);
+    if (freed_bytes) *freed_bytes = (int64_t)freed;
+    return SKM_OK;
+}
 
 SKM_API int skm_effective_lengths(const int64_t *fld, const double *lengths, int64_t n_transcripts,
                                   double *out, int buffers_on_device, int device, void *stream)

@@ -3,6 +3,7 @@
 // targets, graph links) + 2-bit sequence pool + entry-only target lists.  Replaces
 // KMerIndex.__init__/load on the device side (_common.pyx:21-48,287-313) and KMerIndex.map_kmer
 // for vectors of k-mers.
+#include <cstdlib>
 #include <mutex>
 
 #include "kmer.cuh"
@@ -111,6 +112,20 @@ __global__ void contig_links_kernel(const DevIndex ix, ContigRec *__restrict__ r
     const Coord hit = map_kmer(ix, query);
     int2 *dst = k < 4 ? recs[c].right_of_last : recs[c].left_of_first;
     dst[k & 3] = make_int2(hit.entry, hit.offset);
+}
+
+// L2 cache policies for the mapper's loads (DevIndex::pol_hot / pol_stream): kind 0 = normal,
+// 1 = evict_last, 2 = evict_first.  A policy is an opaque 64-bit value made on the device.
+__global__ void make_policies_kernel(uint64_t *out, int hot_kind, int stream_kind)
+{
+    for (int i = 0; i < 2; ++i) {
+        const int kind = i == 0 ? hot_kind : stream_kind;
+        uint64_t p;
+        if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+        else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+        else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+        out[i] = p;
+    }
 }
 
 __device__ __forceinline__ uint32_t code_of(uint8_t b)  // _kmer.pxd:253-273
@@ -226,9 +241,7 @@ SKM_API void skm_index_destroy(skm_index *ix)
     cudaGetDevice(&prev);
     cudaSetDevice(ix->device);
     cudaFree(ix->table);
-    cudaFree(ix->contigs);
-    cudaFree(ix->seq2);
-    cudaFree(ix->targets);
+    cudaFree(ix->hot);  // contigs, seq2 and targets live in this one block
     cudaSetDevice(prev);
     delete ix;
 }
@@ -327,9 +340,23 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         STEP_CUDA(cudaGetLastError());
         ix->bytes += (int64_t)sizeof(Slot) * slots;
     }
+    // -- everything a contig walk touches (contig records, 2-bit sequences, target lists) sits
+    //    in ONE allocation, so that a single L2 access-policy window can keep it resident while
+    //    the 4 GB table and the reads stream through (mapper.cu: launch_chunk)
+    const int64_t n_seq_words = (n_bases + 15) / 16 + 2;
+    {
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_contigs = up(sizeof(ContigRec) * (size_t)n_contigs);
+        const size_t b_seq = up(sizeof(uint32_t) * (size_t)n_seq_words);
+        const size_t b_targets = up(sizeof(int32_t) * (size_t)n_targets);
+        STEP_CUDA(cudaMalloc(&ix->hot, b_contigs + b_seq + b_targets));
+        ix->hot_bytes = (int64_t)(b_contigs + b_seq + b_targets);
+        ix->contigs = reinterpret_cast<ContigRec *>(ix->hot);
+        ix->seq2 = reinterpret_cast<uint32_t *>(ix->hot + b_contigs);
+        ix->targets = reinterpret_cast<int32_t *>(ix->hot + b_contigs + b_seq);
+    }
     // -- targets
     STEP(to_device(targets, n_targets, dev, st, &d_targets, &own_targets));
-    STEP_CUDA(cudaMalloc(&ix->targets, sizeof(int32_t) * (size_t)n_targets));
     extract_targets_kernel<<<(unsigned)((n_targets + 255) / 256), 256, 0, st>>>(
         d_targets, n_targets, ix->targets);
     STEP_CUDA(cudaGetLastError());
@@ -337,7 +364,6 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
 
     // -- contigs
     STEP(to_device(contigs, n_contigs, dev, st, &d_contigs, &own_contigs));
-    STEP_CUDA(cudaMalloc(&ix->contigs, sizeof(ContigRec) * (size_t)n_contigs));
     relayout_contigs_kernel<<<(unsigned)((n_contigs + 255) / 256), 256, 0, st>>>(
         d_contigs, n_contigs, d_targets, ix->contigs, n_bases, n_targets, d_scalars + 1,
         reinterpret_cast<unsigned int *>(d_scalars + 2));
@@ -346,8 +372,7 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
     // -- sequences (2-bit, one padding word so window reads may touch word+1)
     STEP(to_device(sequences, n_bases, dev, st, &d_seq, &own_seq));
     {
-        const int64_t n_words = (n_bases + 15) / 16 + 2;
-        STEP_CUDA(cudaMalloc(&ix->seq2, sizeof(uint32_t) * (size_t)n_words));
+        const int64_t n_words = n_seq_words;
         pack_sequences_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const uint8_t *>(d_seq), n_bases, ix->seq2, n_words);
         STEP_CUDA(cudaGetLastError());
@@ -376,6 +401,25 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
     ix->d.n_contigs = n_contigs;
     ix->d.n_bases = n_bases;
     ix->d.n_targets = n_targets;
+    {
+        // SKM_L2_HINT = last | normal: eviction priority of the contig-side loads (default: last)
+        const char *hint = getenv("SKM_L2_HINT");
+        const int hot_kind = (hint && hint[0] == 'n') ? 0 : 1;
+        uint64_t *d_pol = nullptr, pol[2] = {0, 0};
+        cudaError_t e = cudaMalloc(&d_pol, sizeof(pol));
+        if (e == cudaSuccess) {
+            make_policies_kernel<<<1, 1, 0, st>>>(d_pol, hot_kind, 2);
+            e = cudaMemcpyAsync(pol, d_pol, sizeof(pol), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        cudaFree(d_pol);
+        if (e != cudaSuccess) {
+            skm_index_destroy(ix);
+            return fail(SKM_ERR_CUDA, std::string("skm_index_create: cache policies: ") + cudaGetErrorString(e));
+        }
+        ix->d.pol_hot = pol[0];
+        ix->d.pol_stream = pol[1];
+    }
     contig_links_kernel<<<(unsigned)((n_contigs * 8 + 255) / 256), 256, 0, st>>>(ix->d, ix->contigs, n_contigs);
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
         skm_index_destroy(ix);

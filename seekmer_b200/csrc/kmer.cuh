@@ -15,6 +15,32 @@ struct Coord {
 
 __device__ __forceinline__ Coord coord_invalid() { return Coord{0, -1}; }  // _coordinate.pxd:13-24
 
+// Read-only global loads that carry an L2 eviction policy (ld.global.nc.L2::cache_hint): the
+// index parts a contig walk revisits are kept (evict_last), what streams through once is
+// marked evict_first, so that 4 GB of table buckets do not push 118 MB of contig data out.
+__device__ __forceinline__ ulonglong2 ld_hint_16(const void *p, uint64_t pol)
+{
+    ulonglong2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ int2 ld_hint_8(const void *p, uint64_t pol)
+{
+    int2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_hint_4(const void *p, uint64_t pol)
+{
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // Reverse complement of a 25-mer held in the low 50 bits (_kmer.pxd:146-171).
 // brev reverses all 64 bits; swapping the two bits of every pair restores base
 // codes; the k-mer then sits in the top 50 bits.
@@ -114,6 +140,7 @@ __device__ __forceinline__ Coord probe_canonical(const Slot *table, uint64_t buc
     for (;;) {
         const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(table + BUCKET_SLOTS * b);
         // streaming loads: a bucket is used once, it should not push the read's own lines out of L1
+        // (nor the contig data out of L2)
         const ulonglong2 s0 = __ldcs(p), s1 = __ldcs(p + 1), s2 = __ldcs(p + 2), s3 = __ldcs(p + 3);
         uint64_t v = 0;
         bool found = false;
@@ -150,13 +177,15 @@ struct Contig {
 __device__ __forceinline__ Contig load_contig(const DevIndex &ix, int32_t index)
 {
     const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ix.contigs + index);
-    const ulonglong2 a = __ldg(p);
-    const ulonglong2 b = __ldg(p + 1);
-    const int4 t0 = __ldg(reinterpret_cast<const int4 *>(p + 2));
-    const int4 t1 = __ldg(reinterpret_cast<const int4 *>(p + 3));
+    const ulonglong2 a = ld_hint_16(p, ix.pol_hot);
+    const ulonglong2 b = ld_hint_16(p + 1, ix.pol_hot);
+    const ulonglong2 t0 = ld_hint_16(p + 2, ix.pol_hot);
+    const ulonglong2 t1 = ld_hint_16(p + 3, ix.pol_hot);
     Contig c;
-    c.t[0] = t0.x; c.t[1] = t0.y; c.t[2] = t0.z; c.t[3] = t0.w;
-    c.t[4] = t1.x; c.t[5] = t1.y; c.t[6] = t1.z; c.t[7] = t1.w;
+    c.t[0] = (int32_t)(uint32_t)t0.x; c.t[1] = (int32_t)(uint32_t)(t0.x >> 32);
+    c.t[2] = (int32_t)(uint32_t)t0.y; c.t[3] = (int32_t)(uint32_t)(t0.y >> 32);
+    c.t[4] = (int32_t)(uint32_t)t1.x; c.t[5] = (int32_t)(uint32_t)(t1.x >> 32);
+    c.t[6] = (int32_t)(uint32_t)t1.y; c.t[7] = (int32_t)(uint32_t)(t1.y >> 32);
     c.first_kmer = a.x & KMER_MASK;
     c.last_kmer = a.y & KMER_MASK;
     c.target_count = (int32_t)((a.x >> 50) | ((a.y >> 50) << 14));
@@ -179,7 +208,7 @@ __device__ __forceinline__ Coord contig_link(const DevIndex &ix, Coord anchor, i
     const bool via_last = (dir != 0) == forward;
     const int2 *links = via_last ? rec->right_of_last : rec->left_of_first;
     const bool direct = (dir != 0) == via_last;  // stored queries: append to last, prepend to first
-    const int2 v = __ldg(links + (direct ? b : 3u - b));
+    const int2 v = ld_hint_8(links + (direct ? b : 3u - b), ix.pol_hot);
     if (v.y < 0) return Coord{v.x, v.y};  // a miss: the caller does the real lookup
     return Coord{direct ? v.x : ~v.x, v.y};
 }
@@ -193,9 +222,9 @@ __device__ __forceinline__ uint32_t seq_window8(const DevIndex &ix, int64_t p)
     p = p < 0 ? 0 : (p > ix.n_bases ? ix.n_bases : p);
     const int64_t w = p >> 4;
     const int s = (int)(p & 15);
-    const uint32_t hi = __ldg(ix.seq2 + w);
+    const uint32_t hi = ld_hint_4(ix.seq2 + w, ix.pol_hot);
     uint32_t lo = 0;
-    if (s > 8) lo = __ldg(ix.seq2 + w + 1);
+    if (s > 8) lo = ld_hint_4(ix.seq2 + w + 1, ix.pol_hot);
     const uint64_t both = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(both >> (48 - 2 * s)) & 0xFFFFu;
 }

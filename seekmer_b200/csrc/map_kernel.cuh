@@ -66,6 +66,32 @@ constexpr int SCAN_WIDTH = SKM_SCAN_WIDTH;  // read positions probed per P_SCAN 
 #define SKM_STICKY_LANES 16
 #endif
 constexpr int STICKY_LANES = SKM_STICKY_LANES;  // a phase repeats while this many lanes still have rows for it
+#ifndef SKM_SCAN_PREFETCH
+#define SKM_SCAN_PREFETCH 0
+#endif
+// SKM_STAGE: every item owns a 64-byte LANDING ZONE in shared memory.  The two phases that wait
+// on one 64-byte record from the index (P_LOOKUP: a table bucket, P_CONTIG: a contig record
+// header) fetch it with cp.async (global -> shared, L2 policy attached, no registers held while
+// it is in flight).  A lane claims up to SKM_NSUB waiting rows of such a phase per iteration,
+// starts all their fetches, then runs the phase for one row after the other: the fetch of row
+// k+1 travels while row k is being worked on, so one exposed DRAM latency serves NSUB items.
+// The zone doubles as the stash of the current contig (first/last k-mer, sequence offset).
+#ifndef SKM_STAGE
+#define SKM_STAGE 0
+#endif
+#ifndef SKM_NSUB
+#define SKM_NSUB 1
+#endif
+constexpr bool STAGE = SKM_STAGE != 0;
+constexpr int NSUB = STAGE ? SKM_NSUB : 1;
+static_assert(NSUB >= 1 && NSUB <= 3, "SKM_NSUB must be 1, 2 or 3");
+constexpr int LAND_VECS = 4;  // uint4 words of an item's landing zone
+#ifndef SKM_LOAD_AHEAD
+#define SKM_LOAD_AHEAD 0
+#endif
+// P_LOAD asks L2 for the packed reads of the unit LOAD_AHEAD positions further down the work
+// counter (every unit is asked for once, by whoever takes the unit LOAD_AHEAD before it)
+constexpr long long LOAD_AHEAD = SKM_LOAD_AHEAD;
 
 // What the mapper leaves behind for one unit, field-major so that tally_units_kernel reads it
 // coalesced: units[0][u] = number of targets, units[1][u] = span length of _mapper.pyx:90,
@@ -89,6 +115,7 @@ struct MapArgs {
     int32_t *arena;           // spill space for target lists longer than LIST_CAP
     uint64_t arena_cap;
     unsigned long long *cursors;  // [0]=work counter [1]=arena cursor
+    unsigned long long *short_reads;  // reads shorter than k seen so far (their units are reported unaligned)
 };
 
 enum : int { P_LOAD = 0, P_SCAN, P_LOOKUP, P_CONTIG, P_WALK, P_TALLY, N_PHASES, P_DEAD = N_PHASES };
@@ -103,14 +130,15 @@ enum : int {
 // item flag bits
 enum : uint32_t {
     F_CTX = 7u, F_DIR = 8u, F_MATE = 16u, F_ATTEMPT = 32u, F_FORWARD = 64u, F_L_ARENA = 128u,
-    F_M1_ARENA = 256u, F_CTG_A0 = 512u, F_WILD = 1024u
+    F_M1_ARENA = 256u, F_CTG_A0 = 512u, F_WILD = 1024u, F_VOID = 2048u
 };
 constexpr int STATE_VECS = 5;  // uint4 words of item state
 constexpr int CTG_WORDS = 3;   // contig stash: first_kmer, last_kmer, seq_offset
 
 constexpr size_t map_item_bytes(int code_words)
 {
-    return sizeof(uint64_t) * ((size_t)code_words + CTG_WORDS) + sizeof(int32_t) * 2 * LIST_CAP + 16 * STATE_VECS;
+    return sizeof(uint64_t) * ((size_t)code_words + (STAGE ? 0 : CTG_WORDS)) + sizeof(int32_t) * 2 * LIST_CAP
+           + 16 * (STATE_VECS + (STAGE ? LAND_VECS : 0));
 }
 constexpr size_t map_fixed_bytes() { return sizeof(uint32_t) * (N_PHASES * 32) + 16; }
 
@@ -177,6 +205,7 @@ template <int ITEMS>
 struct Lane {
     int st, ctx, dir, mate, attempt;
     bool forward, ctg_a0, has_wild, m1_dirty;
+    bool void_unit;  // one of the unit's reads is shorter than k: reported unaligned, span length 0
     long long unit;
     int pos, move, len, clen;
     uint64_t kmer;
@@ -193,7 +222,28 @@ template <int ITEMS>
 struct ItemMem {
     uint4 *state;      // &state[0][item]; vector v at state[v * ITEMS]
     uint64_t *codes;   // &codes[0][item]
-    uint64_t *ctg;     // &ctg[0][item]
+    uint64_t *ctg;     // &ctg[0][item]              (without SKM_STAGE)
+    uint4 *land;       // &land[0][item]: landing zone (with SKM_STAGE)
+    // the stash of the current contig: first k-mer, last k-mer, sequence offset
+    __device__ __forceinline__ void stash_kmers(uint64_t &first_kmer, uint64_t &last_kmer) const
+    {
+        if (STAGE) {
+            const uint4 v = land[0];
+            first_kmer = ((uint64_t)v.x | ((uint64_t)v.y << 32)) & KMER_MASK;
+            last_kmer = ((uint64_t)v.z | ((uint64_t)v.w << 32)) & KMER_MASK;
+        } else {
+            first_kmer = ctg[0];
+            last_kmer = ctg[ITEMS];
+        }
+    }
+    __device__ __forceinline__ int64_t stash_seq_offset() const
+    {
+        if (STAGE) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(land + ITEMS);
+            return (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32));
+        }
+        return (int64_t)ctg[2 * ITEMS];
+    }
     int32_t *list0;    // &lists[0][item]; mate 2 uses the second LIST_CAP entries
     int32_t *arena;
     __device__ __forceinline__ List<ITEMS> fresh_list(int mate) const
@@ -217,6 +267,7 @@ __device__ __forceinline__ void lane_load(Lane<ITEMS> &L, const ItemMem<ITEMS> &
     L.forward = (f & F_FORWARD) != 0;
     L.ctg_a0 = (f & F_CTG_A0) != 0;
     L.has_wild = (f & F_WILD) != 0;
+    L.void_unit = (f & F_VOID) != 0;
     L.m1_dirty = false;
     L.pos = (int)(v0.z & 0xFFFFu);
     L.len = (int)(v0.z >> 16);
@@ -248,7 +299,7 @@ __device__ __forceinline__ void lane_store(const Lane<ITEMS> &L, const ItemMem<I
     v0.x = (uint32_t)L.unit;
     v0.y = (uint32_t)L.ctx | (L.dir ? F_DIR : 0u) | (L.mate ? F_MATE : 0u) | (L.attempt ? F_ATTEMPT : 0u)
            | (L.forward ? F_FORWARD : 0u) | (L.l.in_arena() ? F_L_ARENA : 0u) | (L.m1.in_arena() ? F_M1_ARENA : 0u)
-           | (L.ctg_a0 ? F_CTG_A0 : 0u) | (L.has_wild ? F_WILD : 0u);
+           | (L.ctg_a0 ? F_CTG_A0 : 0u) | (L.has_wild ? F_WILD : 0u) | (L.void_unit ? F_VOID : 0u);
     v0.z = ((uint32_t)L.pos & 0xFFFFu) | ((uint32_t)L.len << 16);
     v0.w = (uint32_t)L.move;
     v1.x = (uint32_t)L.kmer;
@@ -327,7 +378,8 @@ __device__ __forceinline__ void load_targets_hi(const DevIndex &ix, const Contig
 {
     const int32_t *src = ix.targets + c.target_offset + INLINE_TARGETS;
 #pragma unroll
-    for (int j = 0; j < INLINE_TARGETS; ++j) t[j] = INLINE_TARGETS + j < c.target_count ? __ldg(src + j) : 0;
+    for (int j = 0; j < INLINE_TARGETS; ++j)
+        t[j] = INLINE_TARGETS + j < c.target_count ? (int32_t)ld_hint_4(src + j, ix.pol_hot) : 0;
 }
 
 // map_contig (_common.pyx:143-179) for an already loaded contig record.  Forward: the
@@ -561,6 +613,75 @@ __device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView<ITEMS> 
     return sift4_unified(ref16, codes, wild, 1 - dir, dir ? rv.len - qoff : qoff + 8);
 }
 
+// ---- cp.async staging (SKM_STAGE) ---------------------------------------------------------------
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, uint64_t policy)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 64 bytes from `src` into the item's landing zone (4 x 16 bytes, vector v at land[v * ITEMS])
+template <int ITEMS>
+__device__ __forceinline__ void fetch_to_land(uint4 *land, const void *src, uint64_t policy)
+{
+    const char *s = reinterpret_cast<const char *>(src);
+#pragma unroll
+    for (int v = 0; v < LAND_VECS; ++v) cp_async_16(land + v * ITEMS, s + 16 * v, policy);
+}
+
+// KMerIndex.map_kmer on a home bucket that already sits in the landing zone; the (rare) overflow
+// into the following buckets reads the table directly
+template <int ITEMS>
+__device__ __forceinline__ Coord probe_landed(const DevIndex &ix, const uint4 *land, uint64_t kmer)
+{
+    const uint64_t rc = revcomp(kmer);
+    Probe p;
+    p.fwd = kmer < rc;
+    p.canon = p.fwd ? kmer : rc;
+    uint64_t v = 0;
+    bool found = false;
+    uint64_t last_key = 0;
+#pragma unroll
+    for (int k = 0; k < BUCKET_SLOTS; ++k) {
+        const uint4 s = land[k * ITEMS];
+        const uint64_t key = (uint64_t)s.x | ((uint64_t)s.y << 32);
+        if (key == p.canon) {
+            v = (uint64_t)s.z | ((uint64_t)s.w << 32);
+            found = true;
+        }
+        last_key = key;
+    }
+    if (found) {
+        const int32_t entry = (int32_t)(uint32_t)v;
+        return Coord{p.fwd ? entry : ~entry, (int32_t)(uint32_t)(v >> 32)};
+    }
+    if (last_key == EMPTY_KEY) return coord_invalid();
+    p.bucket = (uint32_t)(((uint64_t)home_bucket_of(p.canon, ix.bucket_mask) + 1) & ix.bucket_mask);
+    return run_probe(ix, p);
+}
+
+// the contig record header from the landing zone (load_contig's unpacking, kmer.cuh)
+template <int ITEMS>
+__device__ __forceinline__ Contig contig_landed(const uint4 *land)
+{
+    const uint4 a = land[0], b = land[ITEMS], t0 = land[2 * ITEMS], t1 = land[3 * ITEMS];
+    const uint64_t w0 = (uint64_t)a.x | ((uint64_t)a.y << 32), w1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    Contig c;
+    c.t[0] = (int32_t)t0.x; c.t[1] = (int32_t)t0.y; c.t[2] = (int32_t)t0.z; c.t[3] = (int32_t)t0.w;
+    c.t[4] = (int32_t)t1.x; c.t[5] = (int32_t)t1.y; c.t[6] = (int32_t)t1.z; c.t[7] = (int32_t)t1.w;
+    c.first_kmer = w0 & KMER_MASK;
+    c.last_kmer = w1 & KMER_MASK;
+    c.target_count = (int32_t)((w0 >> 50) | ((w1 >> 50) << 14));
+    c.seq_offset = (int64_t)((uint64_t)b.x | ((uint64_t)b.y << 32));
+    c.target_offset = b.z;
+    c.length = (int32_t)b.w;
+    return c;
+}
+
 template <int ROWS>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
@@ -568,9 +689,10 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
     constexpr int ITEMS = ROWS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sm_state = reinterpret_cast<uint4 *>(smem_raw);                            // [STATE_VECS][ITEMS]
-    uint64_t *sm_codes = reinterpret_cast<uint64_t *>(sm_state + STATE_VECS * ITEMS);  // [code_words][ITEMS]
-    uint64_t *sm_ctg = sm_codes + (size_t)a.code_words * ITEMS;                       // [CTG_WORDS][ITEMS]
-    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + CTG_WORDS * ITEMS);      // [2 * LIST_CAP][ITEMS]
+    uint4 *sm_land = sm_state + STATE_VECS * ITEMS;                                    // [LAND_VECS][ITEMS] (SKM_STAGE)
+    uint64_t *sm_codes = reinterpret_cast<uint64_t *>(sm_land + (STAGE ? LAND_VECS * ITEMS : 0));  // [code_words][ITEMS]
+    uint64_t *sm_ctg = sm_codes + (size_t)a.code_words * ITEMS;                       // [CTG_WORDS][ITEMS] (no SKM_STAGE)
+    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + (STAGE ? 0 : CTG_WORDS * ITEMS));  // [2 * LIST_CAP][ITEMS]
     uint32_t *sm_masks = reinterpret_cast<uint32_t *>(sm_lists + 2 * LIST_CAP * ITEMS);  // [N_PHASES][32]
     int *sm_live = reinterpret_cast<int *>(sm_masks + N_PHASES * 32);
 
@@ -619,23 +741,81 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             for (int p = 0; p < N_PHASES; ++p)
                 if (p == phase) mm = m[p];
         }
-        // ---- claim one waiting row of that phase ---------------------------------------------
-        bool mine = false;
-        int row = 0;
-        if (mm) {
-            const unsigned rot = iter & 31u;
-            const uint32_t mr = __funnelshift_r(mm, mm, rot);
-            row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
-            const uint32_t old = atomicAnd(&sm_masks[phase * 32 + lane], ~(1u << row));
-            mine = (old >> row) & 1u;
+        // ---- claim one waiting row of that phase (up to NSUB in the staged phases) -----------------
+        const bool staged = STAGE && (phase == P_LOOKUP || phase == P_CONTIG);  // warp-uniform
+        int row_s[NSUB];
+        bool mine_s[NSUB];
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s) {
+            row_s[s] = 0;
+            mine_s[s] = false;
+            if (mm && (s == 0 || staged)) {
+                const unsigned rot = iter & 31u;
+                const uint32_t mr = __funnelshift_r(mm, mm, rot);
+                row_s[s] = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
+                const uint32_t old = atomicAnd(&sm_masks[phase * 32 + lane], ~(1u << row_s[s]));
+                mine_s[s] = (old >> row_s[s]) & 1u;
+                mm &= ~(1u << row_s[s]);
+            }
         }
         iter += 1;
         __threadfence_block();
+        int nsub = 1;
+        if (staged) {
+            // start every claimed row's fetch: the bucket of its pending k-mer, or the record of
+            // the contig it is about to enter
+#pragma unroll
+            for (int s = 0; s < NSUB; ++s) {
+                if (mine_s[s]) {
+                    const int it = row_s[s] * 32 + lane;
+                    const void *src;
+                    uint64_t pol;
+                    if (phase == P_LOOKUP) {
+                        const uint2 kv = *reinterpret_cast<const uint2 *>(sm_state + ITEMS + it);
+                        const Probe pr = prepare_probe((uint64_t)kv.x | ((uint64_t)kv.y << 32), ix.bucket_mask);
+                        src = ix.table + BUCKET_SLOTS * (uint64_t)pr.bucket;
+                        pol = ix.pol_stream;
+                    } else {
+                        const uint32_t f = sm_state[it].y;
+                        const uint4 v2 = sm_state[2 * ITEMS + it];
+                        const int32_t e = (int)(f & F_CTX) == C_RIGHT_C ? (int32_t)v2.x : (int32_t)v2.z;
+                        src = ix.contigs + (e >= 0 ? e : ~e);
+                        pol = ix.pol_hot;
+                    }
+                    fetch_to_land<ITEMS>(sm_land + it, src, pol);
+                }
+                cp_async_commit();
+            }
+            if (NSUB > 1) {
+                const unsigned second = __ballot_sync(0xffffffffu, mine_s[NSUB > 1 ? 1 : 0]);
+                nsub = second ? 2 : 1;
+                if (NSUB > 2 && __ballot_sync(0xffffffffu, mine_s[NSUB > 2 ? 2 : 0])) nsub = 3;
+            }
+        }
+#pragma unroll 1
+        for (int sub = 0; sub < nsub; ++sub) {
+        bool mine = mine_s[0];
+        int row = row_s[0];
+        if (NSUB > 1 && sub == 1) {
+            mine = mine_s[NSUB > 1 ? 1 : 0];
+            row = row_s[NSUB > 1 ? 1 : 0];
+        }
+        if (NSUB > 2 && sub == 2) {
+            mine = mine_s[NSUB > 2 ? 2 : 0];
+            row = row_s[NSUB > 2 ? 2 : 0];
+        }
+        if (staged) {
+            // groups complete in order: row `sub` has landed once at most NSUB-1-sub groups are pending
+            if (sub == 0) cp_async_wait<NSUB - 1>();
+            else if (sub == 1) cp_async_wait<(NSUB > 1 ? NSUB - 2 : 0)>();
+            else cp_async_wait<0>();
+        }
         const int item = row * 32 + lane;
         ItemMem<ITEMS> I;
         I.state = sm_state + item;
         I.codes = sm_codes + item;
         I.ctg = sm_ctg + item;
+        I.land = sm_land + item;
         I.list0 = sm_lists + item;
         I.arena = a.arena;
         Lane<ITEMS> L;
@@ -644,6 +824,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         L.unit = 0;
         L.len = 0;
         L.has_wild = false;
+        L.void_unit = false;
         if (mine) lane_load(L, I, phase == P_TALLY);
         ReadView<ITEMS> rv;
         rv.w = I.codes;
@@ -670,6 +851,12 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (need) {
                     L.unit = base + __popc(nb & ((1u << lane) - 1u));
                     if (L.unit >= a.n_units) L.st = P_DEAD;
+                    if (LOAD_AHEAD > 0 && L.unit + LOAD_AHEAD < a.n_units) {
+                        const long long r = a.paired ? 2 * (L.unit + LOAD_AHEAD) : L.unit + LOAD_AHEAD;
+                        const char *q = reinterpret_cast<const char *>(a.packed + r * (long long)a.words);
+                        const int bytes = a.words * 8 * (a.paired ? 2 : 1);
+                        for (int o = 0; o < bytes; o += 128) prefetch_l2(q + o);
+                    }
                 }
             }
             if (mine && L.st == P_LOAD) {
@@ -697,14 +884,21 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 L.ctx = C_FIND;
                 if (len >= K) {
                     want_pos = 0;
-                } else {  // undefined in the reference; reported unaligned and flagged
+                } else {
+                    // A read shorter than k is undefined in the reference (_kmer.pxd:46-68 reads past its
+                    // end).  Here its unit is reported unaligned with span length 0, whatever the mate does.
                     atomicOr(status, ST_SHORT_READ);
-                    ev = EV_READ_DONE;
+                    atomicAdd(a.short_reads, 1ULL);
+                    L.void_unit = true;
+                    L.l.n = 0;
+                    L.st = P_TALLY;
                 }
             }
         } else if (phase == P_LOOKUP) {
             if (mine) {
-                const Coord h = run_probe(ix, prepare_probe(L.kmer, ix.bucket_mask));
+                const Coord h = STAGE ? probe_landed<ITEMS>(ix, I.land, L.kmer)
+                                      : run_probe(ix, prepare_probe(L.kmer, ix.bucket_mask));
+                if (STAGE) L.ctg_a0 = false;  // the bucket landed on the stash of the first hit's contig
                 L.sp.anchor = h;
                 if (h.offset >= 0) {
                     L.st = P_CONTIG;
@@ -734,6 +928,11 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     km[j] = k;
                     pr[j] = prepare_probe(k, ix.bucket_mask);
                 }
+                if (SKM_SCAN_PREFETCH) {  // the probes below run one after the other: have the later buckets on their way
+#pragma unroll
+                    for (int j = 0; j + 1 < SCAN_WIDTH; ++j)
+                        if (j < fit) prefetch_l2(ix.table + BUCKET_SLOTS * (uint64_t)pr[j].bucket);
+                }
                 int first = SCAN_WIDTH;
                 Coord hh = coord_invalid();
                 uint64_t kk = k;
@@ -762,10 +961,12 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         } else if (phase == P_CONTIG) {
             if (mine) {
                 const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
-                const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
-                I.ctg[0] = c.first_kmer;
-                I.ctg[ITEMS] = c.last_kmer;
-                I.ctg[2 * ITEMS] = (uint64_t)c.seq_offset;
+                const Contig c = STAGE ? contig_landed<ITEMS>(I.land) : load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
+                if (!STAGE) {
+                    I.ctg[0] = c.first_kmer;
+                    I.ctg[ITEMS] = c.last_kmer;
+                    I.ctg[2 * ITEMS] = (uint64_t)c.seq_offset;
+                }
                 L.clen = c.length;
                 L.forward = at.entry >= 0;
                 const int to_start = L.forward ? at.offset : c.length - at.offset - K;
@@ -815,7 +1016,8 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         } else if (phase == P_WALK) {
             if (mine) {
                 // heads of the loops of _filter_targets_to_left (:234-275) and _to_right (:293-343)
-                const uint64_t first_kmer = I.ctg[0], last_kmer = I.ctg[ITEMS];
+                uint64_t first_kmer, last_kmer;
+                I.stash_kmers(first_kmer, last_kmer);
                 const int dir = L.dir;
                 int rem = dir ? L.len - L.sp.end - K : L.sp.begin;  // bases left towards the read end
                 const bool in_loop = rem > L.move;
@@ -829,7 +1031,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     ref16 = edge_window(first_kmer, last_kmer, L.sp.anchor, dir == 0);
                     qoff = dir ? L.len - rem - ALIGN_LENGTH : rem;
                 } else {
-                    ref16 = contig_window(ix, (int64_t)I.ctg[2 * ITEMS], L.sp.anchor, dir == 0);
+                    ref16 = contig_window(ix, I.stash_seq_offset(), L.sp.anchor, dir == 0);
                     qoff = dir ? L.len - ALIGN_LENGTH : 0;
                 }
                 const int shift = sift4_edge(ref16, rv, qoff, dir);
@@ -875,7 +1077,10 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         } else {  // P_TALLY: the unit is mapped; leave its record for tally_units_kernel
             if (mine) {
                 int length;
-                if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
+                if (L.void_unit) {
+                    length = 0;
+                    L.l.n = 0;
+                } else if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
                     int begin1 = L.m1_begin, end1;
                     if (!intersect(L.m1, L.l)) {
                         L.m1.n = 0;
@@ -909,6 +1114,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     rec[a.n_units] = (int32_t)(off >> 32);
                 }
                 // the item is free again: mate 0 of a new unit
+                L.void_unit = false;
                 L.mate = 0;
                 L.l = I.fresh_list(0);
                 L.m1 = I.fresh_list(0);
@@ -1004,6 +1210,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
         }
         __syncwarp();
+        }  // sub
     }
 
 }
@@ -1019,8 +1226,6 @@ struct UnitIds {
     __device__ __forceinline__ int32_t get(int i) const { return __ldg(p + i * stride); }
 };
 
-constexpr int POOL_CHUNK = 256;  // ids a warp takes from the pool cursor at a time (unused tails stay unused)
-
 __global__ void __launch_bounds__(256)
 tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const int32_t *__restrict__ arena,
                    int64_t n_units, int64_t first_unit, int32_t *__restrict__ out_class,
@@ -1032,9 +1237,9 @@ tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const 
     if (threadIdx.x < 4) sm_totals[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    // every counter that all units share is aggregated: id-pool space per warp in chunks,
-    // class / id / unit totals per block
-    unsigned long long chunk_next = 0, chunk_end = 0;
+    // every counter that all units share is aggregated: id-pool space per warp iteration (exactly
+    // the ids of the warp's new classes, so the pool holds nothing but stored ids), class / id /
+    // unit totals per block
     unsigned new_classes = 0, new_ids = 0, n_unaligned = 0, n_aligned = 0;  // lane 0 only
     for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31LL; base < n_units;
          base += (int64_t)gridDim.x * blockDim.x) {
@@ -1077,15 +1282,10 @@ tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const 
                 if (lane >= o) incl += t;
             }
             const unsigned long long total = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
-            if (chunk_next + total > chunk_end) {
-                const unsigned long long take = total > POOL_CHUNK ? total : POOL_CHUNK;
-                unsigned long long got = 0;
-                if (lane == 0) got = atomicAdd(&dict.scalars[0], take);
-                chunk_next = __shfl_sync(0xffffffffu, got, 0);
-                chunk_end = chunk_next + take;
-            }
-            if (won) dict_store_ids(dict, slot, chunk_next + (unsigned long long)(incl - n), view, n, true);
-            chunk_next += total;
+            unsigned long long got = 0;
+            if (lane == 0) got = atomicAdd(&dict.scalars[0], total);
+            got = __shfl_sync(0xffffffffu, got, 0);
+            if (won) dict_store_ids(dict, slot, got + (unsigned long long)(incl - n), view, n, true);
             new_classes += (unsigned)__popc(winners);
             new_ids += (unsigned)total;
         }

@@ -213,19 +213,19 @@ __global__ void fastq_units_kernel(const uint8_t *__restrict__ text, const int64
 
 // ---- export / merge -------------------------------------------------------------------
 // Compaction of the dictionary to CSR.  One 64-bit atomic hands out the class index
-// (high 24 bits) and the id start (low 40 bits) together, so starts are monotone in the
-// class index and key_offsets is a proper CSR row pointer.  Class order is arbitrary;
+// (high 32 bits) and the id start (low 32 bits: the id pool holds fewer than 2^32 ids) together,
+// so starts are monotone in the class index and key_offsets is a proper CSR row pointer.  Class order is arbitrary;
 // callers sort by first_unit for the reference's insertion order.
 __global__ void __launch_bounds__(256)
 dict_export_kernel(const DictDev d, int64_t slots, unsigned long long *cursor, int64_t *key_offsets,
                    int32_t *key_ids, int64_t *counts, int64_t *first_unit, int32_t *slot_ids)
 {
-    // one atomic per BLOCK on the shared cursor (class index in the high 24 bits, id start in the
-    // low 40): a block-wide exclusive scan of (1, n ids) hands every occupied slot its place
+    // one atomic per BLOCK on the shared cursor (class index in the high 32 bits, id start in the
+    // low 32): a block-wide exclusive scan of (1, n ids) hands every occupied slot its place
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool live = s < slots && !(d.keys[s].x == EMPTY_KEY && d.keys[s].y == EMPTY_KEY);
     const uint32_t n = live ? d.len[s] : 0u;
-    const unsigned long long mine = live ? ((1ULL << 40) | (unsigned long long)n) : 0ULL;
+    const unsigned long long mine = live ? ((1ULL << 32) | (unsigned long long)n) : 0ULL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long incl = mine;
     for (int o = 1; o < 32; o <<= 1) {
@@ -248,8 +248,8 @@ dict_export_kernel(const DictDev d, int64_t slots, unsigned long long *cursor, i
     __syncthreads();
     if (!live) return;
     const unsigned long long old = block_base + warp_total[warp] + (incl - mine);
-    const unsigned long long c = old >> 40;
-    const unsigned long long p = old & ((1ULL << 40) - 1);
+    const unsigned long long c = old >> 32;
+    const unsigned long long p = old & 0xFFFFFFFFULL;
     if (key_offsets) key_offsets[c] = (int64_t)p;
     if (key_ids) {
         const int32_t *src = d.pool + d.pool_off[s];
@@ -357,6 +357,10 @@ struct skm_mapper {
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr};
     size_t smem_max = 0;
     int threads = Q_THREADS, rows_limit = 0;  // SKM_THREADS / SKM_ROWS override for experiments
+    // L2 access-policy window over the index's hot block (contigs | seq2 | targets) for the map
+    // kernel: hit ratio = persisting carve-out / window size; 0 = no window
+    float l2_hit_ratio = 0.f;
+    size_t l2_window_bytes = 0;
     int32_t *d_out = nullptr;
     size_t d_out_cap = 0;
     cudaEvent_t ev_kernel[4] = {nullptr, nullptr, nullptr, nullptr};  // around pack | map | tally of the last chunk
@@ -474,11 +478,31 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
         m->smem_max = (size_t)optin;
         if (const char *t = getenv("SKM_THREADS")) m->threads = std::max(32, std::min(Q_THREADS, atoi(t) & ~31));
         if (const char *r = getenv("SKM_ROWS")) m->rows_limit = atoi(r);
+        // SKM_L2_PERSIST = fraction of the device's maximum persisting-L2 carve-out to claim
+        // (default 0: the per-load eviction hints of DevIndex::pol_hot do the job)
+        double frac = 0.0;
+        if (const char *p = getenv("SKM_L2_PERSIST")) frac = atof(p);
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, m->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, m->device);
+        if (frac > 0.0 && max_persist > 0 && max_window > 0 && index->hot_bytes > 0) {
+            const size_t carve = (size_t)((double)max_persist * std::min(frac, 1.0));
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                m->l2_window_bytes = std::min<size_t>((size_t)index->hot_bytes, (size_t)max_window);
+                m->l2_hit_ratio = (float)std::min(1.0, (double)carve / (double)m->l2_window_bytes);
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (getenv("SKM_TRACE"))
+            fprintf(stderr, "[skm trace] L2: max persisting %d B, max window %d B, hot block %lld B, hit ratio %.3f\n",
+                    max_persist, max_window, (long long)index->hot_bytes, m->l2_hit_ratio);
     }
     // list arena: room for every resident thread to spill its largest possible list a few
     // times over, bounded to 2 GiB
     uint64_t arena = (uint64_t)std::max<int64_t>(index->max_target_count, 64) * 2048ULL * (uint64_t)m->sm_count;
     arena = std::min<uint64_t>(std::max<uint64_t>(arena, 1ULL << 22), 1ULL << 29);
+    if (const char *e = getenv("SKM_ARENA_LOG2")) arena = 1ULL << std::max(16, std::min(31, atoi(e)));
     m->arena_cap = arena;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) {
@@ -594,7 +618,25 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
     const int grid = (int)std::min<int64_t>(m->sm_count, std::max<int64_t>(want, 1));
     // the three kernels are bracketed by events on their own stream (skm_mapper_kernel_ms); the
     // work-counter memset above sits between events 1 and 2 with the map kernel
-    var->fn<<<grid, m->threads, smem, st>>>(m->index->d, a, m->d.status);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3((unsigned)m->threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        if (m->l2_hit_ratio > 0.f) {
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = m->index->hot;
+            attr[0].val.accessPolicyWindow.num_bytes = m->l2_window_bytes;
+            attr[0].val.accessPolicyWindow.hitRatio = m->l2_hit_ratio;
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+        }
+        SKM_CUDA(cudaLaunchKernelEx(&cfg, var->fn, m->index->d, a, m->d.status));
+    }
     SKM_CUDA(cudaGetLastError());
     SKM_CUDA(cudaEventRecord(m->ev_kernel[2], st));
     const int tally_blocks = (int)std::min<int64_t>((n_units + 255) / 256, (int64_t)m->sm_count * 8);
@@ -614,8 +656,8 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     if (!m || !bases) return fail(SKM_ERR_INVALID, "skm_map_batch: NULL argument");
     if (n_units < 0) return fail(SKM_ERR_INVALID, "skm_map_batch: negative unit count");
     if (n_units == 0) return SKM_OK;
-    if (!read_offsets && fixed_read_len < K)
-        return fail(SKM_ERR_INVALID, "skm_map_batch: need read_offsets or fixed_read_len >= 25");
+    if (!read_offsets && fixed_read_len <= 0)
+        return fail(SKM_ERR_INVALID, "skm_map_batch: need read_offsets or a positive fixed_read_len");
     SKM_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int per_unit = paired ? 2 : 1;
@@ -623,16 +665,17 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
 
     if (!read_offsets) max_read_len = fixed_read_len;
     if (!buffers_on_device && read_offsets) {
-        int64_t mx = 0, mn = INT64_MAX;
+        int64_t mx = 0;
         for (int64_t i = 0; i < n_reads; ++i) {
             const int64_t L = read_offsets[i + 1] - read_offsets[i];
+            if (L < 0) return fail(SKM_ERR_INVALID, "skm_map_batch: read_offsets must be non-decreasing");
             mx = std::max(mx, L);
-            mn = std::min(mn, L);
         }
-        if (mn < K) return fail(SKM_ERR_INVALID, "skm_map_batch: read shorter than k=25 (undefined in the reference)");
+        if (mx > 4096) return fail(SKM_ERR_INVALID, "skm_map_batch: reads longer than 4096 bases are not supported");
         max_read_len = (int32_t)mx;
     }
-    if (max_read_len < K) return fail(SKM_ERR_INVALID, "skm_map_batch: max_read_len must be >= 25");
+    // reads shorter than k are legal input (trimmed FASTQ): their units come out unaligned
+    if (max_read_len < K) max_read_len = K;
     if (max_read_len > 4096) return fail(SKM_ERR_INVALID, "skm_map_batch: reads longer than 4096 bases are not supported");
 
     MapArgs a{};
@@ -644,6 +687,7 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     a.arena = m->arena;
     a.arena_cap = m->arena_cap;
     a.cursors = m->cursors;
+    a.short_reads = m->d.scalars + 5;
 
     if (buffers_on_device)
         return launch_chunk(m, bases, read_offsets, read_offsets ? read_offsets + 1 : nullptr, a, n_units, first_unit,
@@ -781,18 +825,18 @@ SKM_API int skm_map_fastq(skm_mapper *m, const uint8_t *text1, int64_t n1, const
     if (paired)
         SKM_CUDA(cudaMemcpyAsync(&last2, m->d_nl[1] + (4 * n_units - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SKM_CUDA(cudaStreamSynchronize(st));
-    if (len_range[1] < K)
-        return fail(SKM_ERR_INVALID, "skm_map_fastq: read shorter than k=25 (undefined in the reference)");
     if (len_range[0] > 4096) return fail(SKM_ERR_INVALID, "skm_map_fastq: reads longer than 4096 bases are not supported");
+    const int longest = std::max(len_range[0], K);  // shorter reads are mapped as unaligned units
     MapArgs a{};
     a.fixed_len = 0;
-    a.code_words = (len_range[0] + 31) / 32;
-    a.wild_words = (len_range[0] + 63) / 64;
+    a.code_words = (longest + 31) / 32;
+    a.wild_words = (longest + 63) / 64;
     a.words = (a.code_words + a.wild_words + 1) & ~1;
     a.paired = paired;
     a.arena = m->arena;
     a.arena_cap = m->arena_cap;
     a.cursors = m->cursors;
+    a.short_reads = m->d.scalars + 5;
     int32_t *d_class = out_class, *d_length = out_length;
     if (!buffers_on_device && (out_class || out_length)) {
         rc = ensure((void **)&m->d_out, &m->d_out_cap, sizeof(int32_t) * 2 * (size_t)n_units);
@@ -844,12 +888,12 @@ SKM_API int skm_mapper_kernel_ms(skm_mapper *m, double ms[3])
     return SKM_OK;
 }
 
-SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[6], void *stream)
+SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[8], void *stream)
 {
     if (!m || !sizes) return fail(SKM_ERR_INVALID, "skm_classes_size: NULL argument");
     SKM_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long sc[5];
+    unsigned long long sc[6];
     uint32_t status = 0;
     SKM_CUDA(cudaMemcpyAsync(sc, m->d.scalars, sizeof(sc), cudaMemcpyDeviceToHost, st));
     SKM_CUDA(cudaMemcpyAsync(&status, m->d.status, sizeof(status), cudaMemcpyDeviceToHost, st));
@@ -860,6 +904,8 @@ SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[6], void *stream)
     sizes[3] = (int64_t)sc[3];
     sizes[4] = m->slots / 2;
     sizes[5] = (int64_t)status;
+    sizes[6] = (int64_t)sc[5];  // reads shorter than k (their units are in `unaligned`)
+    sizes[7] = (int64_t)sc[0];  // id-pool cursor (== sizes[1]: the pool holds stored ids only)
     return SKM_OK;
 }
 
@@ -872,7 +918,7 @@ SKM_API int skm_classes_export(skm_mapper *m, int64_t *key_offsets, int32_t *key
     cudaStream_t st = (cudaStream_t)stream;
     int rc = check_status(m, st, "skm_classes_export");
     if (rc) return rc;
-    int64_t sizes[6];
+    int64_t sizes[8];
     rc = skm_classes_size(m, sizes, stream);
     if (rc) return rc;
     const int64_t n_cls = sizes[0], n_ids = sizes[1];

@@ -280,11 +280,19 @@ def _output_abundance_table(output_path, index, results, est_counts, main_abunda
     ids = index.transcripts['transcript_id']
     lengths = index.transcripts['length']
     eff = results.effective_lengths.astype('f4')
+    # pandas applies float_format to float columns only: `length` is f8 in an index written by
+    # `seekmer index` (`index_builder.py:225-226`) and goes through '%g' like the rest; an index
+    # that carries integer lengths gets them printed in full
+    def column(values):
+        values = numpy.asarray(values)
+        if values.dtype.kind != 'f':
+            return [str(v) for v in values.tolist()]
+        return ['' if v != v else '%g' % v for v in values.tolist()]  # to_csv writes NaN as an empty field
+
+    columns = [[i.decode() for i in ids], column(lengths), column(eff), column(est_counts), column(main_abundance)]
     with (output_path / 'abundance.tsv').open('w') as f:
         f.write('target_id\tlength\teff_length\test_count\ttpm\n')
-        for i in range(len(ids)):
-            f.write('%s\t%g\t%g\t%g\t%g\n' % (ids[i].decode(), lengths[i], eff[i], est_counts[i],
-                                             main_abundance[i]))
+        f.writelines('\t'.join(row) + '\n' for row in zip(*columns))
 
 
 def _output_hdf5(output_path, index, results, run_info, est_counts, bootstrapped_abundance):

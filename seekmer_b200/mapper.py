@@ -164,9 +164,7 @@ def _pack_batch(reads):
     lens = numpy.fromiter(map(len, reads), dtype='i8', count=n)
     bases = numpy.frombuffer(b''.join(reads), dtype='u1')
     lo, hi = (int(lens.min()), int(lens.max())) if n else (0, 0)
-    if n and lo < _lib.K:
-        raise ValueError('read shorter than k=25 cannot be mapped (undefined in the reference)')
-    if lo == hi:
+    if lo == hi and lo > 0:
         return bases, None, lo, hi
     offsets = numpy.zeros(n + 1, dtype='i8')
     numpy.cumsum(lens, out=offsets[1:])
@@ -238,6 +236,10 @@ class ReadMapper:
         finally:
             if self._shared is None:
                 mapper.close()
+        if table.get('short_reads'):
+            # undefined in the reference (`_kmer.pxd:46-68` reads past the end of such a read)
+            _LOG.warn('{} reads are shorter than k={}: their units were counted as unaligned.',
+                      table['short_reads'], _lib.K)
         classes = _class_tuples(table)
         with self.map_result.lock:
             fresh = not self.map_result.counter

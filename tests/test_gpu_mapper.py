@@ -199,8 +199,38 @@ def test_capacity_errors_are_loud(golden_synth, small_tx):
     mp = _lib.DeviceMapper(ix, class_capacity=8, id_capacity=16)
     with pytest.raises(_lib.SeekmerCudaError, match='capacity'):
         mp.map_batch(bases, None, 3000, True, fixed_len=100)
-    with pytest.raises(_lib.SeekmerCudaError):
-        mp.map_batch(bases[:48], numpy.asarray([0, 24, 48], dtype='i8'), 1, True)  # shorter than k
+
+
+def test_reads_shorter_than_k_are_unaligned_units(orc, golden_synth, small_tx):
+    """Trimmed FASTQ holds reads shorter than k=25 (and empty ones).  Undefined in the reference;
+    defined here (oracle and CUDA alike): the unit is unaligned with span length 0, the run goes
+    on, and the reads are counted."""
+    g = golden_synth
+    arrays = g.index_arrays()
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **SYNTH_CASES['pe100'])
+    n = 2000
+    bases, _ = sim.generate(0, n)
+    reads = [bases[i * 100:(i + 1) * 100].tobytes() for i in range(2 * n)]
+    rng = numpy.random.Generator(numpy.random.PCG64(5))
+    cut = rng.choice(2 * n, size=300, replace=False)
+    for j, i in enumerate(cut):
+        reads[i] = reads[i][:int(rng.integers(0, 25))] if j % 3 else b''
+    for paired in (True, False):
+        flat = numpy.frombuffer(b''.join(reads), dtype='u1')
+        offs = numpy.zeros(2 * n + 1, dtype='i8')
+        numpy.cumsum([len(r) for r in reads], out=offs[1:])
+        units = n if paired else 2 * n
+        check_against_oracle(orc, arrays, flat, offs, units, paired)
+        ix = _lib.DeviceIndex(*arrays, 60)
+        mp = _lib.DeviceMapper(ix)
+        mp.map_batch(flat, offs, units, paired)
+        assert mp.sizes()['short_reads'] == 300
+    # a batch of nothing but short reads
+    ix = _lib.DeviceIndex(*arrays, 60)
+    mp = _lib.DeviceMapper(ix)
+    mp.map_batch(numpy.frombuffer(b'ACGT' * 10, dtype='u1'), numpy.asarray([0, 10, 20, 30, 40], dtype='i8'), 2, True)
+    t = mp.export()
+    assert t['unaligned'] == 2 and t['aligned'] == 0 and t['fld'].sum() == 0 and t['short_reads'] == 4
 
 
 def test_merge_equals_single_mapper(golden_synth, small_tx):
@@ -420,3 +450,21 @@ def test_empty_oversized_and_unmappable_inputs(golden_synth):
         assert tpm.shape == (60,) and (tpm == 0).all()
         assert infer.quantify_bootstraps(s, tpm, 2)[1].shape == (60,)
     index.release_device()
+
+
+def test_id_pool_holds_stored_ids_only(golden_synth, small_tx):
+    """Hundreds of small batches with the default capacities: the id-pool cursor must equal the ids
+    stored (a per-warp chunk reservation once leaked ~1 M ids per launch and exhausted the
+    default pool on long runs)."""
+    g = golden_synth
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **SYNTH_CASES['pe100'])
+    n = 2048
+    ix = _lib.DeviceIndex(*g.index_arrays(), 60)
+    mp = _lib.DeviceMapper(ix)
+    for b in range(300):
+        bases, _ = sim.generate(b * n, n)
+        mp.map_batch(bases, None, n, True, first_unit=b * n, fixed_len=100)
+    s = mp.sizes()
+    assert s['n_classes'] > 0 and s['pool_cursor'] == s['n_ids'], s
+    t = mp.export()
+    assert int(t['key_offsets'][-1]) == s['n_ids']

@@ -138,3 +138,42 @@ def test_synthetic_generators_are_deterministic_and_sliceable():
         got = (r[i, :100].tobytes(), r[i, 100:].tobytes())
         assert got == ((m2, m1) if t['swap'][i] else (m1, m2))
     assert 200 < numpy.mean(t['fragment']) < 300
+
+
+def test_abundance_tsv_is_byte_identical_to_the_pandas_writer(tmp_path):
+    """`infer._output_abundance_table` against what the reference writes (`infer.py:219-230`:
+    a DataFrame through `to_csv(sep='\\t', index=False, float_format='%g')`), byte for byte,
+    with values that stress '%g': tiny, huge, zero, NaN, lengths of a million bases and more."""
+    import pandas
+    from seekmer_b200 import infer
+    rng = numpy.random.Generator(numpy.random.PCG64(3))
+    n = 500
+    tr = numpy.zeros(n, dtype=[('transcript_id', 'S12'), ('gene_id', 'S12'), ('length', 'f8')])
+    tr['transcript_id'] = [('TX%06d' % i).encode() for i in range(n)]
+    tr['length'] = rng.integers(30, 200000, size=n)
+    tr['length'][:4] = [1000000, 1234567, 25, 99999999]
+
+    class Index:
+        transcripts = tr
+
+    class Results:
+        effective_lengths = numpy.maximum(tr['length'] - 187.123456, 1.0)
+
+    est = numpy.exp(rng.normal(0, 6, size=n))
+    tpm = numpy.exp(rng.normal(0, 6, size=n))
+    est[:6] = [0.0, 1e-300, 123456789.0, 0.001, 1e6, numpy.nan]
+    tpm[:6] = [0.0, 5e-324, 999999.5, 1e-5, 100000.0, numpy.nan]
+    for lengths in (tr['length'], tr['length'].astype('i8')):
+        Index.transcripts = tr if lengths.dtype.kind == 'f' else tr.astype(
+            [('transcript_id', 'S12'), ('gene_id', 'S12'), ('length', 'i8')])
+        infer._output_abundance_table(tmp_path, Index, Results, est, tpm)
+        table = pandas.DataFrame()
+        table['target_id'] = [i.decode() for i in Index.transcripts['transcript_id']]
+        table['length'] = Index.transcripts['length']
+        table['eff_length'] = Results.effective_lengths.astype('f4')
+        table['est_count'] = est
+        table['tpm'] = tpm
+        table.to_csv(str(tmp_path / 'pandas.tsv'), sep='\t', index=False, float_format='%g')
+        ours = (tmp_path / 'abundance.tsv').read_bytes()
+        want = (tmp_path / 'pandas.tsv').read_bytes()
+        assert ours == want
