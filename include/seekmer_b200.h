@@ -40,11 +40,13 @@ typedef enum skm_status {
     SKM_ERR_INVALID = -1,   /* bad argument */
     SKM_ERR_CUDA = -2,      /* CUDA runtime / no device */
     SKM_ERR_CAPACITY = -3,  /* class table, id pool or list arena exhausted */
-    SKM_ERR_OOM = -4        /* device allocation failed */
+    SKM_ERR_OOM = -4,       /* device allocation failed */
+    SKM_ERR_COLLISION = -5  /* two different classes share a 128-bit dictionary key (p < 1e-24); nothing merged silently */
 } skm_status;
 
 typedef struct skm_index skm_index;
 typedef struct skm_mapper skm_mapper;
+typedef struct skm_em_plan skm_em_plan;
 
 /* ---- index input contract: the arrays held by `KMerIndex` ------------------
  * (_common.pxd:15-35,57-66; dtypes as produced by `seekmer index`,
@@ -128,7 +130,7 @@ int skm_mapper_reset(skm_mapper *mapper, void *stream);
  *   out_length    optional int32[n_units]: span.end - span.begin + k (:90)
  * Reads shorter than k are undefined in the reference (_kmer.pxd:46-68 reads past
  * their end).  Here they are legal input (trimmed FASTQ): a unit with such a read is
- * reported unaligned with span length 0, and the reads are counted (skm_classes_size).
+ * reported unaligned with span length 0, and such units are counted (skm_classes_size).
  * Reads longer than 4096 bases are refused with SKM_ERR_INVALID.
  */
 int skm_map_batch(skm_mapper *mapper, const uint8_t *bases, const int64_t *read_offsets,
@@ -155,7 +157,7 @@ int skm_mapper_kernel_ms(skm_mapper *mapper, double ms[3]);
 
 /* sizes[0]=n_classes, [1]=total ids, [2]=unaligned units, [3]=aligned units,
  * [4]=class slots capacity, [5]=status flags raised on device (0 = none),
- * [6]=reads shorter than k seen (their units are part of [2]), [7]=id-pool cursor */
+ * [6]=units with a read shorter than k (they are part of [2]), [7]=id-pool cursor */
 int skm_classes_size(skm_mapper *mapper, int64_t sizes[8], void *stream);
 
 /* Replaces: reading MapResult.counter / fragment_length_counts
@@ -206,6 +208,34 @@ int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes,
            const double *counts, const double *eff_len, int64_t n_transcripts,
            const double *x0, int64_t n_replicates, int64_t max_iters, double *out_x,
            int32_t *out_iters, int buffers_on_device, int device, void *stream);
+
+/* ---- EM plans: the class structure resident on one device, built once -----------------------
+ * Replaces: the `class_map` / `class_count` arrays that SummarizedResult carries from
+ * MapResult.summarize (mapper.py:77-104) into every quantify call (infer.py:88-130).  A plan
+ * holds the class x transcript structure in both orders (CSR by class, CSC by transcript); the
+ * main EM, the bootstrap replicates (infer.py:79-82) and any repeated call share it.
+ *   skm_em_plan_create       from CSR arrays (host or device); `counts` (int64[n_classes], may be
+ *                            NULL) makes the plan own the integer class counts
+ *   skm_em_plan_from_mapper  from a mapper's dictionary where it lies in HBM: classes in
+ *                            first-seen order (the Counter order at job_count=1), ids in tuple
+ *                            order, counts included; n_transcripts <= 0 = the index's
+ *   skm_em_plan_info         info[0]=n_classes [1]=nnz [2]=n_transcripts [3]=device [4]=owns counts
+ *   skm_em_plan_run          skm_em on the plan; counts NULL = the plan's own (n_replicates 1)
+ *   skm_em_plan_bootstrap    skm_em_bootstrap on the plan; counts NULL = the plan's own */
+int skm_em_plan_create(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes,
+                       int64_t nnz, int64_t n_transcripts, const int64_t *counts,
+                       int buffers_on_device, int device, void *stream, skm_em_plan **out);
+int skm_em_plan_from_mapper(skm_mapper *mapper, int64_t n_transcripts, void *stream,
+                            skm_em_plan **out);
+int skm_em_plan_info(const skm_em_plan *plan, int64_t info[5]);
+void skm_em_plan_destroy(skm_em_plan *plan);
+int skm_em_plan_run(const skm_em_plan *plan, const double *counts, const double *eff_len,
+                    const double *x0, int64_t n_replicates, int64_t max_iters, double *out_x,
+                    int32_t *out_iters, int buffers_on_device, void *stream);
+int skm_em_plan_bootstrap(const skm_em_plan *plan, const int64_t *counts, const double *eff_len,
+                          const double *x0, int64_t n_replicates, int64_t first_replicate,
+                          uint64_t seed, int64_t max_iters, int tpm, double *out_x,
+                          int32_t *out_iters, int buffers_on_device, void *stream);
 
 /* Replaces: scipy.stats.multinomial(n, p).rvs() at infer.py:108-111 — resample
  * n = sum(counts) reads with replacement, n_replicates times.  Integer-exact,

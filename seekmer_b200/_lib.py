@@ -26,7 +26,8 @@ EXPORTS = (
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
     'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_classes_merge_packed', 'skm_release_cache', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
-    'skm_build_kmer_table',
+    'skm_build_kmer_table', 'skm_em_plan_create', 'skm_em_plan_from_mapper', 'skm_em_plan_info',
+    'skm_em_plan_destroy', 'skm_em_plan_run', 'skm_em_plan_bootstrap',
 )
 
 
@@ -94,6 +95,18 @@ def load():
     L.skm_em_samples.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, ci, ci, vp]
     L.skm_em_bootstrap.restype = ci
     L.skm_em_bootstrap.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u64, i64, ci, vp, vp, ci, ci, vp]
+    L.skm_em_plan_create.restype = ci
+    L.skm_em_plan_create.argtypes = [vp, vp, i64, i64, i64, vp, ci, ci, vp, ctypes.POINTER(vp)]
+    L.skm_em_plan_from_mapper.restype = ci
+    L.skm_em_plan_from_mapper.argtypes = [vp, i64, vp, ctypes.POINTER(vp)]
+    L.skm_em_plan_info.restype = ci
+    L.skm_em_plan_info.argtypes = [vp, vp]
+    L.skm_em_plan_destroy.restype = None
+    L.skm_em_plan_destroy.argtypes = [vp]
+    L.skm_em_plan_run.restype = ci
+    L.skm_em_plan_run.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, ci, vp]
+    L.skm_em_plan_bootstrap.restype = ci
+    L.skm_em_plan_bootstrap.argtypes = [vp, vp, vp, vp, i64, i64, u64, i64, ci, vp, vp, ci, vp]
     L.skm_multinomial.restype = ci
     L.skm_multinomial.argtypes = [vp, i64, i64, i64, u64, vp, ci, ci, vp]
     L.skm_synth_reads.restype = ci
@@ -272,7 +285,7 @@ class DeviceMapper:
     def sizes(self, stream=None):
         a = numpy.zeros(8, dtype='i8')
         check(load().skm_classes_size(self._h, _np_ptr(a), stream))
-        keys = ('n_classes', 'n_ids', 'unaligned', 'aligned', 'capacity', 'status', 'short_reads', 'pool_cursor')
+        keys = ('n_classes', 'n_ids', 'unaligned', 'aligned', 'capacity', 'status', 'short_units', 'pool_cursor')
         return dict(zip(keys, a.tolist()))
 
     def export(self, with_slots=False, stream=None):
@@ -299,7 +312,7 @@ class DeviceMapper:
                       + numpy.arange(n_ids, dtype='i8'))
             ids = ids[gather]
         out = dict(key_offsets=new_off, key_ids=ids, counts=counts[order], first_unit=first[order],
-                   fld=fld, unaligned=sz['unaligned'], aligned=sz['aligned'], short_reads=sz['short_reads'])
+                   fld=fld, unaligned=sz['unaligned'], aligned=sz['aligned'], short_units=sz['short_units'])
         if with_slots:
             out['slots'] = slots[order]
         return out
@@ -392,6 +405,78 @@ class DeviceMapper:
     def close(self):
         if getattr(self, '_h', None):
             load().skm_mapper_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EmPlan:
+    """Handle to a device-resident EM class structure (``skm_em_plan``): CSR by class + CSC by
+    transcript, built once; the main EM and the bootstrap replicates run on it."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = numpy.zeros(5, dtype='i8')
+        check(load().skm_em_plan_info(self._h, _np_ptr(info)))
+        self.n_classes, self.nnz, self.n_transcripts, self.device = (int(v) for v in info[:4])
+        self.owns_counts = bool(info[4])
+
+    @classmethod
+    def from_csr(cls, class_ptr, class_tx, n_transcripts, counts=None, device=0, stream=None):
+        """From host CSR arrays (int64[C + 1], int32[nnz]); integer `counts` make bootstraps possible
+        without passing them again."""
+        require_device()
+        class_ptr = numpy.ascontiguousarray(class_ptr, dtype='i8')
+        class_tx = numpy.ascontiguousarray(class_tx, dtype='i4')
+        if counts is not None:
+            counts = numpy.ascontiguousarray(counts, dtype='i8')
+        handle = ctypes.c_void_p()
+        check(load().skm_em_plan_create(_np_ptr(class_ptr), _np_ptr(class_tx), class_ptr.shape[0] - 1,
+                                        class_tx.shape[0], int(n_transcripts), _ptr(counts), 0, int(device),
+                                        stream, ctypes.byref(handle)))
+        return cls(handle)
+
+    @classmethod
+    def from_mapper(cls, mapper, n_transcripts=0, stream=None):
+        """From a `DeviceMapper`'s dictionary, device to device, classes in first-seen order."""
+        handle = ctypes.c_void_p()
+        check(load().skm_em_plan_from_mapper(mapper._h, int(n_transcripts), stream, ctypes.byref(handle)))
+        return cls(handle)
+
+    def run(self, eff_len, x0, counts=None, max_iters=0, stream=None):
+        """`infer.em` for the rows of x0 (R, T); counts (R, C) fp64 or None = the plan's own (R = 1).
+        Returns (x (R, T), iterations (R,))."""
+        x0 = numpy.ascontiguousarray(numpy.atleast_2d(x0), dtype='f8')
+        eff_len = numpy.ascontiguousarray(eff_len, dtype='f8')
+        if counts is not None:
+            counts = numpy.ascontiguousarray(numpy.atleast_2d(counts), dtype='f8')
+        out = numpy.zeros_like(x0)
+        iters = numpy.zeros(x0.shape[0], dtype='i4')
+        check(load().skm_em_plan_run(self._h, _ptr(counts), _np_ptr(eff_len), _np_ptr(x0), x0.shape[0],
+                                     int(max_iters), _np_ptr(out), _np_ptr(iters), 0, stream))
+        return out, iters
+
+    def bootstrap(self, eff_len, x0, n_replicates, seed, first_replicate=0, counts=None, tpm=True, max_iters=0,
+                  stream=None):
+        """Resample + EM (+ TPM step) for replicates [first_replicate, first_replicate + n)."""
+        x0 = numpy.ascontiguousarray(x0, dtype='f8')
+        eff_len = numpy.ascontiguousarray(eff_len, dtype='f8')
+        if counts is not None:
+            counts = numpy.ascontiguousarray(counts, dtype='i8')
+        out = numpy.zeros((n_replicates, x0.shape[0]), dtype='f8')
+        iters = numpy.zeros(n_replicates, dtype='i4')
+        check(load().skm_em_plan_bootstrap(self._h, _ptr(counts), _np_ptr(eff_len), _np_ptr(x0), int(n_replicates),
+                                           int(first_replicate), int(seed) & (2 ** 64 - 1), int(max_iters),
+                                           int(bool(tpm)), _np_ptr(out), _np_ptr(iters), 0, stream))
+        return out, iters
+
+    def close(self):
+        if getattr(self, '_h', None):
+            load().skm_em_plan_destroy(self._h)
             self._h = None
 
     def __del__(self):

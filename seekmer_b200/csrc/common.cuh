@@ -86,6 +86,7 @@ enum : uint32_t {
     ST_DICT_FULL = 2u,
     ST_POOL_FULL = 4u,
     ST_SHORT_READ = 8u,
+    ST_KEY_COLLISION = 16u,  // two different id tuples with the same 128-bit key (never seen; refused)
 };
 
 }  // namespace skm

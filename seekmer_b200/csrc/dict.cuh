@@ -19,6 +19,8 @@ struct DictDev {
     unsigned long long *scalars;  // [0]=pool cursor [1]=n_classes [2]=unaligned [3]=aligned [4]=ids stored
     unsigned long long *fld;      // FLD_BINS
     uint32_t *status;
+    uint32_t weak_keys;           // test hook (SKM_TEST_WEAK_KEYS): keys carry the tuple length only, so
+                                  // different tuples collide and the id comparison below is exercised
 };
 
 struct DenseIds {
@@ -72,6 +74,36 @@ __device__ __forceinline__ ulonglong2 tuple_key(const Ids &ids, int n, bool stri
     return make_ulonglong2(h1, h2);
 }
 
+template <typename Ids>
+__device__ __forceinline__ ulonglong2 dict_key(const DictDev &d, const Ids &ids, int n, bool strip_sign)
+{
+    if (d.weak_keys) return make_ulonglong2((uint64_t)n, (uint64_t)n);
+    return tuple_key(ids, n, strip_sign);
+}
+
+// A unit that found its key already in the table compares its ids with the stored tuple, so that
+// equal keys of different tuples (probability ~ C^2 / 2^129) are refused instead of merged.  `len`
+// is written last by the slot's owner (after a fence): 0 means the ids are not visible yet - only
+// possible for a class inserted by this very launch - and the comparison is left to the class's
+// later units.
+template <typename Ids>
+__device__ __forceinline__ void dict_verify_hit(const DictDev &d, int64_t s, const Ids &ids, int n, bool strip_sign)
+{
+    const uint32_t stored = *reinterpret_cast<volatile const uint32_t *>(&d.len[s]);
+    if (stored == 0) return;
+    bool same = stored == (uint32_t)n;
+    if (same) {
+        __threadfence();  // ids were written before len
+        const volatile int32_t *p = d.pool + *reinterpret_cast<volatile const uint32_t *>(&d.pool_off[s]);
+        for (int i = 0; i < n; ++i) {
+            int32_t e = ids.get(i);
+            if (strip_sign && e < 0) e = ~e;
+            same = same && p[i] == e;
+        }
+    }
+    if (!same) atomicOr(d.status, ST_KEY_COLLISION);
+}
+
 // Find the key's slot or claim an empty one; returns the slot, or -1 when the table is full.
 // `won` tells the caller that it claimed the slot and owes the class its ids in the pool.
 __device__ __forceinline__ int64_t dict_find_or_claim(const DictDev &d, ulonglong2 key, bool &won)
@@ -118,7 +150,8 @@ __device__ __forceinline__ void dict_store_ids(const DictDev &d, int64_t s, unsi
         d.pool[off + i] = e;
     }
     d.pool_off[s] = (uint32_t)off;
-    d.len[s] = (uint32_t)n;
+    __threadfence();  // dict_verify_hit reads len first
+    *reinterpret_cast<volatile uint32_t *>(&d.len[s]) = (uint32_t)n;
 }
 
 // Find-or-insert for callers without warp-level aggregation (the merge path).
@@ -132,6 +165,8 @@ __device__ int64_t dict_find_or_insert(const DictDev &d, ulonglong2 key, const I
         dict_store_ids(d, s, atomicAdd(&d.scalars[0], (unsigned long long)n), ids, n, strip_sign);
         atomicAdd(&d.scalars[1], 1ULL);
         atomicAdd(&d.scalars[4], (unsigned long long)n);
+    } else if (s >= 0) {
+        dict_verify_hit(d, s, ids, n, strip_sign);
     }
     return s;
 }

@@ -14,9 +14,11 @@
 #include <ctime>
 #include <mutex>
 #include <vector>
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "em_plan.cuh"
 
 namespace skm {
 
@@ -281,6 +283,141 @@ __global__ void em_decide_kernel(const EmState s)
     }
     __syncthreads();
     if (threadIdx.x == 0) *s.n_active = still;
+}
+
+// ---- the fused iteration loop --------------------------------------------------------------
+// One cooperative launch runs up to n_iters EM iterations: E step, grid barrier, M step (with the
+// convergence reduction), grid barrier, the loop condition of infer.py:160 per replicate, grid
+// barrier.  Nothing returns to the host between iterations; the whole structure (~46 MB at
+// human scale) stays in L2 from the second iteration on.  Row arithmetic is exactly that of the
+// one-launch-per-step kernels above.  Everything another SM may have written during this
+// launch (x, inner, active, n_active) is read past L1 (ld.global.cg); the class structure,
+// counts and lengths are read-only and may sit in L1.
+namespace cg = cooperative_groups;
+constexpr int EM_LOOP_THREADS = 512;
+
+struct EmLoop {
+    double *xa, *xb;      // ping-pong buffers; iteration 0 reads xa
+    int32_t *executed;    // iterations this launch executed (the result sits in xa when even, xb when odd)
+    int n_iters;
+};
+
+__device__ __forceinline__ void em_decide_block(const EmState &s)
+{
+    __shared__ int still;
+    if (threadIdx.x == 0) still = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < s.R; r += blockDim.x) {
+        if (__ldcg(s.active + r)) {
+            s.iters[r] += 1;
+            const double d = __longlong_as_double((long long)__ldcg(s.maxd + r));
+            if (d > 0.01) atomicAdd(&still, 1);
+            else s.active[r] = 0;
+            s.maxd[r] = 0ULL;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *s.n_active = still;
+}
+
+// MODE 0: one replicate; 1: R replicates of one structure ([row][replicate]); 2: samples laid end to end
+template <int MODE>
+__global__ void __launch_bounds__(EM_LOOP_THREADS) em_loop_kernel(const EmState s, const EmLoop lp)
+{
+    cg::grid_group grid = cg::this_grid();
+    const double *cur = lp.xa;
+    double *nxt = lp.xb;
+    const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+    int it = 0;
+    for (; it < lp.n_iters; ++it) {
+        if (__ldcg(s.n_active) == 0) break;  // the same value for the whole grid: written before the last barrier
+        // ---- E step
+        if (MODE == 1) {
+            const int64_t total = s.n_classes * s.R;
+            for (int64_t e = gtid; e < total; e += gsize) {
+                const int64_t c = e / s.R;
+                const int r = (int)(e - c * s.R);
+                if (!__ldcg(s.active + r)) continue;
+                double sum = 0.0;
+                const int64_t b = __ldg(s.class_ptr + c), en = __ldg(s.class_ptr + c + 1);
+                for (int64_t j = b; j < en; ++j) sum = __dadd_rn(sum, __ldcg(cur + (int64_t)__ldg(s.class_tx + j) * s.R + r));
+                s.inner[e] = __ddiv_rn(sum, __ldg(s.counts + e));
+            }
+        } else {
+            for (int64_t c = gtid; c < s.n_classes; c += gsize) {
+                if (MODE == 2 && !__ldcg(s.active + __ldg(s.class_sample + c))) continue;
+                double sum = 0.0;
+                const int64_t b = __ldg(s.class_ptr + c), en = __ldg(s.class_ptr + c + 1);
+                for (int64_t j = b; j < en; ++j) sum = __dadd_rn(sum, __ldcg(cur + __ldg(s.class_tx + j)));
+                s.inner[c] = __ddiv_rn(sum, __ldg(s.counts + c));
+            }
+        }
+        grid.sync();
+        // ---- M step
+        if (MODE == 1) {
+            const int64_t total = s.n_tx * s.R;
+            for (int64_t e = gtid; e < total; e += gsize) {
+                const int64_t tt = e / s.R;
+                const int r = (int)(e - tt * s.R);
+                const double xt = __ldcg(cur + e);
+                if (!__ldcg(s.active + r)) {
+                    nxt[e] = xt;
+                    continue;
+                }
+                double acc = 0.0;
+                const int64_t b = __ldg(s.tx_ptr + tt), en = __ldg(s.tx_ptr + tt + 1);
+                for (int64_t j = b; j < en; ++j)
+                    acc = __dadd_rn(acc, __ddiv_rn(xt, __ldcg(s.inner + (int64_t)__ldg(s.tx_class + j) * s.R + r)));
+                double v = __ddiv_rn(__ddiv_rn(acc, __ldg(s.eff_len + tt)), __ldg(s.n + r));
+                if (v != v) v = 0.0;
+                note_change(s, r, v, xt);
+                nxt[e] = v;
+            }
+        } else {
+            // 8 lanes per transcript row, strided partial sums, fixed-order shuffle tree
+            const int sub = threadIdx.x & 7;
+            for (int64_t g0 = (gtid >> 5) * 4; g0 < s.n_tx; g0 += gsize >> 3) {  // warp-uniform bound
+                const int64_t g = g0 + ((threadIdx.x & 31) >> 3);
+                const bool ok = g < s.n_tx;
+                int sample = 0;
+                bool live = ok;
+                double acc = 0.0, xt = 0.0;
+                if (ok) {
+                    if (MODE == 2) {
+                        sample = (int)(g / s.tx_per_sample);
+                        live = __ldcg(s.active + sample) != 0;
+                    }
+                    xt = __ldcg(cur + g);
+                    if (live) {
+                        const int64_t b = __ldg(s.tx_ptr + g), en = __ldg(s.tx_ptr + g + 1);
+                        for (int64_t j = b + sub; j < en; j += 8)
+                            acc = __dadd_rn(acc, __ddiv_rn(xt, __ldcg(s.inner + __ldg(s.tx_class + j))));
+                    }
+                }
+                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+                if (ok && sub == 0) {
+                    if (!live) {
+                        nxt[g] = xt;  // a finished sample is carried through the ping-pong unchanged
+                    } else {
+                        double v = __ddiv_rn(__ddiv_rn(acc, __ldg(s.eff_len + g)), __ldg(s.n + sample));
+                        if (v != v) v = 0.0;
+                        note_change(s, sample, v, xt);
+                        nxt[g] = v;
+                    }
+                }
+            }
+        }
+        grid.sync();
+        if (blockIdx.x == 0) em_decide_block(s);
+        grid.sync();
+        const double *t0 = cur;
+        cur = nxt;
+        nxt = const_cast<double *>(t0);
+    }
+    if (gtid == 0) *lp.executed = it;
 }
 
 // ---- many samples with their own class structures (skm_em_samples) ---------------------------
@@ -678,11 +815,84 @@ SKM_API int skm_effective_lengths(const int64_t *fld, const double *lengths, int
     return SKM_OK;
 }
 
+// ---- CSC by transcript: stable radix sort of (row, nnz index) ---------------------------------
+// rows = transcripts (or sample x transcript rows); `d_row` holds the row of every nnz entry in CSR
+// order.  Outputs (cudaMalloc, owned by the caller): tx_ptr[n_rows + 1], tx_class[nnz].
+static int build_csc(const int64_t *d_ptr, const int32_t *d_row, int64_t C, int64_t nnz, int64_t n_rows,
+                     cudaStream_t st, int64_t *tx_ptr, int32_t *tx_class, const char *who)
+{
+    DeviceBuf b_rowof, b_idx, b_keys_out, b_idx_out, b_hist, b_tmp, b_bad;
+    EM_TRY(b_rowof.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_idx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_keys_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_idx_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_hist.alloc(sizeof(unsigned long long) * (size_t)(n_rows + 1), st));
+    EM_TRY(b_bad.alloc(sizeof(unsigned int), st));
+    EM_TRY(cudaMemsetAsync(b_hist.p, 0, sizeof(unsigned long long) * (size_t)(n_rows + 1), st));
+    EM_TRY(cudaMemsetAsync(b_bad.p, 0, sizeof(unsigned int), st));
+    expand_rows_kernel<<<blocks_for(C, 256), 256, 0, st>>>(d_ptr, C, b_rowof.as<int32_t>());
+    iota_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_idx.as<int32_t>(), nnz);
+    histogram_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(d_row, nnz, n_rows, b_hist.as<unsigned long long>(),
+                                                          b_bad.as<unsigned int>());
+    {
+        size_t tmp_sort = 0, tmp_scan = 0;
+        int end_bit = 1;
+        while ((1LL << end_bit) < n_rows) ++end_bit;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, d_row, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
+                                        b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st);
+        cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, b_hist.as<unsigned long long>(),
+                                      reinterpret_cast<unsigned long long *>(tx_ptr), (int)(n_rows + 1), st);
+        EM_TRY(b_tmp.alloc(std::max(tmp_sort, tmp_scan), st));
+        size_t tmp = std::max(tmp_sort, tmp_scan);
+        EM_TRY(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp, d_row, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
+                                               b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st));
+        tmp = std::max(tmp_sort, tmp_scan);
+        EM_TRY(cub::DeviceScan::InclusiveSum(b_tmp.p, tmp, b_hist.as<unsigned long long>(),
+                                             reinterpret_cast<unsigned long long *>(tx_ptr), (int)(n_rows + 1), st));
+    }
+    gather_i32_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_rowof.as<int32_t>(), b_idx_out.as<int32_t>(), nnz, tx_class);
+    EM_TRY(cudaGetLastError());
+    unsigned int bad = 0;
+    EM_TRY(cudaMemcpyAsync(&bad, b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    EM_TRY(cudaStreamSynchronize(st));  // also: the scratch above goes back to the cache after this
+    if (bad) return fail(SKM_ERR_INVALID, std::string(who) + ": transcript index out of range in class_tx");
+    return SKM_OK;
+}
+
+// One cooperative launch of the fused iteration loop; *executed = iterations it ran.
+static int launch_em_loop(int mode, const EmState &s, double *xa, double *xb, int n_iters, int32_t *d_executed,
+                          int device, cudaStream_t st)
+{
+    static std::mutex mu;
+    static int blocks_per_sm[64][3];
+    static int sms[64];
+    const void *fn = mode == 0 ? (const void *)em_loop_kernel<0>
+                   : mode == 1 ? (const void *)em_loop_kernel<1> : (const void *)em_loop_kernel<2>;
+    const int d = device & 63;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (blocks_per_sm[d][mode] == 0) {
+            int b = 0;
+            EM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, EM_LOOP_THREADS, 0));
+            if (b < 1) return fail(SKM_ERR_CUDA, "skm_em: the iteration kernel does not fit on this device");
+            blocks_per_sm[d][mode] = b;
+            EM_TRY(cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, device));
+        }
+    }
+    // all blocks must be resident (grid barrier): at most occupancy x SMs, no more than the rows need
+    const int64_t rows = mode == 1 ? std::max(s.n_classes, s.n_tx) * s.R : std::max(s.n_classes, s.n_tx * 8);
+    const int64_t want = (rows + EM_LOOP_THREADS - 1) / EM_LOOP_THREADS;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)blocks_per_sm[d][mode] * sms[d]));
+    EmState state = s;
+    EmLoop lp{xa, xb, d_executed, n_iters};
+    void *args[] = {&state, &lp};
+    EM_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(EM_LOOP_THREADS), args, 0, st));
+    return SKM_OK;
+}
+
 struct EmInputs {
-    const int64_t *d_ptr;      // CSR by class (device)
-    const int32_t *d_tx;
+    const skm_em_plan *plan;   // structure, both orders (device)
     const double *d_len;       // effective lengths [T]
-    int64_t C, nnz, T;
     int R;
     int64_t max_iters;
     const double *counts_rc;   // class counts [R][C] (ABI layout), or
@@ -694,53 +904,11 @@ struct EmInputs {
 // The EM proper on device-resident inputs; d_out [R][T], d_iters [R] (device).
 static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStream_t st)
 {
-    const int64_t C = in.C, T = in.T, nnz = in.nnz;
+    const int64_t C = in.plan->C, T = in.plan->T;
     const int R = in.R;
     const int64_t max_iters = in.max_iters > 0 ? in.max_iters : 1000000;
+    const int device = in.plan->device;
     Trace trace(st);
-    // ---- CSC by transcript: stable radix sort of (transcript, nnz index)
-    DeviceBuf b_rowof, b_idx, b_keys_out, b_idx_out, b_txclass, b_hist, b_txptr, b_tmp, b_bad;
-    EM_TRY(b_rowof.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_idx.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_keys_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_idx_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_txclass.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_hist.alloc(sizeof(unsigned long long) * (size_t)(T + 1), st));
-    EM_TRY(b_txptr.alloc(sizeof(int64_t) * (size_t)(T + 1), st));
-    EM_TRY(b_bad.alloc(sizeof(unsigned int), st));
-    EM_TRY(cudaMemsetAsync(b_hist.p, 0, sizeof(unsigned long long) * (size_t)(T + 1), st));
-    EM_TRY(cudaMemsetAsync(b_bad.p, 0, sizeof(unsigned int), st));
-    expand_rows_kernel<<<blocks_for(C, 256), 256, 0, st>>>(in.d_ptr, C, b_rowof.as<int32_t>());
-    iota_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_idx.as<int32_t>(), nnz);
-    histogram_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(in.d_tx, nnz, T, b_hist.as<unsigned long long>(),
-                                                          b_bad.as<unsigned int>());
-    {
-        size_t tmp_sort = 0, tmp_scan = 0;
-        int end_bit = 1;
-        while ((1LL << end_bit) < T) ++end_bit;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, in.d_tx, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
-                                        b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st);
-        cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, b_hist.as<unsigned long long>(),
-                                      b_txptr.as<unsigned long long>(), (int)(T + 1), st);
-        EM_TRY(b_tmp.alloc(std::max(tmp_sort, tmp_scan), st));
-        size_t tmp = std::max(tmp_sort, tmp_scan);
-        EM_TRY(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp, in.d_tx, b_keys_out.as<int32_t>(), b_idx.as<int32_t>(),
-                                               b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st));
-        tmp = std::max(tmp_sort, tmp_scan);
-        EM_TRY(cub::DeviceScan::InclusiveSum(b_tmp.p, tmp, b_hist.as<unsigned long long>(),
-                                             b_txptr.as<unsigned long long>(), (int)(T + 1), st));
-    }
-    gather_i32_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_rowof.as<int32_t>(), b_idx_out.as<int32_t>(), nnz,
-                                                           b_txclass.as<int32_t>());
-    EM_TRY(cudaGetLastError());
-    {
-        unsigned int bad = 0;
-        EM_TRY(cudaMemcpyAsync(&bad, b_bad.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
-        EM_TRY(cudaStreamSynchronize(st));
-        if (bad) return fail(SKM_ERR_INVALID, "skm_em: transcript index out of range in class_tx");
-    }
-
-    trace.mark("em: CSC build");
     // ---- state in kernel layout
     DeviceBuf b_cnt, b_xa, b_xb, b_inner, b_n, b_maxd, b_active, b_iters, b_nactive;
     EM_TRY(b_xa.alloc(sizeof(double) * (size_t)(T * R), st));
@@ -750,7 +918,7 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * (size_t)R, st));
     EM_TRY(b_active.alloc(sizeof(int32_t) * (size_t)R, st));
     EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R, st));
-    EM_TRY(b_nactive.alloc(sizeof(int32_t), st));
+    EM_TRY(b_nactive.alloc(sizeof(int32_t) * 2, st));  // [0] = replicates still running, [1] = iterations of the last launch
     const double *d_cnt = in.counts_cr;
     if (!d_cnt) {
         d_cnt = in.counts_rc;  // [R][C]; the same thing as [C][R] for one replicate
@@ -770,10 +938,10 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     fill_i32_kernel<<<1, 32, 0, st>>>(b_nactive.as<int32_t>(), 1, R);
 
     EmState s{};
-    s.class_ptr = in.d_ptr;
-    s.class_tx = in.d_tx;
-    s.tx_ptr = b_txptr.as<int64_t>();
-    s.tx_class = b_txclass.as<int32_t>();
+    s.class_ptr = in.plan->class_ptr;
+    s.class_tx = in.plan->class_tx;
+    s.tx_ptr = in.plan->tx_ptr;
+    s.tx_class = in.plan->tx_class;
     s.counts = d_cnt;
     s.eff_len = in.d_len;
     s.n = b_n.as<double>();
@@ -785,17 +953,15 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     s.n_classes = C;
     s.n_tx = T;
     s.R = R;
+    int32_t *d_executed = b_nactive.as<int32_t>() + 1;
 
     trace.mark("em: state setup");
     double *cur = b_xa.as<double>(), *nxt = b_xb.as<double>();
-    // Iterations are enqueued in groups; once every replicate has met the stop condition the
-    // remaining launches of a group are no-ops (they test *n_active first), so the executed
-    // iteration count is exact while the host only synchronises once per group.
-    //
-    // Replicates stop at very different iteration counts (bootstraps: mean ~40, max > 100), so
-    // whenever at most three quarters of the live columns are still running the finished ones are written
-    // to the output and the state is compacted to the running columns: the work of an
-    // iteration follows the number of replicates that still need it.
+    // One replicate: ONE launch runs the whole EM (the loop condition is evaluated on the device).
+    // Many replicates stop at very different iteration counts (bootstraps: mean ~40, max > 100), so
+    // they run in launches of GROUP iterations; whenever at most three quarters of the live columns
+    // are still running the finished ones are written to the output and the state is compacted to
+    // the running columns: the work of an iteration follows the replicates that still need it.
     const int GROUP = 8;
     int64_t done = 0;
     int32_t n_active = R;
@@ -809,32 +975,20 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     EM_TRY(b_map.alloc(sizeof(int32_t) * 2 * (size_t)R, st));
     const bool may_compact = R > 1 && (in.counts_cr != nullptr || b_cnt.p != nullptr);  // counts buffer is scratch
     double *counts_buf = const_cast<double *>(d_cnt), *inner_buf = b_inner.as<double>();
-    double *group_cur = cur, *group_nxt = nxt;
-    int64_t group_base = 0;
     while (n_active > 0 && done < max_iters) {
-        const int g = (int)std::min<int64_t>(GROUP, max_iters - done);
-        const unsigned grid_c = (unsigned)std::min<int64_t>((C * Rc + EM_BLOCK - 1) / EM_BLOCK, 1 << 20);
-        const unsigned grid_t = (unsigned)std::min<int64_t>((T * Rc + EM_BLOCK - 1) / EM_BLOCK, 1 << 20);
-        group_cur = cur;
-        group_nxt = nxt;
-        group_base = done;
-        for (int k = 0; k < g; ++k) {
-            if (R == 1) {
-                em_class_kernel_r1<<<blocks_for(C, EM_BLOCK), EM_BLOCK, 0, st>>>(s, cur);
-                em_tx_kernel_r1<<<blocks_for(T * 8, EM_BLOCK), EM_BLOCK, 0, st>>>(s, cur, nxt);
-            } else {
-                em_class_kernel<<<grid_c, EM_BLOCK, 0, st>>>(s, cur);
-                em_tx_kernel<<<grid_t, EM_BLOCK, 0, st>>>(s, cur, nxt);
-            }
-            em_decide_kernel<<<1, 128, 0, st>>>(s);
-            std::swap(cur, nxt);
-        }
-        done += g;
-        EM_TRY(cudaGetLastError());
-        EM_TRY(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        const int64_t left = max_iters - done;
+        const int g = (int)std::min<int64_t>(R == 1 ? (int64_t)1 << 30 : GROUP, left);
+        int rc = launch_em_loop(R == 1 ? 0 : 1, s, cur, nxt, g, d_executed, device, st);
+        if (rc) return rc;
+        int32_t h2[2] = {0, 0};
+        EM_TRY(cudaMemcpyAsync(h2, s.n_active, sizeof(h2), cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
+        n_active = h2[0];
+        done += h2[1];
+        if (h2[1] & 1) std::swap(cur, nxt);  // the last executed iteration wrote the other buffer
+        if (h2[1] == 0) break;
         if (!may_compact || n_active <= 0 || 4 * n_active > 3 * Rc || Rc <= 8 || done >= max_iters) continue;
-        // ---- compact to the running columns (every iteration of this group did execute) --------
+        // ---- compact to the running columns ------------------------------------------------------
         EM_TRY(cudaMemcpyAsync(h_active.data(), s.active, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaMemcpyAsync(h_n.data(), s.n, sizeof(double) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
@@ -879,16 +1033,11 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
         Rc = n_keep;
         s.R = Rc;
     }
-    // Kernels of the last group enqueued after the last replicate stopped are no-ops, so the
-    // device stopped ping-ponging while the host kept swapping.  The buffer written by the last
-    // EXECUTED iteration holds every live column's final x: columns that stopped earlier are
-    // copied through on each later iteration.
+    // `cur` holds every live column's final x: columns that stopped earlier are copied through on
+    // each later iteration
     {
         EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
-        const int64_t executed = *std::max_element(h_iters.begin(), h_iters.begin() + Rc);
-        const int64_t in_group = executed - group_base;  // iterations the last group really ran
-        cur = (in_group & 1) ? group_nxt : group_cur;
         for (int c = 0; c < Rc; ++c) final_iters[(size_t)orig[(size_t)c]] = h_iters[(size_t)c];
     }
 
@@ -911,49 +1060,147 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     return SKM_OK;
 }
 
-SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
-                   const double *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
-                   int64_t n_replicates, int64_t max_iters, double *out_x, int32_t *out_iters,
-                   int buffers_on_device, int device, void *stream)
+// ---- plans ---------------------------------------------------------------------------------------
+SKM_API void skm_em_plan_destroy(skm_em_plan *p)
 {
-    if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
-        return fail(SKM_ERR_INVALID, "skm_em: NULL argument");
-    if (n_classes <= 0 || nnz <= 0 || n_transcripts <= 0 || n_replicates <= 0)
-        return fail(SKM_ERR_INVALID, "skm_em: empty problem");
+    if (!p) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(p->device);
+    cudaFree(p->class_ptr);
+    cudaFree(p->class_tx);
+    cudaFree(p->tx_ptr);
+    cudaFree(p->tx_class);
+    cudaFree(p->counts);
+    cudaSetDevice(prev);
+    delete p;
+}
+
+int skm::em_plan_adopt(int device, int64_t C, int64_t nnz, int64_t T, int64_t *class_ptr, int32_t *class_tx,
+                       int64_t *counts, cudaStream_t st, skm_em_plan **out)
+{
+    skm_em_plan *p = new skm_em_plan();
+    p->device = device;
+    p->C = C;
+    p->nnz = nnz;
+    p->T = T;
+    p->class_ptr = class_ptr;
+    p->class_tx = class_tx;
+    p->counts = counts;
+    cudaError_t e = cudaMalloc(&p->tx_ptr, sizeof(int64_t) * (size_t)(T + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->tx_class, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1));
+    if (e != cudaSuccess) {
+        skm_em_plan_destroy(p);
+        return fail(SKM_ERR_OOM, std::string("skm_em_plan: ") + cudaGetErrorString(e));
+    }
+    Trace trace(st);
+    const int rc = build_csc(class_ptr, class_tx, C, nnz, T, st, p->tx_ptr, p->tx_class, "skm_em_plan");
+    trace.mark("em plan: CSC build");
+    if (rc) {
+        skm_em_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return SKM_OK;
+}
+
+static int check_em_shape(const char *who, int64_t n_classes, int64_t nnz, int64_t n_transcripts, int device)
+{
+    if (n_classes <= 0 || nnz <= 0 || n_transcripts <= 0) return fail(SKM_ERR_INVALID, std::string(who) + ": empty problem");
     if (nnz >= (1LL << 31) || n_classes >= (1LL << 31) || n_transcripts >= (1LL << 31))
-        return fail(SKM_ERR_INVALID, "skm_em: structure too large for int32 indices");
+        return fail(SKM_ERR_INVALID, std::string(who) + ": structure too large for int32 indices");
     if (skm_device_count() <= device || device < 0)
-        return fail(SKM_ERR_CUDA, "skm_em: no such CUDA device (there is no CPU fallback)");
+        return fail(SKM_ERR_CUDA, std::string(who) + ": no such CUDA device (there is no CPU fallback)");
+    return SKM_OK;
+}
+
+SKM_API int skm_em_plan_create(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
+                               int64_t n_transcripts, const int64_t *counts, int buffers_on_device, int device,
+                               void *stream, skm_em_plan **out)
+{
+    if (!out) return fail(SKM_ERR_INVALID, "skm_em_plan_create: out is NULL");
+    *out = nullptr;
+    if (!class_ptr || !class_tx) return fail(SKM_ERR_INVALID, "skm_em_plan_create: NULL argument");
+    int rc = check_em_shape("skm_em_plan_create", n_classes, nnz, n_transcripts, device);
+    if (rc) return rc;
     EM_TRY(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int R = (int)n_replicates;
-    const int64_t C = n_classes, T = n_transcripts;
+    int64_t *d_ptr = nullptr, *d_counts = nullptr;
+    int32_t *d_tx = nullptr;
+    const cudaMemcpyKind kind = buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaError_t e = cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(n_classes + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tx, sizeof(int32_t) * (size_t)nnz);
+    if (e == cudaSuccess && counts) e = cudaMalloc(&d_counts, sizeof(int64_t) * (size_t)n_classes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ptr, class_ptr, sizeof(int64_t) * (size_t)(n_classes + 1), kind, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tx, class_tx, sizeof(int32_t) * (size_t)nnz, kind, st);
+    if (e == cudaSuccess && counts) e = cudaMemcpyAsync(d_counts, counts, sizeof(int64_t) * (size_t)n_classes, kind, st);
+    if (e != cudaSuccess) {
+        cudaFree(d_ptr);
+        cudaFree(d_tx);
+        cudaFree(d_counts);
+        return fail(e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,
+                    std::string("skm_em_plan_create: ") + cudaGetErrorString(e));
+    }
+    return em_plan_adopt(device, n_classes, nnz, n_transcripts, d_ptr, d_tx, d_counts, st, out);
+}
 
-    DeviceBuf b_ptr, b_tx, b_cnt_in, b_len, b_x_in, b_out, b_iters;
-    EmInputs in{class_ptr, class_tx, eff_len, C, nnz, T, R, max_iters, counts, nullptr, x0, nullptr};
+SKM_API int skm_em_plan_info(const skm_em_plan *p, int64_t info[5])
+{
+    if (!p || !info) return fail(SKM_ERR_INVALID, "skm_em_plan_info: NULL argument");
+    info[0] = p->C;
+    info[1] = p->nnz;
+    info[2] = p->T;
+    info[3] = p->device;
+    info[4] = p->counts != nullptr;
+    return SKM_OK;
+}
+
+__global__ void i64_to_f64_kernel(const int64_t *__restrict__ src, double *__restrict__ dst, int64_t n)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (double)src[i];
+}
+
+SKM_API int skm_em_plan_run(const skm_em_plan *p, const double *counts, const double *eff_len, const double *x0,
+                            int64_t n_replicates, int64_t max_iters, double *out_x, int32_t *out_iters,
+                            int buffers_on_device, void *stream)
+{
+    if (!p || !eff_len || !x0 || !out_x) return fail(SKM_ERR_INVALID, "skm_em: NULL argument");
+    if (n_replicates <= 0) return fail(SKM_ERR_INVALID, "skm_em: empty problem");
+    if (!counts && (!p->counts || n_replicates != 1))
+        return fail(SKM_ERR_INVALID, "skm_em: counts may only be NULL for one replicate of a plan that owns its counts");
+    EM_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = (int)n_replicates;
+    const int64_t C = p->C, T = p->T;
+    Trace trace(st);
+    DeviceBuf b_cnt_in, b_len, b_x_in, b_out, b_iters;
+    EmInputs in{p, eff_len, R, max_iters, counts, nullptr, x0, nullptr};
     double *d_out = out_x;
     int32_t *d_iters = out_iters;
+    if (!counts) {
+        EM_TRY(b_cnt_in.alloc(sizeof(double) * (size_t)C, st));
+        i64_to_f64_kernel<<<blocks_for(C, 256), 256, 0, st>>>(p->counts, b_cnt_in.as<double>(), C);
+        in.counts_rc = b_cnt_in.as<double>();
+    }
     if (!buffers_on_device) {
-        EM_TRY(b_ptr.alloc(sizeof(int64_t) * (size_t)(C + 1), st));
-        EM_TRY(b_tx.alloc(sizeof(int32_t) * (size_t)nnz, st));
-        EM_TRY(b_cnt_in.alloc(sizeof(double) * (size_t)(C * R), st));
+        if (counts) {
+            EM_TRY(b_cnt_in.alloc(sizeof(double) * (size_t)(C * R), st));
+            EM_TRY(cudaMemcpyAsync(b_cnt_in.p, counts, sizeof(double) * (size_t)(C * R), cudaMemcpyHostToDevice, st));
+            in.counts_rc = b_cnt_in.as<double>();
+        }
         EM_TRY(b_len.alloc(sizeof(double) * (size_t)T, st));
         EM_TRY(b_x_in.alloc(sizeof(double) * (size_t)(T * R), st));
         EM_TRY(b_out.alloc(sizeof(double) * (size_t)(T * R), st));
         EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R, st));
-        EM_TRY(cudaMemcpyAsync(b_ptr.p, class_ptr, sizeof(int64_t) * (size_t)(C + 1), cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_tx.p, class_tx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_cnt_in.p, counts, sizeof(double) * (size_t)(C * R), cudaMemcpyHostToDevice, st));
         EM_TRY(cudaMemcpyAsync(b_len.p, eff_len, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, st));
         EM_TRY(cudaMemcpyAsync(b_x_in.p, x0, sizeof(double) * (size_t)(T * R), cudaMemcpyHostToDevice, st));
-        in.d_ptr = b_ptr.as<int64_t>();
-        in.d_tx = b_tx.as<int32_t>();
-        in.counts_rc = b_cnt_in.as<double>();
         in.d_len = b_len.as<double>();
         in.x_rt = b_x_in.as<double>();
         d_out = b_out.as<double>();
         d_iters = b_iters.as<int32_t>();
     }
+    trace.mark("em: inputs to device");
     const int rc = em_core(in, d_out, d_iters, st);
     if (rc) return rc;
     if (!buffers_on_device) {
@@ -961,7 +1208,25 @@ SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_
         if (out_iters) EM_TRY(cudaMemcpyAsync(out_iters, d_iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
     }
+    trace.mark("em: results out");
     return SKM_OK;
+}
+
+SKM_API int skm_em(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
+                   const double *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
+                   int64_t n_replicates, int64_t max_iters, double *out_x, int32_t *out_iters,
+                   int buffers_on_device, int device, void *stream)
+{
+    if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
+        return fail(SKM_ERR_INVALID, "skm_em: NULL argument");
+    if (n_replicates <= 0) return fail(SKM_ERR_INVALID, "skm_em: empty problem");
+    skm_em_plan *plan = nullptr;
+    int rc = skm_em_plan_create(class_ptr, class_tx, n_classes, nnz, n_transcripts, nullptr, buffers_on_device, device,
+                                stream, &plan);
+    if (rc) return rc;
+    rc = skm_em_plan_run(plan, counts, eff_len, x0, n_replicates, max_iters, out_x, out_iters, buffers_on_device, stream);
+    skm_em_plan_destroy(plan);
+    return rc;
 }
 
 SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, const int64_t *sample_class_ptr,
@@ -1021,45 +1286,19 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
         if (h_sptr[(size_t)p + 1] < h_sptr[(size_t)p])
             return fail(SKM_ERR_INVALID, "skm_em_samples: sample_class_ptr is not monotone");
 
-    // ---- global rows, CSC by (sample, transcript): stable radix sort of (row, nnz index) ------
-    DeviceBuf b_csample, b_rowof, b_gtx, b_idx, b_keys_out, b_idx_out, b_txclass, b_hist, b_txptr, b_tmp, b_bad;
+    // ---- global rows [sample][transcript], CSC by row ------------------------------------------
+    DeviceBuf b_csample, b_rowof, b_gtx, b_txclass, b_txptr, b_bad;
     EM_TRY(b_csample.alloc(sizeof(int32_t) * (size_t)C, st));
     EM_TRY(b_rowof.alloc(sizeof(int32_t) * (size_t)nnz, st));
     EM_TRY(b_gtx.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_idx.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_keys_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_idx_out.alloc(sizeof(int32_t) * (size_t)nnz, st));
     EM_TRY(b_txclass.alloc(sizeof(int32_t) * (size_t)nnz, st));
-    EM_TRY(b_hist.alloc(sizeof(unsigned long long) * (size_t)(rows + 1), st));
     EM_TRY(b_txptr.alloc(sizeof(int64_t) * (size_t)(rows + 1), st));
     EM_TRY(b_bad.alloc(sizeof(unsigned int), st));
-    EM_TRY(cudaMemsetAsync(b_hist.p, 0, sizeof(unsigned long long) * (size_t)(rows + 1), st));
     EM_TRY(cudaMemsetAsync(b_bad.p, 0, sizeof(unsigned int), st));
     expand_rows_kernel<<<blocks_for(P, 256), 256, 0, st>>>(d_sptr, P, b_csample.as<int32_t>());
     expand_rows_kernel<<<blocks_for(C, 256), 256, 0, st>>>(d_ptr, C, b_rowof.as<int32_t>());
     global_tx_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(d_tx_local, b_rowof.as<int32_t>(), b_csample.as<int32_t>(),
                                                           nnz, T, b_gtx.as<int32_t>(), b_bad.as<unsigned int>());
-    iota_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_idx.as<int32_t>(), nnz);
-    histogram_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_gtx.as<int32_t>(), nnz, rows,
-                                                          b_hist.as<unsigned long long>(), b_bad.as<unsigned int>());
-    {
-        size_t tmp_sort = 0, tmp_scan = 0;
-        int end_bit = 1;
-        while ((1LL << end_bit) < rows) ++end_bit;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, b_gtx.as<int32_t>(), b_keys_out.as<int32_t>(),
-                                        b_idx.as<int32_t>(), b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st);
-        cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, b_hist.as<unsigned long long>(),
-                                      b_txptr.as<unsigned long long>(), (int)(rows + 1), st);
-        EM_TRY(b_tmp.alloc(std::max(tmp_sort, tmp_scan), st));
-        size_t tmp = std::max(tmp_sort, tmp_scan);
-        EM_TRY(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp, b_gtx.as<int32_t>(), b_keys_out.as<int32_t>(),
-                                               b_idx.as<int32_t>(), b_idx_out.as<int32_t>(), (int)nnz, 0, end_bit, st));
-        tmp = std::max(tmp_sort, tmp_scan);
-        EM_TRY(cub::DeviceScan::InclusiveSum(b_tmp.p, tmp, b_hist.as<unsigned long long>(),
-                                             b_txptr.as<unsigned long long>(), (int)(rows + 1), st));
-    }
-    gather_i32_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(b_rowof.as<int32_t>(), b_idx_out.as<int32_t>(), nnz,
-                                                           b_txclass.as<int32_t>());
     EM_TRY(cudaGetLastError());
     {
         unsigned int bad = 0;
@@ -1067,6 +1306,10 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
         EM_TRY(cudaStreamSynchronize(st));
         if (bad) return fail(SKM_ERR_INVALID, "skm_em_samples: transcript index out of range in class_tx");
     }
+    b_rowof.release();
+    int rc = build_csc(d_ptr, b_gtx.as<int32_t>(), C, nnz, rows, st, b_txptr.as<int64_t>(), b_txclass.as<int32_t>(),
+                       "skm_em_samples");
+    if (rc) return rc;
 
     // ---- per-sample state ------------------------------------------------------------------
     DeviceBuf b_inner, b_n, b_maxd, b_active, b_iters, b_nactive;
@@ -1075,7 +1318,7 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
     EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * (size_t)P, st));
     EM_TRY(b_active.alloc(sizeof(int32_t) * (size_t)P, st));
     EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)P, st));
-    EM_TRY(b_nactive.alloc(sizeof(int32_t), st));
+    EM_TRY(b_nactive.alloc(sizeof(int32_t) * 2, st));
     sum_counts_samples_kernel<<<(unsigned)P, EM_BLOCK, 0, st>>>(d_cnt, d_sptr, b_n.as<double>());
     EM_TRY(cudaMemsetAsync(b_maxd.p, 0, sizeof(unsigned long long) * (size_t)P, st));
     EM_TRY(cudaMemsetAsync(b_iters.p, 0, sizeof(int32_t) * (size_t)P, st));
@@ -1101,45 +1344,25 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
     s.class_sample = b_csample.as<int32_t>();
     s.tx_per_sample = T;
 
-    // ---- iterations in groups, as em_core: launches after the last sample stopped are no-ops ----
-    const int GROUP = 8;
+    // ---- ONE launch: every sample iterates until its own stop condition holds ----------------------
     double *cur = b_xa.as<double>(), *nxt = b_xb.as<double>();
-    double *group_cur = cur, *group_nxt = nxt;
-    int64_t done = 0, group_base = 0;
-    int32_t n_active = (int32_t)P;
-    while (n_active > 0 && done < max_iters) {
-        const int g = (int)std::min<int64_t>(GROUP, max_iters - done);
-        group_cur = cur;
-        group_nxt = nxt;
-        group_base = done;
-        for (int k = 0; k < g; ++k) {
-            em_class_kernel_samples<<<blocks_for(C, EM_BLOCK), EM_BLOCK, 0, st>>>(s, cur);
-            em_tx_kernel_samples<<<blocks_for(rows * 8, EM_BLOCK), EM_BLOCK, 0, st>>>(s, cur, nxt);
-            em_decide_kernel<<<1, 128, 0, st>>>(s);
-            std::swap(cur, nxt);
-        }
-        done += g;
-        EM_TRY(cudaGetLastError());
-        EM_TRY(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    int64_t done = 0;
+    int32_t h2[2] = {(int32_t)P, 0};
+    while (h2[0] > 0 && done < max_iters) {
+        rc = launch_em_loop(2, s, cur, nxt, (int)std::min<int64_t>(max_iters - done, (int64_t)1 << 30), b_nactive.as<int32_t>() + 1,
+                            device, st);
+        if (rc) return rc;
+        EM_TRY(cudaMemcpyAsync(h2, s.n_active, sizeof(h2), cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
-    }
-    std::vector<int32_t> h_iters((size_t)P);
-    EM_TRY(cudaMemcpyAsync(h_iters.data(), s.iters, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, st));
-    EM_TRY(cudaStreamSynchronize(st));
-    {
-        // the buffer written by the last EXECUTED iteration holds every sample's final x
-        const int64_t executed = *std::max_element(h_iters.begin(), h_iters.end());
-        const int64_t in_group = executed - group_base;
-        cur = (in_group & 1) ? group_nxt : group_cur;
+        done += h2[1];
+        if (h2[1] & 1) std::swap(cur, nxt);
+        if (h2[1] == 0) break;
     }
     EM_TRY(cudaMemcpyAsync(out_x, cur, sizeof(double) * (size_t)rows,
                            buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    if (out_iters) {
-        if (buffers_on_device)
-            EM_TRY(cudaMemcpyAsync(out_iters, s.iters, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToDevice, st));
-        else
-            std::copy(h_iters.begin(), h_iters.end(), out_iters);
-    }
+    if (out_iters)
+        EM_TRY(cudaMemcpyAsync(out_iters, s.iters, sizeof(int32_t) * (size_t)P,
+                               buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     EM_TRY(cudaStreamSynchronize(st));  // scratch buffers are released after this
     return SKM_OK;
 }
@@ -1210,48 +1433,37 @@ SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_
     return SKM_OK;
 }
 
-SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
-                             const int64_t *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
-                             int64_t n_replicates, int64_t first_replicate, uint64_t seed, int64_t max_iters,
-                             int tpm, double *out_x, int32_t *out_iters, int buffers_on_device, int device,
-                             void *stream)
+SKM_API int skm_em_plan_bootstrap(const skm_em_plan *p, const int64_t *counts, const double *eff_len, const double *x0,
+                                  int64_t n_replicates, int64_t first_replicate, uint64_t seed, int64_t max_iters,
+                                  int tpm, double *out_x, int32_t *out_iters, int buffers_on_device, void *stream)
 {
-    if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
-        return fail(SKM_ERR_INVALID, "skm_em_bootstrap: NULL argument");
-    if (n_classes <= 0 || nnz <= 0 || n_transcripts <= 0 || n_replicates <= 0)
-        return fail(SKM_ERR_INVALID, "skm_em_bootstrap: empty problem");
-    if (nnz >= (1LL << 31) || n_classes >= (1LL << 31) || n_transcripts >= (1LL << 31))
-        return fail(SKM_ERR_INVALID, "skm_em_bootstrap: structure too large for int32 indices");
-    if (skm_device_count() <= device || device < 0)
-        return fail(SKM_ERR_CUDA, "skm_em_bootstrap: no such CUDA device (there is no CPU fallback)");
-    EM_TRY(cudaSetDevice(device));
+    if (!p || !eff_len || !x0 || !out_x) return fail(SKM_ERR_INVALID, "skm_em_bootstrap: NULL argument");
+    if (n_replicates <= 0) return fail(SKM_ERR_INVALID, "skm_em_bootstrap: empty problem");
+    if (!counts && !p->counts) return fail(SKM_ERR_INVALID, "skm_em_bootstrap: the plan holds no class counts");
+    EM_TRY(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int R = (int)n_replicates;
-    const int64_t C = n_classes, T = n_transcripts;
+    const int64_t C = p->C, T = p->T;
 
-    DeviceBuf b_ptr, b_tx, b_counts, b_len, b_x, b_out, b_iters, b_draws, b_cr;
-    EmInputs in{class_ptr, class_tx, eff_len, C, nnz, T, R, max_iters, nullptr, nullptr, nullptr, x0};
-    const int64_t *d_counts = counts;
+    DeviceBuf b_counts, b_len, b_x, b_out, b_iters, b_draws, b_cr;
+    EmInputs in{p, eff_len, R, max_iters, nullptr, nullptr, nullptr, x0};
+    const int64_t *d_counts = counts ? counts : p->counts;
     double *d_out = out_x;
     int32_t *d_iters = out_iters;
     if (!buffers_on_device) {
-        EM_TRY(b_ptr.alloc(sizeof(int64_t) * (size_t)(C + 1), st));
-        EM_TRY(b_tx.alloc(sizeof(int32_t) * (size_t)nnz, st));
-        EM_TRY(b_counts.alloc(sizeof(int64_t) * (size_t)C, st));
+        if (counts) {
+            EM_TRY(b_counts.alloc(sizeof(int64_t) * (size_t)C, st));
+            EM_TRY(cudaMemcpyAsync(b_counts.p, counts, sizeof(int64_t) * (size_t)C, cudaMemcpyHostToDevice, st));
+            d_counts = b_counts.as<int64_t>();
+        }
         EM_TRY(b_len.alloc(sizeof(double) * (size_t)T, st));
         EM_TRY(b_x.alloc(sizeof(double) * (size_t)T, st));
         EM_TRY(b_out.alloc(sizeof(double) * (size_t)(T * R), st));
         EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R, st));
-        EM_TRY(cudaMemcpyAsync(b_ptr.p, class_ptr, sizeof(int64_t) * (size_t)(C + 1), cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_tx.p, class_tx, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
-        EM_TRY(cudaMemcpyAsync(b_counts.p, counts, sizeof(int64_t) * (size_t)C, cudaMemcpyHostToDevice, st));
         EM_TRY(cudaMemcpyAsync(b_len.p, eff_len, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, st));
         EM_TRY(cudaMemcpyAsync(b_x.p, x0, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, st));
-        in.d_ptr = b_ptr.as<int64_t>();
-        in.d_tx = b_tx.as<int32_t>();
         in.d_len = b_len.as<double>();
         in.x_t = b_x.as<double>();
-        d_counts = b_counts.as<int64_t>();
         d_out = b_out.as<double>();
         d_iters = b_iters.as<int32_t>();
     }
@@ -1259,11 +1471,12 @@ SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, 
     trace.mark("bootstrap: inputs to device");
     // resample on the device, then straight into the EM's [class][replicate] fp64 layout
     EM_TRY(b_draws.alloc(sizeof(int64_t) * (size_t)(C * R), st));
-    int rc = multinomial_core(d_counts, C, R, first_replicate, seed, b_draws.as<int64_t>(), device, st);
+    int rc = multinomial_core(d_counts, C, R, first_replicate, seed, b_draws.as<int64_t>(), p->device, st);
     if (rc) return rc;
     EM_TRY(b_cr.alloc(sizeof(double) * (size_t)(C * R), st));
     counts_to_f64_kernel<<<blocks_for(C * R, 256), 256, 0, st>>>(b_draws.as<unsigned long long>(), b_cr.as<double>(), C, R);
     EM_TRY(cudaGetLastError());
+    EM_TRY(cudaStreamSynchronize(st));
     b_draws.release();
     trace.mark("bootstrap: resample");
     in.counts_cr = b_cr.as<double>();
@@ -1282,4 +1495,23 @@ SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, 
     EM_TRY(cudaStreamSynchronize(st));
     trace.mark("bootstrap: results to host");
     return SKM_OK;
+}
+
+SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
+                             const int64_t *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
+                             int64_t n_replicates, int64_t first_replicate, uint64_t seed, int64_t max_iters,
+                             int tpm, double *out_x, int32_t *out_iters, int buffers_on_device, int device,
+                             void *stream)
+{
+    if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
+        return fail(SKM_ERR_INVALID, "skm_em_bootstrap: NULL argument");
+    if (n_replicates <= 0) return fail(SKM_ERR_INVALID, "skm_em_bootstrap: empty problem");
+    skm_em_plan *plan = nullptr;
+    int rc = skm_em_plan_create(class_ptr, class_tx, n_classes, nnz, n_transcripts, nullptr, buffers_on_device, device,
+                                stream, &plan);
+    if (rc) return rc;
+    rc = skm_em_plan_bootstrap(plan, counts, eff_len, x0, n_replicates, first_replicate, seed, max_iters, tpm, out_x,
+                               out_iters, buffers_on_device, stream);
+    skm_em_plan_destroy(plan);
+    return rc;
 }

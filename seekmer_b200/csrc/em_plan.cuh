@@ -1,0 +1,25 @@
+// An EM plan: the class x transcript incidence structure resident on one device in both
+// orders (CSR by class, CSC by transcript), built once and shared by the main EM, the bootstrap
+// replicates and repeated calls.  A plan made from a mapper (skm_em_plan_from_mapper) also owns
+// the integer class counts in the dictionary's first-seen order; nothing of it crosses PCIe.
+#pragma once
+
+#include "common.cuh"
+
+struct skm_em_plan {
+    int device = 0;
+    int64_t C = 0, nnz = 0, T = 0;
+    int64_t *class_ptr = nullptr;  // [C + 1]
+    int32_t *class_tx = nullptr;   // [nnz] transcript ids in tuple order
+    int64_t *tx_ptr = nullptr;     // [T + 1]
+    int32_t *tx_class = nullptr;   // [nnz] class of every entry of a transcript, in nnz order
+    int64_t *counts = nullptr;     // [C] integer class counts, or NULL
+};
+
+namespace skm {
+// Takes ownership of class_ptr / class_tx / counts (device memory from cudaMalloc on `device`;
+// counts may be NULL), builds the CSC side on `stream` and returns the plan.  On failure the
+// buffers are freed.
+int em_plan_adopt(int device, int64_t C, int64_t nnz, int64_t T, int64_t *class_ptr, int32_t *class_tx,
+                  int64_t *counts, cudaStream_t stream, skm_em_plan **out);
+}  // namespace skm

@@ -115,7 +115,7 @@ struct MapArgs {
     int32_t *arena;           // spill space for target lists longer than LIST_CAP
     uint64_t arena_cap;
     unsigned long long *cursors;  // [0]=work counter [1]=arena cursor
-    unsigned long long *short_reads;  // reads shorter than k seen so far (their units are reported unaligned)
+    unsigned long long *short_units;  // units with a read shorter than k so far (reported unaligned)
 };
 
 enum : int { P_LOAD = 0, P_SCAN, P_LOOKUP, P_CONTIG, P_WALK, P_TALLY, N_PHASES, P_DEAD = N_PHASES };
@@ -888,7 +888,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     // A read shorter than k is undefined in the reference (_kmer.pxd:46-68 reads past its
                     // end).  Here its unit is reported unaligned with span length 0, whatever the mate does.
                     atomicOr(status, ST_SHORT_READ);
-                    atomicAdd(a.short_reads, 1ULL);
+                    atomicAdd(a.short_units, 1ULL);
                     L.void_unit = true;
                     L.l.n = 0;
                     L.st = P_TALLY;
@@ -1233,17 +1233,20 @@ tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const 
 {
     __shared__ uint32_t sm_fld[SKM_MAX_FRAGMENT_LENGTH];
     __shared__ unsigned long long sm_totals[4];  // new classes, ids stored, unaligned, aligned
+    __shared__ unsigned sm_warp_ids[8];          // ids of the new classes of each warp (this pass)
+    __shared__ unsigned long long sm_pool_base;  // where the block's new classes start in the id pool
     for (int i = threadIdx.x; i < SKM_MAX_FRAGMENT_LENGTH; i += blockDim.x) sm_fld[i] = 0;
     if (threadIdx.x < 4) sm_totals[threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    // every counter that all units share is aggregated: id-pool space per warp iteration (exactly
-    // the ids of the warp's new classes, so the pool holds nothing but stored ids), class / id /
-    // unit totals per block
+    // every counter that all units share is aggregated: id-pool space per BLOCK pass (exactly the
+    // ids of the block's new classes, so the pool holds nothing but stored ids: one atomic on
+    // the pool cursor per pass that found a new class), class / id / unit totals per block
+    const int warp = threadIdx.x >> 5;
     unsigned new_classes = 0, new_ids = 0, n_unaligned = 0, n_aligned = 0;  // lane 0 only
-    for (int64_t base = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31LL; base < n_units;
-         base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t u = base + lane;
+    for (int64_t block_base = blockIdx.x * (int64_t)blockDim.x; block_base < n_units;
+         block_base += (int64_t)gridDim.x * blockDim.x) {  // same trip count for the whole block
+        const int64_t u = block_base + threadIdx.x;
         const bool live = u < n_units;
         long long slot = -1;
         bool won = false;
@@ -1262,7 +1265,8 @@ tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const 
                     const long long off = (long long)(uint32_t)view.get(0) | ((long long)view.get(1) << 32);
                     view = UnitIds{arena + off, 1};
                 }
-                slot = dict_find_or_claim(dict, tuple_key(view, n, true), won);
+                slot = dict_find_or_claim(dict, dict_key(dict, view, n, true), won);
+                if (!won && slot >= 0) dict_verify_hit(dict, slot, view, n, true);
             }
             if (out_class) out_class[u] = (int32_t)slot;
             if (slot >= 0) {
@@ -1271,23 +1275,32 @@ tally_units_kernel(const DictDev dict, const int32_t *__restrict__ units, const 
                     atomicMin(&dict.first[slot], g);
             }
         }
-        __syncwarp();
-        // ---- new classes: pool space for all winners of the warp at once -----------------------
-        const unsigned winners = __ballot_sync(0xffffffffu, won);
-        if (winners) {
+        // ---- new classes: pool space for all winners of the block at once ----------------------
+        if (__syncthreads_or(won)) {
+            const unsigned winners = __ballot_sync(0xffffffffu, won);
             int incl = won ? n : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            const unsigned long long total = (unsigned long long)__shfl_sync(0xffffffffu, incl, 31);
-            unsigned long long got = 0;
-            if (lane == 0) got = atomicAdd(&dict.scalars[0], total);
-            got = __shfl_sync(0xffffffffu, got, 0);
-            if (won) dict_store_ids(dict, slot, got + (unsigned long long)(incl - n), view, n, true);
+            const unsigned total = (unsigned)__shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) sm_warp_ids[warp] = total;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long all = 0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) all += sm_warp_ids[w];
+                sm_pool_base = atomicAdd(&dict.scalars[0], all);
+            }
+            __syncthreads();
+            if (won) {
+                unsigned long long off = sm_pool_base + (unsigned long long)(incl - n);
+                for (int w = 0; w < warp; ++w) off += sm_warp_ids[w];
+                dict_store_ids(dict, slot, off, view, n, true);
+            }
             new_classes += (unsigned)__popc(winners);
-            new_ids += (unsigned)total;
+            new_ids += total;
+            __syncthreads();  // sm_warp_ids / sm_pool_base are rewritten by the next pass
         }
         // ---- one count atomic per distinct class per warp (mapper.py:60-75) -------------------------
         const unsigned same = __match_any_sync(0xffffffffu, slot);

@@ -12,6 +12,7 @@
 
 #include <cub/cub.cuh>
 
+#include "em_plan.cuh"
 #include "map_kernel.cuh"
 
 namespace skm {
@@ -262,6 +263,35 @@ dict_export_kernel(const DictDev d, int64_t slots, unsigned long long *cursor, i
 
 __global__ void set_i64_kernel(int64_t *dst, int64_t v) { *dst = v; }
 
+// ---- the exported dictionary in first-seen order, on the device (skm_em_plan_from_mapper) -------
+__global__ void iota_i32_kernel(int32_t *p, int64_t n)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+
+// lens[i] = ids of the class that comes i-th in first-seen order (lens[n] = 0 closes the scan)
+__global__ void ordered_lens_kernel(const int64_t *__restrict__ off, const int32_t *__restrict__ perm, int64_t n,
+                                    int64_t *__restrict__ lens)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > n) return;
+    lens[i] = i < n ? off[perm[i] + 1] - off[perm[i]] : 0;
+}
+
+__global__ void ordered_gather_kernel(const int64_t *__restrict__ off, const int32_t *__restrict__ ids,
+                                      const int64_t *__restrict__ counts, const int32_t *__restrict__ perm, int64_t n,
+                                      const int64_t *__restrict__ new_off, int32_t *__restrict__ new_ids,
+                                      int64_t *__restrict__ new_counts)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = perm[i];
+    const int64_t src = off[c], dst = new_off[i], len = off[c + 1] - src;
+    for (int64_t k = 0; k < len; ++k) new_ids[dst + k] = ids[src + k];
+    new_counts[i] = counts[c];
+}
+
 __global__ void dict_merge_kernel(const DictDev d, const int64_t *key_offsets, const int32_t *key_ids,
                                   const int64_t *counts, const int64_t *first_unit, int64_t n_classes)
 {
@@ -272,7 +302,7 @@ __global__ void dict_merge_kernel(const DictDev d, const int64_t *key_offsets, c
         const int n = (int)(key_offsets[c + 1] - start);
         if (n > 0) {
             const DenseIds ids{key_ids + start};
-            const ulonglong2 key = tuple_key(ids, n, false);
+            const ulonglong2 key = dict_key(d, ids, n, false);
             const int64_t slot = dict_find_or_insert(d, key, ids, n, false);
             if (slot >= 0) {
                 added = (unsigned long long)counts[c];
@@ -314,7 +344,7 @@ __global__ void dict_merge_packed_kernel(const DictDev d, const int64_t *__restr
             const int n = (int)(key_offsets[c + 1] - start);
             if (n > 0) {
                 const DenseIds ids{key_ids + start};
-                const int64_t slot = dict_find_or_insert(d, tuple_key(ids, n, false), ids, n, false);
+                const int64_t slot = dict_find_or_insert(d, dict_key(d, ids, n, false), ids, n, false);
                 if (slot >= 0) {
                     added = (unsigned long long)counts[c];
                     atomicAdd(&d.counts[slot], added);
@@ -383,6 +413,9 @@ struct skm_mapper {
     void *d_scan_tmp = nullptr;
     size_t d_scan_tmp_cap = 0;
     int *d_len_range = nullptr;
+    // export / merge staging (host-buffer calls): one block, reused
+    void *d_stage = nullptr;
+    size_t d_stage_cap = 0;
 };
 
 static int ensure(void **p, size_t *cap, size_t need)
@@ -434,6 +467,7 @@ SKM_API void skm_mapper_destroy(skm_mapper *m)
     cudaFree(m->d_scan_tmp);
     cudaFree(m->d_len_range);
     cudaFree(m->d_lens);
+    cudaFree(m->d_stage);
     cudaSetDevice(prev);
     delete m;
 }
@@ -531,6 +565,7 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
     }
     m->d.mask = (uint64_t)slots - 1;
     m->d.pool_cap = (uint64_t)id_capacity;
+    m->d.weak_keys = getenv("SKM_TEST_WEAK_KEYS") ? 1u : 0u;
     int rc = skm_mapper_reset(m, nullptr);
     if (rc == 0 && cudaStreamSynchronize(nullptr) != cudaSuccess) rc = fail(SKM_ERR_CUDA, "reset failed");
     if (rc != 0) {
@@ -563,6 +598,9 @@ static int check_status(skm_mapper *m, cudaStream_t st, const char *who)
     uint32_t status = 0;
     SKM_CUDA(cudaMemcpyAsync(&status, m->d.status, sizeof(status), cudaMemcpyDeviceToHost, st));
     SKM_CUDA(cudaStreamSynchronize(st));
+    if (status & ST_KEY_COLLISION)
+        return fail(SKM_ERR_COLLISION, std::string(who) + ": two different classes share a 128-bit dictionary key; "
+                                       "refusing to merge them (results of this mapper are invalid)");
     if (status & (ST_ARENA_FULL | ST_DICT_FULL | ST_POOL_FULL)) {
         std::string msg = std::string(who) + ": device capacity exhausted:";
         if (status & ST_ARENA_FULL) msg += " target-list arena";
@@ -687,7 +725,7 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     a.arena = m->arena;
     a.arena_cap = m->arena_cap;
     a.cursors = m->cursors;
-    a.short_reads = m->d.scalars + 5;
+    a.short_units = m->d.scalars + 5;
 
     if (buffers_on_device)
         return launch_chunk(m, bases, read_offsets, read_offsets ? read_offsets + 1 : nullptr, a, n_units, first_unit,
@@ -836,7 +874,7 @@ SKM_API int skm_map_fastq(skm_mapper *m, const uint8_t *text1, int64_t n1, const
     a.arena = m->arena;
     a.arena_cap = m->arena_cap;
     a.cursors = m->cursors;
-    a.short_reads = m->d.scalars + 5;
+    a.short_units = m->d.scalars + 5;
     int32_t *d_class = out_class, *d_length = out_length;
     if (!buffers_on_device && (out_class || out_length)) {
         rc = ensure((void **)&m->d_out, &m->d_out_cap, sizeof(int32_t) * 2 * (size_t)n_units);
@@ -904,7 +942,7 @@ SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[8], void *stream)
     sizes[3] = (int64_t)sc[3];
     sizes[4] = m->slots / 2;
     sizes[5] = (int64_t)status;
-    sizes[6] = (int64_t)sc[5];  // reads shorter than k (their units are in `unaligned`)
+    sizes[6] = (int64_t)sc[5];  // units with a read shorter than k (they are in `unaligned`)
     sizes[7] = (int64_t)sc[0];  // id-pool cursor (== sizes[1]: the pool holds stored ids only)
     return SKM_OK;
 }
@@ -926,28 +964,22 @@ SKM_API int skm_classes_export(skm_mapper *m, int64_t *key_offsets, int32_t *key
 
     int64_t *d_off = key_offsets, *d_counts = counts, *d_first = first_unit;
     int32_t *d_ids = key_ids, *d_slots = slots;
-    void *owned[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaError_t e = cudaSuccess;
     if (host) {
-        auto A = [&](int k, void **p, bool wanted, size_t bytes) {
-            *p = nullptr;
-            if (!wanted || e != cudaSuccess) return;
-            e = cudaMalloc(&owned[k], std::max<size_t>(bytes, 16));
-            *p = owned[k];
-        };
-        A(0, (void **)&d_off, key_offsets != nullptr, sizeof(int64_t) * (size_t)(n_cls + 1));
-        A(1, (void **)&d_ids, key_ids != nullptr, sizeof(int32_t) * (size_t)n_ids);
-        A(2, (void **)&d_counts, counts != nullptr, sizeof(int64_t) * (size_t)n_cls);
-        A(3, (void **)&d_first, first_unit != nullptr, sizeof(int64_t) * (size_t)n_cls);
-        A(4, (void **)&d_slots, slots != nullptr, sizeof(int32_t) * (size_t)n_cls);
+        // staging for the host copy: one block owned by the mapper, carved into the five arrays
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_off = up(sizeof(int64_t) * (size_t)(n_cls + 1)), b_ids = up(sizeof(int32_t) * (size_t)n_ids);
+        const size_t b_cnt = up(sizeof(int64_t) * (size_t)n_cls), b_slot = up(sizeof(int32_t) * (size_t)n_cls);
+        rc = ensure(&m->d_stage, &m->d_stage_cap, b_off + b_ids + 2 * b_cnt + b_slot);
+        if (rc) return rc;
+        char *base = static_cast<char *>(m->d_stage);
+        d_off = key_offsets ? reinterpret_cast<int64_t *>(base) : nullptr;
+        d_ids = key_ids ? reinterpret_cast<int32_t *>(base + b_off) : nullptr;
+        d_counts = counts ? reinterpret_cast<int64_t *>(base + b_off + b_ids) : nullptr;
+        d_first = first_unit ? reinterpret_cast<int64_t *>(base + b_off + b_ids + b_cnt) : nullptr;
+        d_slots = slots ? reinterpret_cast<int32_t *>(base + b_off + b_ids + 2 * b_cnt) : nullptr;
     }
-    auto cleanup = [&]() {
-        for (void *p : owned) cudaFree(p);
-    };
-    if (e != cudaSuccess) {
-        cleanup();
-        return fail(SKM_ERR_OOM, std::string("skm_classes_export: ") + cudaGetErrorString(e));
-    }
+    auto cleanup = []() {};
     cudaMemsetAsync(m->cursors + 2, 0, sizeof(unsigned long long), st);
     if (n_cls > 0)
         dict_export_kernel<<<(unsigned)((m->slots + 255) / 256), 256, 0, st>>>(
@@ -980,51 +1012,123 @@ SKM_API int skm_classes_merge(skm_mapper *m, const int64_t *key_offsets, const i
     cudaStream_t st = (cudaStream_t)stream;
     if (n_classes > 0 && (!key_offsets || !key_ids || !counts || !first_unit))
         return fail(SKM_ERR_INVALID, "skm_classes_merge: NULL class arrays");
-    int64_t *d_off = nullptr, *d_cnt = nullptr, *d_first = nullptr, *d_fld = nullptr;
-    int32_t *d_ids = nullptr;
     const int64_t *p_off = key_offsets, *p_cnt = counts, *p_first = first_unit, *p_fld = fld;
     const int32_t *p_ids = key_ids;
-    cudaError_t e = cudaSuccess;
     if (!buffers_on_device) {
+        // host arrays go through the mapper's staging block (one allocation, reused)
         const int64_t n_ids = n_classes > 0 ? key_offsets[n_classes] : 0;
-        auto up = [&](void **d, const void *h, size_t bytes) {
-            if (e != cudaSuccess || bytes == 0) return;
-            e = cudaMalloc(d, bytes);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st);
-        };
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_off = up(sizeof(int64_t) * (size_t)(n_classes + 1)), b_ids = up(sizeof(int32_t) * (size_t)n_ids);
+        const size_t b_cnt = up(sizeof(int64_t) * (size_t)n_classes), b_fld = up(sizeof(int64_t) * FLD_BINS);
+        int rc = ensure(&m->d_stage, &m->d_stage_cap, b_off + b_ids + 2 * b_cnt + b_fld);
+        if (rc) return rc;
+        char *base = static_cast<char *>(m->d_stage);
+        int64_t *d_off = reinterpret_cast<int64_t *>(base);
+        int32_t *d_ids = reinterpret_cast<int32_t *>(base + b_off);
+        int64_t *d_cnt = reinterpret_cast<int64_t *>(base + b_off + b_ids);
+        int64_t *d_first = reinterpret_cast<int64_t *>(base + b_off + b_ids + b_cnt);
+        int64_t *d_fld = reinterpret_cast<int64_t *>(base + b_off + b_ids + 2 * b_cnt);
         if (n_classes > 0) {
-            up((void **)&d_off, key_offsets, sizeof(int64_t) * (size_t)(n_classes + 1));
-            up((void **)&d_ids, key_ids, sizeof(int32_t) * (size_t)n_ids);
-            up((void **)&d_cnt, counts, sizeof(int64_t) * (size_t)n_classes);
-            up((void **)&d_first, first_unit, sizeof(int64_t) * (size_t)n_classes);
+            SKM_CUDA(cudaMemcpyAsync(d_off, key_offsets, sizeof(int64_t) * (size_t)(n_classes + 1), cudaMemcpyHostToDevice, st));
+            if (n_ids > 0) SKM_CUDA(cudaMemcpyAsync(d_ids, key_ids, sizeof(int32_t) * (size_t)n_ids, cudaMemcpyHostToDevice, st));
+            SKM_CUDA(cudaMemcpyAsync(d_cnt, counts, sizeof(int64_t) * (size_t)n_classes, cudaMemcpyHostToDevice, st));
+            SKM_CUDA(cudaMemcpyAsync(d_first, first_unit, sizeof(int64_t) * (size_t)n_classes, cudaMemcpyHostToDevice, st));
         }
-        if (fld) up((void **)&d_fld, fld, sizeof(int64_t) * FLD_BINS);
+        if (fld) SKM_CUDA(cudaMemcpyAsync(d_fld, fld, sizeof(int64_t) * FLD_BINS, cudaMemcpyHostToDevice, st));
         p_off = d_off;
         p_ids = d_ids;
         p_cnt = d_cnt;
         p_first = d_first;
         p_fld = d_fld;
     }
-    if (e == cudaSuccess && n_classes > 0) {
-        dict_merge_kernel<<<(unsigned)((n_classes + 127) / 128), 128, 0, st>>>(m->d, p_off, p_ids, p_cnt,
-                                                                             p_first, n_classes);
-        e = cudaGetLastError();
+    if (n_classes > 0) {
+        dict_merge_kernel<<<(unsigned)((n_classes + 127) / 128), 128, 0, st>>>(m->d, p_off, p_ids, p_cnt, p_first, n_classes);
+        SKM_CUDA(cudaGetLastError());
     }
-    if (e == cudaSuccess && fld) {
+    if (fld) {
         add_i64_kernel<<<(FLD_BINS + 255) / 256, 256, 0, st>>>(m->d.fld, p_fld, FLD_BINS);
-        e = cudaGetLastError();
+        SKM_CUDA(cudaGetLastError());
     }
-    if (e == cudaSuccess && unaligned > 0) {
+    if (unaligned > 0) {
         add_value_kernel<<<1, 1, 0, st>>>(m->d.scalars + 2, (unsigned long long)unaligned);
+        SKM_CUDA(cudaGetLastError());
+    }
+    return check_status(m, st, "skm_classes_merge");  // synchronises: the staging block may be reused
+}
+
+// Replaces the host round trip MapResult.summarize -> quantify (mapper.py:77-104, infer.py:88-130):
+// the dictionary becomes the EM's class structure where it lies.  Classes are ordered by their
+// first-seen unit (the Counter's insertion order at job_count=1, which is the order of
+// class_map / class_count), ids stay in tuple order, counts stay integers.
+SKM_API int skm_em_plan_from_mapper(skm_mapper *m, int64_t n_transcripts, void *stream, skm_em_plan **out)
+{
+    if (!out) return fail(SKM_ERR_INVALID, "skm_em_plan_from_mapper: out is NULL");
+    *out = nullptr;
+    if (!m) return fail(SKM_ERR_INVALID, "skm_em_plan_from_mapper: NULL mapper");
+    if (n_transcripts <= 0) n_transcripts = m->index->n_transcripts;
+    if (n_transcripts <= 0 || n_transcripts >= (1LL << 31))
+        return fail(SKM_ERR_INVALID, "skm_em_plan_from_mapper: bad transcript count");
+    SKM_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_status(m, st, "skm_em_plan_from_mapper");
+    if (rc) return rc;
+    int64_t sizes[8];
+    rc = skm_classes_size(m, sizes, stream);
+    if (rc) return rc;
+    const int64_t n = sizes[0], n_ids = sizes[1];
+    if (n <= 0 || n_ids <= 0) return fail(SKM_ERR_INVALID, "skm_em_plan_from_mapper: the dictionary is empty");
+    // raw export (table order) + sort scratch in the mapper's staging block
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_off = up(sizeof(int64_t) * (size_t)(n + 1)), b_ids = up(sizeof(int32_t) * (size_t)n_ids);
+    const size_t b_i64 = up(sizeof(int64_t) * (size_t)(n + 1)), b_i32 = up(sizeof(int32_t) * (size_t)n);
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, 0, 64, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const int64_t *)nullptr, (int64_t *)nullptr, (int)(n + 1), st);
+    const size_t b_tmp = up(std::max(tmp_sort, tmp_scan));
+    rc = ensure(&m->d_stage, &m->d_stage_cap, b_off + b_ids + 4 * b_i64 + 2 * b_i32 + b_tmp);
+    if (rc) return rc;
+    char *base = static_cast<char *>(m->d_stage);
+    int64_t *r_off = reinterpret_cast<int64_t *>(base);
+    int32_t *r_ids = reinterpret_cast<int32_t *>(base + b_off);
+    int64_t *r_cnt = reinterpret_cast<int64_t *>(base + b_off + b_ids);
+    int64_t *r_first = reinterpret_cast<int64_t *>(base + b_off + b_ids + b_i64);
+    int64_t *s_first = reinterpret_cast<int64_t *>(base + b_off + b_ids + 2 * b_i64);
+    int64_t *lens = reinterpret_cast<int64_t *>(base + b_off + b_ids + 3 * b_i64);
+    int32_t *iota = reinterpret_cast<int32_t *>(base + b_off + b_ids + 4 * b_i64);
+    int32_t *perm = reinterpret_cast<int32_t *>(base + b_off + b_ids + 4 * b_i64 + b_i32);
+    void *tmp = base + b_off + b_ids + 4 * b_i64 + 2 * b_i32;
+    SKM_CUDA(cudaMemsetAsync(m->cursors + 2, 0, sizeof(unsigned long long), st));
+    dict_export_kernel<<<(unsigned)((m->slots + 255) / 256), 256, 0, st>>>(m->d, m->slots, m->cursors + 2, r_off, r_ids,
+                                                                          r_cnt, r_first, nullptr);
+    set_i64_kernel<<<1, 1, 0, st>>>(r_off + n, n_ids);
+    iota_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(iota, n);
+    SKM_CUDA(cudaGetLastError());
+    size_t tb = b_tmp;
+    SKM_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, reinterpret_cast<const unsigned long long *>(r_first),
+                                             reinterpret_cast<unsigned long long *>(s_first), iota, perm, (int)n, 0, 64, st));
+    // the plan's own arrays
+    int64_t *p_off = nullptr, *p_cnt = nullptr;
+    int32_t *p_ids = nullptr;
+    cudaError_t e = cudaMalloc(&p_off, sizeof(int64_t) * (size_t)(n + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p_ids, sizeof(int32_t) * (size_t)n_ids);
+    if (e == cudaSuccess) e = cudaMalloc(&p_cnt, sizeof(int64_t) * (size_t)n);
+    if (e == cudaSuccess) {
+        ordered_lens_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(r_off, perm, n, lens);
+        tb = b_tmp;
+        e = cub::DeviceScan::ExclusiveSum(tmp, tb, lens, p_off, (int)(n + 1), st);
+    }
+    if (e == cudaSuccess) {
+        ordered_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r_off, r_ids, r_cnt, perm, n, p_off, p_ids, p_cnt);
         e = cudaGetLastError();
     }
-    int rc = SKM_OK;
-    if (e == cudaSuccess) rc = check_status(m, st, "skm_classes_merge");
-    cudaFree(d_off);
-    cudaFree(d_ids);
-    cudaFree(d_cnt);
-    cudaFree(d_first);
-    cudaFree(d_fld);
-    if (e != cudaSuccess) return fail(SKM_ERR_CUDA, std::string("skm_classes_merge: ") + cudaGetErrorString(e));
-    return rc;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the staging block may be reused after this
+    if (e != cudaSuccess) {
+        cudaFree(p_off);
+        cudaFree(p_ids);
+        cudaFree(p_cnt);
+        return fail(e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,
+                    std::string("skm_em_plan_from_mapper: ") + cudaGetErrorString(e));
+    }
+    return em_plan_adopt(m->device, n, n_ids, n_transcripts, p_off, p_ids, p_cnt, st, out);
 }

@@ -56,7 +56,9 @@ def run(index_path, output_path, fastq_paths, job_count, save_readmap, single_en
               summarized_results.aligned / max(summarized_results.total, 1))
     main_result = quantify(summarized_results)
     _LOG.info('Quantified transcripts')
-    bootstrapped_results = quantify_bootstraps(summarized_results, main_result, bootstrap)
+    # `-j N`: the replicates of `infer.py:79-82` are independent; they are dealt to N GPUs
+    bootstrapped_results = quantify_bootstraps(summarized_results, main_result, bootstrap,
+                                               devices=mapper._devices_for(job_count))
     output_results(output_path, index, start_time, summarized_results, main_result,
                    bootstrapped_results)
     _LOG.info('Wrote results to {}'.format(output_path))
@@ -125,29 +127,52 @@ def _draw_seed():
     return int(numpy.random.randint(0, 2 ** 31 - 1)) | (int(numpy.random.randint(0, 2 ** 31 - 1)) << 31)
 
 
-def quantify(results, x0=None, bootstrap=False, seed=None):
+def _plan_of(results, device=None):
+    """The device-resident class structure of `results` (made by the mapper, device to device),
+    or None when the result did not come from the device mapper or sits on another GPU."""
+    plan = getattr(results, 'plan', None)
+    if plan is None or not plan._h or (device is not None and plan.device != device):
+        return None
+    return plan
+
+
+def quantify(results, x0=None, bootstrap=False, seed=None, return_iters=False):
     """Estimate the transcript abundance (`infer.py:88-130`)."""
     transcript_length = results.effective_lengths.astype('f8')
     if results.class_map.size == 0:
-        return numpy.zeros(results.effective_lengths.size).astype('f8')
-    if bootstrap:
-        class_count = _resample(results.class_count, 1,
-                                _draw_seed() if seed is None else seed)[0].astype('f8')
-    else:
-        class_count = results.class_count
+        z = numpy.zeros(results.effective_lengths.size).astype('f8')
+        return (z, 0) if return_iters else z
     if x0 is None:
         x = numpy.ones(transcript_length.size, dtype='f8') / transcript_length
     else:
         x = x0.copy()
     x /= x.sum()
-    x = em(x, transcript_length, results.class_map, class_count)
-    return _finish(x)
+    plan = _plan_of(results)
+    if bootstrap:
+        if seed is None:
+            seed = _draw_seed()
+        if plan is not None:
+            out, iters = plan.bootstrap(transcript_length, x, 1, seed)
+            return (out[0], int(iters[0])) if return_iters else out[0]
+        class_count = _resample(results.class_count, 1, seed)[0].astype('f8')
+    else:
+        class_count = results.class_count
+    if plan is not None and not bootstrap:
+        # class structure and counts are already in HBM: nothing but x and the lengths go up
+        out, iters = plan.run(transcript_length, x)
+        x, iters = out[0], int(iters[0])
+    else:
+        x, iters = em(x, transcript_length, results.class_map, class_count, return_iters=True)
+    x = _finish(x)
+    return (x, iters) if return_iters else x
 
 
 def quantify_bootstraps(results, x0, n_replicates, seed=None, return_iters=False,
-                        first_replicate=0):
+                        first_replicate=0, devices=None):
     """`[quantify(results, x0=x0, bootstrap=True) for _ in range(n)]` (`infer.py:79-82`) as one
-    batched resample + one batched EM.  Returns a list of n arrays."""
+    batched resample + one batched EM per GPU.  Replicate r is a pure function of (seed, r)
+    (counter-based resampler), so dealing contiguous replicate ranges to `devices` gives exactly
+    the arrays one GPU would.  Returns a list of n arrays."""
     if n_replicates <= 0:
         return ([], numpy.zeros(0, dtype='i4')) if return_iters else []
     transcript_length = results.effective_lengths.astype('f8')
@@ -161,15 +186,53 @@ def quantify_bootstraps(results, x0, n_replicates, seed=None, return_iters=False
         raise ValueError('bootstrap needs integral class counts')
     x = numpy.ascontiguousarray(x0, dtype='f8').copy()
     x /= x.sum()
-    ptr, tx = _csr_from_class_map(results.class_map, counts.shape[0])
+    _lib.require_device()
+    devices = list(devices) if devices else [0]
+    devices = devices[:max(1, min(len(devices), n_replicates))]
+    per = (n_replicates + len(devices) - 1) // len(devices)
+    shares = [(d, k * per, max(0, min(per, n_replicates - k * per))) for k, d in enumerate(devices)]
     xs = numpy.zeros((n_replicates, x.shape[0]), dtype='f8')
     iters = numpy.zeros(n_replicates, dtype='i4')
-    _lib.require_device()
-    # resample + EM for all replicates in one device-resident call
-    _lib.check(_lib.load().skm_em_bootstrap(
-        _lib._np_ptr(ptr), _lib._np_ptr(tx), counts.shape[0], tx.shape[0], _lib._np_ptr(counts),
-        _lib._np_ptr(transcript_length), x.shape[0], _lib._np_ptr(x), n_replicates, first_replicate,
-        int(seed) & (2 ** 64 - 1), 0, 1, _lib._np_ptr(xs), _lib._np_ptr(iters), 0, 0, None))
+    csr = []
+
+    def run(device, start, n):
+        if n <= 0:
+            return
+        plan, own = _plan_of(results, device), False
+        if plan is None:  # a replica of the class structure on this GPU
+            if not csr:
+                csr.append(_csr_from_class_map(results.class_map, counts.shape[0]))
+            plan, own = _lib.EmPlan.from_csr(csr[0][0], csr[0][1], x.shape[0], device=device), True
+        try:
+            # resample + EM + TPM step for this share in one device-resident call
+            o, it = plan.bootstrap(transcript_length, x, n, seed, first_replicate=first_replicate + start,
+                                   counts=None if plan.owns_counts else counts)
+        finally:
+            if own:
+                plan.close()
+        xs[start:start + n] = o
+        iters[start:start + n] = it
+
+    if len(shares) == 1:
+        run(*shares[0])
+    else:
+        import threading
+        if any(_plan_of(results, d) is None for d in devices):
+            csr.append(_csr_from_class_map(results.class_map, counts.shape[0]))
+        errors = []
+
+        def guarded(*a):
+            try:
+                run(*a)
+            except BaseException as exc:  # noqa: BLE001 - re-raised below
+                errors.append(exc)
+        threads = [threading.Thread(target=guarded, args=s) for s in shares]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
     out = list(xs)  # TPM post-processing (`infer.py:127-129`) already applied on the device
     return (out, iters) if return_iters else out
 
@@ -347,7 +410,7 @@ def add_subcommand_parser(subparsers):
     parser.add_argument('fastq_paths', type=pathlib.Path, metavar='fastq', nargs='+',
                         help='specify a FASTQ read file')
     parser.add_argument('-j', '--jobs', type=int, dest='job_count', metavar='N', default=1,
-                        help='specify the maximum parallel job number')
+                        help='specify the maximum parallel job number (here: GPUs to use)')
     parser.add_argument('-m', '--save-readmap', action='store_true', dest='save_readmap',
                         help='output an readmap file')
     parser.add_argument('-s', '--single-ended', action='store_true', dest='single_ended',
