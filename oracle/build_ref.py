@@ -11,13 +11,15 @@ Recipe follows SURVEY.md §8(c) / Appendix A:
   the reference was written for (results identical, 6x faster single-threaded).
 * ``-O3``; numpy include dir.
 
-Only the three ``.pyx`` native modules are built.  The reference's pure-Python
-modules (``mapper.py``, ``infer.py`` ...) cannot travel to the GPU box; they
-are imported straight from ``/root/reference`` in this container when golden
-vectors are (re)generated (``tests/golden/make_golden.py``).
+The three ``.pyx`` native modules are compiled.  The reference's pure-Python modules of the
+path (``mapper.py``, ``infer.py``, ``common.py``) are PLACED next to them, unmodified, so that the
+CPU baseline can call the stock ``mapper.map_reads`` / ``infer.quantify`` on the GPU box, where
+``/root/reference`` does not exist.  ``oracle/_ref/`` is git-ignored: no reference source enters
+history; the directory only travels with the gpurun snapshot like any other build product.
 """
 import os
 import pathlib
+import shutil
 import subprocess
 import sys
 import sysconfig
@@ -26,6 +28,7 @@ HERE = pathlib.Path(__file__).resolve().parent
 REF = pathlib.Path(os.environ.get('SEEKMER_REFERENCE', '/root/reference'))
 OUT = HERE / '_ref'
 MODULES = ('_common', '_mapper', '_index_builder')
+PURE_PYTHON = ('mapper.py', 'infer.py', 'common.py')
 
 
 def ref_available():
@@ -37,9 +40,24 @@ def built():
     return all((OUT / 'seekmer' / (m + suffix)).exists() for m in MODULES)
 
 
+def python_modules_placed():
+    return all((OUT / 'seekmer' / name).exists() for name in PURE_PYTHON)
+
+
+def place_python_modules():
+    """Unmodified copies of the reference's pure-Python modules into the git-ignored build dir."""
+    if not ref_available():
+        return python_modules_placed()
+    (OUT / 'seekmer').mkdir(parents=True, exist_ok=True)
+    for name in PURE_PYTHON:
+        shutil.copyfile(str(REF / 'seekmer' / name), str(OUT / 'seekmer' / name))
+    return True
+
+
 def build(force=False, verbose=False):
     if not ref_available():
         return built()
+    place_python_modules()
     if built() and not force:
         return True
     import numpy

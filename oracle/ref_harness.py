@@ -32,7 +32,7 @@ def available():
 
 
 def have_python_reference():
-    return (REF_PY / 'mapper.py').exists()
+    return (REF_PY / 'mapper.py').exists() or (HERE / '_ref' / 'seekmer' / 'mapper.py').exists()
 
 
 def load_ref():
@@ -48,8 +48,8 @@ def load_ref():
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         pkg = importlib.import_module('seekmer')
-        if have_python_reference():
-            pkg.__path__.append(str(REF_PY))
+        if (REF_PY / 'mapper.py').exists():
+            pkg.__path__.append(str(REF_PY))  # everything else of the reference, where it lies
         importlib.import_module('seekmer._common')
         importlib.import_module('seekmer._mapper')
         importlib.import_module('seekmer._index_builder')

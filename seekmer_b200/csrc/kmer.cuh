@@ -36,10 +36,6 @@ __device__ __forceinline__ uint32_t ld_hint_4(const void *p, uint64_t pol)
     asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
 // Reverse complement of a 25-mer held in the low 50 bits (_kmer.pxd:146-171).
 // brev reverses all 64 bits; swapping the two bits of every pair restores base

@@ -46,7 +46,7 @@
 namespace skm {
 
 #ifndef SKM_LIST_CAP
-#define SKM_LIST_CAP 16
+#define SKM_LIST_CAP 12
 #endif
 #ifndef SKM_Q_THREADS
 #define SKM_Q_THREADS 768
@@ -66,32 +66,6 @@ constexpr int SCAN_WIDTH = SKM_SCAN_WIDTH;  // read positions probed per P_SCAN 
 #define SKM_STICKY_LANES 16
 #endif
 constexpr int STICKY_LANES = SKM_STICKY_LANES;  // a phase repeats while this many lanes still have rows for it
-#ifndef SKM_SCAN_PREFETCH
-#define SKM_SCAN_PREFETCH 0
-#endif
-// SKM_STAGE: every item owns a 64-byte LANDING ZONE in shared memory.  The two phases that wait
-// on one 64-byte record from the index (P_LOOKUP: a table bucket, P_CONTIG: a contig record
-// header) fetch it with cp.async (global -> shared, L2 policy attached, no registers held while
-// it is in flight).  A lane claims up to SKM_NSUB waiting rows of such a phase per iteration,
-// starts all their fetches, then runs the phase for one row after the other: the fetch of row
-// k+1 travels while row k is being worked on, so one exposed DRAM latency serves NSUB items.
-// The zone doubles as the stash of the current contig (first/last k-mer, sequence offset).
-#ifndef SKM_STAGE
-#define SKM_STAGE 0
-#endif
-#ifndef SKM_NSUB
-#define SKM_NSUB 1
-#endif
-constexpr bool STAGE = SKM_STAGE != 0;
-constexpr int NSUB = STAGE ? SKM_NSUB : 1;
-static_assert(NSUB >= 1 && NSUB <= 3, "SKM_NSUB must be 1, 2 or 3");
-constexpr int LAND_VECS = 4;  // uint4 words of an item's landing zone
-#ifndef SKM_LOAD_AHEAD
-#define SKM_LOAD_AHEAD 0
-#endif
-// P_LOAD asks L2 for the packed reads of the unit LOAD_AHEAD positions further down the work
-// counter (every unit is asked for once, by whoever takes the unit LOAD_AHEAD before it)
-constexpr long long LOAD_AHEAD = SKM_LOAD_AHEAD;
 
 // What the mapper leaves behind for one unit, field-major so that tally_units_kernel reads it
 // coalesced: units[0][u] = number of targets, units[1][u] = span length of _mapper.pyx:90,
@@ -137,8 +111,7 @@ constexpr int CTG_WORDS = 3;   // contig stash: first_kmer, last_kmer, seq_offse
 
 constexpr size_t map_item_bytes(int code_words)
 {
-    return sizeof(uint64_t) * ((size_t)code_words + (STAGE ? 0 : CTG_WORDS)) + sizeof(int32_t) * 2 * LIST_CAP
-           + 16 * (STATE_VECS + (STAGE ? LAND_VECS : 0));
+    return sizeof(uint64_t) * ((size_t)code_words + CTG_WORDS) + sizeof(int32_t) * 2 * LIST_CAP + 16 * STATE_VECS;
 }
 constexpr size_t map_fixed_bytes() { return sizeof(uint32_t) * (N_PHASES * 32) + 16; }
 
@@ -222,28 +195,7 @@ template <int ITEMS>
 struct ItemMem {
     uint4 *state;      // &state[0][item]; vector v at state[v * ITEMS]
     uint64_t *codes;   // &codes[0][item]
-    uint64_t *ctg;     // &ctg[0][item]              (without SKM_STAGE)
-    uint4 *land;       // &land[0][item]: landing zone (with SKM_STAGE)
-    // the stash of the current contig: first k-mer, last k-mer, sequence offset
-    __device__ __forceinline__ void stash_kmers(uint64_t &first_kmer, uint64_t &last_kmer) const
-    {
-        if (STAGE) {
-            const uint4 v = land[0];
-            first_kmer = ((uint64_t)v.x | ((uint64_t)v.y << 32)) & KMER_MASK;
-            last_kmer = ((uint64_t)v.z | ((uint64_t)v.w << 32)) & KMER_MASK;
-        } else {
-            first_kmer = ctg[0];
-            last_kmer = ctg[ITEMS];
-        }
-    }
-    __device__ __forceinline__ int64_t stash_seq_offset() const
-    {
-        if (STAGE) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(land + ITEMS);
-            return (int64_t)((uint64_t)v.x | ((uint64_t)v.y << 32));
-        }
-        return (int64_t)ctg[2 * ITEMS];
-    }
+    uint64_t *ctg;     // &ctg[0][item]
     int32_t *list0;    // &lists[0][item]; mate 2 uses the second LIST_CAP entries
     int32_t *arena;
     __device__ __forceinline__ List<ITEMS> fresh_list(int mate) const
@@ -333,8 +285,11 @@ __device__ __forceinline__ void lane_store(const Lane<ITEMS> &L, const ItemMem<I
 __device__ __forceinline__ uint32_t contig_window(const DevIndex &ix, int64_t seq_offset, Coord a, bool left_edge)
 {
     const int64_t p = seq_offset + a.offset;
-    if (a.entry >= 0) return seq_window8(ix, left_edge ? p : p + K - ALIGN_LENGTH);
-    return revcomp8(seq_window8(ix, left_edge ? p + K - ALIGN_LENGTH : p));
+    // one load site for both strands: the window sits at the k-mer's low end when the edge asked
+    // for and the strand agree, at its high end otherwise; the reverse strand complements it
+    const bool forward = a.entry >= 0;
+    const uint32_t w = seq_window8(ix, left_edge == forward ? p : p + K - ALIGN_LENGTH);
+    return forward ? w : revcomp8(w);
 }
 
 // 8-base window at a contig EDGE, taken from the record's first/last k-mer instead of the
@@ -613,75 +568,6 @@ __device__ __forceinline__ int sift4_edge(uint32_t ref16, const ReadView<ITEMS> 
     return sift4_unified(ref16, codes, wild, 1 - dir, dir ? rv.len - qoff : qoff + 8);
 }
 
-// ---- cp.async staging (SKM_STAGE) ---------------------------------------------------------------
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, uint64_t policy)
-{
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// 64 bytes from `src` into the item's landing zone (4 x 16 bytes, vector v at land[v * ITEMS])
-template <int ITEMS>
-__device__ __forceinline__ void fetch_to_land(uint4 *land, const void *src, uint64_t policy)
-{
-    const char *s = reinterpret_cast<const char *>(src);
-#pragma unroll
-    for (int v = 0; v < LAND_VECS; ++v) cp_async_16(land + v * ITEMS, s + 16 * v, policy);
-}
-
-// KMerIndex.map_kmer on a home bucket that already sits in the landing zone; the (rare) overflow
-// into the following buckets reads the table directly
-template <int ITEMS>
-__device__ __forceinline__ Coord probe_landed(const DevIndex &ix, const uint4 *land, uint64_t kmer)
-{
-    const uint64_t rc = revcomp(kmer);
-    Probe p;
-    p.fwd = kmer < rc;
-    p.canon = p.fwd ? kmer : rc;
-    uint64_t v = 0;
-    bool found = false;
-    uint64_t last_key = 0;
-#pragma unroll
-    for (int k = 0; k < BUCKET_SLOTS; ++k) {
-        const uint4 s = land[k * ITEMS];
-        const uint64_t key = (uint64_t)s.x | ((uint64_t)s.y << 32);
-        if (key == p.canon) {
-            v = (uint64_t)s.z | ((uint64_t)s.w << 32);
-            found = true;
-        }
-        last_key = key;
-    }
-    if (found) {
-        const int32_t entry = (int32_t)(uint32_t)v;
-        return Coord{p.fwd ? entry : ~entry, (int32_t)(uint32_t)(v >> 32)};
-    }
-    if (last_key == EMPTY_KEY) return coord_invalid();
-    p.bucket = (uint32_t)(((uint64_t)home_bucket_of(p.canon, ix.bucket_mask) + 1) & ix.bucket_mask);
-    return run_probe(ix, p);
-}
-
-// the contig record header from the landing zone (load_contig's unpacking, kmer.cuh)
-template <int ITEMS>
-__device__ __forceinline__ Contig contig_landed(const uint4 *land)
-{
-    const uint4 a = land[0], b = land[ITEMS], t0 = land[2 * ITEMS], t1 = land[3 * ITEMS];
-    const uint64_t w0 = (uint64_t)a.x | ((uint64_t)a.y << 32), w1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
-    Contig c;
-    c.t[0] = (int32_t)t0.x; c.t[1] = (int32_t)t0.y; c.t[2] = (int32_t)t0.z; c.t[3] = (int32_t)t0.w;
-    c.t[4] = (int32_t)t1.x; c.t[5] = (int32_t)t1.y; c.t[6] = (int32_t)t1.z; c.t[7] = (int32_t)t1.w;
-    c.first_kmer = w0 & KMER_MASK;
-    c.last_kmer = w1 & KMER_MASK;
-    c.target_count = (int32_t)((w0 >> 50) | ((w1 >> 50) << 14));
-    c.seq_offset = (int64_t)((uint64_t)b.x | ((uint64_t)b.y << 32));
-    c.target_offset = b.z;
-    c.length = (int32_t)b.w;
-    return c;
-}
-
 template <int ROWS>
 __global__ void __launch_bounds__(Q_THREADS, 1)
 map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
@@ -689,10 +575,9 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
     constexpr int ITEMS = ROWS * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sm_state = reinterpret_cast<uint4 *>(smem_raw);                            // [STATE_VECS][ITEMS]
-    uint4 *sm_land = sm_state + STATE_VECS * ITEMS;                                    // [LAND_VECS][ITEMS] (SKM_STAGE)
-    uint64_t *sm_codes = reinterpret_cast<uint64_t *>(sm_land + (STAGE ? LAND_VECS * ITEMS : 0));  // [code_words][ITEMS]
-    uint64_t *sm_ctg = sm_codes + (size_t)a.code_words * ITEMS;                       // [CTG_WORDS][ITEMS] (no SKM_STAGE)
-    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + (STAGE ? 0 : CTG_WORDS * ITEMS));  // [2 * LIST_CAP][ITEMS]
+    uint64_t *sm_codes = reinterpret_cast<uint64_t *>(sm_state + STATE_VECS * ITEMS);  // [code_words][ITEMS]
+    uint64_t *sm_ctg = sm_codes + (size_t)a.code_words * ITEMS;                       // [CTG_WORDS][ITEMS]
+    int32_t *sm_lists = reinterpret_cast<int32_t *>(sm_ctg + CTG_WORDS * ITEMS);      // [2 * LIST_CAP][ITEMS]
     uint32_t *sm_masks = reinterpret_cast<uint32_t *>(sm_lists + 2 * LIST_CAP * ITEMS);  // [N_PHASES][32]
     int *sm_live = reinterpret_cast<int *>(sm_masks + N_PHASES * 32);
 
@@ -741,81 +626,23 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             for (int p = 0; p < N_PHASES; ++p)
                 if (p == phase) mm = m[p];
         }
-        // ---- claim one waiting row of that phase (up to NSUB in the staged phases) -----------------
-        const bool staged = STAGE && (phase == P_LOOKUP || phase == P_CONTIG);  // warp-uniform
-        int row_s[NSUB];
-        bool mine_s[NSUB];
-#pragma unroll
-        for (int s = 0; s < NSUB; ++s) {
-            row_s[s] = 0;
-            mine_s[s] = false;
-            if (mm && (s == 0 || staged)) {
-                const unsigned rot = iter & 31u;
-                const uint32_t mr = __funnelshift_r(mm, mm, rot);
-                row_s[s] = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
-                const uint32_t old = atomicAnd(&sm_masks[phase * 32 + lane], ~(1u << row_s[s]));
-                mine_s[s] = (old >> row_s[s]) & 1u;
-                mm &= ~(1u << row_s[s]);
-            }
+        // ---- claim one waiting row of that phase ---------------------------------------------
+        bool mine = false;
+        int row = 0;
+        if (mm) {
+            const unsigned rot = iter & 31u;
+            const uint32_t mr = __funnelshift_r(mm, mm, rot);
+            row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
+            const uint32_t old = atomicAnd(&sm_masks[phase * 32 + lane], ~(1u << row));
+            mine = (old >> row) & 1u;
         }
         iter += 1;
         __threadfence_block();
-        int nsub = 1;
-        if (staged) {
-            // start every claimed row's fetch: the bucket of its pending k-mer, or the record of
-            // the contig it is about to enter
-#pragma unroll
-            for (int s = 0; s < NSUB; ++s) {
-                if (mine_s[s]) {
-                    const int it = row_s[s] * 32 + lane;
-                    const void *src;
-                    uint64_t pol;
-                    if (phase == P_LOOKUP) {
-                        const uint2 kv = *reinterpret_cast<const uint2 *>(sm_state + ITEMS + it);
-                        const Probe pr = prepare_probe((uint64_t)kv.x | ((uint64_t)kv.y << 32), ix.bucket_mask);
-                        src = ix.table + BUCKET_SLOTS * (uint64_t)pr.bucket;
-                        pol = ix.pol_stream;
-                    } else {
-                        const uint32_t f = sm_state[it].y;
-                        const uint4 v2 = sm_state[2 * ITEMS + it];
-                        const int32_t e = (int)(f & F_CTX) == C_RIGHT_C ? (int32_t)v2.x : (int32_t)v2.z;
-                        src = ix.contigs + (e >= 0 ? e : ~e);
-                        pol = ix.pol_hot;
-                    }
-                    fetch_to_land<ITEMS>(sm_land + it, src, pol);
-                }
-                cp_async_commit();
-            }
-            if (NSUB > 1) {
-                const unsigned second = __ballot_sync(0xffffffffu, mine_s[NSUB > 1 ? 1 : 0]);
-                nsub = second ? 2 : 1;
-                if (NSUB > 2 && __ballot_sync(0xffffffffu, mine_s[NSUB > 2 ? 2 : 0])) nsub = 3;
-            }
-        }
-#pragma unroll 1
-        for (int sub = 0; sub < nsub; ++sub) {
-        bool mine = mine_s[0];
-        int row = row_s[0];
-        if (NSUB > 1 && sub == 1) {
-            mine = mine_s[NSUB > 1 ? 1 : 0];
-            row = row_s[NSUB > 1 ? 1 : 0];
-        }
-        if (NSUB > 2 && sub == 2) {
-            mine = mine_s[NSUB > 2 ? 2 : 0];
-            row = row_s[NSUB > 2 ? 2 : 0];
-        }
-        if (staged) {
-            // groups complete in order: row `sub` has landed once at most NSUB-1-sub groups are pending
-            if (sub == 0) cp_async_wait<NSUB - 1>();
-            else if (sub == 1) cp_async_wait<(NSUB > 1 ? NSUB - 2 : 0)>();
-            else cp_async_wait<0>();
-        }
         const int item = row * 32 + lane;
         ItemMem<ITEMS> I;
         I.state = sm_state + item;
         I.codes = sm_codes + item;
         I.ctg = sm_ctg + item;
-        I.land = sm_land + item;
         I.list0 = sm_lists + item;
         I.arena = a.arena;
         Lane<ITEMS> L;
@@ -851,12 +678,6 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (need) {
                     L.unit = base + __popc(nb & ((1u << lane) - 1u));
                     if (L.unit >= a.n_units) L.st = P_DEAD;
-                    if (LOAD_AHEAD > 0 && L.unit + LOAD_AHEAD < a.n_units) {
-                        const long long r = a.paired ? 2 * (L.unit + LOAD_AHEAD) : L.unit + LOAD_AHEAD;
-                        const char *q = reinterpret_cast<const char *>(a.packed + r * (long long)a.words);
-                        const int bytes = a.words * 8 * (a.paired ? 2 : 1);
-                        for (int o = 0; o < bytes; o += 128) prefetch_l2(q + o);
-                    }
                 }
             }
             if (mine && L.st == P_LOAD) {
@@ -896,9 +717,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
         } else if (phase == P_LOOKUP) {
             if (mine) {
-                const Coord h = STAGE ? probe_landed<ITEMS>(ix, I.land, L.kmer)
-                                      : run_probe(ix, prepare_probe(L.kmer, ix.bucket_mask));
-                if (STAGE) L.ctg_a0 = false;  // the bucket landed on the stash of the first hit's contig
+                const Coord h = run_probe(ix, prepare_probe(L.kmer, ix.bucket_mask));
                 L.sp.anchor = h;
                 if (h.offset >= 0) {
                     L.st = P_CONTIG;
@@ -917,7 +736,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
         } else if (phase == P_SCAN) {
             if (mine) {
-                // positions pos .. pos+3 (while they fit); L.kmer is the k-mer at pos-1
+                // positions pos .. pos+2 (while they fit); L.kmer is the k-mer at pos-1
                 uint64_t km[SCAN_WIDTH];
                 Probe pr[SCAN_WIDTH];
                 uint64_t k = L.kmer;
@@ -927,11 +746,6 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     if (j < fit) k = ((k << 2) | rv.code(L.pos + j + K - 1)) & KMER_MASK;
                     km[j] = k;
                     pr[j] = prepare_probe(k, ix.bucket_mask);
-                }
-                if (SKM_SCAN_PREFETCH) {  // the probes below run one after the other: have the later buckets on their way
-#pragma unroll
-                    for (int j = 0; j + 1 < SCAN_WIDTH; ++j)
-                        if (j < fit) prefetch_l2(ix.table + BUCKET_SLOTS * (uint64_t)pr[j].bucket);
                 }
                 int first = SCAN_WIDTH;
                 Coord hh = coord_invalid();
@@ -961,12 +775,10 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         } else if (phase == P_CONTIG) {
             if (mine) {
                 const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
-                const Contig c = STAGE ? contig_landed<ITEMS>(I.land) : load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
-                if (!STAGE) {
-                    I.ctg[0] = c.first_kmer;
-                    I.ctg[ITEMS] = c.last_kmer;
-                    I.ctg[2 * ITEMS] = (uint64_t)c.seq_offset;
-                }
+                const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
+                I.ctg[0] = c.first_kmer;
+                I.ctg[ITEMS] = c.last_kmer;
+                I.ctg[2 * ITEMS] = (uint64_t)c.seq_offset;
                 L.clen = c.length;
                 L.forward = at.entry >= 0;
                 const int to_start = L.forward ? at.offset : c.length - at.offset - K;
@@ -1016,8 +828,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         } else if (phase == P_WALK) {
             if (mine) {
                 // heads of the loops of _filter_targets_to_left (:234-275) and _to_right (:293-343)
-                uint64_t first_kmer, last_kmer;
-                I.stash_kmers(first_kmer, last_kmer);
+                const uint64_t first_kmer = I.ctg[0], last_kmer = I.ctg[ITEMS];
                 const int dir = L.dir;
                 int rem = dir ? L.len - L.sp.end - K : L.sp.begin;  // bases left towards the read end
                 const bool in_loop = rem > L.move;
@@ -1031,7 +842,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     ref16 = edge_window(first_kmer, last_kmer, L.sp.anchor, dir == 0);
                     qoff = dir ? L.len - rem - ALIGN_LENGTH : rem;
                 } else {
-                    ref16 = contig_window(ix, I.stash_seq_offset(), L.sp.anchor, dir == 0);
+                    ref16 = contig_window(ix, (int64_t)I.ctg[2 * ITEMS], L.sp.anchor, dir == 0);
                     qoff = dir ? L.len - ALIGN_LENGTH : 0;
                 }
                 const int shift = sift4_edge(ref16, rv, qoff, dir);
@@ -1210,7 +1021,6 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
         }
         __syncwarp();
-        }  // sub
     }
 
 }

@@ -325,6 +325,9 @@ __global__ void dict_merge_packed_kernel(const DictDev d, const int64_t *__restr
     if (peer == rank) return;
     const int64_t *buf = gathered + (int64_t)peer * cap;
     const int64_t n_classes = buf[0];
+    // a peer whose export did not fit its block only sent the header: nothing of it is read (the
+    // caller checks the headers before it launches this and exchanges again with larger blocks)
+    if (n_classes < 0 || buf[1] < 0 || 3 + SKM_MAX_FRAGMENT_LENGTH + 3 * n_classes + 1 + (buf[1] + 1) / 2 > cap) return;
     const int64_t *fld = buf + 3;
     const int64_t *key_offsets = fld + SKM_MAX_FRAGMENT_LENGTH;
     const int64_t *counts = key_offsets + n_classes + 1;
@@ -532,11 +535,11 @@ SKM_API int skm_mapper_create(skm_index *index, int64_t class_capacity, int64_t 
             fprintf(stderr, "[skm trace] L2: max persisting %d B, max window %d B, hot block %lld B, hit ratio %.3f\n",
                     max_persist, max_window, (long long)index->hot_bytes, m->l2_hit_ratio);
     }
-    // list arena: room for every resident thread to spill its largest possible list a few
-    // times over, bounded to 2 GiB
+    // list arena (target lists longer than LIST_CAP, a bump allocator that starts over with every
+    // launch): room for every resident thread to spill its largest possible list a few times
+    // over; launch_chunk grows it with the units of a launch
     uint64_t arena = (uint64_t)std::max<int64_t>(index->max_target_count, 64) * 2048ULL * (uint64_t)m->sm_count;
     arena = std::min<uint64_t>(std::max<uint64_t>(arena, 1ULL << 22), 1ULL << 29);
-    if (const char *e = getenv("SKM_ARENA_LOG2")) arena = 1ULL << std::max(16, std::min(31, atoi(e)));
     m->arena_cap = arena;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) {
@@ -632,6 +635,19 @@ static int launch_chunk(skm_mapper *m, const uint8_t *d_bases, const int64_t *d_
         d_bases, d_starts, d_ends, a.fixed_len, a.code_words, a.wild_words, a.words, n_reads, m->d_packed, lens);
     SKM_CUDA(cudaGetLastError());
     SKM_CUDA(cudaEventRecord(m->ev_kernel[1], st));
+    if (m->index->max_target_count > LIST_CAP) {
+        // nothing is given back inside a launch: size the arena by the launch (16 entries per unit,
+        // i.e. every read spilling one list of 8 beyond LIST_CAP would still fit)
+        const uint64_t want = std::min<uint64_t>((uint64_t)n_units * 16ULL, 1ULL << 30);
+        if (want > m->arena_cap) {
+            size_t cap_bytes = sizeof(int32_t) * (size_t)m->arena_cap;
+            rc = ensure((void **)&m->arena, &cap_bytes, sizeof(int32_t) * (size_t)want);
+            if (rc) return rc;
+            m->arena_cap = cap_bytes / sizeof(int32_t);
+        }
+    }
+    a.arena = m->arena;
+    a.arena_cap = m->arena_cap;
     a.packed = m->d_packed;
     a.lens = lens;
     a.n_units = n_units;

@@ -139,29 +139,69 @@ def merge_class_tables(table, group=None):
                 scalars=dense[n_global + MAX_FRAGMENT_LENGTH:].clone())
 
 
-def merge_mappers(mp, group=None):
+_CAP_HINT = {}  # words per rank of the packed exchange buffer, per process group
+
+
+def packed_words(n_classes, n_ids):
+    """int64 words of one rank's packed export (`DeviceMapper.pack_raw_torch`)."""
+    return 3 + MAX_FRAGMENT_LENGTH + (n_classes + 1) + 2 * n_classes + (n_ids + 1) // 2
+
+
+def merge_mappers(mp, group=None, stages=None):
     """Collective, CUDA only: make every rank's device dictionary the global one and return the
     global table (same shape and order as `merge_class_tables`).
 
     One exchange step: every rank ships its exported dictionary (CSR keys, counts, first-seen
     units, FLD, unaligned count; ~30 MB) in ONE all-gather over NVLink, then inserts the other
     ranks' classes into its own device dictionary with the library's merge kernel
-    (`skm_classes_merge`: same 128-bit tuple hash, counts added with atomics, first-seen unit
-    by atomicMin).  All ranks end with the same dictionary, exported in first-seen order."""
+    (`skm_classes_merge_packed`: same 128-bit tuple hash, ids compared on a key hit, counts added
+    with atomics, first-seen unit by atomicMin).  All ranks end with the same dictionary,
+    exported in first-seen order.  The buffer size per rank is remembered from the previous
+    exchange (with headroom); the sizes the ranks actually sent are checked after the gather
+    and only an overflow costs a second, larger exchange.
+
+    `stages`, when a dict, receives the device time (ms, CUDA events) of the four stages."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return mp.export_torch()
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if stages is not None else None
+
+    def mark(k):
+        if ev is not None:
+            ev[k].record()
+    mark(0)
     packed = mp.pack_raw_torch()
     dev = packed.device
-    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(sizes, torch.tensor([packed.shape[0]], dtype=torch.int64, device=dev), group=group)
-    cap = int(sizes.max().item())
-    mine = torch.zeros(cap, dtype=torch.int64, device=dev)
-    mine[:packed.shape[0]] = packed
-    gathered = torch.zeros(world * cap, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
+    own = int(packed.shape[0])
+    mark(1)
+    key = id(group) if group is not None else 0
+    cap = _CAP_HINT.get(key)
+    while True:
+        if cap is None:  # first exchange: learn the sizes
+            sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(sizes, torch.tensor([own], dtype=torch.int64, device=dev), group=group)
+            cap = int(sizes.max().item())
+            cap += cap // 4 + 1024
+        mine = torch.zeros(cap, dtype=torch.int64, device=dev)
+        mine[:min(own, cap)] = packed[:cap]  # a buffer that does not fit still carries its header
+        gathered = torch.zeros(world * cap, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        heads = gathered.view(world, cap)[:, :2].cpu().tolist()  # [n_classes, n_ids] of every rank
+        need = max(packed_words(int(n), int(k)) for n, k in heads)
+        if need <= cap:
+            break
+        cap = need + need // 4 + 1024  # every rank sees the same headers: all of them go round again
+    _CAP_HINT[key] = cap
+    mark(2)
     mp.merge_packed(gathered, cap, world, rank)
-    return mp.export_torch()
+    mark(3)
+    table = mp.export_torch()
+    mark(4)
+    if ev is not None:
+        torch.cuda.synchronize()
+        for k, name in enumerate(('export_pack_ms', 'all_gather_ms', 'merge_kernel_ms', 'export_ms')):
+            stages[name] = ev[k].elapsed_time(ev[k + 1])
+    return table
 
 
 def table_to_host(table):
