@@ -90,6 +90,19 @@ int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
                      void *stream, skm_index **out);
 void skm_index_destroy(skm_index *index);
 
+/* Replaces: KMerIndex.save / KMerIndex.load (_common.pyx:268-313) for the device-side form of
+ * the index (the native GPU-layout index file): the re-laid-out table, the
+ * contig records with their graph links, the 2-bit sequences and the target entries are written
+ * as they lie in HBM and read back with plain copies - loading runs no relayout kernel and
+ * none of the 8 table probes per contig.  `trailer` is caller-owned bytes stored after the
+ * image (the Python layer keeps the transcript table there); skm_index_load reports where they
+ * are.  A file written by another layout version is refused ("invalid index version.",
+ * _common.pyx:303-304). */
+int skm_index_save(const skm_index *index, const char *path, const void *trailer,
+                   int64_t trailer_bytes, void *stream);
+int skm_index_load(const char *path, int device, void *stream, skm_index **out,
+                   int64_t *trailer_offset, int64_t *trailer_bytes);
+
 /* info[0]=distinct k-mers, [1]=device table slots, [2]=max target_count,
  * [3]=device bytes held, [4]=n_contigs, [5]=n_targets, [6]=n_transcripts, [7]=device */
 int skm_index_info(const skm_index *index, int64_t info[8]);
@@ -234,16 +247,24 @@ int skm_em_plan_run(const skm_em_plan *plan, const double *counts, const double 
                     int32_t *out_iters, int buffers_on_device, void *stream);
 int skm_em_plan_bootstrap(const skm_em_plan *plan, const int64_t *counts, const double *eff_len,
                           const double *x0, int64_t n_replicates, int64_t first_replicate,
-                          uint64_t seed, int64_t max_iters, int tpm, double *out_x,
+                          uint64_t seed, int method, int64_t max_iters, int tpm, double *out_x,
                           int32_t *out_iters, int buffers_on_device, void *stream);
 
 /* Replaces: scipy.stats.multinomial(n, p).rvs() at infer.py:108-111 — resample
- * n = sum(counts) reads with replacement, n_replicates times.  Integer-exact,
- * counter-based (Philox4x32-10 keyed by seed; counter = (draw pair, replicate); one block
- * of four words yields two 64-bit draws). out is
- * int64[n_replicates * n_classes]; replicate ids start at first_replicate. */
+ * n = sum(counts) reads with replacement, n_replicates times; every replicate sums to n.
+ * Counter-based (Philox4x32-10 keyed by seed), so replicate r is a function of (seed, r) alone:
+ * replicate ids start at first_replicate and shards reproduce the single-call rows.  `method`:
+ *   SKM_RESAMPLE_TREE   O(n_classes) per replicate whatever the read depth: a binary tree of
+ *                       exact binomial splits (inversion / BTPE, csrc/binomial.cuh), one Philox
+ *                       stream per (tree node, replicate).  What the bootstraps use.
+ *   SKM_RESAMPLE_DRAWS  O(n) per replicate: n categorical draws with integer arithmetic only
+ *                       (counter = (draw pair, replicate); one Philox block yields two 64-bit
+ *                       draws); bit-identical to the numpy restatement in oracle/oracle.py.
+ * out is int64[n_replicates * n_classes]. */
+#define SKM_RESAMPLE_DRAWS 0
+#define SKM_RESAMPLE_TREE 1
 int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicates,
-                    int64_t first_replicate, uint64_t seed, int64_t *out,
+                    int64_t first_replicate, uint64_t seed, int method, int64_t *out,
                     int buffers_on_device, int device, void *stream);
 
 /* Replaces: the bootstrap loop of infer.run (infer.py:79-82), i.e. n_replicates times
@@ -255,7 +276,7 @@ int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicat
 int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes,
                      int64_t nnz, const int64_t *counts, const double *eff_len,
                      int64_t n_transcripts, const double *x0, int64_t n_replicates,
-                     int64_t first_replicate, uint64_t seed, int64_t max_iters, int tpm,
+                     int64_t first_replicate, uint64_t seed, int method, int64_t max_iters, int tpm,
                      double *out_x, int32_t *out_iters, int buffers_on_device, int device,
                      void *stream);
 

@@ -14,6 +14,7 @@ LIB_PATH = pathlib.Path(os.environ.get('SEEKMER_B200_LIB', HERE / 'libseekmer_b2
 
 K = 25
 MAX_FRAGMENT_LENGTH = 2000
+RESAMPLE_DRAWS, RESAMPLE_TREE = 0, 1  # skm_multinomial methods (include/seekmer_b200.h)
 
 SLOT_DTYPE = numpy.dtype([('kmer', '<u8'), ('entry', '<i4'), ('offset', '<i4')])
 CONTIG_DTYPE = numpy.dtype([('offset', '<i8'), ('length', '<i8'), ('first_kmer', '<u8'),
@@ -26,7 +27,7 @@ EXPORTS = (
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
     'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_classes_merge_packed', 'skm_release_cache', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
-    'skm_build_kmer_table', 'skm_em_plan_create', 'skm_em_plan_from_mapper', 'skm_em_plan_info',
+    'skm_build_kmer_table', 'skm_index_save', 'skm_index_load', 'skm_em_plan_create', 'skm_em_plan_from_mapper', 'skm_em_plan_info',
     'skm_em_plan_destroy', 'skm_em_plan_run', 'skm_em_plan_bootstrap',
 )
 
@@ -61,6 +62,10 @@ def load():
                                    ctypes.POINTER(vp)]
     L.skm_index_destroy.restype = None
     L.skm_index_destroy.argtypes = [vp]
+    L.skm_index_save.restype = ci
+    L.skm_index_save.argtypes = [vp, ctypes.c_char_p, vp, i64, vp]
+    L.skm_index_load.restype = ci
+    L.skm_index_load.argtypes = [ctypes.c_char_p, ci, vp, ctypes.POINTER(vp), vp, vp]
     L.skm_index_info.restype = ci
     L.skm_index_info.argtypes = [vp, vp]
     L.skm_map_kmers.restype = ci
@@ -94,7 +99,7 @@ def load():
     L.skm_em_samples.restype = ci
     L.skm_em_samples.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, ci, ci, vp]
     L.skm_em_bootstrap.restype = ci
-    L.skm_em_bootstrap.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u64, i64, ci, vp, vp, ci, ci, vp]
+    L.skm_em_bootstrap.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp, i64, i64, u64, ci, i64, ci, vp, vp, ci, ci, vp]
     L.skm_em_plan_create.restype = ci
     L.skm_em_plan_create.argtypes = [vp, vp, i64, i64, i64, vp, ci, ci, vp, ctypes.POINTER(vp)]
     L.skm_em_plan_from_mapper.restype = ci
@@ -106,9 +111,9 @@ def load():
     L.skm_em_plan_run.restype = ci
     L.skm_em_plan_run.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, ci, vp]
     L.skm_em_plan_bootstrap.restype = ci
-    L.skm_em_plan_bootstrap.argtypes = [vp, vp, vp, vp, i64, i64, u64, i64, ci, vp, vp, ci, vp]
+    L.skm_em_plan_bootstrap.argtypes = [vp, vp, vp, vp, i64, i64, u64, ci, i64, ci, vp, vp, ci, vp]
     L.skm_multinomial.restype = ci
-    L.skm_multinomial.argtypes = [vp, i64, i64, i64, u64, vp, ci, ci, vp]
+    L.skm_multinomial.argtypes = [vp, i64, i64, i64, u64, ci, vp, ci, ci, vp]
     L.skm_synth_reads.restype = ci
     L.skm_synth_reads.argtypes = [vp, vp, i64, vp, u64, i32, i32, i32, i32, i32, i32, u64, ci,
                                   i64, i64, vp, ci, vp]
@@ -187,6 +192,26 @@ class DeviceIndex:
         self._h = handle
         self._keep = None
         self.device = int(device)
+
+    @classmethod
+    def load(cls, path, device=0, stream=None):
+        """From a device image file (`skm_index_save`): plain copies, no relayout."""
+        require_device()
+        self = cls.__new__(cls)
+        handle = ctypes.c_void_p()
+        where = numpy.zeros(2, dtype='i8')
+        check(load().skm_index_load(str(path).encode(), int(device), stream, ctypes.byref(handle),
+                                    ctypes.c_void_p(where.ctypes.data), ctypes.c_void_p(where.ctypes.data + 8)))
+        self._h = handle
+        self._keep = None
+        self.device = int(device)
+        self.trailer = (int(where[0]), int(where[1]))
+        return self
+
+    def save(self, path, trailer=b'', stream=None):
+        """Write the device image (+ `trailer` bytes after it)."""
+        buf = ctypes.create_string_buffer(trailer, len(trailer)) if trailer else None
+        check(load().skm_index_save(self._h, str(path).encode(), buf, len(trailer), stream))
 
     def info(self):
         a = numpy.zeros(8, dtype='i8')
@@ -461,7 +486,7 @@ class EmPlan:
         return out, iters
 
     def bootstrap(self, eff_len, x0, n_replicates, seed, first_replicate=0, counts=None, tpm=True, max_iters=0,
-                  stream=None):
+                  method=RESAMPLE_TREE, stream=None):
         """Resample + EM (+ TPM step) for replicates [first_replicate, first_replicate + n)."""
         x0 = numpy.ascontiguousarray(x0, dtype='f8')
         eff_len = numpy.ascontiguousarray(eff_len, dtype='f8')
@@ -470,8 +495,8 @@ class EmPlan:
         out = numpy.zeros((n_replicates, x0.shape[0]), dtype='f8')
         iters = numpy.zeros(n_replicates, dtype='i4')
         check(load().skm_em_plan_bootstrap(self._h, _ptr(counts), _np_ptr(eff_len), _np_ptr(x0), int(n_replicates),
-                                           int(first_replicate), int(seed) & (2 ** 64 - 1), int(max_iters),
-                                           int(bool(tpm)), _np_ptr(out), _np_ptr(iters), 0, stream))
+                                           int(first_replicate), int(seed) & (2 ** 64 - 1), int(method),
+                                           int(max_iters), int(bool(tpm)), _np_ptr(out), _np_ptr(iters), 0, stream))
         return out, iters
 
     def close(self):

@@ -51,3 +51,25 @@ class StderrHandler:
         finally:
             root.removeHandler(handler)
             root.setLevel(old)
+
+
+@contextlib.contextmanager
+def nvtx_range(name):
+    """An NVTX range around a stage of `infer.run` (visible in Nsight Systems / ncu --nvtx); a
+    no-op when torch has not been imported by the caller's process yet or NVTX is unavailable."""
+    nvtx = None
+    torch = sys.modules.get('torch')
+    if torch is not None:
+        try:
+            nvtx = torch.cuda.nvtx
+            nvtx.range_push(name)
+        except Exception:
+            nvtx = None
+    try:
+        yield
+    finally:
+        if nvtx is not None:
+            try:
+                nvtx.range_pop()
+            except Exception:
+                pass

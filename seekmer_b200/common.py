@@ -19,6 +19,7 @@ import io
 import lzma
 import os
 import pathlib
+import struct
 import subprocess
 
 import numpy
@@ -34,6 +35,14 @@ BUFFER_SIZE = 65536
 _LOG = Logger(__name__)
 
 _INDEX_VERSION = '2019.0.0'
+IMAGE_SUFFIX = '.skmidx'  # the native GPU-layout index file (device image + transcript tables)
+_IMAGE_VERSION = 1
+# csrc/index.cu ImageHeader: magic, version, 5 layout constants, 7 counts, 4 sizes/offsets, trailer bytes, check
+_IMAGE_HEADER = struct.Struct('<8s6I12qQ')
+
+
+def _lib_default_device(index):
+    return getattr(index, 'default_device', 0)
 _EXTERNAL = {'.gz': ('zcat', gzip), '.bz2': ('bzcat', bz2), '.xz': ('xzcat', lzma),
              '.lzma': ('xzcat', lzma)}
 
@@ -49,6 +58,7 @@ class KMerIndex:
         self.transcripts = transcripts
         self.exons = exons
         self._device = {}
+        self._image_path = None  # a device image file (".skmidx") this index was loaded from
 
     # -- device image ---------------------------------------------------------------
     def device_index(self, device=0):
@@ -56,8 +66,11 @@ class KMerIndex:
         dev = self._device.get(device)
         if dev is None:
             n_tx = len(self.transcripts) if self.transcripts is not None else 0
-            dev = _lib.DeviceIndex(self.kmers, self.contigs, self.sequences, self.targets, n_tx,
-                                   device=device)
+            if self.kmers is None and self._image_path is not None:
+                dev = _lib.DeviceIndex.load(self._image_path, device=device)  # plain copies, no relayout
+            else:
+                dev = _lib.DeviceIndex(self.kmers, self.contigs, self.sequences, self.targets, n_tx,
+                                       device=device)
             self._device[device] = dev
         return dev
 
@@ -71,6 +84,9 @@ class KMerIndex:
         """HDF5 when PyTables is importable (`_common.pyx:268-285` layout); `.npz` otherwise or
         when the suffix is `.npz`."""
         path = pathlib.Path(path)
+        if path.suffix == IMAGE_SUFFIX:
+            self._save_image(path)
+            return
         if path.suffix != '.npz':
             try:
                 import tables
@@ -97,9 +113,43 @@ class KMerIndex:
                         transcripts=numpy.asarray(self.transcripts), exons=numpy.asarray(exons))
         _LOG.info('Saved index to "{}"', path)
 
+    def _save_image(self, path):
+        """The native GPU-layout index file: the device image as it lies in HBM
+        (`skm_index_save`) + the host-side tables `infer` needs (transcripts, exons) as a trailer.
+        `KMerIndex.load` of such a file uploads with plain copies: no relayout, no link probes."""
+        buf = io.BytesIO()
+        exons = self.exons if self.exons is not None else numpy.zeros(0, dtype='i4')
+        numpy.savez(buf, seekmer_version=numpy.asarray(_INDEX_VERSION),
+                    transcripts=numpy.asarray(self.transcripts), exons=numpy.asarray(exons))
+        self.device_index(_lib_default_device(self)).save(path, buf.getvalue())
+        _LOG.info('Saved index to "{}"', path)
+
+    @classmethod
+    def _load_image(cls, path):
+        with open(str(path), 'rb') as f:
+            raw = f.read(_IMAGE_HEADER.size)
+            if len(raw) < _IMAGE_HEADER.size or raw[:8] != b'SKMB200\0':
+                raise RuntimeError('not a seekmer_b200 device image: %s' % path)
+            fields = _IMAGE_HEADER.unpack(raw)
+            if fields[1] != _IMAGE_VERSION:
+                raise RuntimeError('invalid index version.')
+            table_bytes, hot_bytes, trailer_bytes = fields[14], fields[15], fields[18]
+            f.seek(_IMAGE_HEADER.size + table_bytes + hot_bytes)
+            trailer = f.read(trailer_bytes)
+        with numpy.load(io.BytesIO(trailer), allow_pickle=False) as z:
+            if str(z['seekmer_version']) != _INDEX_VERSION:
+                raise RuntimeError('invalid index version.')
+            transcripts, exons = z['transcripts'], z['exons']
+        index = cls(None, None, None, None, transcripts, exons)
+        index._image_path = path
+        _LOG.info('Loaded index from "{}"', path)
+        return index
+
     @classmethod
     def load(cls, path):
         path = pathlib.Path(path)
+        if path.suffix == IMAGE_SUFFIX:
+            return cls._load_image(path)
         if path.suffix == '.npz':
             with numpy.load(str(path), allow_pickle=False) as z:
                 if str(z['seekmer_version']) != _INDEX_VERSION:

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
+#include "binomial.cuh"
 #include "common.cuh"
 #include "em_plan.cuh"
 
@@ -94,15 +95,47 @@ __global__ void broadcast_kernel(const double *__restrict__ src, double *__restr
     if (i < n * R) dst[i] = src[i / R];
 }
 
-// resampled integer counts [R][C] -> fp64 [C][R]
-__global__ void counts_to_f64_kernel(const unsigned long long *__restrict__ src, double *__restrict__ dst,
-                                     int64_t n_classes, int R)
+// Class counts [R][C] in the caller's class order (int64 or fp64) -> fp64 [C][R] in the plan's
+// class order: row i of the result is the caller's class perm[i].
+template <typename T>
+__global__ void counts_to_plan_kernel(const T *__restrict__ src, const int32_t *__restrict__ perm,
+                                      double *__restrict__ dst, int64_t n_classes, int R)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_classes * R) return;
     const int64_t c = i / R;
     const int r = (int)(i - c * R);
-    dst[i] = (double)src[(int64_t)r * n_classes + c];
+    dst[i] = (double)src[(int64_t)r * n_classes + perm[c]];
+}
+
+// ---- class order of a plan: by first transcript, so that neighbouring threads gather from
+// ---- neighbouring places (see em_plan_adopt)
+__global__ void class_sort_key_kernel(const int64_t *__restrict__ class_ptr, const int32_t *__restrict__ class_tx,
+                                      int64_t n_classes, uint32_t *__restrict__ key, int32_t *__restrict__ idx)
+{
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= n_classes) return;
+    const int64_t b = class_ptr[c];
+    key[c] = class_ptr[c + 1] > b ? (uint32_t)class_tx[b] : 0xFFFFFFFFu;
+    idx[c] = (int32_t)c;
+}
+
+__global__ void permuted_lens_kernel(const int64_t *__restrict__ class_ptr, const int32_t *__restrict__ perm,
+                                     int64_t n_classes, int64_t *__restrict__ lens)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i > n_classes) return;
+    lens[i] = i < n_classes ? class_ptr[perm[i] + 1] - class_ptr[perm[i]] : 0;
+}
+
+__global__ void permuted_ids_kernel(const int64_t *__restrict__ class_ptr, const int32_t *__restrict__ class_tx,
+                                    const int32_t *__restrict__ perm, int64_t n_classes,
+                                    const int64_t *__restrict__ new_ptr, int32_t *__restrict__ new_tx)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_classes) return;
+    const int64_t src = class_ptr[perm[i]], dst = new_ptr[i], len = class_ptr[perm[i] + 1] - src;
+    for (int64_t k = 0; k < len; ++k) new_tx[dst + k] = class_tx[src + k];
 }
 
 // TPM post-processing of infer.py:127-129 for every replicate (one block each), x in [R][T]:
@@ -177,19 +210,22 @@ struct EmState {
     // many-samples variant (skm_em_samples): R counts samples, rows belong to one sample each
     const int32_t *class_sample;  // [C] sample of a class
     int64_t tx_per_sample;        // transcript rows are [sample][transcript]
+    // transcript rows with more than HEAVY_ROW entries (one replicate / samples kernels): a whole
+    // block sums each of them, the 8-lane groups skip them
+    const int32_t *heavy_rows;
+    int32_t n_heavy;
 };
 
-// ---- E step: inner_c = (sum_{j in c} x[t_j]) / count_c  (infer.py:155-156,162-163) ----------
-__global__ void em_class_kernel_r1(const EmState s, const double *__restrict__ x)
+constexpr int HEAVY_ROW = 256;
+
+__global__ void select_heavy_rows_kernel(const int64_t *__restrict__ tx_ptr, int64_t n_rows, int32_t *__restrict__ out,
+                                         int32_t *__restrict__ count)
 {
-    if (*s.n_active == 0) return;
-    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= s.n_classes) return;
-    double sum = 0.0;
-    for (int64_t j = s.class_ptr[c]; j < s.class_ptr[c + 1]; ++j) sum = __dadd_rn(sum, x[s.class_tx[j]]);
-    s.inner[c] = __ddiv_rn(sum, s.counts[c]);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n_rows && tx_ptr[t + 1] - tx_ptr[t] > HEAVY_ROW) out[atomicAdd(count, 1)] = (int32_t)t;
 }
 
+// ---- E step: inner_c = (sum_{j in c} x[t_j]) / count_c  (infer.py:155-156,162-163) ----------
 // R > 1: one thread per (class, replicate), replicates fastest: consecutive lanes read consecutive
 // replicates of the same rows (coalesced), and every lane has work whatever R is (the state is
 // compacted to the running replicates as they finish, so R shrinks during a run).
@@ -217,31 +253,6 @@ __device__ __forceinline__ void note_change(const EmState &s, int r, double xn, 
 }
 
 // ---- M step: x_t = (sum_{j in t} x_t / inner_{c_j}) / l_t / n, NaN -> 0  (infer.py:157-159) ---
-// R == 1: 8 lanes per transcript, strided partial sums, fixed-order shuffle tree.
-__global__ void em_tx_kernel_r1(const EmState s, const double *__restrict__ x, double *__restrict__ xn_out)
-{
-    if (*s.n_active == 0) return;
-    const int sub = threadIdx.x & 7;
-    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
-    const bool ok = t < s.n_tx;
-    double acc = 0.0;
-    double xt = 0.0;
-    if (ok) {
-        xt = x[t];
-        const int64_t b = s.tx_ptr[t], e = s.tx_ptr[t + 1];
-        for (int64_t j = b + sub; j < e; j += 8) acc = __dadd_rn(acc, __ddiv_rn(xt, s.inner[s.tx_class[j]]));
-    }
-    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
-    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
-    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
-    if (ok && sub == 0) {
-        double v = __ddiv_rn(__ddiv_rn(acc, s.eff_len[t]), s.n[0]);
-        if (v != v) v = 0.0;
-        note_change(s, 0, v, xt);
-        xn_out[t] = v;
-    }
-}
-
 __global__ void em_tx_kernel(const EmState s, const double *__restrict__ x, double *__restrict__ xn_out)
 {
     if (*s.n_active == 0) return;
@@ -286,15 +297,25 @@ __global__ void em_decide_kernel(const EmState s)
 }
 
 // ---- the fused iteration loop --------------------------------------------------------------
-// One cooperative launch runs up to n_iters EM iterations: E step, grid barrier, M step (with the
-// convergence reduction), grid barrier, the loop condition of infer.py:160 per replicate, grid
-// barrier.  Nothing returns to the host between iterations; the whole structure (~46 MB at
-// human scale) stays in L2 from the second iteration on.  Row arithmetic is exactly that of the
-// one-launch-per-step kernels above.  Everything another SM may have written during this
-// launch (x, inner, active, n_active) is read past L1 (ld.global.cg); the class structure,
-// counts and lengths are read-only and may sit in L1.
+// One cooperative launch runs up to n_iters EM iterations with TWO grid barriers each: E step,
+// barrier, M step (with the convergence reduction), barrier.  Nothing returns to the host
+// between iterations; the whole structure (~46 MB at human scale) stays in L2 from the second
+// iteration on.  The loop condition of infer.py:160 needs no barrier of its own: every block
+// keeps the run / stop flag of every replicate (sample) in shared memory and updates it from the
+// same maximum-change words after the M-step barrier, so all blocks decide alike; the two
+// max-change buffers alternate, and block 0 clears the one of the previous iteration while
+// nobody reads it.  Everything another SM may have written during this launch (x, inner, the
+// max-change words) is read past L1 (ld.global.cg); the class structure, counts and lengths are
+// read-only and may sit in L1.
 namespace cg = cooperative_groups;
-constexpr int EM_LOOP_THREADS = 512;
+#ifndef SKM_EM_LOOP_THREADS
+#define SKM_EM_LOOP_THREADS 512
+#endif
+#ifndef SKM_EM_LOOP_BLOCKS
+#define SKM_EM_LOOP_BLOCKS 3
+#endif
+constexpr int EM_LOOP_THREADS = SKM_EM_LOOP_THREADS;  // block size of the fused loop
+constexpr int EM_LOOP_BLOCKS = SKM_EM_LOOP_BLOCKS;    // blocks per SM it is compiled (and launched) for
 
 struct EmLoop {
     double *xa, *xb;      // ping-pong buffers; iteration 0 reads xa
@@ -302,122 +323,148 @@ struct EmLoop {
     int n_iters;
 };
 
-__device__ __forceinline__ void em_decide_block(const EmState &s)
-{
-    __shared__ int still;
-    if (threadIdx.x == 0) still = 0;
-    __syncthreads();
-    for (int r = threadIdx.x; r < s.R; r += blockDim.x) {
-        if (__ldcg(s.active + r)) {
-            s.iters[r] += 1;
-            const double d = __longlong_as_double((long long)__ldcg(s.maxd + r));
-            if (d > 0.01) atomicAdd(&still, 1);
-            else s.active[r] = 0;
-            s.maxd[r] = 0ULL;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *s.n_active = still;
-}
-
-// MODE 0: one replicate; 1: R replicates of one structure ([row][replicate]); 2: samples laid end to end
-template <int MODE>
-__global__ void __launch_bounds__(EM_LOOP_THREADS) em_loop_kernel(const EmState s, const EmLoop lp)
+// SAMPLES = false: one replicate of one structure; true: samples laid end to end (skm_em_samples).
+// s.maxd holds 2 x s.R words (zero on entry); s.active / s.iters / s.n_active are read at the
+// start and written at the end.
+template <bool SAMPLES>
+__global__ void __launch_bounds__(EM_LOOP_THREADS, EM_LOOP_BLOCKS) em_loop_kernel(const EmState s, const EmLoop lp)
 {
     cg::grid_group grid = cg::this_grid();
+    extern __shared__ uint32_t sm_run[];  // bit r: replicate / sample r still iterates
+    __shared__ double sm_part[EM_LOOP_THREADS / 32];
+    const int words = (s.R + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32 && 32 * w + b < s.R; ++b) bits |= (s.active[32 * w + b] != 0 ? 1u : 0u) << b;
+        sm_run[w] = bits;
+    }
+    __syncthreads();
+    auto running = [&](int r) { return (sm_run[r >> 5] >> (r & 31)) & 1u; };
+    bool any = false;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) any |= sm_run[w] != 0;
+    any = __syncthreads_or(any);
     const double *cur = lp.xa;
     double *nxt = lp.xb;
     const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
-    int it = 0;
-    for (; it < lp.n_iters; ++it) {
-        if (__ldcg(s.n_active) == 0) break;  // the same value for the whole grid: written before the last barrier
-        // ---- E step
-        if (MODE == 1) {
-            const int64_t total = s.n_classes * s.R;
-            for (int64_t e = gtid; e < total; e += gsize) {
-                const int64_t c = e / s.R;
-                const int r = (int)(e - c * s.R);
-                if (!__ldcg(s.active + r)) continue;
-                double sum = 0.0;
-                const int64_t b = __ldg(s.class_ptr + c), en = __ldg(s.class_ptr + c + 1);
-                for (int64_t j = b; j < en; ++j) sum = __dadd_rn(sum, __ldcg(cur + (int64_t)__ldg(s.class_tx + j) * s.R + r));
-                s.inner[e] = __ddiv_rn(sum, __ldg(s.counts + e));
-            }
-        } else {
-            for (int64_t c = gtid; c < s.n_classes; c += gsize) {
-                if (MODE == 2 && !__ldcg(s.active + __ldg(s.class_sample + c))) continue;
-                double sum = 0.0;
-                const int64_t b = __ldg(s.class_ptr + c), en = __ldg(s.class_ptr + c + 1);
-                for (int64_t j = b; j < en; ++j) sum = __dadd_rn(sum, __ldcg(cur + __ldg(s.class_tx + j)));
-                s.inner[c] = __ddiv_rn(sum, __ldg(s.counts + c));
-            }
+    int it = 0, par = 0;
+    for (; it < lp.n_iters && any; ++it, par ^= 1) {
+        EmState sp = s;
+        sp.maxd = s.maxd + (size_t)par * s.R;  // this iteration's max-change words
+        // ---- E step: one thread per class
+        for (int64_t c = gtid; c < s.n_classes; c += gsize) {
+            if (SAMPLES && !running(__ldg(s.class_sample + c))) continue;
+            double sum = 0.0;
+            const int64_t b = __ldg(s.class_ptr + c), en = __ldg(s.class_ptr + c + 1);
+            for (int64_t j = b; j < en; ++j) sum = __dadd_rn(sum, __ldcg(cur + __ldg(s.class_tx + j)));
+            s.inner[c] = __ddiv_rn(sum, __ldg(s.counts + c));
         }
         grid.sync();
-        // ---- M step
-        if (MODE == 1) {
-            const int64_t total = s.n_tx * s.R;
-            for (int64_t e = gtid; e < total; e += gsize) {
-                const int64_t tt = e / s.R;
-                const int r = (int)(e - tt * s.R);
-                const double xt = __ldcg(cur + e);
-                if (!__ldcg(s.active + r)) {
-                    nxt[e] = xt;
-                    continue;
-                }
-                double acc = 0.0;
-                const int64_t b = __ldg(s.tx_ptr + tt), en = __ldg(s.tx_ptr + tt + 1);
-                for (int64_t j = b; j < en; ++j)
-                    acc = __dadd_rn(acc, __ddiv_rn(xt, __ldcg(s.inner + (int64_t)__ldg(s.tx_class + j) * s.R + r)));
-                double v = __ddiv_rn(__ddiv_rn(acc, __ldg(s.eff_len + tt)), __ldg(s.n + r));
-                if (v != v) v = 0.0;
-                note_change(s, r, v, xt);
-                nxt[e] = v;
-            }
-        } else {
-            // 8 lanes per transcript row, strided partial sums, fixed-order shuffle tree
-            const int sub = threadIdx.x & 7;
-            for (int64_t g0 = (gtid >> 5) * 4; g0 < s.n_tx; g0 += gsize >> 3) {  // warp-uniform bound
-                const int64_t g = g0 + ((threadIdx.x & 31) >> 3);
-                const bool ok = g < s.n_tx;
-                int sample = 0;
-                bool live = ok;
-                double acc = 0.0, xt = 0.0;
-                if (ok) {
-                    if (MODE == 2) {
-                        sample = (int)(g / s.tx_per_sample);
-                        live = __ldcg(s.active + sample) != 0;
-                    }
-                    xt = __ldcg(cur + g);
-                    if (live) {
-                        const int64_t b = __ldg(s.tx_ptr + g), en = __ldg(s.tx_ptr + g + 1);
+        // the words of the previous iteration have been read by every block before it got here
+        if (blockIdx.x == 0)
+            for (int r = threadIdx.x; r < s.R; r += blockDim.x) s.maxd[(size_t)(par ^ 1) * s.R + r] = 0ULL;
+        // ---- M step, rows of up to HEAVY_ROW entries: 8 lanes per row, strided partial sums,
+        // fixed-order shuffle tree.  A row whose x is exactly 0 stays 0 whatever its classes hold
+        // (0 / inner is 0, or NaN -> 0), so its sum is not formed.
+        const int sub = threadIdx.x & 7;
+        for (int64_t g0 = (gtid >> 5) * 4; g0 < s.n_tx; g0 += gsize >> 3) {  // warp-uniform bound
+            const int64_t g = g0 + ((threadIdx.x & 31) >> 3);
+            const bool ok = g < s.n_tx;
+            int sample = 0;
+            bool live = ok, heavy = false;
+            double acc = 0.0, xt = 0.0;
+            if (ok) {
+                if (SAMPLES) sample = (int)(g / s.tx_per_sample);
+                live = running(sample) != 0;
+                xt = __ldcg(cur + g);
+                if (live) {
+                    const int64_t b = __ldg(s.tx_ptr + g), en = __ldg(s.tx_ptr + g + 1);
+                    heavy = en - b > HEAVY_ROW;
+                    if (!heavy && xt != 0.0)
                         for (int64_t j = b + sub; j < en; j += 8)
                             acc = __dadd_rn(acc, __ddiv_rn(xt, __ldcg(s.inner + __ldg(s.tx_class + j))));
-                    }
                 }
-                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
-                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
-                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
-                if (ok && sub == 0) {
-                    if (!live) {
-                        nxt[g] = xt;  // a finished sample is carried through the ping-pong unchanged
-                    } else {
-                        double v = __ddiv_rn(__ddiv_rn(acc, __ldg(s.eff_len + g)), __ldg(s.n + sample));
-                        if (v != v) v = 0.0;
-                        note_change(s, sample, v, xt);
-                        nxt[g] = v;
-                    }
+            }
+            acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+            acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+            acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+            if (ok && sub == 0 && !heavy) {
+                if (!live) {
+                    nxt[g] = xt;  // a finished sample is carried through the ping-pong unchanged
+                } else {
+                    double v = __ddiv_rn(__ddiv_rn(acc, __ldg(s.eff_len + g)), __ldg(s.n + sample));
+                    if (v != v) v = 0.0;
+                    note_change(sp, sample, v, xt);
+                    nxt[g] = v;
                 }
             }
         }
+        // ---- M step, heavy rows (highly expressed transcripts sit in thousands of classes): one
+        // block per row, strided partial sums, fixed-order tree over lanes then over warps
+        for (int h = blockIdx.x; h < s.n_heavy; h += gridDim.x) {
+            const int64_t g = __ldg(s.heavy_rows + h);
+            const int sample = SAMPLES ? (int)(g / s.tx_per_sample) : 0;
+            const bool live = running(sample) != 0;
+            const double xt = __ldcg(cur + g);
+            double acc = 0.0;
+            if (live && xt != 0.0) {
+                const int64_t b = __ldg(s.tx_ptr + g), en = __ldg(s.tx_ptr + g + 1);
+                for (int64_t j = b + threadIdx.x; j < en; j += EM_LOOP_THREADS)
+                    acc = __dadd_rn(acc, __ddiv_rn(xt, __ldcg(s.inner + __ldg(s.tx_class + j))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            if ((threadIdx.x & 31) == 0) sm_part[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (!live) {
+                    nxt[g] = xt;
+                } else {
+                    double total = 0.0;
+                    for (int w = 0; w < EM_LOOP_THREADS / 32; ++w) total = __dadd_rn(total, sm_part[w]);
+                    double v = __ddiv_rn(__ddiv_rn(total, __ldg(s.eff_len + g)), __ldg(s.n + sample));
+                    if (v != v) v = 0.0;
+                    note_change(sp, sample, v, xt);
+                    nxt[g] = v;
+                }
+            }
+            __syncthreads();
+        }
         grid.sync();
-        if (blockIdx.x == 0) em_decide_block(s);
-        grid.sync();
+        // ---- the loop condition (infer.py:160), in every block alike
+        any = false;
+        for (int w = threadIdx.x; w < words; w += blockDim.x) {
+            uint32_t bits = sm_run[w];
+            for (int b = 0; b < 32; ++b) {
+                if (!((bits >> b) & 1u)) continue;
+                const int r = 32 * w + b;
+                if (blockIdx.x == 0) s.iters[r] += 1;
+                const double d = __longlong_as_double((long long)__ldcg(sp.maxd + r));
+                if (!(d > 0.01)) bits &= ~(1u << b);
+            }
+            sm_run[w] = bits;
+            any |= bits != 0;
+        }
+        any = __syncthreads_or(any);
         const double *t0 = cur;
         cur = nxt;
         nxt = const_cast<double *>(t0);
     }
-    if (gtid == 0) *lp.executed = it;
+    if (blockIdx.x == 0) {
+        __shared__ int still;
+        if (threadIdx.x == 0) still = 0;
+        __syncthreads();
+        for (int r = threadIdx.x; r < s.R; r += blockDim.x) {
+            const int on = (int)running(r);
+            s.active[r] = on;
+            if (on) atomicAdd(&still, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *s.n_active = still;
+            *lp.executed = it;
+        }
+    }
 }
 
 // ---- many samples with their own class structures (skm_em_samples) ---------------------------
@@ -455,51 +502,6 @@ __global__ void sum_counts_samples_kernel(const double *__restrict__ counts, con
         __syncthreads();
     }
     if (threadIdx.x == 0) n_out[blockIdx.x] = sm[0];
-}
-
-__global__ void em_class_kernel_samples(const EmState s, const double *__restrict__ x)
-{
-    if (*s.n_active == 0) return;
-    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= s.n_classes) return;
-    if (!s.active[s.class_sample[c]]) return;
-    double sum = 0.0;
-    for (int64_t j = s.class_ptr[c]; j < s.class_ptr[c + 1]; ++j) sum = __dadd_rn(sum, x[s.class_tx[j]]);
-    s.inner[c] = __ddiv_rn(sum, s.counts[c]);
-}
-
-__global__ void em_tx_kernel_samples(const EmState s, const double *__restrict__ x, double *__restrict__ xn_out)
-{
-    if (*s.n_active == 0) return;
-    const int sub = threadIdx.x & 7;
-    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
-    const bool ok = g < s.n_tx;
-    int sample = 0;
-    bool live = false;
-    double acc = 0.0;
-    double xt = 0.0;
-    if (ok) {
-        sample = (int)(g / s.tx_per_sample);
-        live = s.active[sample] != 0;
-        xt = x[g];
-        if (live) {
-            const int64_t b = s.tx_ptr[g], e = s.tx_ptr[g + 1];
-            for (int64_t j = b + sub; j < e; j += 8) acc = __dadd_rn(acc, __ddiv_rn(xt, s.inner[s.tx_class[j]]));
-        }
-    }
-    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
-    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
-    acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
-    if (ok && sub == 0) {
-        if (!live) {
-            xn_out[g] = xt;  // a finished sample is carried through the ping-pong unchanged
-            return;
-        }
-        double v = __ddiv_rn(__ddiv_rn(acc, s.eff_len[g]), s.n[sample]);
-        if (v != v) v = 0.0;
-        note_change(s, sample, v, xt);
-        xn_out[g] = v;
-    }
 }
 
 __global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
@@ -608,6 +610,47 @@ __global__ void multinomial_kernel(const unsigned long long *__restrict__ cum, i
             }
             atomicAdd(&dst[a], 1ULL);
         }
+    }
+}
+
+// ---- O(classes) resampling: a binary tree of binomial splits ------------------------------------
+// Multinomial(n, count / n) factorises over a binary tree on the classes: the n reads of a node
+// go left with probability (weight of the left half) / (weight of the node), i.e. the left count
+// is Binomial(n_node, w_left / w_node), and so on down to single classes.  Every split is drawn
+// exactly (binomial.cuh) from its own Philox stream (node, replicate), so the cost is one
+// binomial draw per class and replicate whatever the read depth, replicates are reproducible and
+// shardable by id, and the counts of a replicate sum to n by construction.
+// Level `level` has 2^level nodes of span 2^(levels - level) classes (the class range is padded
+// to a power of two with weight-0 classes); one thread per (replicate, node).
+__global__ void multinomial_tree_kernel(const unsigned long long *__restrict__ cum, int64_t n_classes, int levels,
+                                        int level, const int64_t *__restrict__ parent, int64_t *__restrict__ child,
+                                        int64_t n_replicates, int64_t first_replicate, uint32_t k0, uint32_t k1)
+{
+    const int64_t nodes = 1LL << level;
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= nodes * n_replicates) return;
+    const int64_t r = idx >> level, i = idx & (nodes - 1);
+    const int64_t span = 1LL << (levels - level);
+    const int64_t lo = min(i * span, n_classes), mid = min(i * span + span / 2, n_classes), hi = min((i + 1) * span, n_classes);
+    const unsigned long long w_lo = lo ? cum[lo - 1] : 0ULL, w_mid = mid ? cum[mid - 1] : 0ULL,
+                             w_hi = hi ? cum[hi - 1] : 0ULL;
+    const int64_t n_node = level == 0 ? (int64_t)cum[n_classes - 1] : parent[r * nodes + i];
+    const unsigned long long w_left = w_mid - w_lo, w_node = w_hi - w_lo;
+    int64_t left = 0;
+    if (n_node > 0 && w_left > 0) {
+        if (w_left == w_node) {
+            left = n_node;
+        } else {
+            UniformStream rng{k0, k1, (uint32_t)(nodes + i), (uint32_t)(first_replicate + r), 0x54524545u, 0u};
+            left = binomial_draw(n_node, (double)w_left / (double)w_node, rng);
+        }
+    }
+    if (level == levels - 1) {  // the children are classes 2i and 2i + 1 of the output [replicate][class]
+        int64_t *out = child + r * n_classes;
+        if (2 * i < n_classes) out[2 * i] = left;
+        if (2 * i + 1 < n_classes) out[2 * i + 1] = n_node - left;
+    } else {
+        *reinterpret_cast<longlong2 *>(child + (r * nodes + i) * 2) = make_longlong2(left, n_node - left);
     }
 }
 
@@ -860,33 +903,58 @@ static int build_csc(const int64_t *d_ptr, const int32_t *d_row, int64_t C, int6
 }
 
 // One cooperative launch of the fused iteration loop; *executed = iterations it ran.
-static int launch_em_loop(int mode, const EmState &s, double *xa, double *xb, int n_iters, int32_t *d_executed,
+static int launch_em_loop(bool samples, const EmState &s, double *xa, double *xb, int n_iters, int32_t *d_executed,
                           int device, cudaStream_t st)
 {
     static std::mutex mu;
-    static int blocks_per_sm[64][3];
+    static int blocks_per_sm[64][2];
     static int sms[64];
-    const void *fn = mode == 0 ? (const void *)em_loop_kernel<0>
-                   : mode == 1 ? (const void *)em_loop_kernel<1> : (const void *)em_loop_kernel<2>;
+    const int mode = samples ? 1 : 0;
+    const void *fn = samples ? (const void *)em_loop_kernel<true> : (const void *)em_loop_kernel<false>;
     const int d = device & 63;
     {
         std::lock_guard<std::mutex> lock(mu);
         if (blocks_per_sm[d][mode] == 0) {
             int b = 0;
-            EM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, EM_LOOP_THREADS, 0));
+            EM_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, fn, EM_LOOP_THREADS, 4096));
             if (b < 1) return fail(SKM_ERR_CUDA, "skm_em: the iteration kernel does not fit on this device");
-            blocks_per_sm[d][mode] = b;
+            blocks_per_sm[d][mode] = std::min(b, EM_LOOP_BLOCKS);
             EM_TRY(cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, device));
         }
     }
     // all blocks must be resident (grid barrier): at most occupancy x SMs, no more than the rows need
-    const int64_t rows = mode == 1 ? std::max(s.n_classes, s.n_tx) * s.R : std::max(s.n_classes, s.n_tx * 8);
+    const int64_t rows = std::max(s.n_classes, s.n_tx * 8);
     const int64_t want = (rows + EM_LOOP_THREADS - 1) / EM_LOOP_THREADS;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)blocks_per_sm[d][mode] * sms[d]));
     EmState state = s;
     EmLoop lp{xa, xb, d_executed, n_iters};
     void *args[] = {&state, &lp};
-    EM_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(EM_LOOP_THREADS), args, 0, st));
+    const size_t run_bytes = sizeof(uint32_t) * (size_t)((s.R + 31) / 32);
+    if (run_bytes > 4096) return fail(SKM_ERR_INVALID, "skm_em: more than 32768 samples in one call");
+    EM_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(EM_LOOP_THREADS), args, run_bytes, st));
+    return SKM_OK;
+}
+
+// rows with more than HEAVY_ROW entries, in any order (each is summed by a block of its own)
+static int select_heavy_rows(const int64_t *tx_ptr, int64_t n_rows, cudaStream_t st, int32_t **out, int32_t *n_out)
+{
+    *out = nullptr;
+    *n_out = 0;
+    int32_t *list = nullptr, *count = nullptr;
+    EM_TRY(cudaMalloc(&list, sizeof(int32_t) * (size_t)n_rows));
+    cudaError_t e = cudaMalloc(&count, sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(count, 0, sizeof(int32_t), st);
+    if (e == cudaSuccess) {
+        select_heavy_rows_kernel<<<blocks_for(n_rows, 256), 256, 0, st>>>(tx_ptr, n_rows, list, count);
+        e = cudaMemcpyAsync(n_out, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(count);
+    if (e != cudaSuccess) {
+        cudaFree(list);
+        return fail(SKM_ERR_CUDA, std::string("skm_em: heavy rows: ") + cudaGetErrorString(e));
+    }
+    *out = list;
     return SKM_OK;
 }
 
@@ -895,8 +963,7 @@ struct EmInputs {
     const double *d_len;       // effective lengths [T]
     int R;
     int64_t max_iters;
-    const double *counts_rc;   // class counts [R][C] (ABI layout), or
-    const double *counts_cr;   // ... already in kernel layout [C][R]
+    double *counts_cr;         // class counts in kernel layout [C][R], plan class order; scratch of the call
     const double *x_rt;        // initial guess [R][T] (ABI layout), or
     const double *x_t;         // ... one guess [T] shared by all replicates
 };
@@ -910,29 +977,21 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     const int device = in.plan->device;
     Trace trace(st);
     // ---- state in kernel layout
-    DeviceBuf b_cnt, b_xa, b_xb, b_inner, b_n, b_maxd, b_active, b_iters, b_nactive;
+    DeviceBuf b_xa, b_xb, b_inner, b_n, b_maxd, b_active, b_iters, b_nactive;
     EM_TRY(b_xa.alloc(sizeof(double) * (size_t)(T * R), st));
     EM_TRY(b_xb.alloc(sizeof(double) * (size_t)(T * R), st));
     EM_TRY(b_inner.alloc(sizeof(double) * (size_t)(C * R), st));
     EM_TRY(b_n.alloc(sizeof(double) * (size_t)R, st));
-    EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * (size_t)R, st));
+    EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * 2 * (size_t)R, st));  // the fused loop alternates between two
     EM_TRY(b_active.alloc(sizeof(int32_t) * (size_t)R, st));
     EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)R, st));
     EM_TRY(b_nactive.alloc(sizeof(int32_t) * 2, st));  // [0] = replicates still running, [1] = iterations of the last launch
     const double *d_cnt = in.counts_cr;
-    if (!d_cnt) {
-        d_cnt = in.counts_rc;  // [R][C]; the same thing as [C][R] for one replicate
-        if (R > 1) {
-            EM_TRY(b_cnt.alloc(sizeof(double) * (size_t)(C * R), st));
-            transpose_kernel<<<blocks_for(C * R, 256), 256, 0, st>>>(in.counts_rc, b_cnt.as<double>(), R, C);
-            d_cnt = b_cnt.as<double>();
-        }
-    }
     if (in.x_t) broadcast_kernel<<<blocks_for(T * R, 256), 256, 0, st>>>(in.x_t, b_xa.as<double>(), T, R);
     else if (R > 1) transpose_kernel<<<blocks_for(T * R, 256), 256, 0, st>>>(in.x_rt, b_xa.as<double>(), R, T);
     else EM_TRY(cudaMemcpyAsync(b_xa.p, in.x_rt, sizeof(double) * (size_t)T, cudaMemcpyDeviceToDevice, st));
     sum_counts_kernel<<<R, EM_BLOCK, 0, st>>>(d_cnt, C, R, b_n.as<double>());
-    EM_TRY(cudaMemsetAsync(b_maxd.p, 0, sizeof(unsigned long long) * (size_t)R, st));
+    EM_TRY(cudaMemsetAsync(b_maxd.p, 0, sizeof(unsigned long long) * 2 * (size_t)R, st));
     EM_TRY(cudaMemsetAsync(b_iters.p, 0, sizeof(int32_t) * (size_t)R, st));
     fill_i32_kernel<<<blocks_for(R, 256), 256, 0, st>>>(b_active.as<int32_t>(), R, 1);
     fill_i32_kernel<<<1, 32, 0, st>>>(b_nactive.as<int32_t>(), 1, R);
@@ -953,15 +1012,20 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     s.n_classes = C;
     s.n_tx = T;
     s.R = R;
+    s.heavy_rows = in.plan->heavy_rows;
+    s.n_heavy = in.plan->n_heavy;
     int32_t *d_executed = b_nactive.as<int32_t>() + 1;
 
     trace.mark("em: state setup");
     double *cur = b_xa.as<double>(), *nxt = b_xb.as<double>();
-    // One replicate: ONE launch runs the whole EM (the loop condition is evaluated on the device).
-    // Many replicates stop at very different iteration counts (bootstraps: mean ~40, max > 100), so
-    // they run in launches of GROUP iterations; whenever at most three quarters of the live columns
-    // are still running the finished ones are written to the output and the state is compacted to
-    // the running columns: the work of an iteration follows the replicates that still need it.
+    // One replicate: ONE cooperative launch runs the whole EM (the loop condition is evaluated on the
+    // device, nothing returns to the host between iterations).  Many replicates are bandwidth-bound
+    // (100 columns of x and inner do not fit L2) and stop at very different iteration counts
+    // (bootstraps: mean ~40, max > 100): they run as full-occupancy E / M / decide launches enqueued
+    // in groups of GROUP iterations - launches after the last replicate stopped are no-ops - and
+    // whenever at most three quarters of the live columns are still running the finished ones are
+    // written to the output and the state is compacted to the running columns: the work of an
+    // iteration follows the replicates that still need it.
     const int GROUP = 8;
     int64_t done = 0;
     int32_t n_active = R;
@@ -970,23 +1034,49 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     for (int r = 0; r < R; ++r) orig[(size_t)r] = r;
     std::vector<int32_t> final_iters((size_t)R, 0);
     std::vector<int32_t> h_active((size_t)R), h_iters((size_t)R), h_map;
+    std::vector<int32_t> group_iters((size_t)R, 0);  // iteration counts of the live columns when a group starts
     std::vector<double> h_n((size_t)R);
     DeviceBuf b_map;
     EM_TRY(b_map.alloc(sizeof(int32_t) * 2 * (size_t)R, st));
-    const bool may_compact = R > 1 && (in.counts_cr != nullptr || b_cnt.p != nullptr);  // counts buffer is scratch
-    double *counts_buf = const_cast<double *>(d_cnt), *inner_buf = b_inner.as<double>();
+    const bool may_compact = R > 1;  // the counts buffer is scratch of this call
+    double *counts_buf = in.counts_cr, *inner_buf = b_inner.as<double>();
     while (n_active > 0 && done < max_iters) {
         const int64_t left = max_iters - done;
-        const int g = (int)std::min<int64_t>(R == 1 ? (int64_t)1 << 30 : GROUP, left);
-        int rc = launch_em_loop(R == 1 ? 0 : 1, s, cur, nxt, g, d_executed, device, st);
-        if (rc) return rc;
-        int32_t h2[2] = {0, 0};
-        EM_TRY(cudaMemcpyAsync(h2, s.n_active, sizeof(h2), cudaMemcpyDeviceToHost, st));
+        if (R == 1) {
+            int rc = launch_em_loop(false, s, cur, nxt, (int)std::min<int64_t>((int64_t)1 << 30, left), d_executed, device, st);
+            if (rc) return rc;
+            int32_t h2[2] = {0, 0};
+            EM_TRY(cudaMemcpyAsync(h2, s.n_active, sizeof(h2), cudaMemcpyDeviceToHost, st));
+            EM_TRY(cudaStreamSynchronize(st));
+            n_active = h2[0];
+            done += h2[1];
+            if (h2[1] & 1) std::swap(cur, nxt);  // the last executed iteration wrote the other buffer
+            if (h2[1] == 0) break;
+            continue;
+        }
+        const int g = (int)std::min<int64_t>(GROUP, left);
+        const unsigned grid_c = (unsigned)std::min<int64_t>((C * Rc + EM_BLOCK - 1) / EM_BLOCK, 1 << 20);
+        const unsigned grid_t = (unsigned)std::min<int64_t>((T * Rc + EM_BLOCK - 1) / EM_BLOCK, 1 << 20);
+        double *group_cur = cur, *group_nxt = nxt;
+        for (int k = 0; k < g; ++k) {
+            em_class_kernel<<<grid_c, EM_BLOCK, 0, st>>>(s, cur);
+            em_tx_kernel<<<grid_t, EM_BLOCK, 0, st>>>(s, cur, nxt);
+            em_decide_kernel<<<1, 128, 0, st>>>(s);
+            std::swap(cur, nxt);
+        }
+        EM_TRY(cudaGetLastError());
+        // how many iterations of the group really ran = the largest increase of a column's count
+        EM_TRY(cudaMemcpyAsync(h_active.data(), s.iters, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
+        EM_TRY(cudaMemcpyAsync(&n_active, s.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         EM_TRY(cudaStreamSynchronize(st));
-        n_active = h2[0];
-        done += h2[1];
-        if (h2[1] & 1) std::swap(cur, nxt);  // the last executed iteration wrote the other buffer
-        if (h2[1] == 0) break;
+        int ran = 0;
+        for (int c = 0; c < Rc; ++c) ran = std::max(ran, h_active[(size_t)c] - group_iters[(size_t)c]);
+        for (int c = 0; c < Rc; ++c) group_iters[(size_t)c] = h_active[(size_t)c];
+        done += ran;
+        // the device stopped ping-ponging after `ran` iterations while the host kept swapping
+        cur = (ran & 1) ? group_nxt : group_cur;
+        nxt = (ran & 1) ? group_cur : group_nxt;
+        if (ran == 0) break;
         if (!may_compact || n_active <= 0 || 4 * n_active > 3 * Rc || Rc <= 8 || done >= max_iters) continue;
         // ---- compact to the running columns ------------------------------------------------------
         EM_TRY(cudaMemcpyAsync(h_active.data(), s.active, sizeof(int32_t) * (size_t)Rc, cudaMemcpyDeviceToHost, st));
@@ -1030,6 +1120,7 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
         EM_TRY(cudaGetLastError());
         EM_TRY(cudaStreamSynchronize(st));  // host vectors above go out of scope
         orig = keep_orig;
+        group_iters = keep_iters;
         Rc = n_keep;
         s.R = Rc;
     }
@@ -1060,6 +1151,45 @@ static int em_core(const EmInputs &in, double *d_out, int32_t *d_iters, cudaStre
     return SKM_OK;
 }
 
+// The EM's gathers (x of a class's transcripts, inner of a transcript's classes) are 8 useful
+// bytes per 32-byte sector when classes come in first-seen order.  For the iterations the classes
+// are renumbered by their first row (a stable sort): the classes neighbouring threads work on
+// then share sectors, and a row's classes sit close together.  The caller's order stays on the
+// outside: counts go through `perm` (new class i = the caller's class perm[i]) on their way in.
+// Outputs into caller-provided device arrays perm[C], new_ptr[C + 1], new_rows[nnz].
+static cudaError_t reorder_classes(const int64_t *class_ptr, const int32_t *class_rows, int64_t C, int64_t n_rows,
+                                   cudaStream_t st, int32_t *perm, int64_t *new_ptr, int32_t *new_rows)
+{
+    DeviceBuf b_key, b_key2, b_idx, b_lens, b_tmp;
+    cudaError_t e = b_key.alloc(sizeof(uint32_t) * (size_t)C, st);
+    if (e == cudaSuccess) e = b_key2.alloc(sizeof(uint32_t) * (size_t)C, st);
+    if (e == cudaSuccess) e = b_idx.alloc(sizeof(int32_t) * (size_t)C, st);
+    if (e == cudaSuccess) e = b_lens.alloc(sizeof(int64_t) * (size_t)(C + 1), st);
+    if (e != cudaSuccess) return e;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    int end_bit = 1;
+    while ((1LL << end_bit) < n_rows) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, b_key.as<uint32_t>(), b_key2.as<uint32_t>(), b_idx.as<int32_t>(),
+                                    perm, (int)C, 0, end_bit, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, b_lens.as<int64_t>(), new_ptr, (int)(C + 1), st);
+    e = b_tmp.alloc(std::max(tmp_sort, tmp_scan), st);
+    if (e != cudaSuccess) return e;
+    class_sort_key_kernel<<<blocks_for(C, 256), 256, 0, st>>>(class_ptr, class_rows, C, b_key.as<uint32_t>(),
+                                                             b_idx.as<int32_t>());
+    size_t tb = std::max(tmp_sort, tmp_scan);
+    e = cub::DeviceRadixSort::SortPairs(b_tmp.p, tb, b_key.as<uint32_t>(), b_key2.as<uint32_t>(), b_idx.as<int32_t>(), perm,
+                                        (int)C, 0, end_bit, st);
+    if (e != cudaSuccess) return e;
+    permuted_lens_kernel<<<blocks_for(C + 1, 256), 256, 0, st>>>(class_ptr, perm, C, b_lens.as<int64_t>());
+    tb = std::max(tmp_sort, tmp_scan);
+    e = cub::DeviceScan::ExclusiveSum(b_tmp.p, tb, b_lens.as<int64_t>(), new_ptr, (int)(C + 1), st);
+    if (e != cudaSuccess) return e;
+    permuted_ids_kernel<<<blocks_for(C, 256), 256, 0, st>>>(class_ptr, class_rows, perm, C, new_ptr, new_rows);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the scratch above goes back to the cache
+    return e;
+}
+
 // ---- plans ---------------------------------------------------------------------------------------
 SKM_API void skm_em_plan_destroy(skm_em_plan *p)
 {
@@ -1072,6 +1202,8 @@ SKM_API void skm_em_plan_destroy(skm_em_plan *p)
     cudaFree(p->tx_ptr);
     cudaFree(p->tx_class);
     cudaFree(p->counts);
+    cudaFree(p->heavy_rows);
+    cudaFree(p->perm);
     cudaSetDevice(prev);
     delete p;
 }
@@ -1087,14 +1219,29 @@ int skm::em_plan_adopt(int device, int64_t C, int64_t nnz, int64_t T, int64_t *c
     p->class_ptr = class_ptr;
     p->class_tx = class_tx;
     p->counts = counts;
-    cudaError_t e = cudaMalloc(&p->tx_ptr, sizeof(int64_t) * (size_t)(T + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&p->tx_class, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1));
-    if (e != cudaSuccess) {
-        skm_em_plan_destroy(p);
-        return fail(SKM_ERR_OOM, std::string("skm_em_plan: ") + cudaGetErrorString(e));
-    }
     Trace trace(st);
-    const int rc = build_csc(class_ptr, class_tx, C, nnz, T, st, p->tx_ptr, p->tx_class, "skm_em_plan");
+    // classes renumbered by their first transcript for the iterations (reorder_classes)
+    int64_t *s_ptr = nullptr;
+    int32_t *s_tx = nullptr;
+    cudaError_t e = cudaMalloc(&p->perm, sizeof(int32_t) * (size_t)C);
+    if (e == cudaSuccess) e = cudaMalloc(&s_ptr, sizeof(int64_t) * (size_t)(C + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&s_tx, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->tx_ptr, sizeof(int64_t) * (size_t)(T + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&p->tx_class, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1));
+    if (e == cudaSuccess) e = reorder_classes(class_ptr, class_tx, C, T, st, p->perm, s_ptr, s_tx);
+    if (e != cudaSuccess) {
+        cudaFree(s_ptr);
+        cudaFree(s_tx);
+        skm_em_plan_destroy(p);
+        return fail(e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA, std::string("skm_em_plan: ") + cudaGetErrorString(e));
+    }
+    cudaFree(p->class_ptr);
+    cudaFree(p->class_tx);
+    p->class_ptr = class_ptr = s_ptr;
+    p->class_tx = class_tx = s_tx;
+    trace.mark("em plan: class order");
+    int rc = build_csc(class_ptr, class_tx, C, nnz, T, st, p->tx_ptr, p->tx_class, "skm_em_plan");
+    if (rc == 0) rc = select_heavy_rows(p->tx_ptr, T, st, &p->heavy_rows, &p->n_heavy);
     trace.mark("em plan: CSC build");
     if (rc) {
         skm_em_plan_destroy(p);
@@ -1155,12 +1302,6 @@ SKM_API int skm_em_plan_info(const skm_em_plan *p, int64_t info[5])
     return SKM_OK;
 }
 
-__global__ void i64_to_f64_kernel(const int64_t *__restrict__ src, double *__restrict__ dst, int64_t n)
-{
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (double)src[i];
-}
-
 SKM_API int skm_em_plan_run(const skm_em_plan *p, const double *counts, const double *eff_len, const double *x0,
                             int64_t n_replicates, int64_t max_iters, double *out_x, int32_t *out_iters,
                             int buffers_on_device, void *stream)
@@ -1174,21 +1315,26 @@ SKM_API int skm_em_plan_run(const skm_em_plan *p, const double *counts, const do
     const int R = (int)n_replicates;
     const int64_t C = p->C, T = p->T;
     Trace trace(st);
-    DeviceBuf b_cnt_in, b_len, b_x_in, b_out, b_iters;
-    EmInputs in{p, eff_len, R, max_iters, counts, nullptr, x0, nullptr};
+    DeviceBuf b_cnt_in, b_cnt, b_len, b_x_in, b_out, b_iters;
+    EmInputs in{p, eff_len, R, max_iters, nullptr, x0, nullptr};
     double *d_out = out_x;
     int32_t *d_iters = out_iters;
+    // class counts: the caller's order [R][C] -> the plan's order and layout [C][R]
+    EM_TRY(b_cnt.alloc(sizeof(double) * (size_t)(C * R), st));
+    in.counts_cr = b_cnt.as<double>();
     if (!counts) {
-        EM_TRY(b_cnt_in.alloc(sizeof(double) * (size_t)C, st));
-        i64_to_f64_kernel<<<blocks_for(C, 256), 256, 0, st>>>(p->counts, b_cnt_in.as<double>(), C);
-        in.counts_rc = b_cnt_in.as<double>();
-    }
-    if (!buffers_on_device) {
-        if (counts) {
+        counts_to_plan_kernel<int64_t><<<blocks_for(C, 256), 256, 0, st>>>(p->counts, p->perm, b_cnt.as<double>(), C, 1);
+    } else {
+        const double *d_counts = counts;
+        if (!buffers_on_device) {
             EM_TRY(b_cnt_in.alloc(sizeof(double) * (size_t)(C * R), st));
             EM_TRY(cudaMemcpyAsync(b_cnt_in.p, counts, sizeof(double) * (size_t)(C * R), cudaMemcpyHostToDevice, st));
-            in.counts_rc = b_cnt_in.as<double>();
+            d_counts = b_cnt_in.as<double>();
         }
+        counts_to_plan_kernel<double><<<blocks_for(C * R, 256), 256, 0, st>>>(d_counts, p->perm, b_cnt.as<double>(), C, R);
+    }
+    EM_TRY(cudaGetLastError());
+    if (!buffers_on_device) {
         EM_TRY(b_len.alloc(sizeof(double) * (size_t)T, st));
         EM_TRY(b_x_in.alloc(sizeof(double) * (size_t)(T * R), st));
         EM_TRY(b_out.alloc(sizeof(double) * (size_t)(T * R), st));
@@ -1307,7 +1453,22 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
         if (bad) return fail(SKM_ERR_INVALID, "skm_em_samples: transcript index out of range in class_tx");
     }
     b_rowof.release();
-    int rc = build_csc(d_ptr, b_gtx.as<int32_t>(), C, nnz, rows, st, b_txptr.as<int64_t>(), b_txclass.as<int32_t>(),
+    // classes renumbered by their first row for the iterations, as in a plan (samples stay contiguous:
+    // rows are sample-major; the order inside a sample is the order a plan of that sample has,
+    // so results stay bit-identical to one skm_em call per sample)
+    DeviceBuf b_perm, b_sptr2, b_gtx2, b_cnt2;
+    EM_TRY(b_perm.alloc(sizeof(int32_t) * (size_t)C, st));
+    EM_TRY(b_sptr2.alloc(sizeof(int64_t) * (size_t)(C + 1), st));
+    EM_TRY(b_gtx2.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_cnt2.alloc(sizeof(double) * (size_t)C, st));
+    EM_TRY(reorder_classes(d_ptr, b_gtx.as<int32_t>(), C, rows, st, b_perm.as<int32_t>(), b_sptr2.as<int64_t>(),
+                           b_gtx2.as<int32_t>()));
+    counts_to_plan_kernel<double><<<blocks_for(C, 256), 256, 0, st>>>(d_cnt, b_perm.as<int32_t>(), b_cnt2.as<double>(), C, 1);
+    EM_TRY(cudaGetLastError());
+    d_ptr = b_sptr2.as<int64_t>();
+    d_cnt = b_cnt2.as<double>();
+    b_gtx.release();
+    int rc = build_csc(d_ptr, b_gtx2.as<int32_t>(), C, nnz, rows, st, b_txptr.as<int64_t>(), b_txclass.as<int32_t>(),
                        "skm_em_samples");
     if (rc) return rc;
 
@@ -1315,19 +1476,19 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
     DeviceBuf b_inner, b_n, b_maxd, b_active, b_iters, b_nactive;
     EM_TRY(b_inner.alloc(sizeof(double) * (size_t)C, st));
     EM_TRY(b_n.alloc(sizeof(double) * (size_t)P, st));
-    EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * (size_t)P, st));
+    EM_TRY(b_maxd.alloc(sizeof(unsigned long long) * 2 * (size_t)P, st));
     EM_TRY(b_active.alloc(sizeof(int32_t) * (size_t)P, st));
     EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)P, st));
     EM_TRY(b_nactive.alloc(sizeof(int32_t) * 2, st));
     sum_counts_samples_kernel<<<(unsigned)P, EM_BLOCK, 0, st>>>(d_cnt, d_sptr, b_n.as<double>());
-    EM_TRY(cudaMemsetAsync(b_maxd.p, 0, sizeof(unsigned long long) * (size_t)P, st));
+    EM_TRY(cudaMemsetAsync(b_maxd.p, 0, sizeof(unsigned long long) * 2 * (size_t)P, st));
     EM_TRY(cudaMemsetAsync(b_iters.p, 0, sizeof(int32_t) * (size_t)P, st));
     fill_i32_kernel<<<blocks_for(P, 256), 256, 0, st>>>(b_active.as<int32_t>(), P, 1);
     fill_i32_kernel<<<1, 32, 0, st>>>(b_nactive.as<int32_t>(), 1, (int32_t)P);
 
     EmState s{};
     s.class_ptr = d_ptr;
-    s.class_tx = b_gtx.as<int32_t>();
+    s.class_tx = b_gtx2.as<int32_t>();
     s.tx_ptr = b_txptr.as<int64_t>();
     s.tx_class = b_txclass.as<int32_t>();
     s.counts = d_cnt;
@@ -1343,13 +1504,22 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
     s.R = (int)P;
     s.class_sample = b_csample.as<int32_t>();
     s.tx_per_sample = T;
+    int32_t *heavy = nullptr, n_heavy = 0;
+    rc = select_heavy_rows(b_txptr.as<int64_t>(), rows, st, &heavy, &n_heavy);
+    if (rc) return rc;
+    struct FreeOnExit {
+        void *p;
+        ~FreeOnExit() { cudaFree(p); }
+    } free_heavy{heavy};
+    s.heavy_rows = heavy;
+    s.n_heavy = n_heavy;
 
     // ---- ONE launch: every sample iterates until its own stop condition holds ----------------------
     double *cur = b_xa.as<double>(), *nxt = b_xb.as<double>();
     int64_t done = 0;
     int32_t h2[2] = {(int32_t)P, 0};
     while (h2[0] > 0 && done < max_iters) {
-        rc = launch_em_loop(2, s, cur, nxt, (int)std::min<int64_t>(max_iters - done, (int64_t)1 << 30), b_nactive.as<int32_t>() + 1,
+        rc = launch_em_loop(true, s, cur, nxt, (int)std::min<int64_t>(max_iters - done, (int64_t)1 << 30), b_nactive.as<int32_t>() + 1,
                             device, st);
         if (rc) return rc;
         EM_TRY(cudaMemcpyAsync(h2, s.n_active, sizeof(h2), cudaMemcpyDeviceToHost, st));
@@ -1368,9 +1538,42 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
 }
 
 // Resample n = sum(counts) reads with replacement, n_replicates times, on device buffers.
-static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t n_replicates, int64_t first_replicate,
-                            uint64_t seed, int64_t *d_out, int device, cudaStream_t st)
+static int multinomial_tree(const unsigned long long *d_cum, int64_t n_classes, int64_t n_replicates,
+                            int64_t first_replicate, uint64_t seed, int64_t *d_out, cudaStream_t st)
 {
+    int levels = 0;
+    while ((1LL << levels) < n_classes) ++levels;
+    if (levels == 0) {  // one class takes every read
+        EM_TRY(cudaMemcpyAsync(d_out, d_cum, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        for (int64_t r = 1; r < n_replicates; ++r)
+            EM_TRY(cudaMemcpyAsync(d_out + r, d_cum, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        return SKM_OK;
+    }
+    DeviceBuf b_a, b_b;
+    if (levels > 1) {
+        EM_TRY(b_a.alloc(sizeof(int64_t) * (size_t)(n_replicates << (levels - 1)), st));
+        EM_TRY(b_b.alloc(sizeof(int64_t) * (size_t)(n_replicates << (levels - 1)), st));
+    }
+    int64_t *parent = nullptr, *child = b_a.as<int64_t>();
+    for (int level = 0; level < levels; ++level) {
+        int64_t *dst = level == levels - 1 ? d_out : child;
+        const int64_t threads = n_replicates << level;
+        multinomial_tree_kernel<<<blocks_for(threads, 128), 128, 0, st>>>(d_cum, n_classes, levels, level, parent, dst,
+                                                                       n_replicates, first_replicate, (uint32_t)seed,
+                                                                       (uint32_t)(seed >> 32));
+        parent = child;
+        child = child == b_a.as<int64_t>() ? b_b.as<int64_t>() : b_a.as<int64_t>();
+    }
+    EM_TRY(cudaGetLastError());
+    EM_TRY(cudaStreamSynchronize(st));  // the level buffers go back to the cache
+    return SKM_OK;
+}
+
+static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t n_replicates, int64_t first_replicate,
+                            uint64_t seed, int method, int64_t *d_out, int device, cudaStream_t st)
+{
+    if (method != SKM_RESAMPLE_DRAWS && method != SKM_RESAMPLE_TREE)
+        return fail(SKM_ERR_INVALID, "skm_multinomial: unknown resampling method");
     DeviceBuf b_cum, b_lo, b_tmp;
     EM_TRY(b_cum.alloc(sizeof(unsigned long long) * (size_t)n_classes, st));
     // about two buckets per class: the search that follows the bucket lookup is then 0-1 steps
@@ -1383,6 +1586,8 @@ static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t 
     EM_TRY(b_tmp.alloc(tmp, st));
     EM_TRY(cub::DeviceScan::InclusiveSum(b_tmp.p, tmp, reinterpret_cast<const unsigned long long *>(d_counts),
                                          b_cum.as<unsigned long long>(), (int)n_classes, st));
+    if (method == SKM_RESAMPLE_TREE)
+        return multinomial_tree(b_cum.as<unsigned long long>(), n_classes, n_replicates, first_replicate, seed, d_out, st);
     unsigned long long n = 0;
     EM_TRY(cudaMemcpyAsync(&n, b_cum.as<unsigned long long>() + (n_classes - 1), sizeof(n), cudaMemcpyDeviceToHost, st));
     EM_TRY(cudaStreamSynchronize(st));
@@ -1404,7 +1609,7 @@ static int multinomial_core(const int64_t *d_counts, int64_t n_classes, int64_t 
 }
 
 SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_replicates,
-                            int64_t first_replicate, uint64_t seed, int64_t *out, int buffers_on_device,
+                            int64_t first_replicate, uint64_t seed, int method, int64_t *out, int buffers_on_device,
                             int device, void *stream)
 {
     if (!counts || !out) return fail(SKM_ERR_INVALID, "skm_multinomial: NULL argument");
@@ -1424,7 +1629,7 @@ SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_
         d_counts = b_counts.as<int64_t>();
         d_out = b_out.as<int64_t>();
     }
-    const int rc = multinomial_core(d_counts, n_classes, n_replicates, first_replicate, seed, d_out, device, st);
+    const int rc = multinomial_core(d_counts, n_classes, n_replicates, first_replicate, seed, method, d_out, device, st);
     if (rc) return rc;
     if (!buffers_on_device) {
         EM_TRY(cudaMemcpyAsync(out, d_out, sizeof(int64_t) * (size_t)(n_classes * n_replicates), cudaMemcpyDeviceToHost, st));
@@ -1434,8 +1639,9 @@ SKM_API int skm_multinomial(const int64_t *counts, int64_t n_classes, int64_t n_
 }
 
 SKM_API int skm_em_plan_bootstrap(const skm_em_plan *p, const int64_t *counts, const double *eff_len, const double *x0,
-                                  int64_t n_replicates, int64_t first_replicate, uint64_t seed, int64_t max_iters,
-                                  int tpm, double *out_x, int32_t *out_iters, int buffers_on_device, void *stream)
+                                  int64_t n_replicates, int64_t first_replicate, uint64_t seed, int method,
+                                  int64_t max_iters, int tpm, double *out_x, int32_t *out_iters, int buffers_on_device,
+                                  void *stream)
 {
     if (!p || !eff_len || !x0 || !out_x) return fail(SKM_ERR_INVALID, "skm_em_bootstrap: NULL argument");
     if (n_replicates <= 0) return fail(SKM_ERR_INVALID, "skm_em_bootstrap: empty problem");
@@ -1446,7 +1652,7 @@ SKM_API int skm_em_plan_bootstrap(const skm_em_plan *p, const int64_t *counts, c
     const int64_t C = p->C, T = p->T;
 
     DeviceBuf b_counts, b_len, b_x, b_out, b_iters, b_draws, b_cr;
-    EmInputs in{p, eff_len, R, max_iters, nullptr, nullptr, nullptr, x0};
+    EmInputs in{p, eff_len, R, max_iters, nullptr, nullptr, x0};
     const int64_t *d_counts = counts ? counts : p->counts;
     double *d_out = out_x;
     int32_t *d_iters = out_iters;
@@ -1471,10 +1677,10 @@ SKM_API int skm_em_plan_bootstrap(const skm_em_plan *p, const int64_t *counts, c
     trace.mark("bootstrap: inputs to device");
     // resample on the device, then straight into the EM's [class][replicate] fp64 layout
     EM_TRY(b_draws.alloc(sizeof(int64_t) * (size_t)(C * R), st));
-    int rc = multinomial_core(d_counts, C, R, first_replicate, seed, b_draws.as<int64_t>(), p->device, st);
+    int rc = multinomial_core(d_counts, C, R, first_replicate, seed, method, b_draws.as<int64_t>(), p->device, st);
     if (rc) return rc;
     EM_TRY(b_cr.alloc(sizeof(double) * (size_t)(C * R), st));
-    counts_to_f64_kernel<<<blocks_for(C * R, 256), 256, 0, st>>>(b_draws.as<unsigned long long>(), b_cr.as<double>(), C, R);
+    counts_to_plan_kernel<int64_t><<<blocks_for(C * R, 256), 256, 0, st>>>(b_draws.as<int64_t>(), p->perm, b_cr.as<double>(), C, R);
     EM_TRY(cudaGetLastError());
     EM_TRY(cudaStreamSynchronize(st));
     b_draws.release();
@@ -1499,9 +1705,9 @@ SKM_API int skm_em_plan_bootstrap(const skm_em_plan *p, const int64_t *counts, c
 
 SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, int64_t n_classes, int64_t nnz,
                              const int64_t *counts, const double *eff_len, int64_t n_transcripts, const double *x0,
-                             int64_t n_replicates, int64_t first_replicate, uint64_t seed, int64_t max_iters,
-                             int tpm, double *out_x, int32_t *out_iters, int buffers_on_device, int device,
-                             void *stream)
+                             int64_t n_replicates, int64_t first_replicate, uint64_t seed, int method,
+                             int64_t max_iters, int tpm, double *out_x, int32_t *out_iters, int buffers_on_device,
+                             int device, void *stream)
 {
     if (!class_ptr || !class_tx || !counts || !eff_len || !x0 || !out_x)
         return fail(SKM_ERR_INVALID, "skm_em_bootstrap: NULL argument");
@@ -1510,8 +1716,8 @@ SKM_API int skm_em_bootstrap(const int64_t *class_ptr, const int32_t *class_tx, 
     int rc = skm_em_plan_create(class_ptr, class_tx, n_classes, nnz, n_transcripts, nullptr, buffers_on_device, device,
                                 stream, &plan);
     if (rc) return rc;
-    rc = skm_em_plan_bootstrap(plan, counts, eff_len, x0, n_replicates, first_replicate, seed, max_iters, tpm, out_x,
-                               out_iters, buffers_on_device, stream);
+    rc = skm_em_plan_bootstrap(plan, counts, eff_len, x0, n_replicates, first_replicate, seed, method, max_iters, tpm,
+                               out_x, out_iters, buffers_on_device, stream);
     skm_em_plan_destroy(plan);
     return rc;
 }

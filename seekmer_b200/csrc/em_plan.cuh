@@ -9,11 +9,14 @@
 struct skm_em_plan {
     int device = 0;
     int64_t C = 0, nnz = 0, T = 0;
-    int64_t *class_ptr = nullptr;  // [C + 1]
+    int32_t *perm = nullptr;       // [C] plan class i = the caller's class perm[i] (classes sorted by first transcript)
+    int64_t *class_ptr = nullptr;  // [C + 1], plan class order
     int32_t *class_tx = nullptr;   // [nnz] transcript ids in tuple order
     int64_t *tx_ptr = nullptr;     // [T + 1]
     int32_t *tx_class = nullptr;   // [nnz] class of every entry of a transcript, in nnz order
-    int64_t *counts = nullptr;     // [C] integer class counts, or NULL
+    int64_t *counts = nullptr;     // [C] integer class counts in the CALLER's class order, or NULL
+    int32_t *heavy_rows = nullptr; // transcripts with more entries than one 8-lane group should sum
+    int32_t n_heavy = 0;
 };
 
 namespace skm {

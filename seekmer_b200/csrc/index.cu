@@ -3,7 +3,10 @@
 // targets, graph links) + 2-bit sequence pool + entry-only target lists.  Replaces
 // KMerIndex.__init__/load on the device side (_common.pyx:21-48,287-313) and KMerIndex.map_kmer
 // for vectors of k-mers.
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "kmer.cuh"
@@ -220,6 +223,27 @@ static int to_device(const T *src, int64_t n, bool on_device, cudaStream_t st, c
 
 using namespace skm;
 
+// DevIndex::pol_hot / pol_stream for an index whose arrays are in place
+static int make_policies(skm_index *ix, cudaStream_t st)
+{
+    // SKM_L2_HINT = last | normal: eviction priority of the contig-side loads (default: last)
+    const char *hint = getenv("SKM_L2_HINT");
+    const int hot_kind = (hint && hint[0] == 'n') ? 0 : 1;
+    uint64_t *d_pol = nullptr, pol[2] = {0, 0};
+    cudaError_t e = cudaMalloc(&d_pol, sizeof(pol));
+    if (e == cudaSuccess) {
+        skm::make_policies_kernel<<<1, 1, 0, st>>>(d_pol, hot_kind, 2);
+        e = cudaMemcpyAsync(pol, d_pol, sizeof(pol), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(d_pol);
+    if (e != cudaSuccess)
+        return skm::fail(SKM_ERR_CUDA, std::string("skm_index: cache policies: ") + cudaGetErrorString(e));
+    ix->d.pol_hot = pol[0];
+    ix->d.pol_stream = pol[1];
+    return 0;
+}
+
 SKM_API const char *skm_last_error(void) { return skm::last_error(); }
 
 SKM_API const char *skm_version(void) { return "seekmer_b200 0.1 (sm_100a)"; }
@@ -351,6 +375,7 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         const size_t b_targets = up(sizeof(int32_t) * (size_t)n_targets);
         STEP_CUDA(cudaMalloc(&ix->hot, b_contigs + b_seq + b_targets));
         ix->hot_bytes = (int64_t)(b_contigs + b_seq + b_targets);
+        ix->bytes += ix->hot_bytes;
         ix->contigs = reinterpret_cast<ContigRec *>(ix->hot);
         ix->seq2 = reinterpret_cast<uint32_t *>(ix->hot + b_contigs);
         ix->targets = reinterpret_cast<int32_t *>(ix->hot + b_contigs + b_seq);
@@ -360,7 +385,6 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
     extract_targets_kernel<<<(unsigned)((n_targets + 255) / 256), 256, 0, st>>>(
         d_targets, n_targets, ix->targets);
     STEP_CUDA(cudaGetLastError());
-    ix->bytes += (int64_t)sizeof(int32_t) * n_targets;
 
     // -- contigs
     STEP(to_device(contigs, n_contigs, dev, st, &d_contigs, &own_contigs));
@@ -368,7 +392,6 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         d_contigs, n_contigs, d_targets, ix->contigs, n_bases, n_targets, d_scalars + 1,
         reinterpret_cast<unsigned int *>(d_scalars + 2));
     STEP_CUDA(cudaGetLastError());
-    ix->bytes += (int64_t)sizeof(ContigRec) * n_contigs;
     // -- sequences (2-bit, one padding word so window reads may touch word+1)
     STEP(to_device(sequences, n_bases, dev, st, &d_seq, &own_seq));
     {
@@ -376,7 +399,6 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         pack_sequences_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const uint8_t *>(d_seq), n_bases, ix->seq2, n_words);
         STEP_CUDA(cudaGetLastError());
-        ix->bytes += (int64_t)sizeof(uint32_t) * n_words;
     }
     unsigned long long scal[4] = {0, 0, 0, 0};
     STEP_CUDA(cudaMemcpyAsync(scal, d_scalars, sizeof(scal), cudaMemcpyDeviceToHost, st));
@@ -402,23 +424,11 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
     ix->d.n_bases = n_bases;
     ix->d.n_targets = n_targets;
     {
-        // SKM_L2_HINT = last | normal: eviction priority of the contig-side loads (default: last)
-        const char *hint = getenv("SKM_L2_HINT");
-        const int hot_kind = (hint && hint[0] == 'n') ? 0 : 1;
-        uint64_t *d_pol = nullptr, pol[2] = {0, 0};
-        cudaError_t e = cudaMalloc(&d_pol, sizeof(pol));
-        if (e == cudaSuccess) {
-            make_policies_kernel<<<1, 1, 0, st>>>(d_pol, hot_kind, 2);
-            e = cudaMemcpyAsync(pol, d_pol, sizeof(pol), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        }
-        cudaFree(d_pol);
-        if (e != cudaSuccess) {
+        const int prc = make_policies(ix, st);
+        if (prc) {
             skm_index_destroy(ix);
-            return fail(SKM_ERR_CUDA, std::string("skm_index_create: cache policies: ") + cudaGetErrorString(e));
+            return prc;
         }
-        ix->d.pol_hot = pol[0];
-        ix->d.pol_stream = pol[1];
     }
     contig_links_kernel<<<(unsigned)((n_contigs * 8 + 255) / 256), 256, 0, st>>>(ix->d, ix->contigs, n_contigs);
     if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
@@ -500,5 +510,188 @@ SKM_API int skm_build_kmer_table(const uint64_t *kmers, const int32_t *entry, co
                                                             (uint64_t)n_slots - 1);
         SKM_CUDA(cudaGetLastError());
     }
+    return SKM_OK;
+}
+
+// ---- the device image on disk -----------------------------------------------------------------
+// a native GPU-layout index file.  The HBM-resident form (bucketed canonical-key
+// table, contig records with inline targets and graph links, 2-bit sequences, target entries)
+// is written as it lies and read back with plain copies: loading skips the relayout kernels
+// and the 8 table probes per contig of contig_links_kernel.  A trailer of caller-owned bytes
+// rides along (the Python layer keeps the transcript table there).
+namespace {
+
+constexpr char IMAGE_MAGIC[8] = {'S', 'K', 'M', 'B', '2', '0', '0', '\0'};
+constexpr uint32_t IMAGE_VERSION = 1;
+
+struct ImageHeader {
+    char magic[8];
+    uint32_t version;
+    uint32_t kmer_size, bucket_slots, slot_bytes, contig_bytes, inline_targets;
+    int64_t n_slots, n_kmers, n_contigs, n_bases, n_targets, n_transcripts, max_target_count;
+    int64_t table_bytes, hot_bytes, off_seq2, off_targets;  // offsets inside the hot block
+    int64_t trailer_bytes;
+    uint64_t check;  // sum of the fields above, a cheap guard against truncated / foreign files
+};
+
+uint64_t header_check(const ImageHeader &h)
+{
+    const int64_t f[] = {h.version, h.kmer_size, h.bucket_slots, h.slot_bytes, h.contig_bytes, h.inline_targets,
+                         h.n_slots, h.n_kmers, h.n_contigs, h.n_bases, h.n_targets, h.n_transcripts,
+                         h.max_target_count, h.table_bytes, h.hot_bytes, h.off_seq2, h.off_targets, h.trailer_bytes};
+    uint64_t s = 0x9E3779B97F4A7C15ULL;
+    for (int64_t v : f) s = (s ^ (uint64_t)v) * 0xBF58476D1CE4E5B9ULL + 0x632BE59BD9B4E019ULL;
+    return s;
+}
+
+constexpr size_t IO_CHUNK = 64u << 20;
+
+int copy_out(FILE *f, const void *d_src, size_t bytes, void *pinned, cudaStream_t st)
+{
+    const char *src = static_cast<const char *>(d_src);
+    for (size_t done = 0; done < bytes; done += IO_CHUNK) {
+        const size_t n = std::min(IO_CHUNK, bytes - done);
+        SKM_CUDA(cudaMemcpyAsync(pinned, src + done, n, cudaMemcpyDeviceToHost, st));
+        SKM_CUDA(cudaStreamSynchronize(st));
+        if (fwrite(pinned, 1, n, f) != n) return fail(SKM_ERR_INVALID, "skm_index_save: short write");
+    }
+    return 0;
+}
+
+int copy_in(FILE *f, void *d_dst, size_t bytes, void *pinned[2], cudaStream_t st)
+{
+    // file -> pinned buffer k while the copy out of buffer 1-k is in flight
+    char *dst = static_cast<char *>(d_dst);
+    int k = 0;
+    for (size_t done = 0; done < bytes; done += IO_CHUNK, k ^= 1) {
+        const size_t n = std::min(IO_CHUNK, bytes - done);
+        if (fread(pinned[k], 1, n, f) != n) return fail(SKM_ERR_INVALID, "skm_index_load: the file is truncated");
+        SKM_CUDA(cudaStreamSynchronize(st));  // the previous copy (other buffer) is done before it is refilled next round
+        SKM_CUDA(cudaMemcpyAsync(dst + done, pinned[k], n, cudaMemcpyHostToDevice, st));
+    }
+    SKM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace
+
+SKM_API int skm_index_save(const skm_index *ix, const char *path, const void *trailer, int64_t trailer_bytes,
+                           void *stream)
+{
+    if (!ix || !path || trailer_bytes < 0 || (trailer_bytes > 0 && !trailer))
+        return fail(SKM_ERR_INVALID, "skm_index_save: bad argument");
+    SKM_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ImageHeader h{};
+    memcpy(h.magic, IMAGE_MAGIC, 8);
+    h.version = IMAGE_VERSION;
+    h.kmer_size = K;
+    h.bucket_slots = BUCKET_SLOTS;
+    h.slot_bytes = sizeof(Slot);
+    h.contig_bytes = sizeof(ContigRec);
+    h.inline_targets = INLINE_TARGETS;
+    h.n_slots = ix->n_slots;
+    h.n_kmers = ix->n_kmers;
+    h.n_contigs = ix->n_contigs;
+    h.n_bases = ix->n_bases;
+    h.n_targets = ix->n_targets;
+    h.n_transcripts = ix->n_transcripts;
+    h.max_target_count = ix->max_target_count;
+    h.table_bytes = (int64_t)sizeof(Slot) * ix->n_slots;
+    h.hot_bytes = ix->hot_bytes;
+    h.off_seq2 = (int64_t)(reinterpret_cast<const unsigned char *>(ix->seq2) - ix->hot);
+    h.off_targets = (int64_t)(reinterpret_cast<const unsigned char *>(ix->targets) - ix->hot);
+    h.trailer_bytes = trailer_bytes;
+    h.check = header_check(h);
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(SKM_ERR_INVALID, std::string("skm_index_save: cannot open ") + path);
+    void *pinned = nullptr;
+    int rc = 0;
+    if (cudaMallocHost(&pinned, IO_CHUNK) != cudaSuccess) rc = fail(SKM_ERR_OOM, "skm_index_save: no pinned staging buffer");
+    if (!rc && fwrite(&h, sizeof(h), 1, f) != 1) rc = fail(SKM_ERR_INVALID, "skm_index_save: short write");
+    if (!rc) rc = copy_out(f, ix->table, (size_t)h.table_bytes, pinned, st);
+    if (!rc) rc = copy_out(f, ix->hot, (size_t)h.hot_bytes, pinned, st);
+    if (!rc && trailer_bytes > 0 && fwrite(trailer, 1, (size_t)trailer_bytes, f) != (size_t)trailer_bytes)
+        rc = fail(SKM_ERR_INVALID, "skm_index_save: short write");
+    cudaFreeHost(pinned);
+    if (fclose(f) != 0 && !rc) rc = fail(SKM_ERR_INVALID, "skm_index_save: close failed");
+    return rc;
+}
+
+SKM_API int skm_index_load(const char *path, int device, void *stream, skm_index **out, int64_t *trailer_offset,
+                           int64_t *trailer_bytes)
+{
+    if (!out) return fail(SKM_ERR_INVALID, "skm_index_load: out is NULL");
+    *out = nullptr;
+    if (!path) return fail(SKM_ERR_INVALID, "skm_index_load: NULL path");
+    if (skm_device_count() <= device || device < 0)
+        return fail(SKM_ERR_CUDA, "skm_index_load: no such CUDA device (there is no CPU fallback)");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(SKM_ERR_INVALID, std::string("skm_index_load: cannot open ") + path);
+    ImageHeader h{};
+    const bool got = fread(&h, sizeof(h), 1, f) == 1;
+    if (!got || memcmp(h.magic, IMAGE_MAGIC, 8) != 0) {
+        fclose(f);
+        return fail(SKM_ERR_INVALID, "skm_index_load: not a seekmer_b200 device image");
+    }
+    if (h.version != IMAGE_VERSION || h.kmer_size != (uint32_t)K || h.bucket_slots != (uint32_t)BUCKET_SLOTS
+        || h.slot_bytes != sizeof(Slot) || h.contig_bytes != sizeof(ContigRec) || h.inline_targets != (uint32_t)INLINE_TARGETS) {
+        fclose(f);
+        return fail(SKM_ERR_INVALID, "skm_index_load: invalid index version.");  // _common.pyx:303-304
+    }
+    if (h.check != header_check(h) || h.n_slots <= 0 || (h.n_slots & (h.n_slots - 1)) != 0 || h.n_contigs <= 0
+        || h.table_bytes != (int64_t)sizeof(Slot) * h.n_slots || h.hot_bytes <= 0 || h.off_seq2 < 0 || h.off_targets < h.off_seq2
+        || h.off_targets > h.hot_bytes) {
+        fclose(f);
+        return fail(SKM_ERR_INVALID, "skm_index_load: corrupt header");
+    }
+    cudaError_t e = cudaSetDevice(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    skm_index *ix = new skm_index();
+    ix->device = device;
+    ix->n_slots = h.n_slots;
+    ix->n_kmers = h.n_kmers;
+    ix->n_contigs = h.n_contigs;
+    ix->n_bases = h.n_bases;
+    ix->n_targets = h.n_targets;
+    ix->n_transcripts = h.n_transcripts;
+    ix->max_target_count = h.max_target_count;
+    ix->hot_bytes = h.hot_bytes;
+    ix->bytes = h.table_bytes + h.hot_bytes;
+    void *pinned[2] = {nullptr, nullptr};
+    if (e == cudaSuccess) e = cudaMalloc(&ix->table, (size_t)h.table_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->hot, (size_t)h.hot_bytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&pinned[0], IO_CHUNK);
+    if (e == cudaSuccess) e = cudaMallocHost(&pinned[1], IO_CHUNK);
+    int rc = e == cudaSuccess ? 0 : fail(e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,
+                                         std::string("skm_index_load: ") + cudaGetErrorString(e));
+    if (!rc) rc = copy_in(f, ix->table, (size_t)h.table_bytes, pinned, st);
+    if (!rc) rc = copy_in(f, ix->hot, (size_t)h.hot_bytes, pinned, st);
+    cudaFreeHost(pinned[0]);
+    cudaFreeHost(pinned[1]);
+    fclose(f);
+    if (rc) {
+        skm_index_destroy(ix);
+        return rc;
+    }
+    ix->contigs = reinterpret_cast<ContigRec *>(ix->hot);
+    ix->seq2 = reinterpret_cast<uint32_t *>(ix->hot + h.off_seq2);
+    ix->targets = reinterpret_cast<int32_t *>(ix->hot + h.off_targets);
+    ix->d.table = ix->table;
+    ix->d.bucket_mask = (uint64_t)ix->n_slots / BUCKET_SLOTS - 1;
+    ix->d.contigs = ix->contigs;
+    ix->d.seq2 = ix->seq2;
+    ix->d.targets = ix->targets;
+    ix->d.n_contigs = ix->n_contigs;
+    ix->d.n_bases = ix->n_bases;
+    ix->d.n_targets = ix->n_targets;
+    rc = make_policies(ix, st);
+    if (rc) {
+        skm_index_destroy(ix);
+        return rc;
+    }
+    if (trailer_offset) *trailer_offset = (int64_t)sizeof(ImageHeader) + h.table_bytes + h.hot_bytes;
+    if (trailer_bytes) *trailer_bytes = h.trailer_bytes;
+    *out = ix;
     return SKM_OK;
 }

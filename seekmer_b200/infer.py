@@ -21,7 +21,7 @@ import numpy
 from . import _lib
 from . import common
 from . import mapper
-from ._log import Logger
+from ._log import Logger, nvtx_range
 
 __all__ = ['run', 'quantify', 'quantify_bootstraps', 'quantify_samples', 'em', 'output_results',
            'add_subcommand_parser']
@@ -45,8 +45,9 @@ def run(index_path, output_path, fastq_paths, job_count, save_readmap, single_en
         read_feeder = common.feed_single_ended_reads(*fastq_paths)
     else:
         read_feeder = common.feed_pair_ended_reads(*fastq_paths)
-    map_result = mapper.map_reads(index, read_feeder, job_count=job_count, readmap=readmap,
-                                  debug=debug)
+    with nvtx_range('seekmer: map reads'):
+        map_result = mapper.map_reads(index, read_feeder, job_count=job_count, readmap=readmap,
+                                      debug=debug)
     _LOG.info('Mapped all reads')
     mean_fragment_length = map_result.harmonic_mean_fragment_length
     _LOG.info('Estimated fragment length: {:.2f}', mean_fragment_length)
@@ -54,11 +55,13 @@ def run(index_path, output_path, fastq_paths, job_count, save_readmap, single_en
     _LOG.info('Quantifying transcripts')
     _LOG.info('Aligned {} reads ({:.2%})', summarized_results.aligned,
               summarized_results.aligned / max(summarized_results.total, 1))
-    main_result = quantify(summarized_results)
+    with nvtx_range('seekmer: EM'):
+        main_result = quantify(summarized_results)
     _LOG.info('Quantified transcripts')
     # `-j N`: the replicates of `infer.py:79-82` are independent; they are dealt to N GPUs
-    bootstrapped_results = quantify_bootstraps(summarized_results, main_result, bootstrap,
-                                               devices=mapper._devices_for(job_count))
+    with nvtx_range('seekmer: bootstraps'):
+        bootstrapped_results = quantify_bootstraps(summarized_results, main_result, bootstrap,
+                                                   devices=mapper._devices_for(job_count))
     output_results(output_path, index, start_time, summarized_results, main_result,
                    bootstrapped_results)
     _LOG.info('Wrote results to {}'.format(output_path))
@@ -109,14 +112,15 @@ def _finish(x):
     return x
 
 
-def _resample(class_count, n_replicates, seed, first_replicate=0, device=0):
+def _resample(class_count, n_replicates, seed, first_replicate=0, device=0, method=_lib.RESAMPLE_TREE):
+    """Multinomial(n, count / n) for `n_replicates` replicates (`infer.py:108-111`) on the device."""
     counts = numpy.ascontiguousarray(class_count, dtype='i8')
     if not (counts == class_count).all():
         raise ValueError('bootstrap needs integral class counts')
     out = numpy.zeros((n_replicates, counts.shape[0]), dtype='i8')
     _lib.require_device()
     _lib.check(_lib.load().skm_multinomial(_lib._np_ptr(counts), counts.shape[0], n_replicates,
-                                           first_replicate, int(seed) & (2 ** 64 - 1),
+                                           first_replicate, int(seed) & (2 ** 64 - 1), int(method),
                                            _lib._np_ptr(out), 0, device, None))
     return out
 

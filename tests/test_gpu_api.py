@@ -6,7 +6,7 @@ import json
 import numpy
 import pytest
 
-from seekmer_b200 import common, infer, mapper
+from seekmer_b200 import _lib, common, infer, mapper
 from seekmer_b200.__main__ import main as cli_main
 
 pytestmark = pytest.mark.gpu
@@ -91,3 +91,36 @@ def test_single_end_and_multiple_samples(golden_synth, small_tx):
     assert dict(results[0].counter) == want
     assert (results[0].fragment_length_counts == g['se75_fld']).all()
     assert sum(results[1].counter.values()) == 1500
+
+
+def test_device_image_round_trip(orc, golden_synth, small_tx, tmp_path):
+    """The native GPU-layout index file: save the device image, load it back with
+    plain copies (no relayout, no link probes) and map: the same class table, bit for bit."""
+    from conftest import SYNTH_CASES
+    from seekmer_b200 import synth
+    g = golden_synth
+    index = common.KMerIndex(*g.index_arrays(), g['transcripts'], None)
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **SYNTH_CASES['pe150'])
+    want = mapper.map_reads(index, sim.batches(0, 4000, batch=1000))
+    path = tmp_path / 'small.skmidx'
+    index.save(path)
+    index.release_device()
+    again = common.KMerIndex.load(path)
+    assert again.kmers is None and (again.transcripts == index.transcripts).all()
+    got = mapper.map_reads(again, sim.batches(0, 4000, batch=1000))
+    for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'):
+        assert (got._table[k] == want._table[k]).all(), k
+    assert dict(got.counter) == dict(want.counter)
+    info_a, info_b = again.device_index(0).info(), common.KMerIndex(*g.index_arrays(), g['transcripts'], None).device_index(0).info()
+    assert info_a == info_b
+    # a truncated file and a foreign layout version are refused by the library as well
+    raw = path.read_bytes()
+    (tmp_path / 'cut.skmidx').write_bytes(raw[:len(raw) // 2])
+    with pytest.raises(_lib.SeekmerCudaError, match='truncated'):
+        _lib.DeviceIndex.load(tmp_path / 'cut.skmidx')
+    bumped = bytearray(raw)
+    bumped[8] = 99
+    (tmp_path / 'v99.skmidx').write_bytes(bytes(bumped))
+    with pytest.raises(_lib.SeekmerCudaError, match='invalid index version'):
+        _lib.DeviceIndex.load(tmp_path / 'v99.skmidx')
+    again.release_device()

@@ -92,20 +92,73 @@ def test_multinomial_bit_exact_and_batched_bootstrap(orc):
     class_map, counts, eff = synthetic_structure(3000, 12000, 5)
     counts = numpy.floor(counts / 10)
     R, seed = 37, 0xDEADBEEFCAFE
+    # the per-draw resampler is bit-identical to its numpy restatement
     want = orc.bootstrap_counts(counts, R, seed)
-    got = infer._resample(counts, R, seed)
+    got = infer._resample(counts, R, seed, method=_lib.RESAMPLE_DRAWS)
     assert (got == want).all()
     assert (got.sum(axis=1) == counts.sum()).all()
     # replicate ids are global: a shard starting at replicate 20 reproduces rows 20..
-    assert (infer._resample(counts, 5, seed, first_replicate=20) == want[20:25]).all()
+    assert (infer._resample(counts, 5, seed, first_replicate=20, method=_lib.RESAMPLE_DRAWS) == want[20:25]).all()
 
+    # the bootstraps resample with the O(classes) split tree; the parity gate of BASELINE.md: the
+    # reference EM (numpy restatement) fed the GPU-resampled counts agrees to 1e-6, equal iterations
+    tree = infer._resample(counts, R, seed)
+    assert (tree.sum(axis=1) == counts.sum()).all() and (tree[:, counts == 0] == 0).all()
+    assert (infer._resample(counts, 5, seed, first_replicate=20) == tree[20:25]).all()
     res = mapper.SummarizedResult(int(counts.sum()), 0, int(counts.sum()), class_map, counts, None, eff)
     main = orc.quantify(eff, class_map, counts)
     outs, iters = infer.quantify_bootstraps(res, main, R, seed=seed, return_iters=True)
     for r in range(R):
-        w, wi = orc.quantify(eff, class_map, want[r].astype('f8'), x0=main, return_iters=True)
+        w, wi = orc.quantify(eff, class_map, tree[r].astype('f8'), x0=main, return_iters=True)
         assert iters[r] == wi, r
         assert rel_close(outs[r], w), r
+    # a plan that owns its counts (what the mapper hands over) gives the same replicates
+    ptr, tx = infer._csr_from_class_map(class_map, counts.shape[0])
+    plan = _lib.EmPlan.from_csr(ptr, tx, eff.shape[0], counts=counts.astype('i8'))
+    x = main / main.sum()
+    o2, i2 = plan.bootstrap(eff, x, 7, seed, first_replicate=3)
+    assert (i2 == iters[3:10]).all() and all((o2[k] == outs[3 + k]).all() for k in range(7))
+    m2, mi = plan.run(eff, numpy.ones(eff.shape[0]) / eff / (1.0 / eff).sum())
+    wm, wmi = orc.em(numpy.ones(eff.shape[0]) / eff / (1.0 / eff).sum(), eff, class_map, counts, return_iters=True)
+    assert int(mi[0]) == wmi and rel_close(m2[0], wm)
+    plan.close()
+
+
+def test_tree_resampler_matches_its_host_build_and_the_multinomial(tmp_path):
+    """The device split tree against the host build of the same header (tests/binomial_host.cpp):
+    identical streams, so the counts agree except where the device's and the host's log/exp
+    differ in the last place at an accept/reject boundary; and the marginals are binomial."""
+    import ctypes
+    import subprocess
+    from conftest import ROOT
+    so = tmp_path / 'libbinomial_host.so'
+    subprocess.run(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', str(ROOT / 'tests' / 'binomial_host.cpp'), '-o',
+                    str(so)], check=True)
+    host = ctypes.CDLL(str(so))
+    host.multinomial_tree_host.restype = None
+    host.multinomial_tree_host.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int64,
+                                           ctypes.c_void_p]
+    rng = numpy.random.Generator(numpy.random.PCG64(4))
+    counts = numpy.floor(numpy.exp(rng.normal(2.5, 2.2, size=5000))).astype('i8')
+    counts[rng.random(5000) < 0.15] = 0
+    counts[17] = 3_000_000
+    n, seed, R = int(counts.sum()), 0x1234ABCD5678, 400
+    got = infer._resample(counts, R, seed)
+    assert (got.sum(axis=1) == n).all() and (got[:, counts == 0] == 0).all()
+    want = numpy.zeros((8, counts.shape[0]), dtype='i8')
+    for r in range(8):
+        host.multinomial_tree_host(counts.ctypes.data, counts.shape[0], seed, r, want[r].ctypes.data)
+    assert (got[:8] != want).mean() < 1e-4
+    p = counts / n
+    live = counts > 0
+    z = (got.mean(axis=0)[live] - n * p[live]) / numpy.sqrt(n * p[live] * (1 - p[live]) / R)
+    assert abs(z).max() < 5.5 and abs(z.mean()) < 0.2 and 0.85 < z.std() < 1.15
+    big = counts >= 50
+    ratio = got.var(axis=0, ddof=1)[big] / (n * p[big] * (1 - p[big]))
+    assert 0.93 < ratio.mean() < 1.07
+    # one class, and a single replicate of many classes
+    assert (infer._resample(numpy.asarray([41]), 3, 1) == 41).all()
+    assert infer._resample(counts, 1, 9).sum() == n
 
 
 def test_effective_lengths_bit_exact(orc):

@@ -177,3 +177,34 @@ def test_abundance_tsv_is_byte_identical_to_the_pandas_writer(tmp_path):
         ours = (tmp_path / 'abundance.tsv').read_bytes()
         want = (tmp_path / 'pandas.tsv').read_bytes()
         assert ours == want
+
+
+def test_device_image_of_a_wrong_version_is_refused(tmp_path):
+    """`KMerIndex.load` of a native GPU-layout index file checks the layout version before
+    anything is uploaded, like `_common.pyx:303-304` ("invalid index version.")."""
+    import io
+    buf = io.BytesIO()
+    numpy.savez(buf, seekmer_version=numpy.asarray('2019.0.0'), transcripts=numpy.zeros(3), exons=numpy.zeros(0))
+    trailer = buf.getvalue()
+
+    def image(version, trailer_bytes=trailer, magic=b'SKMB200\0'):
+        head = common._IMAGE_HEADER.pack(magic, version, 25, 4, 16, 128, 8, 1024, 10, 5, 100, 7, 3, 2, 0, 0, 0, 0,
+                                         len(trailer_bytes), 0)
+        return head + trailer_bytes
+
+    good = tmp_path / 'ok.skmidx'
+    good.write_bytes(image(common._IMAGE_VERSION))
+    index = common.KMerIndex.load(good)  # host side only: nothing is uploaded before a mapper asks
+    assert index.kmers is None and len(index.transcripts) == 3 and index._image_path == good
+    bad = tmp_path / 'bad.skmidx'
+    bad.write_bytes(image(common._IMAGE_VERSION + 1))
+    with pytest.raises(RuntimeError, match='invalid index version'):
+        common.KMerIndex.load(bad)
+    other = io.BytesIO()
+    numpy.savez(other, seekmer_version=numpy.asarray('2018.0.0'), transcripts=numpy.zeros(3), exons=numpy.zeros(0))
+    bad.write_bytes(image(common._IMAGE_VERSION, other.getvalue()))
+    with pytest.raises(RuntimeError, match='invalid index version'):
+        common.KMerIndex.load(bad)
+    bad.write_bytes(image(common._IMAGE_VERSION, magic=b'NOTANIDX'))
+    with pytest.raises(RuntimeError, match='not a seekmer_b200 device image'):
+        common.KMerIndex.load(bad)
