@@ -393,16 +393,18 @@ def run_ours(args):
         barrier()
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D copies inside
-    h_bases = torch.empty(n_pairs * 2 * READ_LEN, dtype=torch.uint8, pin_memory=True)
-    h_bases.copy_(d_bases)
+    # (at most 30 M pairs of the rank's shard: 9 GB of pinned host memory; a rate, so the slice is enough)
+    n_e2e = min(n_pairs, 30_000_000)
+    h_bases = torch.empty(n_e2e * 2 * READ_LEN, dtype=torch.uint8, pin_memory=True)
+    h_bases.copy_(d_bases[:n_e2e * 2 * READ_LEN])
     torch.cuda.synchronize()
     h_np = h_bases.numpy()
 
     def step_e2e():
         mp.reset()
-        batch = args.e2e_batch or n_pairs
-        for s in range(0, n_pairs, batch):
-            n = min(batch, n_pairs - s)
+        batch = args.e2e_batch or n_e2e
+        for s in range(0, n_e2e, batch):
+            n = min(batch, n_e2e - s)
             mp.map_batch(h_np[s * 2 * READ_LEN:(s + n) * 2 * READ_LEN], None, n, True, first_unit=first_unit + s,
                          fixed_len=READ_LEN)
         tab = sdist.merge_mappers(mp) if world > 1 else mp.export_torch()
@@ -420,12 +422,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t[0])
-    e2e_value = total_pairs / e2e_s
-    d2h_bytes = int(sum(host_table[k].nbytes for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld')))
-    assert (e2e_table['counts'] == host_table['counts']).all() and (e2e_table['key_ids'] == host_table['key_ids']).all()
+    e2e_value = world * n_e2e / e2e_s
+    d2h_bytes = int(sum(e2e_table[k].nbytes for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld')))
+    if n_e2e == n_pairs:
+        assert (e2e_table['counts'] == host_table['counts']).all() and (e2e_table['key_ids'] == host_table['key_ids']).all()
 
     # ---- what the box gives when every rank copies its reads host -> device at the same time
-    scratch = torch.empty_like(d_bases)
+    scratch = torch.empty(h_bases.numel(), dtype=torch.uint8, device=device)
     scratch.copy_(h_bases, non_blocking=True)
     barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -448,8 +451,13 @@ def run_ours(args):
             transcripts = numpy.zeros(lengths.shape[0], dtype=[('length', 'f8')])
         FakeIndex.transcripts['length'] = lengths
         FakeIndex.default_device = local
-        # `mp` still holds the (merged) dictionary of the last end-to-end pass: the same classes, counts
-        # and first-seen order as `host_table` (asserted above)
+        if n_e2e != n_pairs:  # the end-to-end pass only mapped a slice: map the whole shard again
+            mp.reset()
+            mp.map_batch(d_bases, None, n_pairs, True, first_unit=first_unit, fixed_len=READ_LEN)
+            if world > 1:
+                sdist.merge_mappers(mp)
+        # `mp` holds the (merged) dictionary of the whole job: the same classes, counts and first-seen
+        # order as `host_table` (asserted above for the end-to-end pass)
         barrier()
         w0 = time.perf_counter()
         plan = _lib.EmPlan.from_mapper(mp, lengths.shape[0])
@@ -522,7 +530,7 @@ def run_ours(args):
     e2e_fastq = None
     if world == 1 and args.fastq_pairs > 0:
         try:
-            n_fq = min(args.fastq_pairs, n_pairs)
+            n_fq = min(args.fastq_pairs, n_e2e)
             with tempfile.TemporaryDirectory(prefix='skm_bench_') as folder:
                 paths, fq_bytes = write_fastq_pair(folder, h_np, n_fq, READ_LEN)
 
@@ -563,7 +571,7 @@ def run_ours(args):
         from oracle import oracle as orc
         arrays = built.numpy_arrays()
         oidx = orc.OracleIndex(*arrays)
-        sample = min(args.cpu_sample, n_pairs)
+        sample = min(args.cpu_sample, n_e2e)
         hb = h_np[:sample * 2 * READ_LEN]
         b_step, b_kernel, per_read = algorithmic_bytes_per_pair(orc, oidx, hb, min(100_000, sample))
         peak, peak_src = _peak_hbm()
@@ -617,7 +625,7 @@ def run_ours(args):
                       'aligned_equal': bool(chk['aligned'] == aligned),
                       'unit_lengths_equal': bool((g_len == length).all()),
                       'unit_classes_equal': bool(one_to_one and ((g_cls >= 0) == (cnt > 0)).all())}
-            if em is not None:
+            if em is not None and world == 1:  # a baseline of rank 0 at N = 1 (12 s of numpy EM)
                 em['cpu_baseline'] = em_cpu_baseline(orc, host_table, em['eff'], em['main_x'], em['main_iters'],
                                                      args.cpu_bootstraps, args.bootstraps, 'port')
     except Exception as exc:  # the oracle is optional infrastructure for the bench line
@@ -641,11 +649,12 @@ def run_ours(args):
                    % (d_bases.numel() / 1e9, info['table_slots'] * 16 / 1e9),
                    'parallelism': 'reads sharded x%d, index replicated' % world, 'host_placement': placement},
         'clocks': clocks,
-        'e2e': {'value': round(e2e_value, 1), 'unit': UNIT, 'h2d_bytes_per_step': int(n_pairs * 2 * READ_LEN),
+        'e2e': {'value': round(e2e_value, 1), 'unit': UNIT, 'h2d_bytes_per_step': int(n_e2e * 2 * READ_LEN),
+                'pairs_per_gpu': n_e2e,
                 'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': round(e2e_s * 1e3, 3),
                 'h2d_ceiling_gbs': round(h2d_ceiling_gbs, 2),
-                'h2d_achieved_gbs': round(total_pairs * 2 * READ_LEN / e2e_s / 1e9, 2),
-                'frac_of_h2d_ceiling': round(total_pairs * 2 * READ_LEN / e2e_s / 1e9 / h2d_ceiling_gbs, 3),
+                'h2d_achieved_gbs': round(world * n_e2e * 2 * READ_LEN / e2e_s / 1e9, 2),
+                'frac_of_h2d_ceiling': round(world * n_e2e * 2 * READ_LEN / e2e_s / 1e9 / h2d_ceiling_gbs, 3),
                 'ceiling_note': 'all %d ranks copying their pinned read buffer host -> device at the same time '
                                 '(cudaMemcpyAsync, CUDA events, slowest rank)' % world},
         'gpu_launches': gpu_launches,

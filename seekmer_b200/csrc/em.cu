@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <ctime>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 #include <cooperative_groups.h>
 #include <cub/cub.cuh>
@@ -309,10 +310,10 @@ __global__ void em_decide_kernel(const EmState s)
 // read-only and may sit in L1.
 namespace cg = cooperative_groups;
 #ifndef SKM_EM_LOOP_THREADS
-#define SKM_EM_LOOP_THREADS 512
+#define SKM_EM_LOOP_THREADS 1024
 #endif
 #ifndef SKM_EM_LOOP_BLOCKS
-#define SKM_EM_LOOP_BLOCKS 3
+#define SKM_EM_LOOP_BLOCKS 2
 #endif
 constexpr int EM_LOOP_THREADS = SKM_EM_LOOP_THREADS;  // block size of the fused loop
 constexpr int EM_LOOP_BLOCKS = SKM_EM_LOOP_BLOCKS;    // blocks per SM it is compiled (and launched) for
@@ -757,6 +758,40 @@ struct BlockCache {
 };
 static BlockCache g_blocks;
 
+// Device memory that outlives a call (the arrays of an EM plan) from the same cache: making and
+// dropping a plan per sample then costs no cudaMalloc / cudaFree (each of which synchronises the
+// device: ~20 of them took 20+ ms per plan).
+static std::mutex g_owned_mu;
+static std::unordered_map<void *, size_t> g_owned[64];
+
+cudaError_t dev_alloc(int device, size_t bytes, void **out)
+{
+    size_t got = 0;
+    const cudaError_t e = g_blocks.take(device, std::max<size_t>(bytes, 256), out, &got);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        return e;
+    }
+    std::lock_guard<std::mutex> lock(g_owned_mu);
+    g_owned[device & 63][*out] = got;
+    return cudaSuccess;
+}
+
+void dev_free(int device, void *p)
+{
+    if (!p) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_owned_mu);
+        auto &m = g_owned[device & 63];
+        auto it = m.find(p);
+        if (it == m.end()) return;
+        bytes = it->second;
+        m.erase(it);
+    }
+    g_blocks.give(device, p, bytes);
+}
+
 struct DeviceBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -941,17 +976,19 @@ static int select_heavy_rows(const int64_t *tx_ptr, int64_t n_rows, cudaStream_t
     *out = nullptr;
     *n_out = 0;
     int32_t *list = nullptr, *count = nullptr;
-    EM_TRY(cudaMalloc(&list, sizeof(int32_t) * (size_t)n_rows));
-    cudaError_t e = cudaMalloc(&count, sizeof(int32_t));
+    int device = 0;
+    EM_TRY(cudaGetDevice(&device));
+    EM_TRY(dev_alloc(device, sizeof(int32_t) * (size_t)n_rows, (void **)&list));
+    cudaError_t e = dev_alloc(device, sizeof(int32_t), (void **)&count);
     if (e == cudaSuccess) e = cudaMemsetAsync(count, 0, sizeof(int32_t), st);
     if (e == cudaSuccess) {
         select_heavy_rows_kernel<<<blocks_for(n_rows, 256), 256, 0, st>>>(tx_ptr, n_rows, list, count);
         e = cudaMemcpyAsync(n_out, count, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(count);
+    dev_free(device, count);
     if (e != cudaSuccess) {
-        cudaFree(list);
+        dev_free(device, list);
         return fail(SKM_ERR_CUDA, std::string("skm_em: heavy rows: ") + cudaGetErrorString(e));
     }
     *out = list;
@@ -1197,13 +1234,15 @@ SKM_API void skm_em_plan_destroy(skm_em_plan *p)
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(p->device);
-    cudaFree(p->class_ptr);
-    cudaFree(p->class_tx);
-    cudaFree(p->tx_ptr);
-    cudaFree(p->tx_class);
-    cudaFree(p->counts);
-    cudaFree(p->heavy_rows);
-    cudaFree(p->perm);
+    cudaStreamSynchronize(nullptr);  // nothing of the plan is in flight on the default stream ...
+    cudaDeviceSynchronize();         // ... nor on any other, before its blocks can be handed out again
+    dev_free(p->device, p->class_ptr);
+    dev_free(p->device, p->class_tx);
+    dev_free(p->device, p->tx_ptr);
+    dev_free(p->device, p->tx_class);
+    dev_free(p->device, p->counts);
+    dev_free(p->device, p->heavy_rows);
+    dev_free(p->device, p->perm);
     cudaSetDevice(prev);
     delete p;
 }
@@ -1223,20 +1262,20 @@ int skm::em_plan_adopt(int device, int64_t C, int64_t nnz, int64_t T, int64_t *c
     // classes renumbered by their first transcript for the iterations (reorder_classes)
     int64_t *s_ptr = nullptr;
     int32_t *s_tx = nullptr;
-    cudaError_t e = cudaMalloc(&p->perm, sizeof(int32_t) * (size_t)C);
-    if (e == cudaSuccess) e = cudaMalloc(&s_ptr, sizeof(int64_t) * (size_t)(C + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&s_tx, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1));
-    if (e == cudaSuccess) e = cudaMalloc(&p->tx_ptr, sizeof(int64_t) * (size_t)(T + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&p->tx_class, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1));
+    cudaError_t e = dev_alloc(device, sizeof(int32_t) * (size_t)C, (void **)&p->perm);
+    if (e == cudaSuccess) e = dev_alloc(device, sizeof(int64_t) * (size_t)(C + 1), (void **)&s_ptr);
+    if (e == cudaSuccess) e = dev_alloc(device, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1), (void **)&s_tx);
+    if (e == cudaSuccess) e = dev_alloc(device, sizeof(int64_t) * (size_t)(T + 1), (void **)&p->tx_ptr);
+    if (e == cudaSuccess) e = dev_alloc(device, sizeof(int32_t) * (size_t)std::max<int64_t>(nnz, 1), (void **)&p->tx_class);
     if (e == cudaSuccess) e = reorder_classes(class_ptr, class_tx, C, T, st, p->perm, s_ptr, s_tx);
     if (e != cudaSuccess) {
-        cudaFree(s_ptr);
-        cudaFree(s_tx);
+        dev_free(device, s_ptr);
+        dev_free(device, s_tx);
         skm_em_plan_destroy(p);
         return fail(e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA, std::string("skm_em_plan: ") + cudaGetErrorString(e));
     }
-    cudaFree(p->class_ptr);
-    cudaFree(p->class_tx);
+    dev_free(device, p->class_ptr);
+    dev_free(device, p->class_tx);
     p->class_ptr = class_ptr = s_ptr;
     p->class_tx = class_tx = s_tx;
     trace.mark("em plan: class order");
@@ -1275,16 +1314,16 @@ SKM_API int skm_em_plan_create(const int64_t *class_ptr, const int32_t *class_tx
     int64_t *d_ptr = nullptr, *d_counts = nullptr;
     int32_t *d_tx = nullptr;
     const cudaMemcpyKind kind = buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    cudaError_t e = cudaMalloc(&d_ptr, sizeof(int64_t) * (size_t)(n_classes + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_tx, sizeof(int32_t) * (size_t)nnz);
-    if (e == cudaSuccess && counts) e = cudaMalloc(&d_counts, sizeof(int64_t) * (size_t)n_classes);
+    cudaError_t e = dev_alloc(device, sizeof(int64_t) * (size_t)(n_classes + 1), (void **)&d_ptr);
+    if (e == cudaSuccess) e = dev_alloc(device, sizeof(int32_t) * (size_t)nnz, (void **)&d_tx);
+    if (e == cudaSuccess && counts) e = dev_alloc(device, sizeof(int64_t) * (size_t)n_classes, (void **)&d_counts);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ptr, class_ptr, sizeof(int64_t) * (size_t)(n_classes + 1), kind, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_tx, class_tx, sizeof(int32_t) * (size_t)nnz, kind, st);
     if (e == cudaSuccess && counts) e = cudaMemcpyAsync(d_counts, counts, sizeof(int64_t) * (size_t)n_classes, kind, st);
     if (e != cudaSuccess) {
-        cudaFree(d_ptr);
-        cudaFree(d_tx);
-        cudaFree(d_counts);
+        dev_free(device, d_ptr);
+        dev_free(device, d_tx);
+        dev_free(device, d_counts);
         return fail(e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,
                     std::string("skm_em_plan_create: ") + cudaGetErrorString(e));
     }
@@ -1509,8 +1548,9 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
     if (rc) return rc;
     struct FreeOnExit {
         void *p;
-        ~FreeOnExit() { cudaFree(p); }
-    } free_heavy{heavy};
+        int device;
+        ~FreeOnExit() { dev_free(device, p); }
+    } free_heavy{heavy, device};
     s.heavy_rows = heavy;
     s.n_heavy = n_heavy;
 

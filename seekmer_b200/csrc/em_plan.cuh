@@ -20,7 +20,12 @@ struct skm_em_plan {
 };
 
 namespace skm {
-// Takes ownership of class_ptr / class_tx / counts (device memory from cudaMalloc on `device`;
+// Device memory from the per-device block cache of em.cu (no cudaMalloc / cudaFree in steady
+// state); what a plan is made of.
+cudaError_t dev_alloc(int device, size_t bytes, void **out);
+void dev_free(int device, void *p);
+
+// Takes ownership of class_ptr / class_tx / counts (device memory from dev_alloc on `device`;
 // counts may be NULL), builds the CSC side on `stream` and returns the plan.  On failure the
 // buffers are freed.
 int em_plan_adopt(int device, int64_t C, int64_t nnz, int64_t T, int64_t *class_ptr, int32_t *class_tx,

@@ -1126,9 +1126,9 @@ SKM_API int skm_em_plan_from_mapper(skm_mapper *m, int64_t n_transcripts, void *
     // the plan's own arrays
     int64_t *p_off = nullptr, *p_cnt = nullptr;
     int32_t *p_ids = nullptr;
-    cudaError_t e = cudaMalloc(&p_off, sizeof(int64_t) * (size_t)(n + 1));
-    if (e == cudaSuccess) e = cudaMalloc(&p_ids, sizeof(int32_t) * (size_t)n_ids);
-    if (e == cudaSuccess) e = cudaMalloc(&p_cnt, sizeof(int64_t) * (size_t)n);
+    cudaError_t e = dev_alloc(m->device, sizeof(int64_t) * (size_t)(n + 1), (void **)&p_off);
+    if (e == cudaSuccess) e = dev_alloc(m->device, sizeof(int32_t) * (size_t)n_ids, (void **)&p_ids);
+    if (e == cudaSuccess) e = dev_alloc(m->device, sizeof(int64_t) * (size_t)n, (void **)&p_cnt);
     if (e == cudaSuccess) {
         ordered_lens_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(r_off, perm, n, lens);
         tb = b_tmp;
@@ -1140,9 +1140,9 @@ SKM_API int skm_em_plan_from_mapper(skm_mapper *m, int64_t n_transcripts, void *
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the staging block may be reused after this
     if (e != cudaSuccess) {
-        cudaFree(p_off);
-        cudaFree(p_ids);
-        cudaFree(p_cnt);
+        dev_free(m->device, p_off);
+        dev_free(m->device, p_ids);
+        dev_free(m->device, p_cnt);
         return fail(e == cudaErrorMemoryAllocation ? SKM_ERR_OOM : SKM_ERR_CUDA,
                     std::string("skm_em_plan_from_mapper: ") + cudaGetErrorString(e));
     }

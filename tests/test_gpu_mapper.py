@@ -470,3 +470,28 @@ def test_id_pool_holds_stored_ids_only(golden_synth, small_tx):
     assert s['n_classes'] > 0 and s['pool_cursor'] == s['n_ids'], s
     t = mp.export()
     assert int(t['key_offsets'][-1]) == s['n_ids']
+
+
+def test_dictionary_key_collisions_are_refused(golden_synth, small_tx, monkeypatch):
+    """Classes are found by a 128-bit hash of their id tuple, and a unit that finds its key present
+    compares its ids with the stored tuple.  With deliberately weak keys (only the tuple length)
+    different tuples collide: the library must refuse them (SKM_ERR_COLLISION) instead of
+    counting them as one class."""
+    g = golden_synth
+    sim = synth.ReadSimulator(small_tx, synth.make_expression(small_tx.n_transcripts, seed=3), **SYNTH_CASES['pe100'])
+    bases, _ = sim.generate(0, 4000)
+    ix = _lib.DeviceIndex(*g.index_arrays(), 60)
+    monkeypatch.setenv('SKM_TEST_WEAK_KEYS', '1')
+    weak = _lib.DeviceMapper(ix)
+    monkeypatch.delenv('SKM_TEST_WEAK_KEYS')
+    with pytest.raises(_lib.SeekmerCudaError, match='share a 128-bit dictionary key'):
+        # ids of a class inserted by a launch become comparable when the launch ends: the second
+        # batch at the latest meets them
+        weak.map_batch(bases[:2000 * 200], None, 2000, True, fixed_len=100)
+        weak.map_batch(bases[2000 * 200:], None, 2000, True, first_unit=2000, fixed_len=100)
+    # the same reads with the real keys: fine, and more than one class per tuple length
+    ok = _lib.DeviceMapper(ix)
+    ok.map_batch(bases, None, 4000, True, fixed_len=100)
+    t = ok.export()
+    lens = t['key_offsets'][1:] - t['key_offsets'][:-1]
+    assert numpy.unique(lens).size < lens.size
