@@ -168,6 +168,12 @@ int skm_map_fastq(skm_mapper *mapper, const uint8_t *text1, int64_t n1, const ui
  * ms[1] = map_reads_kernel, ms[2] = tally_units_kernel.  Blocks until that chunk is done. */
 int skm_mapper_kernel_ms(skm_mapper *mapper, double ms[3]);
 
+/* Diagnostics of map_reads_kernel, filled only by a library built with -DSKM_STATS=1
+ * (otherwise SKM_ERR_INVALID): for each of the six phases [iterations, items claimed, of them
+ * borrowed from another lane's column, clock cycles], then the number of idle polls.  No
+ * reference counterpart; used by tools/sweep_map.py. */
+int skm_debug_map_stats(uint64_t stats[32], int reset);
+
 /* sizes[0]=n_classes, [1]=total ids, [2]=unaligned units, [3]=aligned units,
  * [4]=class slots capacity, [5]=status flags raised on device (0 = none),
  * [6]=units with a read shorter than k (they are part of [2]), [7]=id-pool cursor */

@@ -25,7 +25,7 @@ TARGET_DTYPE = numpy.dtype([('entry', '<i4'), ('offset', '<i4')])
 EXPORTS = (
     'skm_last_error', 'skm_device_count', 'skm_version', 'skm_index_create', 'skm_index_destroy',
     'skm_index_info', 'skm_map_kmers', 'skm_mapper_create', 'skm_mapper_destroy',
-    'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_classes_size', 'skm_classes_export',
+    'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_debug_map_stats', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_classes_merge_packed', 'skm_release_cache', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
     'skm_build_kmer_table', 'skm_index_save', 'skm_index_load', 'skm_em_plan_create', 'skm_em_plan_from_mapper', 'skm_em_plan_info',
     'skm_em_plan_destroy', 'skm_em_plan_run', 'skm_em_plan_bootstrap',
@@ -80,6 +80,8 @@ def load():
     L.skm_map_batch.argtypes = [vp, vp, vp, i32, i32, i64, ci, i64, ci, vp, vp, vp]
     L.skm_map_fastq.restype = ci
     L.skm_map_fastq.argtypes = [vp, vp, i64, vp, i64, i64, ci, vp, vp, vp, vp, vp, vp]
+    L.skm_debug_map_stats.restype = ci
+    L.skm_debug_map_stats.argtypes = [vp, ci]
     L.skm_mapper_kernel_ms.restype = ci
     L.skm_mapper_kernel_ms.argtypes = [vp, vp]
     L.skm_classes_size.restype = ci

@@ -66,6 +66,44 @@ constexpr int SCAN_WIDTH = SKM_SCAN_WIDTH;  // read positions probed per P_SCAN 
 #define SKM_STICKY_LANES 16
 #endif
 constexpr int STICKY_LANES = SKM_STICKY_LANES;  // a phase repeats while this many lanes still have rows for it
+#ifndef SKM_BORROW
+#define SKM_BORROW 0
+#endif
+
+// how many lanes of the warp a phase can keep busy, given every lane's mask of waiting rows
+__device__ __forceinline__ unsigned lanes_served(uint32_t m)
+{
+    const unsigned own = (unsigned)__popc(__ballot_sync(0xffffffffu, m != 0));
+#if SKM_BORROW == 2
+    const unsigned spare = (unsigned)__popc(__ballot_sync(0xffffffffu, (m & (m - 1u)) != 0));  // columns with 2+ rows
+    return own + min(32u - own, spare);
+#else
+    return own;
+#endif
+}
+
+#ifndef SKM_STATS
+#define SKM_STATS 0
+#endif
+// Diagnostics build (-DSKM_STATS=1, tools/build_variants.py): per phase [iterations, items claimed,
+// of them borrowed, clock cycles of the iterations], then the idle polls; skm_debug_map_stats.
+__device__ unsigned long long g_map_stats[32];
+
+// position of the k-th (0-based) set bit of m; popc(m) > k
+__device__ __forceinline__ int kth_set_bit(uint32_t m, int k)
+{
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w; w >>= 1) {
+        const int c = __popc(m & ((1u << w) - 1u));
+        if (k >= c) {
+            k -= c;
+            m >>= w;
+            pos += w;
+        }
+    }
+    return pos;
+}
 
 // What the mapper leaves behind for one unit, field-major so that tally_units_kernel reads it
 // coalesced: units[0][u] = number of targets, units[1][u] = span length of _mapper.pyx:90,
@@ -600,7 +638,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         bool again = false;
         if (phase >= 0) {
             mm = vmasks[phase * 32 + lane];
-            again = __popc(__ballot_sync(0xffffffffu, mm != 0)) >= STICKY_LANES;
+            again = lanes_served(mm) >= (unsigned)STICKY_LANES;
         }
         if (!again) {
             uint32_t m[N_PHASES];
@@ -608,7 +646,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
 #pragma unroll
             for (int p = 0; p < N_PHASES; ++p) {
                 m[p] = vmasks[p * 32 + lane];
-                const unsigned c = (unsigned)__popc(__ballot_sync(0xffffffffu, m[p] != 0));
+                const unsigned c = lanes_served(m[p]);
                 const unsigned cand = c ? (c << 3) | (unsigned)p : 0u;
                 best = cand > best ? cand : best;
             }
@@ -617,6 +655,9 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (lane == 0) live = *reinterpret_cast<volatile int *>(sm_live);
                 live = __shfl_sync(0xffffffffu, live, 0);
                 if (live == 0) break;
+#if SKM_STATS
+                if (lane == 0) atomicAdd(&g_map_stats[N_PHASES * 4], 1ULL);
+#endif
                 __nanosleep(SKM_IDLE_NS);
                 phase = -1;
                 continue;
@@ -627,18 +668,51 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (p == phase) mm = m[p];
         }
         // ---- claim one waiting row of that phase ---------------------------------------------
+        // A lane serves its own column first.  A lane whose column has nothing waiting for this
+        // phase borrows a row from a column that has more than one (SKM_BORROW): the k-th empty
+        // lane takes from the k-th such column.  The borrowed item's shared memory sits in the
+        // lender's banks (a 2-way conflict for that pair of lanes), which costs less than an
+        // idle lane does: the phase body is issued once for the warp whatever its fill.
         bool mine = false;
-        int row = 0;
+        int row = 0, col = lane;
+        const unsigned rot = iter & 31u;
+        uint32_t rest = 0;  // what my column still has waiting once I have taken my row
         if (mm) {
-            const unsigned rot = iter & 31u;
             const uint32_t mr = __funnelshift_r(mm, mm, rot);
             row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
-            const uint32_t old = atomicAnd(&sm_masks[phase * 32 + lane], ~(1u << row));
+            rest = mm & ~(1u << row);
+        }
+#if SKM_BORROW
+        {
+            const unsigned takers = __ballot_sync(0xffffffffu, mm == 0);
+            const unsigned lenders = __ballot_sync(0xffffffffu, rest != 0);
+            if (takers && lenders) {
+                int src = lane;
+                const int k = __popc(takers & ((1u << lane) - 1u));
+                const bool take = mm == 0 && k < __popc(lenders);
+                if (take) src = kth_set_bit(lenders, k);
+                const uint32_t theirs = __shfl_sync(0xffffffffu, rest, src);
+                if (take) {
+                    col = src;
+                    mm = theirs;
+                    const uint32_t mr = __funnelshift_r(theirs, theirs, rot);
+                    row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
+                }
+            }
+        }
+#endif
+        if (mm) {
+            const uint32_t old = atomicAnd(&sm_masks[phase * 32 + col], ~(1u << row));
             mine = (old >> row) & 1u;
         }
         iter += 1;
+#if SKM_STATS
+        const long long stat_t0 = clock64();
+        const unsigned stat_got = __ballot_sync(0xffffffffu, mine);
+        const unsigned stat_bor = __ballot_sync(0xffffffffu, mine && col != lane);
+#endif
         __threadfence_block();
-        const int item = row * 32 + lane;
+        const int item = row * 32 + col;
         ItemMem<ITEMS> I;
         I.state = sm_state + item;
         I.codes = sm_codes + item;
@@ -1017,12 +1091,19 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             } else {
                 lane_store(L, I);
                 __threadfence_block();
-                atomicOr(&sm_masks[L.st * 32 + lane], 1u << row);
+                atomicOr(&sm_masks[L.st * 32 + col], 1u << row);
             }
         }
         __syncwarp();
+#if SKM_STATS
+        if (lane == 0) {
+            atomicAdd(&g_map_stats[phase * 4 + 0], 1ULL);
+            atomicAdd(&g_map_stats[phase * 4 + 1], (unsigned long long)__popc(stat_got));
+            atomicAdd(&g_map_stats[phase * 4 + 2], (unsigned long long)__popc(stat_bor));
+            atomicAdd(&g_map_stats[phase * 4 + 3], (unsigned long long)(clock64() - stat_t0));
+        }
+#endif
     }
-
 }
 
 // Pass 3: tally.  One thread per unit reads what the mapper left (coalesced, field-major),

@@ -942,6 +942,16 @@ SKM_API int skm_mapper_kernel_ms(skm_mapper *m, double ms[3])
     return SKM_OK;
 }
 
+SKM_API int skm_debug_map_stats(uint64_t stats[32], int reset)
+{
+    if (stats) SKM_CUDA(cudaMemcpyFromSymbol(stats, g_map_stats, sizeof(uint64_t) * 32));
+    if (reset) {
+        const uint64_t zero[32] = {};
+        SKM_CUDA(cudaMemcpyToSymbol(g_map_stats, zero, sizeof(zero)));
+    }
+    return SKM_STATS ? SKM_OK : fail(SKM_ERR_INVALID, "skm_debug_map_stats: the library was built without -DSKM_STATS=1");
+}
+
 SKM_API int skm_classes_size(skm_mapper *m, int64_t sizes[8], void *stream)
 {
     if (!m || !sizes) return fail(SKM_ERR_INVALID, "skm_classes_size: NULL argument");

@@ -77,6 +77,23 @@ def main():
                 k['wall_ms'] = wall
                 times.append(k)
             best = min(times, key=lambda k: k['map_reads_kernel'])
+            # a diagnostics build (-DSKM_STATS=1): one more pass, counted
+            st = numpy.zeros(32, dtype='u8')
+            L = _lib.load()
+            if L.skm_debug_map_stats(None, 1) == 0:
+                mp.reset()
+                mp.map_batch(d_bases, None, a.pairs, True, fixed_len=bench.READ_LEN)
+                torch.cuda.synchronize()
+                L.skm_debug_map_stats(st.ctypes.data, 1)
+                names = ['load', 'scan', 'lookup', 'contig', 'walk', 'tally']
+                row['stats'] = {n: {'iters': int(st[4 * i]), 'fill': round(float(st[4 * i + 1]) / max(1, int(st[4 * i])), 2),
+                                    'borrowed': round(float(st[4 * i + 2]) / max(1, int(st[4 * i])), 2),
+                                    'cycles_per_iter': round(float(st[4 * i + 3]) / max(1, int(st[4 * i])), 1),
+                                    'steps_per_read': round(float(st[4 * i + 1]) / (2 * a.pairs), 3)}
+                                for i, n in enumerate(names)}
+                row['stats']['idle_polls'] = int(st[24])
+                row['stats']['iters_per_read'] = round(float(st[0:24:4].sum()) / (2 * a.pairs), 4)
+                row['stats']['fill'] = round(float(st[1:24:4].sum()) / max(1.0, float(st[0:24:4].sum())), 2)
             dg = table_digest(mp.export())
             if digest0 is None:
                 digest0 = dg
