@@ -24,6 +24,16 @@ __device__ __forceinline__ ulonglong2 ld_hint_16(const void *p, uint64_t pol)
     asm("ld.global.nc.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
     return v;
 }
+// 32 bytes per lane in one instruction (LDG.E.256, sm_100), streaming: packed reads are read once
+struct Quad64 {
+    uint64_t a, b, c, d;
+};
+__device__ __forceinline__ Quad64 ld_cs_32(const void *p)
+{
+    Quad64 v;
+    asm("ld.global.cs.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ int2 ld_hint_8(const void *p, uint64_t pol)
 {
     int2 v;

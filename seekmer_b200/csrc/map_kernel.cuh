@@ -66,44 +66,18 @@ constexpr int SCAN_WIDTH = SKM_SCAN_WIDTH;  // read positions probed per P_SCAN 
 #define SKM_STICKY_LANES 16
 #endif
 constexpr int STICKY_LANES = SKM_STICKY_LANES;  // a phase repeats while this many lanes still have rows for it
-#ifndef SKM_BORROW
-#define SKM_BORROW 0
-#endif
-
-// how many lanes of the warp a phase can keep busy, given every lane's mask of waiting rows
+// how many lanes of the warp have a row waiting for a phase, given every lane's mask of waiting rows
 __device__ __forceinline__ unsigned lanes_served(uint32_t m)
 {
-    const unsigned own = (unsigned)__popc(__ballot_sync(0xffffffffu, m != 0));
-#if SKM_BORROW == 2
-    const unsigned spare = (unsigned)__popc(__ballot_sync(0xffffffffu, (m & (m - 1u)) != 0));  // columns with 2+ rows
-    return own + min(32u - own, spare);
-#else
-    return own;
-#endif
+    return (unsigned)__popc(__ballot_sync(0xffffffffu, m != 0));
 }
 
 #ifndef SKM_STATS
 #define SKM_STATS 0
 #endif
 // Diagnostics build (-DSKM_STATS=1, tools/build_variants.py): per phase [iterations, items claimed,
-// of them borrowed, clock cycles of the iterations], then the idle polls; skm_debug_map_stats.
+// unused, clock cycles of the iterations], then the idle polls; skm_debug_map_stats.
 __device__ unsigned long long g_map_stats[32];
-
-// position of the k-th (0-based) set bit of m; popc(m) > k
-__device__ __forceinline__ int kth_set_bit(uint32_t m, int k)
-{
-    int pos = 0;
-#pragma unroll
-    for (int w = 16; w; w >>= 1) {
-        const int c = __popc(m & ((1u << w) - 1u));
-        if (k >= c) {
-            k -= c;
-            m >>= w;
-            pos += w;
-        }
-    }
-    return pos;
-}
 
 // What the mapper leaves behind for one unit, field-major so that tally_units_kernel reads it
 // coalesced: units[0][u] = number of targets, units[1][u] = span length of _mapper.pyx:90,
@@ -119,7 +93,7 @@ struct MapArgs {
     int32_t fixed_len;
     int32_t code_words;       // u64 words of 2-bit codes per read (from max read length)
     int32_t wild_words;       // u64 words of wildcard bits per read
-    int32_t words;            // code_words + wild_words, rounded up to even (16-byte records)
+    int32_t words;            // code_words + wild_words, rounded up to a multiple of four (32-byte records)
     int32_t paired;
     int64_t n_units;
     int64_t first_unit;
@@ -668,51 +642,22 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (p == phase) mm = m[p];
         }
         // ---- claim one waiting row of that phase ---------------------------------------------
-        // A lane serves its own column first.  A lane whose column has nothing waiting for this
-        // phase borrows a row from a column that has more than one (SKM_BORROW): the k-th empty
-        // lane takes from the k-th such column.  The borrowed item's shared memory sits in the
-        // lender's banks (a 2-way conflict for that pair of lanes), which costs less than an
-        // idle lane does: the phase body is issued once for the warp whatever its fill.
         bool mine = false;
-        int row = 0, col = lane;
-        const unsigned rot = iter & 31u;
-        uint32_t rest = 0;  // what my column still has waiting once I have taken my row
+        int row = 0;
         if (mm) {
+            const unsigned rot = iter & 31u;
             const uint32_t mr = __funnelshift_r(mm, mm, rot);
             row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
-            rest = mm & ~(1u << row);
-        }
-#if SKM_BORROW
-        {
-            const unsigned takers = __ballot_sync(0xffffffffu, mm == 0);
-            const unsigned lenders = __ballot_sync(0xffffffffu, rest != 0);
-            if (takers && lenders) {
-                int src = lane;
-                const int k = __popc(takers & ((1u << lane) - 1u));
-                const bool take = mm == 0 && k < __popc(lenders);
-                if (take) src = kth_set_bit(lenders, k);
-                const uint32_t theirs = __shfl_sync(0xffffffffu, rest, src);
-                if (take) {
-                    col = src;
-                    mm = theirs;
-                    const uint32_t mr = __funnelshift_r(theirs, theirs, rot);
-                    row = (int)((unsigned)(__ffs((int)mr) - 1) + rot) & 31;
-                }
-            }
-        }
-#endif
-        if (mm) {
-            const uint32_t old = atomicAnd(&sm_masks[phase * 32 + col], ~(1u << row));
+            const uint32_t old = atomicAnd(&sm_masks[phase * 32 + lane], ~(1u << row));
             mine = (old >> row) & 1u;
         }
         iter += 1;
 #if SKM_STATS
         const long long stat_t0 = clock64();
         const unsigned stat_got = __ballot_sync(0xffffffffu, mine);
-        const unsigned stat_bor = __ballot_sync(0xffffffffu, mine && col != lane);
 #endif
         __threadfence_block();
-        const int item = row * 32 + col;
+        const int item = row * 32 + lane;
         ItemMem<ITEMS> I;
         I.state = sm_state + item;
         I.codes = sm_codes + item;
@@ -756,14 +701,18 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
             if (mine && L.st == P_LOAD) {
                 const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
-                const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(a.packed + read_idx * (long long)a.words);
+                const uint64_t *src = a.packed + read_idx * (long long)a.words;
                 uint64_t any_wild = 0;
-                for (int k = 0; k < a.words; k += 2) {  // 16-byte records: words is even
-                    const ulonglong2 v = __ldg(src + (k >> 1));
-                    if (k < a.code_words) I.codes[k * ITEMS] = v.x;
-                    else any_wild |= v.x;  // wildcard words; the padding word is zero
-                    if (k + 1 < a.code_words) I.codes[(k + 1) * ITEMS] = v.y;
-                    else any_wild |= v.y;
+                for (int k = 0; k < a.words; k += 4) {  // 32-byte records: words is a multiple of four
+                    const Quad64 v = ld_cs_32(src + k);  // one LDG.E.256 per four words, read once
+                    if (k < a.code_words) I.codes[k * ITEMS] = v.a;
+                    else any_wild |= v.a;  // wildcard words; the padding words are zero
+                    if (k + 1 < a.code_words) I.codes[(k + 1) * ITEMS] = v.b;
+                    else any_wild |= v.b;
+                    if (k + 2 < a.code_words) I.codes[(k + 2) * ITEMS] = v.c;
+                    else any_wild |= v.c;
+                    if (k + 3 < a.code_words) I.codes[(k + 3) * ITEMS] = v.d;
+                    else any_wild |= v.d;
                 }
                 int len = a.lens ? __ldg(a.lens + read_idx) : a.fixed_len;
                 const int max_len = a.code_words * 32;
@@ -810,29 +759,21 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
         } else if (phase == P_SCAN) {
             if (mine) {
-                // positions pos .. pos+2 (while they fit); L.kmer is the k-mer at pos-1
-                uint64_t km[SCAN_WIDTH];
-                Probe pr[SCAN_WIDTH];
-                uint64_t k = L.kmer;
+                // positions pos .. pos+2 (while they fit), one after the other, first hit wins;
+                // L.kmer is the k-mer at pos-1.  (One copy of the hash + probe code instead of three:
+                // the kernel text sits at the edge of what the instruction caches hold)
+                uint64_t kk = L.kmer;
                 const int fit = L.len - K + 1 - L.pos;  // >= 1
-#pragma unroll
-                for (int j = 0; j < SCAN_WIDTH; ++j) {
-                    if (j < fit) k = ((k << 2) | rv.code(L.pos + j + K - 1)) & KMER_MASK;
-                    km[j] = k;
-                    pr[j] = prepare_probe(k, ix.bucket_mask);
-                }
                 int first = SCAN_WIDTH;
                 Coord hh = coord_invalid();
-                uint64_t kk = k;
-#pragma unroll
-                for (int j = SCAN_WIDTH - 1; j >= 0; --j) {
-                    if (j < fit) {
-                        const Coord h = run_probe(ix, pr[j]);
-                        if (h.offset >= 0) {
-                            first = j;
-                            hh = h;
-                            kk = km[j];
-                        }
+#pragma unroll 1
+                for (int j = 0; j < SCAN_WIDTH && j < fit; ++j) {
+                    kk = ((kk << 2) | rv.code(L.pos + j + K - 1)) & KMER_MASK;
+                    const Coord h = run_probe(ix, prepare_probe(kk, ix.bucket_mask));
+                    if (h.offset >= 0) {
+                        first = j;
+                        hh = h;
+                        break;
                     }
                 }
                 L.sp.anchor = hh;
@@ -1091,7 +1032,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             } else {
                 lane_store(L, I);
                 __threadfence_block();
-                atomicOr(&sm_masks[L.st * 32 + col], 1u << row);
+                atomicOr(&sm_masks[L.st * 32 + lane], 1u << row);
             }
         }
         __syncwarp();
@@ -1099,7 +1040,6 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         if (lane == 0) {
             atomicAdd(&g_map_stats[phase * 4 + 0], 1ULL);
             atomicAdd(&g_map_stats[phase * 4 + 1], (unsigned long long)__popc(stat_got));
-            atomicAdd(&g_map_stats[phase * 4 + 2], (unsigned long long)__popc(stat_bor));
             atomicAdd(&g_map_stats[phase * 4 + 3], (unsigned long long)(clock64() - stat_t0));
         }
 #endif

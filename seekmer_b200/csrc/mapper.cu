@@ -44,7 +44,7 @@ __device__ __forceinline__ void convert4(uint32_t x, uint32_t &codes8, uint32_t 
 }
 
 // One thread per 32 bases = one 64-bit code word and half a wildcard word of the packed record
-// [code_words | wild_words | pad to even].  Consecutive threads convert consecutive 32-byte
+// [code_words | wild_words | pad to a multiple of four words].  Consecutive threads convert consecutive 32-byte
 // pieces of the input, so loads and stores are coalesced whatever the read length; the piece is
 // fetched with three aligned 16-byte loads and shifted into place.
 __global__ void __launch_bounds__(256)
@@ -69,7 +69,7 @@ pack_reads_kernel(const uint8_t *__restrict__ bases, const int64_t *__restrict__
     uint64_t *out = packed + read * (int64_t)words;
     if (w == 0) {
         if (lens) lens[read] = len;
-        if (code_words + wild_words < words) out[words - 1] = 0;  // padding word
+        for (int k = code_words + wild_words; k < words; ++k) out[k] = 0;  // padding words
     }
     const int max_len = code_words * 32;
     if (len > max_len) len = max_len;  // the host sizes code_words from the longest read
@@ -736,7 +736,7 @@ SKM_API int skm_map_batch(skm_mapper *m, const uint8_t *bases, const int64_t *re
     a.fixed_len = read_offsets ? 0 : fixed_read_len;
     a.code_words = (max_read_len + 31) / 32;
     a.wild_words = (max_read_len + 63) / 64;
-    a.words = (a.code_words + a.wild_words + 1) & ~1;  // 16-byte records
+    a.words = (a.code_words + a.wild_words + 3) & ~3;  // 32-byte records: one LDG.E.256 per four words
     a.paired = paired ? 1 : 0;
     a.arena = m->arena;
     a.arena_cap = m->arena_cap;
@@ -885,7 +885,7 @@ SKM_API int skm_map_fastq(skm_mapper *m, const uint8_t *text1, int64_t n1, const
     a.fixed_len = 0;
     a.code_words = (longest + 31) / 32;
     a.wild_words = (longest + 63) / 64;
-    a.words = (a.code_words + a.wild_words + 1) & ~1;
+    a.words = (a.code_words + a.wild_words + 3) & ~3;
     a.paired = paired;
     a.arena = m->arena;
     a.arena_cap = m->arena_cap;

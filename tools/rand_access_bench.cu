@@ -39,19 +39,22 @@ __global__ void chase(const ulonglong2 *table, uint64_t mask, int chain, int dep
 
 int main(int argc, char **argv)
 {
-    const size_t bytes = (argc > 1 ? atoll(argv[1]) : 4096LL) << 20;
+    // usage: rand_access_bench [max MB]: 64-byte random reads over tables of 64 MB .. max MB
+    const size_t max_bytes = (argc > 1 ? atoll(argv[1]) : 16384LL) << 20;
     void *table;
-    cudaMalloc(&table, bytes);
-    cudaMemset(table, 1, bytes);
+    if (cudaMalloc(&table, max_bytes) != cudaSuccess) { printf("cudaMalloc failed\n"); return 1; }
+    cudaMemset(table, 1, max_bytes);
     unsigned long long *out;
     cudaMalloc(&out, 8);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const long long n = 1LL << 26;
-    for (int size = 32; size <= 128; size *= 2)
-        for (int dep = 0; dep <= 1; ++dep)
-            for (int threads_per_sm = 512; threads_per_sm <= 2048; threads_per_sm *= 2) {
+    for (size_t bytes = 64ULL << 20; bytes <= max_bytes; bytes *= 2)
+        for (int size = 32; size <= 128; size *= 2)
+            for (int dep = 0; dep <= 1; ++dep) {
+                if (size != 64 && dep) continue;
+                const int threads_per_sm = 1024;
                 const int block = 256, grid = 148 * threads_per_sm / block;
                 const uint64_t mask = bytes / size - 1;
                 float best = 1e9f;
@@ -66,9 +69,9 @@ int main(int argc, char **argv)
                     cudaEventElapsedTime(&ms, e0, e1);
                     best = ms < best ? ms : best;
                 }
-                printf("{\"bytes_per_access\": %d, \"dependent\": %d, \"threads_per_sm\": %d, \"ms\": %.3f, "
+                printf("{\"table_mb\": %zu, \"bytes_per_access\": %d, \"dependent\": %d, \"threads_per_sm\": %d, \"ms\": %.3f, "
                        "\"G_access_per_s\": %.2f, \"GB_per_s\": %.1f}\n",
-                       size, dep, threads_per_sm, best, n / best / 1e6, (double)n * size / best / 1e6);
+                       bytes >> 20, size, dep, threads_per_sm, best, n / best / 1e6, (double)n * size / best / 1e6);
             }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

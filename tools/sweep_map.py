@@ -87,7 +87,6 @@ def main():
                 L.skm_debug_map_stats(st.ctypes.data, 1)
                 names = ['load', 'scan', 'lookup', 'contig', 'walk', 'tally']
                 row['stats'] = {n: {'iters': int(st[4 * i]), 'fill': round(float(st[4 * i + 1]) / max(1, int(st[4 * i])), 2),
-                                    'borrowed': round(float(st[4 * i + 2]) / max(1, int(st[4 * i])), 2),
                                     'cycles_per_iter': round(float(st[4 * i + 3]) / max(1, int(st[4 * i])), 1),
                                     'steps_per_read': round(float(st[4 * i + 1]) / (2 * a.pairs), 3)}
                                 for i, n in enumerate(names)}
