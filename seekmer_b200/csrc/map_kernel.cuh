@@ -188,9 +188,30 @@ struct Span {
 
 template <int ITEMS>
 struct Lane {
-    int st, ctx, dir, mate, attempt;
-    bool forward, ctg_a0, has_wild, m1_dirty;
-    bool void_unit;  // one of the unit's reads is shorter than k: reported unaligned, span length 0
+    int st;
+    // The item's flag word (F_* bits) stays packed in one register; the accessors below test and
+    // set single bits, so nothing is unpacked on load or re-packed on store.
+    uint32_t flags;
+    bool m1_dirty;
+    __device__ __forceinline__ int ctx() const { return (int)(flags & F_CTX); }
+    __device__ __forceinline__ void set_ctx(int c) { flags = (flags & ~F_CTX) | (uint32_t)c; }
+    __device__ __forceinline__ bool bit(uint32_t f) const { return (flags & f) != 0; }
+    __device__ __forceinline__ void set_bit(uint32_t f, bool on) { flags = on ? flags | f : flags & ~f; }
+    __device__ __forceinline__ int dir() const { return bit(F_DIR) ? 1 : 0; }
+    __device__ __forceinline__ void set_dir(int d) { set_bit(F_DIR, d != 0); }
+    __device__ __forceinline__ int mate() const { return bit(F_MATE) ? 1 : 0; }
+    __device__ __forceinline__ void set_mate(int m) { set_bit(F_MATE, m != 0); }
+    __device__ __forceinline__ int attempt() const { return bit(F_ATTEMPT) ? 1 : 0; }
+    __device__ __forceinline__ void set_attempt(int v) { set_bit(F_ATTEMPT, v != 0); }
+    __device__ __forceinline__ bool forward() const { return bit(F_FORWARD); }
+    __device__ __forceinline__ void set_forward(bool b) { set_bit(F_FORWARD, b); }
+    __device__ __forceinline__ bool ctg_a0() const { return bit(F_CTG_A0); }
+    __device__ __forceinline__ void set_ctg_a0(bool b) { set_bit(F_CTG_A0, b); }
+    __device__ __forceinline__ bool has_wild() const { return bit(F_WILD); }
+    __device__ __forceinline__ void set_has_wild(bool b) { set_bit(F_WILD, b); }
+    // one of the unit's reads is shorter than k: reported unaligned, span length 0
+    __device__ __forceinline__ bool void_unit() const { return bit(F_VOID); }
+    __device__ __forceinline__ void set_void_unit(bool b) { set_bit(F_VOID, b); }
     long long unit;
     int pos, move, len, clen;
     uint64_t kmer;
@@ -224,24 +245,17 @@ __device__ __forceinline__ void lane_load(Lane<ITEMS> &L, const ItemMem<ITEMS> &
     const uint4 v0 = I.state[0], v1 = I.state[ITEMS], v2 = I.state[2 * ITEMS], v3 = I.state[3 * ITEMS];
     L.unit = (long long)v0.x;
     const uint32_t f = v0.y;
-    L.ctx = (int)(f & F_CTX);
-    L.dir = (f & F_DIR) ? 1 : 0;
-    L.mate = (f & F_MATE) ? 1 : 0;
-    L.attempt = (f & F_ATTEMPT) ? 1 : 0;
-    L.forward = (f & F_FORWARD) != 0;
-    L.ctg_a0 = (f & F_CTG_A0) != 0;
-    L.has_wild = (f & F_WILD) != 0;
-    L.void_unit = (f & F_VOID) != 0;
+    L.flags = f;
     L.m1_dirty = false;
     L.pos = (int)(v0.z & 0xFFFFu);
     L.len = (int)(v0.z >> 16);
     L.move = (int)v0.w;
     L.kmer = (uint64_t)v1.x | ((uint64_t)v1.y << 32);
-    L.sp.begin = sx16(v1.w);
-    L.sp.end = sx16(v1.w >> 16);
+    L.sp.begin = (int)v1.z;
+    L.sp.end = (int)v1.w;
     L.anchor0 = Coord{(int32_t)v2.x, (int32_t)v2.y};
     L.sp.anchor = Coord{(int32_t)v2.z, (int32_t)v2.w};
-    L.l = I.fresh_list(L.mate);
+    L.l = I.fresh_list(L.mate());
     L.l.n = (int)(v3.x & 0xFFFFu);
     if (f & F_L_ARENA) L.l = List<ITEMS>{I.arena + v3.z, 1, L.l.n};
     L.m1 = I.fresh_list(0);
@@ -261,15 +275,13 @@ __device__ __forceinline__ void lane_store(const Lane<ITEMS> &L, const ItemMem<I
 {
     uint4 v0, v1, v2, v3;
     v0.x = (uint32_t)L.unit;
-    v0.y = (uint32_t)L.ctx | (L.dir ? F_DIR : 0u) | (L.mate ? F_MATE : 0u) | (L.attempt ? F_ATTEMPT : 0u)
-           | (L.forward ? F_FORWARD : 0u) | (L.l.in_arena() ? F_L_ARENA : 0u) | (L.m1.in_arena() ? F_M1_ARENA : 0u)
-           | (L.ctg_a0 ? F_CTG_A0 : 0u) | (L.has_wild ? F_WILD : 0u) | (L.void_unit ? F_VOID : 0u);
+    v0.y = (L.flags & ~(F_L_ARENA | F_M1_ARENA)) | (L.l.in_arena() ? F_L_ARENA : 0u) | (L.m1.in_arena() ? F_M1_ARENA : 0u);
     v0.z = ((uint32_t)L.pos & 0xFFFFu) | ((uint32_t)L.len << 16);
     v0.w = (uint32_t)L.move;
     v1.x = (uint32_t)L.kmer;
     v1.y = (uint32_t)(L.kmer >> 32);
-    v1.z = 0;
-    v1.w = ((uint32_t)L.sp.begin & 0xFFFFu) | ((uint32_t)L.sp.end << 16);
+    v1.z = (uint32_t)L.sp.begin;
+    v1.w = (uint32_t)L.sp.end;
     v2.x = (uint32_t)L.anchor0.entry;
     v2.y = (uint32_t)L.anchor0.offset;
     v2.z = (uint32_t)L.sp.anchor.entry;
@@ -666,19 +678,17 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         I.arena = a.arena;
         Lane<ITEMS> L;
         L.st = phase;
-        L.mate = 0;
+        L.flags = 0;
         L.unit = 0;
         L.len = 0;
-        L.has_wild = false;
-        L.void_unit = false;
         if (mine) lane_load(L, I, phase == P_TALLY);
         ReadView<ITEMS> rv;
         rv.w = I.codes;
         rv.len = L.len;
         rv.wild_words = a.wild_words;
         rv.wild = nullptr;
-        if (L.has_wild) {
-            const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
+        if (L.has_wild()) {
+            const long long read_idx = a.paired ? 2 * L.unit + L.mate() : L.unit;
             rv.wild = a.packed + read_idx * (long long)a.words + a.code_words;
         }
         int ev = EV_NONE;
@@ -688,7 +698,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
 
         if (phase == P_LOAD) {
             // ---- new units for finished items (mate 0): one global atomic per warp -------------
-            const bool need = mine && L.mate == 0;
+            const bool need = mine && L.mate() == 0;
             const unsigned nb = __ballot_sync(0xffffffffu, need);
             if (nb) {
                 long long base = 0;
@@ -700,7 +710,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 }
             }
             if (mine && L.st == P_LOAD) {
-                const long long read_idx = a.paired ? 2 * L.unit + L.mate : L.unit;
+                const long long read_idx = a.paired ? 2 * L.unit + L.mate() : L.unit;
                 const uint64_t *src = a.packed + read_idx * (long long)a.words;
                 uint64_t any_wild = 0;
                 for (int k = 0; k < a.words; k += 4) {  // 32-byte records: words is a multiple of four
@@ -719,13 +729,13 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 if (len > max_len) len = max_len;
                 L.len = len;
                 rv.len = len;
-                L.has_wild = any_wild != 0;
+                L.set_has_wild(any_wild != 0);
                 L.sp = Span{0, 0, coord_invalid()};
-                L.l = I.fresh_list(L.mate);
-                L.attempt = 0;
+                L.l = I.fresh_list(L.mate());
+                L.set_attempt(0);
                 L.pos = 0;
-                L.ctg_a0 = false;
-                L.ctx = C_FIND;
+                L.set_ctg_a0(false);
+                L.set_ctx(C_FIND);
                 if (len >= K) {
                     want_pos = 0;
                 } else {
@@ -733,7 +743,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     // end).  Here its unit is reported unaligned with span length 0, whatever the mate does.
                     atomicOr(status, ST_SHORT_READ);
                     atomicAdd(a.short_units, 1ULL);
-                    L.void_unit = true;
+                    L.set_void_unit(true);
                     L.l.n = 0;
                     L.st = P_TALLY;
                 }
@@ -744,13 +754,13 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 L.sp.anchor = h;
                 if (h.offset >= 0) {
                     L.st = P_CONTIG;
-                } else if (L.ctx == C_FIND) {
+                } else if (L.ctx() == C_FIND) {
                     // _find_first_kmer keeps rolling (:208-212); an exhausted scan leaves the
                     // targets empty and map_read returns (:170-171, :186-187)
                     L.pos += 1;
                     if (L.pos + K <= L.len) L.st = P_SCAN;
                     else ev = EV_READ_DONE;
-                } else if (L.ctx == C_RIGHT_J) {
+                } else if (L.ctx() == C_RIGHT_J) {
                     L.l.n = 0;  // :312-315
                     ev = EV_AFTER_ATTEMPT;
                 } else {
@@ -789,43 +799,43 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
         } else if (phase == P_CONTIG) {
             if (mine) {
-                const Coord at = L.ctx == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
+                const Coord at = L.ctx() == C_RIGHT_C ? L.anchor0 : L.sp.anchor;
                 const Contig c = load_contig(ix, at.entry >= 0 ? at.entry : ~at.entry);
                 I.ctg[0] = c.first_kmer;
                 I.ctg[ITEMS] = c.last_kmer;
                 I.ctg[2 * ITEMS] = (uint64_t)c.seq_offset;
                 L.clen = c.length;
-                L.forward = at.entry >= 0;
-                const int to_start = L.forward ? at.offset : c.length - at.offset - K;
-                const int to_end = L.forward ? c.length - at.offset - K : at.offset;
-                if (L.ctx == C_FIND) {
+                L.set_forward(at.entry >= 0);
+                const int to_start = L.forward() ? at.offset : c.length - at.offset - K;
+                const int to_end = L.forward() ? c.length - at.offset - K : at.offset;
+                if (L.ctx() == C_FIND) {
                     map_contig(ix, a, status, c, at, L.l);
                     L.sp.begin = L.pos;
                     L.sp.end = L.pos;
                     L.anchor0 = at;
-                    L.ctg_a0 = true;
+                    L.set_ctg_a0(true);
                     if (L.l.n == 0) {
                         ev = EV_READ_DONE;  // `if is_empty(targets): return span`
                     } else if (L.sp.begin > 0) {
                         L.move = to_start;
-                        L.dir = 0;
+                        L.set_dir(0);
                         L.st = P_WALK;
                     } else {
                         ev = EV_AFTER_LEFT;
                     }
                 } else {
                     bool ok = true;
-                    if (L.ctx != C_RIGHT_C) {
+                    if (L.ctx() != C_RIGHT_C) {
                         ok = filter_on_contig(ix, c, at, L.l);
-                        L.ctg_a0 = false;
+                        L.set_ctg_a0(false);
                     } else {
                         L.sp.anchor = at;  // :283-284 — same k-mer as the scan hit, lookup cached
-                        L.ctg_a0 = true;
+                        L.set_ctg_a0(true);
                     }
-                    if (L.ctx == C_RIGHT_C || L.ctx == C_RIGHT_J) {
+                    if (L.ctx() == C_RIGHT_C || L.ctx() == C_RIGHT_J) {
                         if (ok) {
                             L.move = to_end;
-                            L.dir = 1;
+                            L.set_dir(1);
                             L.st = P_WALK;
                         } else {
                             L.l.n = 0;  // :312-315
@@ -833,7 +843,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                         }
                     } else if (ok) {
                         L.move = to_start;
-                        L.dir = 0;
+                        L.set_dir(0);
                         L.st = P_WALK;
                     } else {
                         ev = EV_LEFT_FAILED;
@@ -844,11 +854,11 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             if (mine) {
                 // heads of the loops of _filter_targets_to_left (:234-275) and _to_right (:293-343)
                 const uint64_t first_kmer = I.ctg[0], last_kmer = I.ctg[ITEMS];
-                const int dir = L.dir;
+                const int dir = L.dir();
                 int rem = dir ? L.len - L.sp.end - K : L.sp.begin;  // bases left towards the read end
                 const bool in_loop = rem > L.move;
                 const int step = in_loop ? L.move : rem;
-                const int delta = L.forward ? step : -step;
+                const int delta = L.forward() ? step : -step;
                 L.sp.anchor.offset += dir ? delta : -delta;
                 uint32_t ref16;
                 int qoff;
@@ -882,7 +892,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                         // the junction k-mer is the contig's edge k-mer shifted by one read base
                         // (:247-249, :309-311); where it lives is a link of the contig record
                         const uint32_t base = rv.code(dir ? L.sp.end + K - 1 : L.sp.begin);
-                        L.ctx = dir ? C_RIGHT_J : C_LEFT_J;
+                        L.set_ctx(dir ? C_RIGHT_J : C_LEFT_J);
                         const Coord next = contig_link(ix, L.sp.anchor, dir, base);
                         if (next.offset >= 0) {
                             L.sp.anchor = next;
@@ -903,7 +913,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         } else {  // P_TALLY: the unit is mapped; leave its record for tally_units_kernel
             if (mine) {
                 int length;
-                if (L.void_unit) {
+                if (L.void_unit()) {
                     length = 0;
                     L.l.n = 0;
                 } else if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
@@ -940,8 +950,8 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     rec[a.n_units] = (int32_t)(off >> 32);
                 }
                 // the item is free again: mate 0 of a new unit
-                L.void_unit = false;
-                L.mate = 0;
+                L.set_void_unit(false);
+                L.set_mate(0);
                 L.l = I.fresh_list(0);
                 L.m1 = I.fresh_list(0);
                 L.st = P_LOAD;
@@ -951,13 +961,13 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
         // ---- transitions (one copy, all phases) ------------------------------------------------
         if (mine) {
             if (ev == EV_LEFT_FAILED) {
-                if (L.ctx == C_LEFT_J) {
+                if (L.ctx() == C_LEFT_J) {
                     if (L.sp.begin < K) {
                         L.sp.begin = 0;
                         ev = EV_AFTER_LEFT;
                     } else {
                         L.sp.begin -= K;
-                        L.ctx = C_LEFT_F;
+                        L.set_ctx(C_LEFT_F);
                         want_pos = L.sp.begin;
                         ev = EV_NONE;
                     }
@@ -968,17 +978,17 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
             }
             if (ev == EV_AFTER_LEFT) {
                 if (L.l.n != 0 && L.sp.end < L.len - K) {
-                    if (L.ctg_a0) {
+                    if (L.ctg_a0()) {
                         // the stash still holds the contig of the first hit (no junction was
                         // crossed): _filter_targets_to_right starts there (:283-295) without
                         // another record load
                         L.sp.anchor = L.anchor0;
-                        L.forward = L.anchor0.entry >= 0;
-                        L.move = L.forward ? L.clen - L.anchor0.offset - K : L.anchor0.offset;
-                        L.dir = 1;
+                        L.set_forward(L.anchor0.entry >= 0);
+                        L.move = L.forward() ? L.clen - L.anchor0.offset - K : L.anchor0.offset;
+                        L.set_dir(1);
                         L.st = P_WALK;
                     } else {
-                        L.ctx = C_RIGHT_C;
+                        L.set_ctx(C_RIGHT_C);
                         L.st = P_CONTIG;
                     }
                     ev = EV_NONE;
@@ -987,29 +997,29 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 }
             }
             if (ev == EV_AFTER_ATTEMPT) {
-                if (L.l.n != 0 || L.attempt == 1) {
+                if (L.l.n != 0 || L.attempt() == 1) {
                     ev = EV_READ_DONE;
                 } else {
-                    L.attempt = 1;
+                    L.set_attempt(1);
                     L.sp.anchor = coord_invalid();
                     L.sp.begin += K;
                     if (L.sp.begin + K > L.len) L.sp.begin = L.len - K;
                     L.sp.end = L.sp.begin;
                     L.pos = L.sp.begin;
-                    L.l = I.fresh_list(L.mate);
-                    L.ctx = C_FIND;
+                    L.l = I.fresh_list(L.mate());
+                    L.set_ctx(C_FIND);
                     want_pos = L.pos;
                     ev = EV_NONE;
                 }
             }
             if (ev == EV_READ_DONE) {
-                if (a.paired && L.mate == 0) {
+                if (a.paired && L.mate() == 0) {
                     L.m1_begin = L.sp.begin;
                     L.m1_anchor = L.sp.anchor;
                     L.m1_len = L.len;
                     L.m1 = L.l;
                     L.m1_dirty = true;
-                    L.mate = 1;
+                    L.set_mate(1);
                     L.st = P_LOAD;
                 } else {
                     L.st = P_TALLY;
