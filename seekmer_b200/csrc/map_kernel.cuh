@@ -363,9 +363,12 @@ __device__ __forceinline__ void load_targets_hi(const DevIndex &ix, const Contig
 
 // map_contig (_common.pyx:143-179) for an already loaded contig record.  Forward: the
 // contig's targets in order; reverse: reversed order, every entry bit-negated.
+// `sp` is the list's home in shared memory (&lists[0][item] of the mate): the short path writes
+// through it, so that the stores are plain STS with immediate offsets (l.p may also point into the
+// arena, which makes every access through it a generic one).
 template <int ITEMS>
 __device__ __forceinline__ void map_contig(const DevIndex &ix, const MapArgs &a, uint32_t *status, const Contig &c,
-                                           Coord at, List<ITEMS> &l)
+                                           Coord at, List<ITEMS> &l, int32_t *sp)
 {
     const bool forward = at.entry >= 0;
     const int n = c.target_count;
@@ -375,13 +378,13 @@ __device__ __forceinline__ void map_contig(const DevIndex &ix, const MapArgs &a,
         // straight-line: the first 8 entries came with the record, 8 more are fetched if needed
 #pragma unroll
         for (int j = 0; j < INLINE_TARGETS; ++j)
-            if (j < n) l.set(forward ? j : n - 1 - j, c.t[j] ^ x);
+            if (j < n) sp[(forward ? j : n - 1 - j) * ITEMS] = c.t[j] ^ x;
         if (n > INLINE_TARGETS) {
             int32_t t[INLINE_TARGETS];
             load_targets_hi(ix, c, t);
 #pragma unroll
             for (int j = 0; j < INLINE_TARGETS; ++j)
-                if (INLINE_TARGETS + j < n) l.set(forward ? INLINE_TARGETS + j : n - 1 - INLINE_TARGETS - j, t[j] ^ x);
+                if (INLINE_TARGETS + j < n) sp[(forward ? INLINE_TARGETS + j : n - 1 - INLINE_TARGETS - j) * ITEMS] = t[j] ^ x;
         }
         return;
     }
@@ -425,7 +428,8 @@ __device__ __noinline__ int filter_long(const int32_t *t, int length, int forwar
 // span's list with the contig's list; equal entries pair off one to one; zero matches leave
 // the list intact and return false.
 template <int ITEMS>
-__device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Contig &c, Coord at, List<ITEMS> &l)
+__device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Contig &c, Coord at, List<ITEMS> &l,
+                                                 int32_t *sp)
 {
     if (l.n == 0) return true;
     const bool forward = at.entry >= 0;
@@ -433,7 +437,7 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
     if (length == 0) return false;
     const int32_t x = forward ? 0 : -1;
     int w;
-    if (length <= 2 * INLINE_TARGETS) {
+    if (length <= 2 * INLINE_TARGETS && !l.in_arena()) {
         // Both lists are ascending (targets are sorted per contig, _index_builder.pyx:540, and
         // map_contig / this filter keep that order), so the merge keeps the r-th occurrence of a
         // value v in the span's list exactly when the contig's list holds more than r copies of
@@ -459,7 +463,7 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
         w = 0;
 #pragma unroll 1
         for (int i = 0; i < n; ++i) {
-            const int32_t v = l.get(i);
+            const int32_t v = sp[i * ITEMS];
             run = (i > 0 && v == prev) ? run + 1 : 0;
             prev = v;
             bool keep = false;
@@ -477,7 +481,7 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
                 keep = run < copies;
             }
             if (keep) {
-                l.set(w, v);
+                sp[w * ITEMS] = v;
                 w += 1;
             }
         }
@@ -489,19 +493,17 @@ __device__ __forceinline__ bool filter_on_contig(const DevIndex &ix, const Conti
     return true;
 }
 
-// mate intersection (_mapper.pyx:350-397): list 1 ascending vs list 2 descending, negated
-template <int ITEMS>
-__device__ __forceinline__ bool intersect(List<ITEMS> &l1, const List<ITEMS> &l2)
+// mate intersection (_mapper.pyx:350-397): list 1 ascending vs list 2 descending, negated.
+// Returns the new length of list 1 (0 = nothing in common, list left intact).
+__device__ __noinline__ int intersect_generic(int32_t *p1, int stride1, int n1, const int32_t *p2, int stride2, int n2)
 {
-    if (l1.n == 0) return true;
-    if (l2.n == 0) return false;
-    int cursor1_read = 0, cursor1_write = 0, cursor2 = l2.n - 1;
+    int cursor1_read = 0, cursor1_write = 0, cursor2 = n2 - 1;
 #pragma unroll 1
-    while (cursor1_read != l1.n && cursor2 != -1) {
-        const int32_t entry1 = l1.get(cursor1_read);
-        const int32_t entry2 = ~l2.get(cursor2);
+    while (cursor1_read != n1 && cursor2 != -1) {
+        const int32_t entry1 = p1[cursor1_read * stride1];
+        const int32_t entry2 = ~p2[cursor2 * stride2];
         if (entry1 == entry2) {
-            l1.set(cursor1_write, entry1);
+            p1[cursor1_write * stride1] = entry1;
             cursor1_read += 1;
             cursor1_write += 1;
             cursor2 -= 1;
@@ -509,6 +511,37 @@ __device__ __forceinline__ bool intersect(List<ITEMS> &l1, const List<ITEMS> &l2
             cursor1_read += 1;
         } else {
             cursor2 -= 1;
+        }
+    }
+    return cursor1_write;
+}
+
+// sp1 / sp2: the shared-memory homes of the two lists (mate 1: &lists[0][item], mate 2: LIST_CAP rows on)
+template <int ITEMS>
+__device__ __forceinline__ bool intersect(List<ITEMS> &l1, const List<ITEMS> &l2, int32_t *sp1, const int32_t *sp2)
+{
+    if (l1.n == 0) return true;
+    if (l2.n == 0) return false;
+    int cursor1_write;
+    if (l1.in_arena() || l2.in_arena()) {
+        cursor1_write = intersect_generic(l1.p, l1.stride, l1.n, l2.p, l2.stride, l2.n);
+    } else {
+        int cursor1_read = 0, cursor2 = l2.n - 1;
+        cursor1_write = 0;
+#pragma unroll 1
+        while (cursor1_read != l1.n && cursor2 != -1) {
+            const int32_t entry1 = sp1[cursor1_read * ITEMS];
+            const int32_t entry2 = ~sp2[cursor2 * ITEMS];
+            if (entry1 == entry2) {
+                sp1[cursor1_write * ITEMS] = entry1;
+                cursor1_read += 1;
+                cursor1_write += 1;
+                cursor2 -= 1;
+            } else if (entry1 < entry2) {
+                cursor1_read += 1;
+            } else {
+                cursor2 -= 1;
+            }
         }
     }
     if (cursor1_write == 0) return false;
@@ -809,7 +842,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 const int to_start = L.forward() ? at.offset : c.length - at.offset - K;
                 const int to_end = L.forward() ? c.length - at.offset - K : at.offset;
                 if (L.ctx() == C_FIND) {
-                    map_contig(ix, a, status, c, at, L.l);
+                    map_contig(ix, a, status, c, at, L.l, I.list0 + (L.mate() ? LIST_CAP * ITEMS : 0));
                     L.sp.begin = L.pos;
                     L.sp.end = L.pos;
                     L.anchor0 = at;
@@ -826,7 +859,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 } else {
                     bool ok = true;
                     if (L.ctx() != C_RIGHT_C) {
-                        ok = filter_on_contig(ix, c, at, L.l);
+                        ok = filter_on_contig(ix, c, at, L.l, I.list0 + (L.mate() ? LIST_CAP * ITEMS : 0));
                         L.set_ctg_a0(false);
                     } else {
                         L.sp.anchor = at;  // :283-284 — same k-mer as the scan hit, lookup cached
@@ -918,7 +951,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                     L.l.n = 0;
                 } else if (a.paired) {  // map_read_pair (:127-145): span1 = m1, span2 = (sp, l)
                     int begin1 = L.m1_begin, end1;
-                    if (!intersect(L.m1, L.l)) {
+                    if (!intersect(L.m1, L.l, I.list0, I.list0 + LIST_CAP * ITEMS)) {
                         L.m1.n = 0;
                         begin1 = 0;
                         end1 = -K;
@@ -941,7 +974,13 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 rec[0] = n;
                 rec[a.n_units] = length;
                 rec += 2 * a.n_units;
-                if (n <= REC_IDS) {
+                if (n <= REC_IDS && !L.l.in_arena()) {
+                    // the final list of a unit is that of mate 1 for a pair, of the read otherwise:
+                    // either way the first LIST_CAP rows of the item's lists
+                    const int32_t *sp = I.list0;
+#pragma unroll 1
+                    for (int i = 0; i < n; ++i) rec[i * a.n_units] = sp[i * ITEMS];
+                } else if (n <= REC_IDS) {
 #pragma unroll 1
                     for (int i = 0; i < n; ++i) rec[i * a.n_units] = L.l.get(i);
                 } else {
