@@ -58,6 +58,9 @@ constexpr int INVALID_SHIFT = SIFT4_INVALID_SHIFT;  // _mapper.pyx:28
 #ifndef SKM_SCAN_WIDTH
 #define SKM_SCAN_WIDTH 3
 #endif
+#ifndef SKM_COOP_PROBE
+#define SKM_COOP_PROBE 0  // table buckets fetched by lane pairs, one warp instruction per bucket (lookup_warp)
+#endif
 constexpr int SCAN_WIDTH = SKM_SCAN_WIDTH;  // read positions probed per P_SCAN step
 #ifndef SKM_IDLE_NS
 #define SKM_IDLE_NS 200
@@ -591,6 +594,67 @@ __device__ __forceinline__ Coord run_probe(const DevIndex &ix, const Probe &p)
     return Coord{(int32_t)(uint32_t)v, (int32_t)(uint32_t)(v >> 32)};
 }
 
+// The pending k-mers of a whole warp, probed TOGETHER (all 32 lanes call this converged; `active`
+// says which lanes have a k-mer).  Why: the table (4.3 GB) is far beyond the 256 MB the TLB
+// reaches, and what a random probe costs there is one page walk per lane REQUEST, not bytes
+// (tools/rand_access_bench2.cu on B200, 4 GB table: a lane fetching its own 64-byte bucket with
+// 4 x LDG.128: 15.9 G buckets/s; the same buckets fetched by lane pairs, one LDG.256 each, so that
+// a bucket is touched by ONE warp instruction: 37.7 G buckets/s, the walker's ceiling).  Two rounds
+// of 16 owners; lanes 2o and 2o+1 fetch the two halves of owner o's bucket, both rounds' loads are
+// issued before the first compare.  Returns the slot's value word (entry | offset << 32) for the
+// canonical key, or offset -1; the caller applies the strand.  Same probe sequence and the same
+// "last slot empty = bucket not full = stop" rule as probe_canonical (kmer.cuh).
+constexpr unsigned long long LOOKUP_MISS = 0xFFFFFFFF00000000ULL;
+__device__ __noinline__ unsigned long long lookup_warp(const Slot *table, uint64_t bucket_mask, uint64_t canon,
+                                                       uint32_t bucket, int active)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned half = lane & 1u, pair = lane >> 1, own = 2u * (lane & 15u);
+    unsigned long long result = LOOKUP_MISS;
+    unsigned pending = __ballot_sync(0xffffffffu, active);
+    while (pending) {
+        Quad64 s[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const unsigned src = (unsigned)r * 16u + pair;
+            const uint32_t b = __shfl_sync(0xffffffffu, bucket, src);
+            s[r] = Quad64{EMPTY_KEY, 0, EMPTY_KEY, 0};
+            if ((pending >> src) & 1u) s[r] = ld_cs_32(table + (uint64_t)b * BUCKET_SLOTS + 2u * half);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const unsigned src = (unsigned)r * 16u + pair;
+            const uint64_t c = __shfl_sync(0xffffffffu, canon, src);
+            const bool h0 = s[r].a == c, h1 = s[r].c == c;
+            const unsigned hits = __ballot_sync(0xffffffffu, h0 || h1);
+            const unsigned open = __ballot_sync(0xffffffffu, s[r].c == EMPTY_KEY);  // odd lanes: the bucket's last slot
+            const uint64_t v = h0 ? s[r].b : s[r].d;
+            const unsigned got = (hits >> own) & 3u;
+            const uint64_t word = __shfl_sync(0xffffffffu, v, own + (got >> 1));
+            if ((lane >> 4) == (unsigned)r && active) {
+                if (got) {
+                    result = word;
+                    active = 0;
+                } else if ((open >> (own + 1u)) & 1u) {
+                    active = 0;
+                } else {
+                    bucket = (bucket + 1u) & (uint32_t)bucket_mask;
+                }
+            }
+        }
+        pending = __ballot_sync(0xffffffffu, active);
+    }
+    return result;
+}
+
+__device__ __forceinline__ Coord run_probe_warp(const DevIndex &ix, const Probe &p, bool active)
+{
+    const unsigned long long v = lookup_warp(ix.table, ix.bucket_mask, p.canon, p.bucket, active ? 1 : 0);
+    const int32_t entry = (int32_t)(uint32_t)v, offset = (int32_t)(uint32_t)(v >> 32);
+    if (offset < 0) return coord_invalid();
+    return Coord{p.fwd ? entry : ~entry, offset};
+}
+
 // A final list longer than a unit record: make sure it lives in the arena, return its offset.
 __device__ __noinline__ long long emit_long_list(const int32_t *p, int stride, int n, int32_t *arena,
                                                  unsigned long long arena_cap, unsigned long long *cursor,
@@ -782,8 +846,15 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 }
             }
         } else if (phase == P_LOOKUP) {
+#if SKM_COOP_PROBE
+            Probe pr{0, 0, false};
+            if (mine) pr = prepare_probe(L.kmer, ix.bucket_mask);
+            const Coord h = run_probe_warp(ix, pr, mine);
+            if (mine) {
+#else
             if (mine) {
                 const Coord h = run_probe(ix, prepare_probe(L.kmer, ix.bucket_mask));
+#endif
                 L.sp.anchor = h;
                 if (h.offset >= 0) {
                     L.st = P_CONTIG;
@@ -801,6 +872,34 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                 }
             }
         } else if (phase == P_SCAN) {
+#if SKM_COOP_PROBE
+            // positions pos .. pos+2 (while they fit), one after the other, first hit wins; L.kmer is
+            // the k-mer at pos-1.  Every step is one warp-wide probe (lookup_warp) of the lanes still
+            // scanning.
+            uint64_t kk = 0;
+            int fit = 0, first = SCAN_WIDTH;
+            Coord hh = coord_invalid();
+            if (mine) {
+                kk = L.kmer;
+                fit = L.len - K + 1 - L.pos;  // >= 1
+            }
+#pragma unroll 1
+            for (int j = 0; j < SCAN_WIDTH; ++j) {
+                const bool go = mine && j < fit && first == SCAN_WIDTH;
+                if (!__any_sync(0xffffffffu, go)) break;
+                Probe pr{0, 0, false};
+                if (go) {
+                    kk = ((kk << 2) | rv.code(L.pos + j + K - 1)) & KMER_MASK;
+                    pr = prepare_probe(kk, ix.bucket_mask);
+                }
+                const Coord h = run_probe_warp(ix, pr, go);
+                if (go && h.offset >= 0) {
+                    first = j;
+                    hh = h;
+                }
+            }
+            if (mine) {
+#else
             if (mine) {
                 // positions pos .. pos+2 (while they fit), one after the other, first hit wins;
                 // L.kmer is the k-mer at pos-1.  (One copy of the hash + probe code instead of three:
@@ -819,6 +918,7 @@ map_reads_kernel(const DevIndex ix, const MapArgs a, uint32_t *const status)
                         break;
                     }
                 }
+#endif
                 L.sp.anchor = hh;
                 L.kmer = kk;
                 if (first < SCAN_WIDTH) {

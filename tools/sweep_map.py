@@ -64,7 +64,8 @@ def main():
         try:
             use_library(os.path.join(ROOT, path) if path else '')
             index = _lib.DeviceIndex(built.kmers, built.contigs, built.sequences, built.targets, built.n_transcripts)
-            mp = _lib.DeviceMapper(index, class_capacity=1 << 23, id_capacity=1 << 27)
+            cap = int(os.environ.get('SWEEP_CLASS_CAP_LOG2', '23'))  # dictionary slots = 2 x class capacity
+            mp = _lib.DeviceMapper(index, class_capacity=1 << cap, id_capacity=1 << min(27, cap + 4))
             times = []
             for p in range(a.passes):
                 mp.reset()
