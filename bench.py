@@ -35,6 +35,7 @@ METRIC = 'read_pairs_pseudoaligned_per_sec'
 UNIT = 'pairs/s'
 READ_LEN, FRAG_MEAN, FRAG_SD = 150, 350, 50
 SEED_TX, SEED_EXPR, SEED_READS = 2, 3, 10
+DICT_CLASSES, DICT_IDS = 1 << 21, 1 << 24  # class dictionary of the mapping legs: classes, ids over all classes
 C5_READ_LEN, C5_SUB_RATE = 75, 0.02
 
 
@@ -305,8 +306,11 @@ def run_ours(args):
     strong = args.scaling == 'strong'
     n_pairs = args.total_pairs // world if strong else args.pairs
     total_pairs = n_pairs * world
-    # dictionary sized for the classes of the whole job (weak scaling grows it with the ranks)
-    mp = _lib.DeviceMapper(index, class_capacity=1 << 22, id_capacity=1 << 26)
+    # dictionary sized for the classes of the whole job (~0.8 M at one rank, ~1.0 M at eight): 2^22
+    # slots.  Its arrays (40 B per slot + the id pool) then stay inside the 256 MB the TLB reaches,
+    # which is what the random accesses of the merge kernel and the slot scan of the export cost
+    # (profiles/r02c_*: one page walk per access beyond that reach).
+    mp = _lib.DeviceMapper(index, class_capacity=DICT_CLASSES, id_capacity=DICT_IDS)
 
     first_unit = rank * n_pairs
     d_bases = torch.empty(n_pairs * 2 * READ_LEN, dtype=torch.uint8, device=device)
@@ -378,7 +382,7 @@ def run_ours(args):
     merged_equals_single = None
     if world > 1:
         if rank == 0:
-            single = _lib.DeviceMapper(index, class_capacity=1 << 22, id_capacity=1 << 26)
+            single = _lib.DeviceMapper(index, class_capacity=DICT_CLASSES, id_capacity=DICT_IDS)
             scratch = torch.empty_like(d_bases)
             for r in range(world):
                 synth_reads(sim, r * n_pairs, n_pairs, scratch, local)

@@ -16,6 +16,7 @@
 #include <unordered_map>
 #include <vector>
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <cub/cub.cuh>
 
 #include "binomial.cuh"
@@ -660,6 +661,47 @@ __global__ void multinomial_tree_kernel(const unsigned long long *__restrict__ c
 // buffer and cudaFree synchronises the device; the stream-ordered pool was measured to stall
 // for hundreds of ms on these sizes).  All users run on one stream at a time per device and
 // synchronise it before returning, so a cached block is never still in use.
+// Scratch blocks come from the virtual-memory-management API, with access for the OWNING device
+// only.  Why not cudaMalloc: once peer access is on (NCCL turns it on for every NVLink peer), a
+// cudaMalloc also maps the new block into every peer's address space, and that is what took the
+// time of the first bootstrap call in a multi-GPU job (2 x B200, 1.1 GB of scratch for 50
+// replicates: resample stage 157 ms, plan 187 ms; 13 ms and 4 ms with NCCL_P2P_DISABLE=1, i.e.
+// with the same kernels and no peer mappings - profiles/r02c_alloc_peer_access.txt).  Nothing in
+// this cache is ever read by a peer GPU.  The driver entry points are looked up at run time
+// (cudaGetDriverEntryPoint): the library does not link against libcuda, so it still loads on a
+// machine without a driver.  SKM_NO_VMM=1 goes back to cudaMalloc.
+struct Vmm {
+    CUresult (*create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*address_free)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*granularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    bool ok = false;
+    Vmm()
+    {
+        if (getenv("SKM_NO_VMM")) return;
+        auto find = [](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult st = cudaDriverEntryPointSymbolNotFound;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess &&
+                   st == cudaDriverEntryPointSuccess && *fn != nullptr;
+        };
+        ok = find("cuMemCreate", (void **)&create) && find("cuMemAddressReserve", (void **)&reserve) &&
+             find("cuMemMap", (void **)&map) && find("cuMemSetAccess", (void **)&set_access) &&
+             find("cuMemUnmap", (void **)&unmap) && find("cuMemRelease", (void **)&release) &&
+             find("cuMemAddressFree", (void **)&address_free) &&
+             find("cuMemGetAllocationGranularity", (void **)&granularity);
+        if (!ok) cudaGetLastError();
+    }
+};
+static Vmm &vmm_api()
+{
+    static Vmm v;  // resolved on first use, when the CUDA runtime is up
+    return v;
+}
+
 struct BlockCache {
     struct Block {
         void *p;
@@ -673,6 +715,59 @@ struct BlockCache {
     std::vector<void *> slabs[64];
     char *slab_next[64] = {};
     size_t slab_left[64] = {};
+    std::unordered_map<void *, size_t> mapped[64];  // blocks that came from the VMM API: mapped size
+    // one block of device memory nobody else maps (mu held)
+    cudaError_t raw_alloc(int d, size_t bytes, void **out)
+    {
+        Vmm &vmm = vmm_api();
+        if (vmm.ok) {
+            CUmemAllocationProp prop = {};
+            prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+            prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+            prop.location.id = d;
+            size_t gran = 0;
+            if (vmm.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && gran > 0) {
+                const size_t size = (bytes + gran - 1) / gran * gran;
+                CUmemGenericAllocationHandle h;
+                const CUresult made = vmm.create(&h, size, &prop, 0);
+                if (made == CUDA_ERROR_OUT_OF_MEMORY) return cudaErrorMemoryAllocation;
+                if (made == CUDA_SUCCESS) {
+                    CUdeviceptr va = 0;
+                    bool good = vmm.reserve(&va, size, 0, 0, 0) == CUDA_SUCCESS;
+                    bool is_mapped = false;
+                    if (good) good = is_mapped = vmm.map(va, size, 0, h, 0) == CUDA_SUCCESS;
+                    if (good) {
+                        CUmemAccessDesc acc = {};
+                        acc.location = prop.location;
+                        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+                        good = vmm.set_access(va, size, &acc, 1) == CUDA_SUCCESS;
+                    }
+                    vmm.release(h);  // the mapping keeps the memory until it is unmapped
+                    if (good) {
+                        *out = reinterpret_cast<void *>(va);
+                        mapped[d][*out] = size;
+                        return cudaSuccess;
+                    }
+                    if (is_mapped) vmm.unmap(va, size);
+                    if (va) vmm.address_free(va, size);
+                }
+            }
+        }
+        return cudaMalloc(out, bytes);
+    }
+    void raw_free(int d, void *p)
+    {
+        auto it = mapped[d].find(p);
+        if (it == mapped[d].end()) {
+            cudaFree(p);
+            return;
+        }
+        Vmm &vmm = vmm_api();
+        cudaDeviceSynchronize();  // what cudaFree does: nothing in flight may still use the block
+        vmm.unmap(reinterpret_cast<CUdeviceptr>(p), it->second);
+        vmm.address_free(reinterpret_cast<CUdeviceptr>(p), it->second);
+        mapped[d].erase(it);
+    }
     // give idle own blocks back to the driver until at most `keep` bytes of them stay cached
     // (mu held; cudaFree synchronises the device, so this only runs on pressure or on request)
     size_t trim_locked(int d, size_t keep)
@@ -686,7 +781,7 @@ struct BlockCache {
             for (int i = 0; i < (int)v.size(); ++i)
                 if (v[i].own && (big < 0 || v[i].bytes > v[big].bytes)) big = i;
             if (big < 0) break;
-            cudaFree(v[big].p);
+            raw_free(d, v[big].p);
             idle -= v[big].bytes;
             freed += v[big].bytes;
             v.erase(v.begin() + big);
@@ -723,10 +818,10 @@ struct BlockCache {
         if (bytes <= SLAB / 4) {
             if (slab_left[d] < bytes) {
                 void *slab = nullptr;
-                cudaError_t e = cudaMalloc(&slab, SLAB);
+                cudaError_t e = raw_alloc(d, SLAB, &slab);
                 if (e == cudaErrorMemoryAllocation && trim_locked(d, 0) > 0) {  // our own idle blocks first
                     cudaGetLastError();
-                    e = cudaMalloc(&slab, SLAB);
+                    e = raw_alloc(d, SLAB, &slab);
                 }
                 if (e != cudaSuccess) return e;
                 slabs[d].push_back(slab);
@@ -739,10 +834,10 @@ struct BlockCache {
             return cudaSuccess;
         }
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = raw_alloc(d, bytes, &p);
         if (e == cudaErrorMemoryAllocation && trim_locked(d, 0) > 0) {
             cudaGetLastError();
-            e = cudaMalloc(&p, bytes);
+            e = raw_alloc(d, bytes, &p);
         }
         if (e != cudaSuccess) return e;
         *out = p;
