@@ -11,8 +11,10 @@
 // (numpy.bincount accumulates sequentially in nnz order).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <ctime>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include <cooperative_groups.h>
@@ -729,18 +731,32 @@ struct BlockCache {
             if (vmm.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && gran > 0) {
                 const size_t size = (bytes + gran - 1) / gran * gran;
                 CUmemGenericAllocationHandle h;
+                const bool tr = getenv("SKM_TRACE_ALLOC") != nullptr;
+                timespec ts0, ts1, ts2, ts3, ts4;
+                if (tr) clock_gettime(CLOCK_MONOTONIC, &ts0);
                 const CUresult made = vmm.create(&h, size, &prop, 0);
+                if (tr) clock_gettime(CLOCK_MONOTONIC, &ts1);
                 if (made == CUDA_ERROR_OUT_OF_MEMORY) return cudaErrorMemoryAllocation;
                 if (made == CUDA_SUCCESS) {
                     CUdeviceptr va = 0;
                     bool good = vmm.reserve(&va, size, 0, 0, 0) == CUDA_SUCCESS;
+                    if (tr) clock_gettime(CLOCK_MONOTONIC, &ts2);
                     bool is_mapped = false;
                     if (good) good = is_mapped = vmm.map(va, size, 0, h, 0) == CUDA_SUCCESS;
+                    if (tr) clock_gettime(CLOCK_MONOTONIC, &ts3);
                     if (good) {
                         CUmemAccessDesc acc = {};
                         acc.location = prop.location;
                         acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
                         good = vmm.set_access(va, size, &acc, 1) == CUDA_SUCCESS;
+                    }
+                    if (tr) {
+                        clock_gettime(CLOCK_MONOTONIC, &ts4);
+                        auto ms = [](const timespec &a, const timespec &b) {
+                            return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6;
+                        };
+                        fprintf(stderr, "[skm alloc] %8.1f MB: create %.3f reserve %.3f map %.3f set_access %.3f ms\n",
+                                size / 1048576.0, ms(ts0, ts1), ms(ts1, ts2), ms(ts2, ts3), ms(ts3, ts4));
                     }
                     vmm.release(h);  // the mapping keeps the memory until it is unmapped
                     if (good) {
@@ -887,6 +903,26 @@ void dev_free(int device, void *p)
     g_blocks.give(device, p, bytes);
 }
 
+void scratch_warm(int device)
+{
+    static std::mutex mu;
+    static bool done[64] = {};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (done[device & 63]) return;
+        done[device & 63] = true;
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    void *small = nullptr, *large = nullptr;
+    if (dev_alloc(device, 1u << 20, &small) != cudaSuccess) cudaGetLastError();
+    if (dev_alloc(device, 256u << 20, &large) != cudaSuccess) cudaGetLastError();
+    dev_free(device, large);
+    dev_free(device, small);
+    cudaSetDevice(prev);
+}
+
 struct DeviceBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -935,6 +971,59 @@ struct Trace {
         t0 = t;
     }
 };
+
+// Large results into PAGEABLE host memory (a fresh numpy array): cudaMemcpy stages such a copy
+// through the driver's own bounce buffer with one host thread, which then takes every first-touch
+// page fault of the destination (160 MB of bootstrap results: 32-38 ms, 4.5 GB/s).  Here chunks
+// land in two page-locked buffers at link speed and a few host threads copy each chunk on to the
+// caller's buffer while the next chunk is in flight.  The stream is idle when this returns.
+static std::mutex g_bounce_mu;
+static unsigned char *g_bounce[2] = {nullptr, nullptr};
+static cudaError_t copy_to_pageable(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    constexpr size_t CHUNK = 16u << 20;
+    constexpr int THREADS = 4;
+    if (bytes < 4 * CHUNK || getenv("SKM_PLAIN_D2H")) {
+        const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+    }
+    std::lock_guard<std::mutex> lock(g_bounce_mu);
+    for (int i = 0; i < 2; ++i)
+        if (!g_bounce[i] && cudaHostAlloc((void **)&g_bounce[i], CHUNK, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            g_bounce[i] = nullptr;
+            const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+            return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+        }
+    std::thread workers[2][THREADS];
+    bool busy[2] = {false, false};
+    auto join = [&](int b) {
+        if (busy[b])
+            for (auto &w : workers[b]) w.join();
+        busy[b] = false;
+    };
+    cudaError_t err = cudaSuccess;
+    int k = 0;
+    for (size_t off = 0; off < bytes && err == cudaSuccess; off += CHUNK, ++k) {
+        const int b = k & 1;
+        const size_t n = std::min(CHUNK, bytes - off);
+        join(b);  // the host copy out of this bounce buffer two chunks ago
+        err = cudaMemcpyAsync(g_bounce[b], static_cast<const unsigned char *>(src) + off, n, cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+        if (err != cudaSuccess) break;
+        const size_t piece = (n + THREADS - 1) / THREADS;
+        for (int t = 0; t < THREADS; ++t) {
+            const size_t lo = std::min(n, (size_t)t * piece), hi = std::min(n, lo + piece);
+            unsigned char *to = static_cast<unsigned char *>(dst) + off + lo;
+            const unsigned char *from = g_bounce[b] + lo;
+            workers[b][t] = std::thread([to, from, lo, hi] { memcpy(to, from, hi - lo); });
+        }
+        busy[b] = true;
+    }
+    join(0);
+    join(1);
+    return err;
+}
 
 #define EM_TRY(expr)                                                                            \
     do {                                                                                        \
@@ -1830,8 +1919,8 @@ SKM_API int skm_em_plan_bootstrap(const skm_em_plan *p, const int64_t *counts, c
     }
     trace.mark("bootstrap: tpm");
     if (!buffers_on_device) {
-        EM_TRY(cudaMemcpyAsync(out_x, d_out, sizeof(double) * (size_t)(T * R), cudaMemcpyDeviceToHost, st));
         if (out_iters) EM_TRY(cudaMemcpyAsync(out_iters, d_iters, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
+        EM_TRY(copy_to_pageable(out_x, d_out, sizeof(double) * (size_t)(T * R), st));
     }
     EM_TRY(cudaStreamSynchronize(st));
     trace.mark("bootstrap: results to host");

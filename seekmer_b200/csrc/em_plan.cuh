@@ -24,6 +24,11 @@ namespace skm {
 // state); what a plan is made of.
 cudaError_t dev_alloc(int device, size_t bytes, void **out);
 void dev_free(int device, void *p);
+// Called when an index has been put on a device: the cache takes its first slab and one large
+// block from the driver and keeps them, so that the allocator's one-off costs (first VMM calls of
+// a process on a cold device: tens of ms each, whatever the size) are paid with the index load
+// and not inside the first EM call.
+void scratch_warm(int device);
 
 // Takes ownership of class_ptr / class_tx / counts (device memory from dev_alloc on `device`;
 // counts may be NULL), builds the CSC side on `stream` and returns the plan.  On failure the

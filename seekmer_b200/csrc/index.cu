@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "em_plan.cuh"
 #include "kmer.cuh"
 
 namespace skm {
@@ -435,6 +436,7 @@ SKM_API int skm_index_create(const skm_kmer_slot *kmers, int64_t n_slots,
         skm_index_destroy(ix);
         return fail(SKM_ERR_CUDA, "skm_index_create: contig link kernel failed");
     }
+    skm::scratch_warm(ix->device);  // the EM scratch cache takes its first blocks now, not inside the first EM call
     *out = ix;
     return SKM_OK;
 }
@@ -692,6 +694,7 @@ SKM_API int skm_index_load(const char *path, int device, void *stream, skm_index
     }
     if (trailer_offset) *trailer_offset = (int64_t)sizeof(ImageHeader) + h.table_bytes + h.hot_bytes;
     if (trailer_bytes) *trailer_bytes = h.trailer_bytes;
+    skm::scratch_warm(ix->device);  // the EM scratch cache takes its first blocks now, not inside the first EM call
     *out = ix;
     return SKM_OK;
 }
