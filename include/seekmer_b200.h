@@ -304,6 +304,15 @@ int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx,
                    int64_t n_transcripts, const double *x0, int64_t max_iters, double *out_x,
                    int32_t *out_iters, int buffers_on_device, int device, void *stream);
 
+/* The same for samples whose class structures are already on the device as PLANS (one per
+ * sample, skm_em_plan_from_mapper: the mapper.py:196-234 / impute.py:101 flow without the host
+ * round trip of class_map): n_plans independent EMs in one set of launches.  All plans sit on
+ * one device, share n_transcripts and own their counts.  eff_len, x0, out_x: [n_plans][T];
+ * out_iters[n_plans].  Bit-identical to one skm_em_plan_run per plan. */
+int skm_em_plans_run(const skm_em_plan *const *plans, int64_t n_plans, const double *eff_len,
+                     const double *x0, int64_t max_iters, double *out_x, int32_t *out_iters,
+                     int buffers_on_device, void *stream);
+
 /* Workload generation twin of seekmer_b200/synth.py (bench/test support, not
  * part of the reference surface): fills `bases` (device) with ASCII reads for
  * global units [first_unit, first_unit+n_units). */

@@ -28,7 +28,7 @@ EXPORTS = (
     'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_debug_map_stats', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_classes_merge_packed', 'skm_release_cache', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
     'skm_build_kmer_table', 'skm_index_save', 'skm_index_load', 'skm_em_plan_create', 'skm_em_plan_from_mapper', 'skm_em_plan_info',
-    'skm_em_plan_destroy', 'skm_em_plan_run', 'skm_em_plan_bootstrap',
+    'skm_em_plan_destroy', 'skm_em_plan_run', 'skm_em_plan_bootstrap', 'skm_em_plans_run',
 )
 
 
@@ -112,6 +112,8 @@ def load():
     L.skm_em_plan_destroy.argtypes = [vp]
     L.skm_em_plan_run.restype = ci
     L.skm_em_plan_run.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, ci, vp]
+    L.skm_em_plans_run.restype = ci
+    L.skm_em_plans_run.argtypes = [vp, i64, vp, vp, i64, vp, vp, ci, vp]
     L.skm_em_plan_bootstrap.restype = ci
     L.skm_em_plan_bootstrap.argtypes = [vp, vp, vp, vp, i64, i64, u64, ci, i64, ci, vp, vp, ci, vp]
     L.skm_multinomial.restype = ci
@@ -485,6 +487,22 @@ class EmPlan:
         iters = numpy.zeros(x0.shape[0], dtype='i4')
         check(load().skm_em_plan_run(self._h, _ptr(counts), _np_ptr(eff_len), _np_ptr(x0), x0.shape[0],
                                      int(max_iters), _np_ptr(out), _np_ptr(iters), 0, stream))
+        return out, iters
+
+    @staticmethod
+    def run_many(plans, eff_lens, x0s, max_iters=0, stream=None):
+        """`[p.run(l, x) for p, l, x in zip(plans, eff_lens, x0s)]` in ONE set of launches
+        (`skm_em_plans_run`): plans of different samples on one device, each with its own counts.
+        eff_lens, x0s: (P, T).  Returns (x (P, T), iterations (P,)), bit-identical to the loop."""
+        x0s = numpy.ascontiguousarray(numpy.atleast_2d(x0s), dtype='f8')
+        eff_lens = numpy.ascontiguousarray(numpy.atleast_2d(eff_lens), dtype='f8')
+        if x0s.shape != eff_lens.shape or x0s.shape[0] != len(plans):
+            raise ValueError('run_many: one row of lengths and of first guesses per plan')
+        handles = (ctypes.c_void_p * len(plans))(*[p._h for p in plans])
+        out = numpy.zeros_like(x0s)
+        iters = numpy.zeros(len(plans), dtype='i4')
+        check(load().skm_em_plans_run(ctypes.cast(handles, ctypes.c_void_p), len(plans), _np_ptr(eff_lens),
+                                      _np_ptr(x0s), int(max_iters), _np_ptr(out), _np_ptr(iters), 0, stream))
         return out, iters
 
     def bootstrap(self, eff_len, x0, n_replicates, seed, first_replicate=0, counts=None, tpm=True, max_iters=0,

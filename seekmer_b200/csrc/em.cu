@@ -112,6 +112,14 @@ __global__ void counts_to_plan_kernel(const T *__restrict__ src, const int32_t *
     dst[i] = (double)src[(int64_t)r * n_classes + perm[c]];
 }
 
+// dst[i] = src[i] + add: the CSR row pointer of one plan moved to its place behind the entries of
+// the plans before it (skm_em_plans_run)
+__global__ void offset_i64_kernel(const int64_t *__restrict__ src, int64_t n, int64_t add, int64_t *__restrict__ dst)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i] + add;
+}
+
 // ---- class order of a plan: by first transcript, so that neighbouring threads gather from
 // ---- neighbouring places (see em_plan_adopt)
 __global__ void class_sort_key_kernel(const int64_t *__restrict__ class_ptr, const int32_t *__restrict__ class_tx,
@@ -1758,6 +1766,78 @@ SKM_API int skm_em_samples(const int64_t *class_ptr, const int32_t *class_tx, co
         EM_TRY(cudaMemcpyAsync(out_iters, s.iters, sizeof(int32_t) * (size_t)P,
                                buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     EM_TRY(cudaStreamSynchronize(st));  // scratch buffers are released after this
+    return SKM_OK;
+}
+
+// Many samples, each with its own plan (made from its mapper, device to device), in ONE set of
+// launches: the plans' structures are laid end to end on the device (plan class order, so the
+// class order skm_em_samples gives every sample is the one its plan has) and handed to
+// skm_em_samples - no host CSR, nothing but the lengths and first guesses cross PCIe.
+SKM_API int skm_em_plans_run(const skm_em_plan *const *plans, int64_t n_plans, const double *eff_len, const double *x0,
+                             int64_t max_iters, double *out_x, int32_t *out_iters, int buffers_on_device, void *stream)
+{
+    if (!plans || !eff_len || !x0 || !out_x) return fail(SKM_ERR_INVALID, "skm_em_plans_run: NULL argument");
+    if (n_plans <= 0) return fail(SKM_ERR_INVALID, "skm_em_plans_run: empty problem");
+    const int64_t P = n_plans;
+    int64_t C = 0, nnz = 0;
+    for (int64_t k = 0; k < P; ++k) {
+        const skm_em_plan *p = plans[k];
+        if (!p) return fail(SKM_ERR_INVALID, "skm_em_plans_run: NULL plan");
+        if (p->device != plans[0]->device || p->T != plans[0]->T)
+            return fail(SKM_ERR_INVALID, "skm_em_plans_run: the plans must sit on one device and share the transcript set");
+        if (!p->counts) return fail(SKM_ERR_INVALID, "skm_em_plans_run: every plan must own its class counts");
+        if (p->C <= 0 || p->nnz <= 0) return fail(SKM_ERR_INVALID, "skm_em_plans_run: empty plan");
+        C += p->C;
+        nnz += p->nnz;
+    }
+    const int device = plans[0]->device;
+    const int64_t T = plans[0]->T;
+    EM_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceBuf b_ptr, b_tx, b_cnt, b_sptr, b_len, b_x, b_out, b_iters;
+    EM_TRY(b_ptr.alloc(sizeof(int64_t) * (size_t)(C + 1), st));
+    EM_TRY(b_tx.alloc(sizeof(int32_t) * (size_t)nnz, st));
+    EM_TRY(b_cnt.alloc(sizeof(double) * (size_t)C, st));
+    EM_TRY(b_sptr.alloc(sizeof(int64_t) * (size_t)(P + 1), st));
+    std::vector<int64_t> h_sptr((size_t)P + 1, 0);
+    int64_t c_off = 0, e_off = 0;
+    for (int64_t k = 0; k < P; ++k) {
+        const skm_em_plan *p = plans[k];
+        // C + 1 entries each: the closing entry of a plan is the first entry of the next
+        offset_i64_kernel<<<blocks_for(p->C + 1, 256), 256, 0, st>>>(p->class_ptr, p->C + 1, e_off, b_ptr.as<int64_t>() + c_off);
+        EM_TRY(cudaMemcpyAsync(b_tx.as<int32_t>() + e_off, p->class_tx, sizeof(int32_t) * (size_t)p->nnz,
+                               cudaMemcpyDeviceToDevice, st));
+        counts_to_plan_kernel<int64_t><<<blocks_for(p->C, 256), 256, 0, st>>>(p->counts, p->perm, b_cnt.as<double>() + c_off, p->C, 1);
+        c_off += p->C;
+        e_off += p->nnz;
+        h_sptr[(size_t)k + 1] = c_off;
+    }
+    EM_TRY(cudaGetLastError());
+    EM_TRY(cudaMemcpyAsync(b_sptr.p, h_sptr.data(), sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
+    const double *d_len = eff_len, *d_x = x0;
+    double *d_out = out_x;
+    int32_t *d_iters = out_iters;
+    EM_TRY(b_iters.alloc(sizeof(int32_t) * (size_t)P, st));
+    if (!d_iters || !buffers_on_device) d_iters = b_iters.as<int32_t>();
+    if (!buffers_on_device) {
+        EM_TRY(b_len.alloc(sizeof(double) * (size_t)(P * T), st));
+        EM_TRY(b_x.alloc(sizeof(double) * (size_t)(P * T), st));
+        EM_TRY(b_out.alloc(sizeof(double) * (size_t)(P * T), st));
+        EM_TRY(cudaMemcpyAsync(b_len.p, eff_len, sizeof(double) * (size_t)(P * T), cudaMemcpyHostToDevice, st));
+        EM_TRY(cudaMemcpyAsync(b_x.p, x0, sizeof(double) * (size_t)(P * T), cudaMemcpyHostToDevice, st));
+        d_len = b_len.as<double>();
+        d_x = b_x.as<double>();
+        d_out = b_out.as<double>();
+    }
+    EM_TRY(cudaStreamSynchronize(st));  // h_sptr is read by the copy above
+    const int rc = skm_em_samples(b_ptr.as<int64_t>(), b_tx.as<int32_t>(), b_sptr.as<int64_t>(), P, C, nnz, b_cnt.as<double>(),
+                                  d_len, T, d_x, max_iters, d_out, d_iters, 1, device, stream);
+    if (rc) return rc;
+    if (!buffers_on_device) {
+        EM_TRY(cudaMemcpyAsync(out_x, d_out, sizeof(double) * (size_t)(P * T), cudaMemcpyDeviceToHost, st));
+        if (out_iters) EM_TRY(cudaMemcpyAsync(out_iters, d_iters, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, st));
+    }
+    EM_TRY(cudaStreamSynchronize(st));
     return SKM_OK;
 }
 

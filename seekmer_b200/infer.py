@@ -256,6 +256,29 @@ def quantify_samples(results_list, return_iters=False, device=0):
     iters = numpy.zeros(len(results_list), dtype='i4')
     live = [i for i, r in enumerate(results_list) if r.class_map.size]  # `infer.py:104-105`
     per_call = max(1, _SAMPLE_ROWS_PER_CALL // max(n_tx, 1))
+    # samples whose class structure is still on a GPU as a plan (the mapper left it there,
+    # `map_multiple_samples`) iterate on those plans, one call per GPU: nothing but lengths and
+    # first guesses goes up; the others take the host CSR route
+    by_device = {}
+    for i in live:
+        plan = _plan_of(results_list[i])
+        if plan is not None and plan.owns_counts and plan.n_transcripts == n_tx:
+            by_device.setdefault(plan.device, []).append(i)
+    planned = set()
+    for dev, members in by_device.items():
+        for start in range(0, len(members), per_call):
+            chunk = members[start:start + per_call]
+            lengths = numpy.stack([results_list[i].effective_lengths.astype('f8') for i in chunk])
+            x0 = numpy.empty_like(lengths)
+            for k in range(len(chunk)):  # row by row: the same arithmetic as `quantify`
+                x0[k] = numpy.ones(n_tx, dtype='f8') / lengths[k]
+                x0[k] /= x0[k].sum()
+            xs, its = _lib.EmPlan.run_many([_plan_of(results_list[i]) for i in chunk], lengths, x0)
+            for k, i in enumerate(chunk):
+                out[i] = _finish(xs[k])
+                iters[i] = its[k]
+                planned.add(i)
+    live = [i for i in live if i not in planned]
     for start in range(0, len(live), per_call):
         chunk = live[start:start + per_call]
         xs, its = _em_samples_device([results_list[i] for i in chunk], n_tx, device)

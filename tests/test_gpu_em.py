@@ -208,3 +208,43 @@ def test_em_samples_bit_identical_to_one_call_per_sample(golden_synth):
                                   g['pe100_fld'], bulk[0].effective_lengths)
     with pytest.raises(_lib.SeekmerCudaError, match='out of range'):
         infer.quantify_samples([cells[0], bad])
+
+
+def test_plans_of_many_samples_run_in_one_set_of_launches(golden_synth):
+    """`skm_em_plans_run` (`EmPlan.run_many`): samples whose class structures sit on the device as
+    plans iterate side by side, bit-identical to one `plan.run` each; `quantify_samples` takes
+    that route for results that carry a plan and stays bit-identical to `quantify`."""
+    g = golden_synth
+    lengths = g['transcripts']['length']
+    samples = [summarized(g, case + '_', lengths) for case in sorted(SYNTH_CASES)]
+    plans, effs, x0s = [], [], []
+    for r in samples:
+        counts = numpy.ascontiguousarray(r.class_count, dtype='i8')
+        ptr, tx = infer._csr_from_class_map(r.class_map, counts.shape[0])
+        plans.append(_lib.EmPlan.from_csr(ptr, tx, lengths.shape[0], counts=counts))
+        eff = r.effective_lengths.astype('f8')
+        x0 = numpy.ones(eff.size) / eff
+        x0 /= x0.sum()
+        effs.append(eff)
+        x0s.append(x0)
+    xs, its = _lib.EmPlan.run_many(plans, numpy.stack(effs), numpy.stack(x0s))
+    for k, plan in enumerate(plans):
+        one, it = plan.run(effs[k], x0s[k])
+        assert (xs[k] == one[0]).all() and its[k] == it[0], k
+        assert its[k] == int(g[sorted(SYNTH_CASES)[k] + '_em_iters'])
+    assert len(set(its.tolist())) > 1
+    # through the host API: results with a plan attached + one without
+    for r, plan in zip(samples[:-1], plans[:-1]):
+        r.plan = plan
+    got, iters = infer.quantify_samples(samples, return_iters=True)
+    for k, r in enumerate(samples):
+        assert (got[k] == infer.quantify(r)).all(), k
+        assert iters[k] == its[k]
+    # error behaviour: a plan without counts of its own is refused
+    r = samples[0]
+    ptr, tx = infer._csr_from_class_map(r.class_map, r.class_count.shape[0])
+    bare = _lib.EmPlan.from_csr(ptr, tx, lengths.shape[0])
+    with pytest.raises(_lib.SeekmerCudaError, match='own its class counts'):
+        _lib.EmPlan.run_many([plans[0], bare], numpy.stack(effs[:2]), numpy.stack(x0s[:2]))
+    for plan in plans + [bare]:
+        plan.close()
