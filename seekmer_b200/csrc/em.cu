@@ -787,7 +787,13 @@ struct BlockCache {
             return;
         }
         Vmm &vmm = vmm_api();
-        cudaDeviceSynchronize();  // what cudaFree does: nothing in flight may still use the block
+        // what cudaFree does: nothing in flight on the OWNING device may still use the block (the
+        // calling thread may be working on another GPU)
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        cudaSetDevice(prev);
         vmm.unmap(reinterpret_cast<CUdeviceptr>(p), it->second);
         vmm.address_free(reinterpret_cast<CUdeviceptr>(p), it->second);
         mapped[d].erase(it);

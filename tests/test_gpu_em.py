@@ -248,3 +248,32 @@ def test_plans_of_many_samples_run_in_one_set_of_launches(golden_synth):
         _lib.EmPlan.run_many([plans[0], bare], numpy.stack(effs[:2]), numpy.stack(x0s[:2]))
     for plan in plans + [bare]:
         plan.close()
+
+
+def test_scratch_cache_can_be_released_and_refilled(golden_synth):
+    """`skm_release_cache` gives the idle scratch blocks back to the driver (they come from the
+    virtual-memory API with access for the owning device only; SKM_NO_VMM=1: cudaMalloc); the next
+    call simply allocates again and gives the same results."""
+    import ctypes
+    g = golden_synth
+    lengths = g['transcripts']['length']
+    r = summarized(g, sorted(SYNTH_CASES)[0] + '_', lengths)
+    counts = numpy.ascontiguousarray(r.class_count, dtype='i8')
+    ptr, tx = infer._csr_from_class_map(r.class_map, counts.shape[0])
+    eff = r.effective_lengths.astype('f8')
+    x0 = numpy.ones(eff.size) / eff
+    x0 /= x0.sum()
+    plan = _lib.EmPlan.from_csr(ptr, tx, lengths.shape[0], counts=counts)
+    # 300 replicates of 60 transcripts are small; the draws / tree scratch of 1 500 000 padded
+    # classes x replicates is not: blocks of their own, which the cache keeps when the call ends
+    big_counts = numpy.ones(1_500_000, dtype='i8')
+    first = infer._resample(big_counts, 24, 7)
+    before, _ = plan.bootstrap(eff, x0, 8, 99)
+    freed = ctypes.c_int64(0)
+    _lib.check(_lib.load().skm_release_cache(0, ctypes.byref(freed)))
+    assert freed.value > 0
+    again = infer._resample(big_counts, 24, 7)
+    after, _ = plan.bootstrap(eff, x0, 8, 99)
+    assert (first == again).all() and (before == after).all()
+    _lib.check(_lib.load().skm_release_cache(0, ctypes.byref(freed)))
+    plan.close()
