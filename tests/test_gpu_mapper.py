@@ -500,8 +500,10 @@ def test_dictionary_key_collisions_are_refused(golden_synth, small_tx, monkeypat
 def test_reference_built_index_against_the_compiled_reference_mapper(ref, tmp_path):
     """tools/ref_index_parity.py at a small scale: index from the reference's ContigAssembler, reads
     mapped by the CUDA library and by the reference's compiled ReadMapper - class dictionary,
-    unaligned count, FLD and first-seen order equal.  (At benchmark scale - 200 000 transcripts,
-    2 M pairs - the same run is kept as profiles/r02c_ref_index_parity.json.)"""
+    unaligned count, FLD and first-seen order equal, abundances of the device EM within 1e-6 of the
+    stock `infer.quantify` with equal iteration counts.  (BASELINE configs[0] in full - 2 000
+    transcripts, 1 M 2x100 pairs - is kept as profiles/r02c_c1_parity.json; benchmark scale - 200 000
+    transcripts, 2 M 2x150 pairs - as profiles/r02c_ref_index_parity.json.)"""
     import json
     import os
     import subprocess
@@ -509,6 +511,7 @@ def test_reference_built_index_against_the_compiled_reference_mapper(ref, tmp_pa
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = tmp_path / 'parity.json'
     subprocess.run([sys.executable, os.path.join(root, 'tools', 'ref_index_parity.py'), '--transcripts', '2000',
-                    '--pairs', '50000', '--ordered-pairs', '20000', '--out', str(out)], check=True, cwd=root)
+                    '--pairs', '50000', '--ordered-pairs', '20000', '--read-len', '100', '--frag-mean', '250', '--em',
+                    '--out', str(out)], check=True, cwd=root)
     line = json.load(open(out))
     assert line['ok'], line['checks']

@@ -50,11 +50,15 @@ def main():
     ap.add_argument('--transcripts', type=int, default=200_000)
     ap.add_argument('--pairs', type=int, default=2_000_000)
     ap.add_argument('--ordered-pairs', type=int, default=200_000)
+    ap.add_argument('--read-len', type=int, default=bench.READ_LEN)
+    ap.add_argument('--frag-mean', type=int, default=bench.FRAG_MEAN)
+    ap.add_argument('--em', action='store_true', help='also: abundances of the GPU EM against the stock infer.quantify')
     ap.add_argument('--out', default='gpurun_out/ref_index_parity.json')
     a = ap.parse_args()
     torch.cuda.set_device(0)
     dev = torch.device('cuda', 0)
-    line = {'transcripts': a.transcripts, 'pairs': a.pairs, 'read_len': bench.READ_LEN}
+    line = {'transcripts': a.transcripts, 'pairs': a.pairs, 'read_len': a.read_len}
+    L = a.read_len
     t0 = time.time()
     tx = synth.make_transcriptome(a.transcripts, seed=bench.SEED_TX, mean_exons=11)
     line['cdna_mb'] = round(tx.codes.shape[0] / 1e6, 1)
@@ -71,26 +75,37 @@ def main():
     # simulated reads, generated on the device by the benchmark's generator
     lengths = (tx.offsets[1:] - tx.offsets[:-1])
     expr = synth.make_expression(lengths.shape[0], seed=bench.SEED_EXPR)
-    w = expr * numpy.maximum(lengths - bench.FRAG_MEAN + 1, 1)
+    w = expr * numpy.maximum(lengths - a.frag_mean + 1, 1)
     w = w / w.sum()
     cum = numpy.cumsum(numpy.floor(w * float(1 << 40)).astype('u8')).astype('u8')
     sim = dict(codes=torch.from_numpy(tx.codes).to(dev), offsets=torch.from_numpy(tx.offsets).to(dev),
                cum=torch.from_numpy(cum.view('i8')).to(dev), total=int(cum[-1]), n_tx=lengths.shape[0])
-    d_bases = torch.empty(a.pairs * 2 * bench.READ_LEN, dtype=torch.uint8, device=dev)
-    bench.synth_reads(sim, 0, a.pairs, d_bases, 0)
+    d_bases = torch.empty(a.pairs * 2 * L, dtype=torch.uint8, device=dev)
+    bench.synth_reads(sim, 0, a.pairs, d_bases, 0, read_len=L, frag_mean=a.frag_mean)
     torch.cuda.synchronize()
 
     # CUDA path
     index = _lib.DeviceIndex(rk, rc, rs, rt, tx.n_transcripts)
     mp = _lib.DeviceMapper(index, class_capacity=1 << 22, id_capacity=1 << 26)
-    mp.map_batch(d_bases, None, a.pairs, True, fixed_len=bench.READ_LEN)
+    mp.map_batch(d_bases, None, a.pairs, True, fixed_len=L)
     torch.cuda.synchronize()
     line['gpu_kernel_ms'] = {k: round(v, 3) for k, v in mp.kernel_ms().items()}
     table = mp.export()
     gpu = table_dict(table)
+    gpu_em = None
+    if a.em:
+        from seekmer_b200 import infer
+        from oracle import oracle as orc
+        eff = orc.effective_lengths(numpy.asarray(table['fld']), lengths.astype('f8'))
+        plan = _lib.EmPlan.from_mapper(mp, tx.n_transcripts)
+        x0 = numpy.ones(eff.size) / eff
+        x0 /= x0.sum()
+        out, its = plan.run(eff, x0)
+        gpu_em = (infer._finish(out[0]), int(its[0]), eff)
+        plan.close()
     # ... and the first --ordered-pairs of them alone, for the first-seen order
     mp.reset()
-    mp.map_batch(d_bases[:a.ordered_pairs * 2 * bench.READ_LEN], None, a.ordered_pairs, True, fixed_len=bench.READ_LEN)
+    mp.map_batch(d_bases[:a.ordered_pairs * 2 * L], None, a.ordered_pairs, True, fixed_len=L)
     torch.cuda.synchronize()
     head = mp.export()
     mp.close()
@@ -101,13 +116,13 @@ def main():
     ridx = rh.ref_index_from_arrays(rk, rc, rs, rt)
     cores = os.cpu_count() or 1
     t3 = time.time()
-    res = rh.ref_map_threads(ridx, feeder_batches(raw, 0, a.pairs, bench.READ_LEN), cores)
+    res = rh.ref_map_threads(ridx, feeder_batches(raw, 0, a.pairs, L), cores)
     t4 = time.time()
     want = dict(res.counter)
     want_unaligned = want.pop((), 0)
     line['reference_mapper'] = {'cores': cores, 'seconds': round(t4 - t3, 2),
                                 'pairs_per_s': round(a.pairs / (t4 - t3), 1)}
-    one = rh.ref_map(ridx, feeder_batches(raw, 0, a.ordered_pairs, bench.READ_LEN))
+    one = rh.ref_map(ridx, feeder_batches(raw, 0, a.ordered_pairs, L))
     order = [k for k in one.counter.keys() if k]
     off, ids = head['key_offsets'].tolist(), head['key_ids'].tolist()
     gpu_order = [tuple(ids[off[i]:off[i + 1]]) for i in range(len(off) - 1)]
@@ -125,10 +140,33 @@ def main():
         'ordered_classes': [len(gpu_order), len(order)],
         'ordered_counts_equal': [int(c) for c in head['counts'].tolist()] == [one.counter[k] for k in order],
     }
+    if gpu_em is not None and rh.have_python_reference():
+        # the reference's own result objects and its own infer.quantify on ITS class table
+        import importlib
+        ref_mapper = importlib.import_module('seekmer.mapper')
+        ref_infer = importlib.import_module('seekmer.infer')
+        keys = [k for k in res.counter.keys() if k]
+        class_map = numpy.asarray([[c, t] for c, k in enumerate(keys) for t in k], dtype='i8').T
+        class_count = numpy.asarray([res.counter[k] for k in keys], dtype='f8')
+        tpm_gpu, its_gpu, eff = gpu_em
+        summ = ref_mapper.SummarizedResult(int(class_count.sum()), int(want_unaligned), a.pairs, class_map,
+                                           class_count, None, eff)
+        t5 = time.time()
+        tpm_ref = ref_infer.quantify(summ)
+        line['reference_quantify_s'] = round(time.time() - t5, 2)
+        from oracle import oracle as orc
+        # iteration count: the numpy restatement of infer.em on the SAME class order as the device's
+        # (first-seen order; the 16-thread reference Counter has the same classes in another order)
+        _, its_ref = orc.quantify(eff, orc.class_map_from_csr(table['key_offsets'], table['key_ids']),
+                                  numpy.asarray(table['counts'], dtype='f8'), return_iters=True)
+        checks['tpm_rel_1e-6'] = bool(numpy.allclose(tpm_gpu, tpm_ref, rtol=1e-6, atol=0))
+        checks['em_iterations'] = [its_gpu, int(its_ref)]
     line['checks'] = checks
     line['ok'] = bool(checks['class_dictionary_equal'] and checks['fld_equal'] and checks['first_seen_order_equal']
                       and checks['ordered_counts_equal'] and checks['unaligned'][0] == checks['unaligned'][1]
-                      and checks['aligned'][0] == checks['aligned'][1])
+                      and checks['aligned'][0] == checks['aligned'][1]
+                      and checks.get('tpm_rel_1e-6', True)
+                      and len(set(checks.get('em_iterations', [0]))) == 1)
     os.makedirs(os.path.dirname(os.path.join(ROOT, a.out)) or '.', exist_ok=True)
     json.dump(line, open(os.path.join(ROOT, a.out), 'w'), indent=1)
     print(json.dumps(line), flush=True)
