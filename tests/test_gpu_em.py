@@ -240,6 +240,14 @@ def test_plans_of_many_samples_run_in_one_set_of_launches(golden_synth):
     for k, r in enumerate(samples):
         assert (got[k] == infer.quantify(r)).all(), k
         assert iters[k] == its[k]
+    # large samples run one after the other on their plans (same results)
+    saved = infer._BATCH_CLASSES_PER_SAMPLE
+    infer._BATCH_CLASSES_PER_SAMPLE = 0
+    try:
+        serial, serial_iters = infer.quantify_samples(samples, return_iters=True)
+    finally:
+        infer._BATCH_CLASSES_PER_SAMPLE = saved
+    assert (serial == got).all() and (serial_iters == iters).all()
     # error behaviour: a plan without counts of its own is refused
     r = samples[0]
     ptr, tx = infer._csr_from_class_map(r.class_map, r.class_count.shape[0])
