@@ -202,6 +202,13 @@ int skm_classes_merge(skm_mapper *mapper, const int64_t *key_offsets, const int3
 int skm_classes_merge_packed(skm_mapper *mapper, const int64_t *gathered, int64_t words_per_rank,
                              int world, int rank, void *stream);
 
+/* Where the EM's scratch blocks come from.  on = 1: the virtual-memory-management API with
+ * access for the owning device only - for a process that has peer access to other GPUs switched
+ * on (NCCL, peer copies), where every cudaMalloc also maps the block into the peers (100+ ms per
+ * GB); on = 0 (default): cudaMalloc.  No reference counterpart (the reference's scratch is numpy).
+ * Returns the previous setting. */
+int skm_scratch_local_only(int on);
+
 /* The EM entry points keep their large scratch blocks cached per device between calls (a
  * cudaMalloc/cudaFree pair per call cost more than the EM); at most 8 GiB stay idle, and the
  * cache is emptied before an allocation is reported as failed.  This gives every idle cached

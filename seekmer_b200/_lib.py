@@ -28,7 +28,7 @@ EXPORTS = (
     'skm_mapper_reset', 'skm_map_batch', 'skm_map_fastq', 'skm_mapper_kernel_ms', 'skm_debug_map_stats', 'skm_classes_size', 'skm_classes_export',
     'skm_classes_merge', 'skm_classes_merge_packed', 'skm_release_cache', 'skm_effective_lengths', 'skm_em', 'skm_em_samples', 'skm_multinomial', 'skm_em_bootstrap', 'skm_synth_reads',
     'skm_build_kmer_table', 'skm_index_save', 'skm_index_load', 'skm_em_plan_create', 'skm_em_plan_from_mapper', 'skm_em_plan_info',
-    'skm_em_plan_destroy', 'skm_em_plan_run', 'skm_em_plan_bootstrap', 'skm_em_plans_run',
+    'skm_em_plan_destroy', 'skm_em_plan_run', 'skm_em_plan_bootstrap', 'skm_em_plans_run', 'skm_scratch_local_only',
 )
 
 
@@ -94,6 +94,8 @@ def load():
     L.skm_classes_merge_packed.argtypes = [vp, vp, i64, ci, ci, vp]
     L.skm_release_cache.restype = ci
     L.skm_release_cache.argtypes = [ci, vp]
+    L.skm_scratch_local_only.restype = ci
+    L.skm_scratch_local_only.argtypes = [ci]
     L.skm_effective_lengths.restype = ci
     L.skm_effective_lengths.argtypes = [vp, vp, i64, vp, ci, ci, vp]
     L.skm_em.restype = ci
@@ -443,6 +445,33 @@ class DeviceMapper:
             pass
 
 
+_PEERS = {'on': False}
+
+
+def uses_peer_gpus(on=True):
+    """Tell the library that this process has (or will have) peer access to other GPUs switched on
+    - NCCL, or one host thread per device with peer copies: EM scratch then comes from blocks only
+    the owning device maps (`skm_scratch_local_only`), because `cudaMalloc` under peer access
+    costs 100+ ms per GB.  Called by the multi-GPU entry points; idempotent."""
+    if _PEERS['on'] != bool(on):
+        load().skm_scratch_local_only(1 if on else 0)
+        _PEERS['on'] = bool(on)
+
+
+def _note_process_group():
+    """NCCL process group with more than one rank -> `uses_peer_gpus()` (checked when EM scratch is
+    about to be taken: the group may be created long after this module was loaded)."""
+    if _PEERS['on']:
+        return
+    import sys
+    dist = sys.modules.get('torch.distributed')
+    try:
+        if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            uses_peer_gpus()
+    except Exception:
+        pass
+
+
 class EmPlan:
     """Handle to a device-resident EM class structure (``skm_em_plan``): CSR by class + CSC by
     transcript, built once; the main EM and the bootstrap replicates run on it."""
@@ -459,6 +488,7 @@ class EmPlan:
         """From host CSR arrays (int64[C + 1], int32[nnz]); integer `counts` make bootstraps possible
         without passing them again."""
         require_device()
+        _note_process_group()
         class_ptr = numpy.ascontiguousarray(class_ptr, dtype='i8')
         class_tx = numpy.ascontiguousarray(class_tx, dtype='i4')
         if counts is not None:
@@ -472,6 +502,7 @@ class EmPlan:
     @classmethod
     def from_mapper(cls, mapper, n_transcripts=0, stream=None):
         """From a `DeviceMapper`'s dictionary, device to device, classes in first-seen order."""
+        _note_process_group()
         handle = ctypes.c_void_p()
         check(load().skm_em_plan_from_mapper(mapper._h, int(n_transcripts), stream, ctypes.byref(handle)))
         return cls(handle)

@@ -680,6 +680,13 @@ __global__ void multinomial_tree_kernel(const unsigned long long *__restrict__ c
 // this cache is ever read by a peer GPU.  The driver entry points are looked up at run time
 // (cudaGetDriverEntryPoint): the library does not link against libcuda, so it still loads on a
 // machine without a driver.  SKM_NO_VMM=1 goes back to cudaMalloc.
+// 0 = cudaMalloc, 1 = VMM blocks with access for the owning device only.  The host layer switches it
+// on when the process talks to peer GPUs (skm_scratch_local_only): with peer access on, cudaMalloc
+// costs 100+ ms per GB; without, it is the steadier of the two (one GPU, EM + 100 bootstraps over
+// ten fresh boxes: 180 - 220 ms with cudaMalloc, 150 - 410 ms with VMM blocks, whose first calls
+// on a cold device sometimes take 50 ms each).  SKM_SCRATCH=vmm / malloc overrides.
+static int g_scratch_local_only = 0;
+
 struct Vmm {
     CUresult (*create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
     CUresult (*reserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
@@ -693,6 +700,9 @@ struct Vmm {
     Vmm()
     {
         if (getenv("SKM_NO_VMM")) return;
+        if (const char *m = getenv("SKM_SCRATCH")) {
+            if (!strcmp(m, "malloc")) return;
+        }
         auto find = [](const char *name, void **fn) {
             cudaDriverEntryPointQueryResult st = cudaDriverEntryPointSymbolNotFound;
             return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess &&
@@ -730,7 +740,8 @@ struct BlockCache {
     cudaError_t raw_alloc(int d, size_t bytes, void **out)
     {
         Vmm &vmm = vmm_api();
-        if (vmm.ok) {
+        static const bool forced = getenv("SKM_SCRATCH") && !strcmp(getenv("SKM_SCRATCH"), "vmm");
+        if (vmm.ok && (forced || g_scratch_local_only)) {
             CUmemAllocationProp prop = {};
             prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
             prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
@@ -1048,6 +1059,13 @@ static cudaError_t copy_to_pageable(void *dst, const void *src, size_t bytes, cu
     } while (0)
 
 static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)std::max<int64_t>((n + per - 1) / per, 1); }
+
+SKM_API int skm_scratch_local_only(int on)
+{
+    const int was = g_scratch_local_only;
+    g_scratch_local_only = on ? 1 : 0;
+    return was;
+}
 
 SKM_API int skm_release_cache(int device, int64_t *freed_bytes)
 {

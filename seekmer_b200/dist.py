@@ -163,6 +163,8 @@ def merge_mappers(mp, group=None, stages=None):
     `stages`, when a dict, receives the device time (ms, CUDA events) of the four stages."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return mp.export_torch()
+    from . import _lib
+    _lib.uses_peer_gpus()  # NCCL has peer access on: EM scratch from blocks only this device maps
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if stages is not None else None
 

@@ -221,6 +221,7 @@ def quantify_bootstraps(results, x0, n_replicates, seed=None, return_iters=False
         run(*shares[0])
     else:
         import threading
+        _lib.uses_peer_gpus()
         if any(_plan_of(results, d) is None for d in devices):
             csr.append(_csr_from_class_map(results.class_map, counts.shape[0]))
         errors = []

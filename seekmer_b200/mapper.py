@@ -383,6 +383,7 @@ def _map_reads_on_devices(index, read_feeder, devices, map_result):
     """One host thread and one device mapper per GPU (`mapper.py:174-189` with devices in place
     of threads)."""
     import torch
+    _lib.uses_peer_gpus()  # the dictionaries are merged by peer copies: EM scratch must stay unmapped there
     work, shared_iter = None, None
     if isinstance(read_feeder, common.FastqSource):
         size = 2 if read_feeder.paired else 1
@@ -470,6 +471,7 @@ def map_multiple_samples(index, read_feeders, job_count=1, debug=False):
     if len(devices) == 1:
         run(devices[0], shares[0])
     else:
+        _lib.uses_peer_gpus()
         for d in devices:  # upload the index replicas one after the other (not thread-safe per object)
             index.device_index(d)
         threads = [threading.Thread(target=run, args=(d, s)) for d, s in zip(devices, shares)]

@@ -259,8 +259,8 @@ def test_plans_of_many_samples_run_in_one_set_of_launches(golden_synth):
 
 
 def test_scratch_cache_can_be_released_and_refilled(golden_synth):
-    """`skm_release_cache` gives the idle scratch blocks back to the driver (they come from the
-    virtual-memory API with access for the owning device only; SKM_NO_VMM=1: cudaMalloc); the next
+    """`skm_release_cache` gives the idle scratch blocks back to the driver (cudaMalloc blocks, or - in a
+    process with peer GPUs - blocks from the virtual-memory API that only the owning device maps); the next
     call simply allocates again and gives the same results."""
     import ctypes
     g = golden_synth
@@ -278,10 +278,15 @@ def test_scratch_cache_can_be_released_and_refilled(golden_synth):
     first = infer._resample(big_counts, 24, 7)
     before, _ = plan.bootstrap(eff, x0, 8, 99)
     freed = ctypes.c_int64(0)
-    _lib.check(_lib.load().skm_release_cache(0, ctypes.byref(freed)))
-    assert freed.value > 0
-    again = infer._resample(big_counts, 24, 7)
-    after, _ = plan.bootstrap(eff, x0, 8, 99)
-    assert (first == again).all() and (before == after).all()
+    try:
+        for peers in (False, True, False):  # cudaMalloc blocks, VMM blocks (a process with peer GPUs), back
+            _lib.uses_peer_gpus(peers)
+            _lib.check(_lib.load().skm_release_cache(0, ctypes.byref(freed)))
+            assert freed.value > 0
+            again = infer._resample(big_counts, 24, 7)
+            after, _ = plan.bootstrap(eff, x0, 8, 99)
+            assert (first == again).all() and (before == after).all()
+    finally:
+        _lib.uses_peer_gpus(False)
     _lib.check(_lib.load().skm_release_cache(0, ctypes.byref(freed)))
     plan.close()
