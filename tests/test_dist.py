@@ -58,6 +58,12 @@ def _worker(rank, world, port, case, result_path):
         merged = sdist.table_to_host(sdist.merge_class_tables(sdist.table_from_host(shards[rank])))
         ok = all((merged[k] == whole[k]).all() for k in ('key_offsets', 'key_ids', 'counts', 'first_unit', 'fld'))
         ok = ok and merged['unaligned'] == whole['unaligned'] and merged['aligned'] == whole['aligned']
+        # a process group of more than one rank: the library is told to keep its EM scratch out of
+        # the peers' address spaces (`_lib._note_process_group` -> skm_scratch_local_only)
+        from seekmer_b200 import _lib
+        ok = ok and _lib.load().skm_scratch_local_only(0) == 0   # default: cudaMalloc blocks
+        _lib._note_process_group()
+        ok = ok and _lib._PEERS['on'] and _lib.load().skm_scratch_local_only(1) == 1
         numpy.save(result_path % rank, numpy.asarray([int(ok), merged['counts'].shape[0]]))
     finally:
         dist.destroy_process_group()
@@ -86,3 +92,6 @@ def test_reconcile_orders_by_first_seen_and_detects_duplicates():
     t = dict(key_offsets=off, key_ids=ids, counts=torch.ones(5, dtype=torch.int64), first_unit=first,
              fld=torch.zeros(2000, dtype=torch.int64), scalars=torch.zeros(2, dtype=torch.int64))
     assert sdist.merge_class_tables(t) is t  # not initialised => single process no-op
+    from seekmer_b200 import _lib
+    _lib._note_process_group()                # ... and no peers: the scratch policy stays at its default
+    assert not _lib._PEERS['on'] and _lib.load().skm_scratch_local_only(0) == 0
